@@ -1,0 +1,801 @@
+// C-ABI of the sampler (include/bae_b200.h): host-side state, phase-program construction, launches.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bae_common.cuh"
+
+namespace bae {
+int max_coop_blocks_per_sm();
+cudaError_t launch_program(const DevState* dS, int grid, int ph_begin, int ph_end, int n_rep, int c_begin, int c_end,
+                           int force_swap, cudaStream_t st);
+cudaError_t launch_phase(const DevState* dS, int grid, int pi, int c_begin, int c_end, cudaStream_t st);
+cudaError_t launch_debug_draws(const DevState* dS, int chain, int step, float* noise, double* scalars, cudaStream_t st);
+cudaError_t launch_debug_swap_u(const DevState* dS, int ens, int round, int pair, double* out, cudaStream_t st);
+cudaError_t launch_pack(const DevState* dS, const float* ref_vec, float* pad_vec, cudaStream_t st);
+cudaError_t launch_unpack(const DevState* dS, const float* pad_vec, float* ref_vec, cudaStream_t st);
+}  // namespace bae
+
+using namespace bae;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(x)                                                                                       \
+  do {                                                                                              \
+    cudaError_t e_ = (x);                                                                           \
+    if (e_ != cudaSuccess)                                                                          \
+      return fail(BAE_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(e_));                   \
+  } while (0)
+
+// Phase index map of the step program (see build_program).
+enum PhaseIdx : int {
+  P_PRO = 0,
+  P_FWD1 = 1,    // 7 phases
+  P_BWD1 = 8,    // 7 phases
+  P_ADAM1 = 15,
+  P_FWD2 = 16,
+  P_BWD2 = 23,
+  P_ADAM2 = 30,
+  P_FWDT = 31,
+  P_EPI = 38,
+  P_SWAP = 39,   // decide, gather, scatter
+  P_END = 42
+};
+
+struct bae_handle {
+  bae_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevState hs;            // host copy (device pointers inside)
+  DevState* dS = nullptr;
+  std::vector<void*> allocs;
+  int grid = 0;
+  bool data_loaded = false;
+  float* stage_ref = nullptr;    // [w_size] device staging, reference order
+  float* stage_noise = nullptr;  // [w_size]
+  double* stage_d = nullptr;     // small device scratch for doubles
+  int64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  bool phase_launch = false;
+};
+
+template <typename T>
+static cudaError_t dalloc(bae_handle* h, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, n * sizeof(T) + 256);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(q, 0, n * sizeof(T) + 256, h->stream);
+  h->allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return e;
+}
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+static void build_layout(DevState& s) {
+  const int d0 = s.d0, d1 = s.d1, d2 = s.d2, d3 = s.d3;
+  struct Sh { int rows, cols, tr; };
+  const Sh sh[kNumSegs] = {
+      {1, d3, 1}, {1, 1, 0}, {1, d3, 0}, {1, d3, 0}, {1, d3, 1},  // BN bias, nbt, rm, rv, weight
+      {1, d2, 1}, {d2, d3, 1},                                      // decode.1
+      {1, d1, 1}, {d1, d2, 1},                                      // decode.3
+      {1, d0, 1}, {d0, d1, 1},                                      // decode.5
+      {1, d1, 1}, {d1, d0, 1},                                      // encode.0
+      {1, d2, 1}, {d2, d1, 1},                                      // encode.2
+      {1, d3, 1}, {d3, d2, 1}};                                     // encode.4
+  int ref = 0, pad = 0;
+  for (int i = 0; i < kNumSegs; ++i) {
+    Seg& g = s.seg[i];
+    g.rows = sh[i].rows;
+    g.cols = sh[i].cols;
+    g.ld = round_up(sh[i].cols, 4);
+    g.trainable = sh[i].tr;
+    g.ref_off = ref;
+    g.pad_off = pad;
+    ref += g.rows * g.cols;
+    pad += round_up(g.rows * g.ld, 32);
+  }
+  s.w_size = ref;
+  s.Pp = round_up(pad, kAdamChunk);
+  s.n_adam_items = s.Pp / kAdamChunk;
+  s.nbuf = 2 * d3 + 1;
+  const int tidx[13] = {0, 100, 10000, 5000, 2000, 3000, 4000, 5000, 6000, 7000, 8000, 9000, 11000};  // MAIN:568-592
+  for (int k = 0; k < 13; ++k) {
+    s.trace_idx_pad[k] = -1;
+    if (tidx[k] >= s.w_size) continue;
+    for (int i = 0; i < kNumSegs; ++i) {
+      const Seg& g = s.seg[i];
+      if (tidx[k] >= g.ref_off && tidx[k] < g.ref_off + g.rows * g.cols) {
+        int e = tidx[k] - g.ref_off;
+        s.trace_idx_pad[k] = g.pad_off + (e / g.cols) * g.ld + (e % g.cols);
+      }
+    }
+  }
+}
+
+static GemmDesc make_gemm(const DevState& s, int M, int N, int K) {
+  GemmDesc g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K;
+  g.big = (M >= 128 && N > 64) ? 1 : 0;
+  const int bt = g.big ? 128 : 64;
+  g.tm = (M + bt - 1) / bt;
+  g.tn = (N + bt - 1) / bt;
+  return g;
+}
+
+static void build_program(bae_handle* h) {
+  DevState& s = h->hs;
+  const long long P = s.Pp;
+  const long long a1 = (long long)s.n_max * s.ld1, a2 = (long long)s.n_max * s.ld2, a3 = (long long)s.n_max * s.ld3,
+                  a0 = (long long)s.n_max * s.ld0;
+  auto W = [&](int seg) { return s.theta + s.seg[seg].pad_off; };
+  auto G = [&](int seg) { return s.grad + s.seg[seg].pad_off; };
+  int ng = 0;
+  // ---- forward descriptors for (train, first pass), (train, second pass), (test)
+  int fwd_base[3];
+  for (int pass = 0; pass < 3; ++pass) {
+    const float* X = (pass == 2) ? s.Xtest : s.Xtrain;
+    const int N = (pass == 2) ? s.n_test : s.n_train;
+    const int need = (pass == 0) ? 1 : 0;
+    fwd_base[pass] = ng;
+    struct L { const float* A; long long sA; int lda; int wseg, bseg; float* C; long long sC; int ldc; int din, dout; int epi; };
+    const L ls[6] = {
+        {X, 0, s.ld0, SEG_E0_W, SEG_E0_B, s.H1, a1, s.ld1, s.d0, s.d1, EPI_SIGMOID},
+        {s.H1, a1, s.ld1, SEG_E2_W, SEG_E2_B, s.H2, a2, s.ld2, s.d1, s.d2, EPI_SIGMOID},
+        {s.H2, a2, s.ld2, SEG_E4_W, SEG_E4_B, s.Z, a3, s.ld3, s.d2, s.d3, EPI_BIAS},
+        {s.Y, a3, s.ld3, SEG_D1_W, SEG_D1_B, s.H4, a2, s.ld2, s.d3, s.d2, EPI_SIGMOID},
+        {s.H4, a2, s.ld2, SEG_D3_W, SEG_D3_B, s.H5, a1, s.ld1, s.d2, s.d1, EPI_SIGMOID},
+        {s.H5, a1, s.ld1, SEG_D5_W, SEG_D5_B, s.DOUT, a0, s.ld0, s.d1, s.d0, EPI_LOSS}};
+    for (int l = 0; l < 6; ++l) {
+      GemmDesc g = make_gemm(s, N, ls[l].dout, ls[l].din);
+      g.A = ls[l].A; g.sA = ls[l].sA; g.lda = ls[l].lda; g.aMode = 0;
+      g.B = W(ls[l].wseg); g.sB = P; g.ldb = s.seg[ls[l].wseg].ld; g.bMode = 0;
+      g.C = ls[l].C; g.sC = ls[l].sC; g.ldc = ls[l].ldc;
+      g.epi = ls[l].epi;
+      g.bias = W(ls[l].bseg); g.sBias = P;
+      g.needLang = need;
+      if (ls[l].epi == EPI_LOSS) {
+        g.aux = X; g.sAux = 0; g.ldaux = s.ld0;
+        g.scale = 2.0f / ((float)N * (float)s.d0);   // d MSELoss / d out (mean over all N*d0 elements, MAIN:150,223)
+        g.part = s.loss_part + (size_t)pass * s.C_alloc * s.loss_stride * 2;
+        g.partStride = s.loss_stride;
+      }
+      s.gemm[ng++] = g;
+    }
+  }
+  // ---- backward descriptors (shared by both drift calls)
+  const int N = s.n_train;
+  int bwd_base = ng;
+  struct BL { float* dOut; long long sD; int ldd; int dout; const float* Ain; long long sAin; int ldain; int din;
+              int wseg, bseg; float* dIn; long long sDin; int lddin; const float* Hin; int epi_x; };
+  const BL bl[6] = {
+      // layer 6: dOut = DOUT [N x d0], input H5
+      {s.DOUT, a0, s.ld0, s.d0, s.H5, a1, s.ld1, s.d1, SEG_D5_W, SEG_D5_B, s.D5, a1, s.ld1, s.H5, EPI_DSIG},
+      {s.D5, a1, s.ld1, s.d1, s.H4, a2, s.ld2, s.d2, SEG_D3_W, SEG_D3_B, s.D4, a2, s.ld2, s.H4, EPI_DSIG},
+      {s.D4, a2, s.ld2, s.d2, s.Y, a3, s.ld3, s.d3, SEG_D1_W, SEG_D1_B, s.DY, a3, s.ld3, nullptr, EPI_PLAIN},
+      {s.DY, a3, s.ld3, s.d3, s.H2, a2, s.ld2, s.d2, SEG_E4_W, -1 /* encode.4.bias gradient is exactly 0 */, s.D2, a2, s.ld2, s.H2, EPI_DSIG},
+      {s.D2, a2, s.ld2, s.d2, s.H1, a1, s.ld1, s.d1, SEG_E2_W, SEG_E2_B, s.D1, a1, s.ld1, s.H1, EPI_DSIG},
+      {s.D1, a1, s.ld1, s.d1, s.Xtrain, 0, s.ld0, s.d0, SEG_E0_W, SEG_E0_B, nullptr, 0, 0, nullptr, EPI_PLAIN}};
+  int bw_idx[6], bx_idx[6];
+  for (int l = 0; l < 6; ++l) {
+    // dW[o,i] = sum_n dOut[n,o] * Ain[n,i]
+    GemmDesc g = make_gemm(s, bl[l].dout, bl[l].din, N);
+    g.A = bl[l].dOut; g.sA = bl[l].sD; g.lda = bl[l].ldd; g.aMode = 1;
+    g.B = bl[l].Ain; g.sB = bl[l].sAin; g.ldb = bl[l].ldain; g.bMode = 1;
+    g.C = G(bl[l].wseg); g.sC = P; g.ldc = s.seg[bl[l].wseg].ld;
+    g.epi = EPI_GRADW;
+    if (bl[l].bseg >= 0) { g.gbias = G(bl[l].bseg); g.sGb = P; }
+    g.needLang = 1;
+    bw_idx[l] = ng;
+    s.gemm[ng++] = g;
+    bx_idx[l] = -1;
+    if (bl[l].dIn) {
+      // dIn[n,i] = sum_o dOut[n,o] * W[o,i]   (x sigmoid' of the layer input)
+      GemmDesc x = make_gemm(s, N, bl[l].din, bl[l].dout);
+      x.A = bl[l].dOut; x.sA = bl[l].sD; x.lda = bl[l].ldd; x.aMode = 0;
+      x.B = W(bl[l].wseg); x.sB = P; x.ldb = s.seg[bl[l].wseg].ld; x.bMode = 1;
+      x.C = bl[l].dIn; x.sC = bl[l].sDin; x.ldc = bl[l].lddin;
+      x.epi = bl[l].epi_x;
+      if (bl[l].Hin) { x.aux = bl[l].Hin; x.sAux = bl[l].sDin; x.ldaux = bl[l].lddin; }
+      x.needLang = 1;
+      bx_idx[l] = ng;
+      s.gemm[ng++] = x;
+    }
+  }
+  (void)bwd_base;
+  s.n_gemm = ng;
+  // ---- phases
+  auto set = [&](int pi, int kind, int g0, int g1, int arg, int rows, int need) {
+    PhaseDesc& p = s.phase[pi];
+    p.kind = kind; p.g0 = g0; p.g1 = g1; p.arg = arg; p.argRows = rows; p.needLang = need;
+  };
+  set(P_PRO, PH_PROLOGUE, -1, -1, 0, 0, 0);
+  const int fstart[3] = {P_FWD1, P_FWD2, P_FWDT};
+  for (int pass = 0; pass < 3; ++pass) {
+    const int b = fwd_base[pass], p0 = fstart[pass];
+    const int rows = (pass == 2) ? s.n_test : s.n_train;
+    const int need = (pass == 0) ? 1 : 0;
+    set(p0 + 0, PH_GEMM, b + 0, -1, 0, 0, need);
+    set(p0 + 1, PH_GEMM, b + 1, -1, 0, 0, need);
+    set(p0 + 2, PH_GEMM, b + 2, -1, 0, 0, need);
+    set(p0 + 3, PH_BN_FWD, -1, -1, pass, rows, need);
+    set(p0 + 4, PH_GEMM, b + 3, -1, 0, 0, need);
+    set(p0 + 5, PH_GEMM, b + 4, -1, 0, 0, need);
+    set(p0 + 6, PH_GEMM, b + 5, -1, 0, 0, need);
+  }
+  const int bstart[2] = {P_BWD1, P_BWD2};
+  for (int pass = 0; pass < 2; ++pass) {
+    const int p0 = bstart[pass];
+    set(p0 + 0, PH_GEMM, bw_idx[0], bx_idx[0], 0, 0, 1);
+    set(p0 + 1, PH_GEMM, bw_idx[1], bx_idx[1], 0, 0, 1);
+    set(p0 + 2, PH_GEMM, bw_idx[2], bx_idx[2], 0, 0, 1);
+    set(p0 + 3, PH_BN_BWD, -1, -1, pass, s.n_train, 1);
+    set(p0 + 4, PH_GEMM, bw_idx[3], bx_idx[3], 0, 0, 1);
+    set(p0 + 5, PH_GEMM, bw_idx[4], bx_idx[4], 0, 0, 1);
+    set(p0 + 6, PH_GEMM, bw_idx[5], -1, 0, 0, 1);
+  }
+  set(P_ADAM1, PH_ADAM1, -1, -1, 0, 0, 0);
+  set(P_ADAM2, PH_ADAM2, -1, -1, 0, 0, 1);
+  set(P_EPI, PH_EPILOGUE, -1, -1, 0, 0, 0);
+  set(P_SWAP + 0, PH_SWAP_DECIDE, -1, -1, 0, 0, 0);
+  set(P_SWAP + 1, PH_SWAP_GATHER, -1, -1, 0, 0, 0);
+  set(P_SWAP + 2, PH_SWAP_SCATTER, -1, -1, 0, 0, 0);
+  s.n_phase = P_END;
+}
+
+static int upload_state(bae_handle* h) {
+  CU(cudaMemcpyAsync(h->dS, &h->hs, sizeof(DevState), cudaMemcpyHostToDevice, h->stream));
+  return BAE_OK;
+}
+
+extern "C" {
+
+const char* bae_last_error(void) { return g_err.c_str(); }
+int bae_version(void) { return 100; }
+
+int bae_create(const bae_config* cfg, int device, bae_handle** out) {
+  if (!cfg || !out) return fail(BAE_ERR_INVALID, "null argument");
+  for (int i = 0; i < 4; ++i)
+    if (cfg->dims[i] < 1) return fail(BAE_ERR_INVALID, "dims must be >= 1");
+  if (cfg->n_train < 2 || cfg->n_test < 2) return fail(BAE_ERR_INVALID, "need at least 2 rows (BatchNorm batch statistics)");
+  if (cfg->n_chains < 1 || cfg->n_rungs < 1 || cfg->n_chains % cfg->n_rungs != 0)
+    return fail(BAE_ERR_INVALID, "n_chains must be a positive multiple of n_rungs");
+  if (cfg->swap_interval < 1 || cfg->samples < 1) return fail(BAE_ERR_INVALID, "swap_interval and samples must be >= 1");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return fail(BAE_ERR_NO_DEVICE, "no CUDA device: this library has no CPU fallback");
+  }
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(BAE_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                       ", this library is built for sm_100a only");
+  CU(cudaSetDevice(device));
+  bae_handle* h = new bae_handle();
+  h->cfg = *cfg;
+  h->device = device;
+  h->phase_launch = getenv("BAE_PHASE_LAUNCH") != nullptr && getenv("BAE_PHASE_LAUNCH")[0] == '1';
+  CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CU(cudaEventCreate(&h->ev0));
+  CU(cudaEventCreate(&h->ev1));
+  DevState& s = h->hs;
+  memset(&s, 0, sizeof(s));
+  s.d0 = cfg->dims[0]; s.d1 = cfg->dims[1]; s.d2 = cfg->dims[2]; s.d3 = cfg->dims[3];
+  s.ld0 = round_up(s.d0, 4); s.ld1 = round_up(s.d1, 4); s.ld2 = round_up(s.d2, 4); s.ld3 = round_up(s.d3, 4);
+  s.n_train = cfg->n_train; s.n_test = cfg->n_test; s.n_max = std::max(cfg->n_train, cfg->n_test);
+  s.C = cfg->n_chains; s.C_alloc = s.C + 1; s.n_rungs = cfg->n_rungs; s.chain_id_base = cfg->chain_id_base;
+  s.samples = cfg->samples; s.pt_step = cfg->pt_switch_step; s.swap_interval = cfg->swap_interval;
+  s.use_langevin = cfg->use_langevin;
+  s.lr = cfg->lr; s.step_w = cfg->step_w; s.step_eta = cfg->step_eta; s.l_prob = cfg->l_prob;
+  s.sigma_sq = cfg->sigma_squared; s.nu1 = cfg->nu_1; s.nu2 = cfg->nu_2;
+  s.seed_lo = (unsigned)(cfg->seed & 0xffffffffull); s.seed_hi = (unsigned)(cfg->seed >> 32);
+  build_layout(s);
+  const size_t CA = s.C_alloc, P = s.Pp;
+  CU(dalloc(h, &s.theta, CA * P)); CU(dalloc(h, &s.m, CA * P)); CU(dalloc(h, &s.v, CA * P));
+  CU(dalloc(h, &s.wcur, CA * P)); CU(dalloc(h, &s.grad, CA * P));
+  CU(dalloc(h, &s.wb, CA * s.nbuf)); CU(dalloc(h, &s.wb_tmp, CA * s.nbuf));
+  CU(dalloc(h, &s.bn_mu, 3 * CA * s.ld3)); CU(dalloc(h, &s.bn_var, 3 * CA * s.ld3)); CU(dalloc(h, &s.bn_inv, CA * s.ld3));
+  CU(dalloc(h, &s.Xtrain, (size_t)s.n_train * s.ld0)); CU(dalloc(h, &s.Xtest, (size_t)s.n_test * s.ld0));
+  const size_t nm = s.n_max;
+  CU(dalloc(h, &s.H1, CA * nm * s.ld1)); CU(dalloc(h, &s.H2, CA * nm * s.ld2)); CU(dalloc(h, &s.Z, CA * nm * s.ld3));
+  CU(dalloc(h, &s.Y, CA * nm * s.ld3)); CU(dalloc(h, &s.H4, CA * nm * s.ld2)); CU(dalloc(h, &s.H5, CA * nm * s.ld1));
+  CU(dalloc(h, &s.DOUT, CA * nm * s.ld0)); CU(dalloc(h, &s.D5, CA * nm * s.ld1)); CU(dalloc(h, &s.D4, CA * nm * s.ld2));
+  CU(dalloc(h, &s.DY, CA * nm * s.ld3)); CU(dalloc(h, &s.D2, CA * nm * s.ld2)); CU(dalloc(h, &s.D1, CA * nm * s.ld1));
+  {
+    GemmDesc t = make_gemm(s, s.n_max, s.d0, s.d1);
+    s.loss_stride = t.tm * t.tn;
+    GemmDesc t2 = make_gemm(s, std::min(s.n_train, s.n_test), s.d0, s.d1);
+    s.loss_stride = std::max(s.loss_stride, t2.tm * t2.tn);
+  }
+  CU(dalloc(h, &s.loss_part, 3 * CA * (size_t)s.loss_stride * 2));
+  CU(dalloc(h, &s.adam_part, CA * (size_t)s.n_adam_items * 3));
+  ChainArrays& c = s.ch;
+  CU(dalloc(h, &c.eta, CA)); CU(dalloc(h, &c.lik, CA)); CU(dalloc(h, &c.prior_cur, CA)); CU(dalloc(h, &c.last_sse, CA)); CU(dalloc(h, &c.prop_sse, CA));
+  CU(dalloc(h, &c.mse_tr, CA)); CU(dalloc(h, &c.mse_te, CA)); CU(dalloc(h, &c.T, CA)); CU(dalloc(h, &c.adapt, CA));
+  CU(dalloc(h, &c.adam_t, CA)); CU(dalloc(h, &c.alias, CA)); CU(dalloc(h, &c.init_count, CA)); CU(dalloc(h, &c.nacc, CA));
+  CU(dalloc(h, &c.nlang, CA)); CU(dalloc(h, &c.step, CA)); CU(dalloc(h, &c.is_lang, CA));
+  CU(dalloc(h, &c.lx, CA)); CU(dalloc(h, &c.eta_noise, CA)); CU(dalloc(h, &c.u, CA));
+  CU(dalloc(h, &c.ss1, CA)); CU(dalloc(h, &c.sq1, CA)); CU(dalloc(h, &c.ss2, CA)); CU(dalloc(h, &c.sq2, CA));
+  CU(dalloc(h, &s.traces, (size_t)s.C * s.samples));
+  CU(dalloc(h, &s.swap_src, CA)); CU(dalloc(h, &s.swap_flag, CA)); CU(dalloc(h, &s.swap_tmp, CA * 2));
+  CU(dalloc(h, &s.num_swap, 1)); CU(dalloc(h, &s.total_swap, 1));
+  CU(dalloc(h, &h->stage_ref, (size_t)s.w_size + 8)); CU(dalloc(h, &h->stage_noise, (size_t)s.w_size + 8));
+  CU(dalloc(h, &h->stage_d, 64));
+  {
+    void* q = nullptr;
+    CU(cudaMalloc(&q, sizeof(DevState)));
+    h->allocs.push_back(q);
+    h->dS = reinterpret_cast<DevState*>(q);
+  }
+  build_program(h);
+  int rc = upload_state(h);
+  if (rc) return rc;
+  const int bps = max_coop_blocks_per_sm();
+  if (bps < 1) return fail(BAE_ERR_CUDA, "step kernel cannot be made resident (occupancy 0)");
+  h->grid = prop.multiProcessorCount * bps;
+  CU(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return BAE_OK;
+}
+
+int bae_destroy(bae_handle* h) {
+  if (!h) return BAE_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return BAE_OK;
+}
+
+int bae_w_size(const bae_handle* h) { return h ? h->hs.w_size : BAE_ERR_INVALID; }
+int bae_n_trainable(const bae_handle* h) { return h ? h->hs.w_size - h->hs.nbuf : BAE_ERR_INVALID; }
+int bae_gemm_path(const bae_handle* h) { return h ? 1 : BAE_ERR_INVALID; }
+void* bae_stream(bae_handle* h) { return h ? (void*)h->stream : nullptr; }
+int64_t bae_launch_count(const bae_handle* h) { return h ? h->launches : 0; }
+
+int bae_synchronize(bae_handle* h) {
+  if (!h) return fail(BAE_ERR_INVALID, "null handle");
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+
+int bae_upload_data(bae_handle* h, const float* train, const float* test) {
+  if (!h || !train || !test) return fail(BAE_ERR_INVALID, "null argument");
+  const DevState& s = h->hs;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpy2DAsync(s.Xtrain, (size_t)s.ld0 * 4, train, (size_t)s.d0 * 4, (size_t)s.d0 * 4, s.n_train,
+                       cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpy2DAsync(s.Xtest, (size_t)s.ld0 * 4, test, (size_t)s.d0 * 4, (size_t)s.d0 * 4, s.n_test,
+                       cudaMemcpyHostToDevice, h->stream));
+  h->data_loaded = true;
+  return BAE_OK;
+}
+
+int bae_set_ladder(bae_handle* h, const double* T) {
+  if (!h || !T) return fail(BAE_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->hs.ch.T, T, sizeof(double) * h->hs.C, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->hs.ch.adapt, T, sizeof(double) * h->hs.C, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+
+}  // extern "C"
+
+// ---- helpers -----------------------------------------------------------------------------------
+static int put_vec(bae_handle* h, const float* host_ref, float* dev_pad_chain) {
+  const DevState& s = h->hs;
+  CU(cudaMemcpyAsync(h->stage_ref, host_ref, sizeof(float) * s.w_size, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemsetAsync(dev_pad_chain, 0, sizeof(float) * s.Pp, h->stream));
+  CU(launch_pack(h->dS, h->stage_ref, dev_pad_chain, h->stream));
+  h->launches++;
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+
+static int get_vec(bae_handle* h, const float* dev_pad_chain, float* host_ref) {
+  const DevState& s = h->hs;
+  CU(launch_unpack(h->dS, dev_pad_chain, h->stage_ref, h->stream));
+  h->launches++;
+  CU(cudaMemcpyAsync(host_ref, h->stage_ref, sizeof(float) * s.w_size, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+
+template <typename T>
+static int put1(bae_handle* h, T* dev_arr, int idx, T v) {
+  CU(cudaMemcpyAsync(dev_arr + idx, &v, sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+template <typename T>
+static int get1(bae_handle* h, const T* dev_arr, int idx, T* v) {
+  CU(cudaMemcpyAsync(v, dev_arr + idx, sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+
+static int run_phases_plain(bae_handle* h, int p_begin, int p_end, int c_begin, int c_end) {
+  for (int p = p_begin; p < p_end; ++p) {
+    CU(launch_phase(h->dS, h->grid, p, c_begin, c_end, h->stream));
+    h->launches++;
+  }
+  return BAE_OK;
+}
+
+// forward of slot `pass` (0: train via FWD1 phases, 2: test via FWDT phases) for one chain; returns SSE and sum(d)
+static int forward_one(bae_handle* h, int chain, int pass, double* sse, double* sumd) {
+  const DevState& s = h->hs;
+  int rc = put1<int>(h, s.ch.is_lang, chain, 1);
+  if (rc) return rc;
+  const int p0 = (pass == 0) ? P_FWD1 : P_FWDT;
+  rc = run_phases_plain(h, p0, p0 + 7, chain, chain + 1);
+  if (rc) return rc;
+  std::vector<double> part((size_t)s.loss_stride * 2);
+  CU(cudaMemcpyAsync(part.data(), s.loss_part + ((size_t)pass * s.C_alloc + chain) * s.loss_stride * 2,
+                     sizeof(double) * part.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  double a = 0, b = 0;
+  for (int i = 0; i < s.loss_stride; ++i) { a += part[2 * i]; b += part[2 * i + 1]; }
+  *sse = a;
+  if (sumd) *sumd = b;
+  return BAE_OK;
+}
+
+static double loglik_h(double sse, double n, double tau_sq, double temp) {
+  return (-(n * 0.5) * std::log(2.0 * M_PI * tau_sq) - 0.5 * tau_sq * sse) / temp;
+}
+
+extern "C" {
+
+int bae_init_chain(bae_handle* h, int chain, const float* theta_init, const double* w0) {
+  if (!h || !theta_init || !w0) return fail(BAE_ERR_INVALID, "null argument");
+  if (!h->data_loaded) return fail(BAE_ERR_STATE, "upload data before initialising chains");
+  const DevState& s = h->hs;
+  if (chain < 0 || chain >= s.C) return fail(BAE_ERR_INVALID, "chain out of range");
+  CU(cudaSetDevice(h->device));
+  float* th = s.theta + (size_t)chain * s.Pp;
+  int rc = put_vec(h, theta_init, th);
+  if (rc) return rc;
+  // eta0 = log var(pred_train - train) with the torch-default-initialised model   MAIN:381-385
+  double sse = 0, sd = 0;
+  rc = forward_one(h, chain, 0, &sse, &sd);
+  if (rc) return rc;
+  const double n = (double)s.n_train * s.d0;
+  const double var = sse / n - (sd / n) * (sd / n);
+  const double eta = std::log(var);
+  const double tau = std::exp(eta);
+  // w_proposal = dictfromlist(randn) -> fp32; prior on the UNquantised float64 vector   MAIN:389-399
+  std::vector<float> wq(s.w_size);
+  double sumsq = 0;
+  for (int i = 0; i < s.w_size; ++i) { wq[i] = (float)w0[i]; sumsq += w0[i] * w0[i]; }
+  const double prior = -((double)s.w_size * 0.5) * std::log((double)s.sigma_sq) - sumsq / (2.0 * (double)s.sigma_sq) -
+                       (1.0 + (double)s.nu1) * std::log(tau) - ((double)s.nu2 / tau);
+  const int nbt_ref = s.seg[SEG_BN_NBT].ref_off, rm_ref = s.seg[SEG_BN_RM].ref_off, rv_ref = s.seg[SEG_BN_RV].ref_off;
+  std::vector<float> loaded = wq;
+  loaded[nbt_ref] = std::trunc(wq[nbt_ref]);   // load_state_dict into the int64 buffer
+  rc = put_vec(h, loaded.data(), th);
+  if (rc) return rc;
+  rc = forward_one(h, chain, 0, &sse, nullptr);                                       // MAIN:401
+  if (rc) return rc;
+  double T = 1.0;
+  rc = get1<double>(h, s.ch.T, chain, &T);
+  if (rc) return rc;
+  const double lik = loglik_h(sse, n, tau, T);
+  // the forward updated the live model's running statistics
+  std::vector<float> mu(s.ld3), va(s.ld3);
+  CU(cudaMemcpyAsync(mu.data(), s.bn_mu + ((size_t)0 * s.C_alloc + chain) * s.ld3, sizeof(float) * s.ld3, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(va.data(), s.bn_var + ((size_t)0 * s.C_alloc + chain) * s.ld3, sizeof(float) * s.ld3, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const float ub = (float)s.n_train / (float)(s.n_train - 1);
+  for (int c = 0; c < s.d3; ++c) {
+    loaded[rm_ref + c] = 0.9f * loaded[rm_ref + c] + 0.1f * mu[c];
+    loaded[rv_ref + c] = 0.9f * loaded[rv_ref + c] + 0.1f * va[c] * ub;
+  }
+  loaded[nbt_ref] += 1.0f;
+  rc = put_vec(h, loaded.data(), th);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(s.m + (size_t)chain * s.Pp, 0, sizeof(float) * s.Pp, h->stream));
+  CU(cudaMemsetAsync(s.v + (size_t)chain * s.Pp, 0, sizeof(float) * s.Pp, h->stream));
+  bae_chain_scalars sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.eta = eta; sc.likelihood = lik; sc.prior_current = prior; sc.last_sse_train = sse; sc.prop_sse_train = sse;
+  sc.temperature = T; sc.adapttemp = T; sc.w_is_alias = 1;
+  return bae_set_state(h, chain, nullptr, nullptr, nullptr, nullptr, &sc);
+}
+
+int bae_get_state(bae_handle* h, int chain, float* theta, float* w, float* m, float* v, bae_chain_scalars* sc) {
+  if (!h) return fail(BAE_ERR_INVALID, "null handle");
+  const DevState& s = h->hs;
+  if (chain < 0 || chain >= s.C) return fail(BAE_ERR_INVALID, "chain out of range");
+  CU(cudaSetDevice(h->device));
+  int rc;
+  const size_t o = (size_t)chain * s.Pp;
+  if (theta && (rc = get_vec(h, s.theta + o, theta))) return rc;
+  if (m && (rc = get_vec(h, s.m + o, m))) return rc;
+  if (v && (rc = get_vec(h, s.v + o, v))) return rc;
+  if (w) {
+    // `w` = trainables of the live model (they coincide at every step boundary) + the detached buffers
+    if ((rc = get_vec(h, s.theta + o, w))) return rc;
+    int alias = 1;
+    if ((rc = get1<int>(h, s.ch.alias, chain, &alias))) return rc;
+    if (!alias) {
+      std::vector<float> wb(s.nbuf);
+      CU(cudaMemcpyAsync(wb.data(), s.wb + (size_t)chain * s.nbuf, sizeof(float) * s.nbuf, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      for (int c = 0; c < s.d3; ++c) {
+        w[s.seg[SEG_BN_RM].ref_off + c] = wb[c];
+        w[s.seg[SEG_BN_RV].ref_off + c] = wb[s.d3 + c];
+      }
+      w[s.seg[SEG_BN_NBT].ref_off] = wb[2 * s.d3];
+    }
+  }
+  if (sc) {
+    const ChainArrays& c = s.ch;
+    if ((rc = get1(h, c.eta, chain, &sc->eta))) return rc;
+    get1(h, c.lik, chain, &sc->likelihood); get1(h, c.prior_cur, chain, &sc->prior_current);
+    get1(h, c.last_sse, chain, &sc->last_sse_train); get1(h, c.mse_tr, chain, &sc->mse_train);
+    get1(h, c.prop_sse, chain, &sc->prop_sse_train);
+    get1(h, c.mse_te, chain, &sc->mse_test); get1(h, c.T, chain, &sc->temperature); get1(h, c.adapt, chain, &sc->adapttemp);
+    get1(h, c.adam_t, chain, &sc->adam_t); get1(h, c.alias, chain, &sc->w_is_alias); get1(h, c.init_count, chain, &sc->init_count);
+    get1(h, c.nacc, chain, &sc->num_accepted); get1(h, c.nlang, chain, &sc->langevin_count); get1(h, c.step, chain, &sc->step);
+  }
+  return BAE_OK;
+}
+
+int bae_set_state(bae_handle* h, int chain, const float* theta, const float* w, const float* m, const float* v,
+                  const bae_chain_scalars* sc) {
+  if (!h) return fail(BAE_ERR_INVALID, "null handle");
+  const DevState& s = h->hs;
+  if (chain < 0 || chain >= s.C) return fail(BAE_ERR_INVALID, "chain out of range");
+  CU(cudaSetDevice(h->device));
+  int rc;
+  const size_t o = (size_t)chain * s.Pp;
+  if (theta && (rc = put_vec(h, theta, s.theta + o))) return rc;
+  if (m && (rc = put_vec(h, m, s.m + o))) return rc;
+  if (v && (rc = put_vec(h, v, s.v + o))) return rc;
+  if (w) {
+    std::vector<float> wb(s.nbuf);
+    for (int c = 0; c < s.d3; ++c) {
+      wb[c] = w[s.seg[SEG_BN_RM].ref_off + c];
+      wb[s.d3 + c] = w[s.seg[SEG_BN_RV].ref_off + c];
+    }
+    wb[2 * s.d3] = w[s.seg[SEG_BN_NBT].ref_off];
+    CU(cudaMemcpyAsync(s.wb + (size_t)chain * s.nbuf, wb.data(), sizeof(float) * s.nbuf, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  if (sc) {
+    const ChainArrays& c = s.ch;
+    if ((rc = put1(h, c.eta, chain, sc->eta))) return rc;
+    put1(h, c.lik, chain, sc->likelihood); put1(h, c.prior_cur, chain, sc->prior_current);
+    put1(h, c.last_sse, chain, sc->last_sse_train); put1(h, c.mse_tr, chain, sc->mse_train);
+    put1(h, c.prop_sse, chain, sc->prop_sse_train);
+    put1(h, c.mse_te, chain, sc->mse_test); put1(h, c.T, chain, sc->temperature); put1(h, c.adapt, chain, sc->adapttemp);
+    put1(h, c.adam_t, chain, sc->adam_t); put1(h, c.alias, chain, sc->w_is_alias); put1(h, c.init_count, chain, sc->init_count);
+    put1(h, c.nacc, chain, sc->num_accepted); put1(h, c.nlang, chain, sc->langevin_count); put1(h, c.step, chain, sc->step);
+  }
+  return BAE_OK;
+}
+
+static int coop_launch(bae_handle* h, int p_begin, int p_end, int n_rep, int force_swap) {
+  if (!h->data_loaded) return fail(BAE_ERR_STATE, "upload data first");
+  CU(cudaSetDevice(h->device));
+  CU(cudaEventRecord(h->ev0, h->stream));
+  if (h->phase_launch) {
+    // profiling aid (BAE_PHASE_LAUNCH=1): one plain launch per phase, so ncu lists each phase separately.
+    // Exchange phases need the step counter test that the cooperative kernel does on the device.
+    for (int r = 0; r < n_rep; ++r) {
+      for (int p = p_begin; p < p_end; ++p) {
+        if (p >= P_SWAP && !force_swap) {
+          int st = 0;
+          CU(cudaMemcpyAsync(&st, h->hs.ch.step, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+          CU(cudaStreamSynchronize(h->stream));
+          if (st == 0 || st % h->hs.swap_interval != 0) continue;
+        }
+        CU(launch_phase(h->dS, h->grid, p, 0, h->hs.C, h->stream));
+        h->launches++;
+      }
+    }
+  } else {
+    CU(launch_program(h->dS, h->grid, p_begin, p_end, n_rep, 0, h->hs.C, force_swap, h->stream));
+    h->launches++;
+  }
+  CU(cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  return BAE_OK;
+}
+
+int bae_step(bae_handle* h, int n_steps) {
+  if (!h || n_steps < 0) return fail(BAE_ERR_INVALID, "bad argument");
+  if (n_steps == 0) return BAE_OK;
+  return coop_launch(h, P_PRO, P_EPI + 1, n_steps, 0);
+}
+
+int bae_swap_local(bae_handle* h) {
+  if (!h) return fail(BAE_ERR_INVALID, "null handle");
+  return coop_launch(h, P_SWAP, P_END, 1, 1);
+}
+
+int bae_run(bae_handle* h, int n_steps) {
+  if (!h || n_steps < 0) return fail(BAE_ERR_INVALID, "bad argument");
+  if (n_steps == 0) return BAE_OK;
+  return coop_launch(h, P_PRO, P_END, n_steps, 0);
+}
+
+int bae_last_step_ms(bae_handle* h, float* ms) {
+  if (!h || !ms) return fail(BAE_ERR_INVALID, "null argument");
+  if (!h->timed) return fail(BAE_ERR_STATE, "no launch recorded");
+  CU(cudaEventSynchronize(h->ev1));
+  CU(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return BAE_OK;
+}
+
+int bae_eval(bae_handle* h, int chain, int which, const float* w, double* sse, double* mse, float* grads, float* out) {
+  if (!h) return fail(BAE_ERR_INVALID, "null handle");
+  if (!h->data_loaded) return fail(BAE_ERR_STATE, "upload data first");
+  const DevState& s = h->hs;
+  if (chain < 0 || chain >= s.C) return fail(BAE_ERR_INVALID, "chain out of range");
+  if (which != 0 && which != 1) return fail(BAE_ERR_INVALID, "which must be 0 (train) or 1 (test)");
+  if (grads && which != 0) return fail(BAE_ERR_INVALID, "gradients are defined on the training matrix only (MAIN:473)");
+  CU(cudaSetDevice(h->device));
+  const int E = s.C;  // scratch chain slot
+  float* th = s.theta + (size_t)E * s.Pp;
+  int rc;
+  if (w) {
+    if ((rc = put_vec(h, w, th))) return rc;
+  } else {
+    CU(cudaMemcpyAsync(th, s.theta + (size_t)chain * s.Pp, sizeof(float) * s.Pp, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  const int pass = which == 0 ? 0 : 2;
+  const int rows = which == 0 ? s.n_train : s.n_test;
+  double a = 0;
+  if ((rc = forward_one(h, E, pass, &a, nullptr))) return rc;
+  if (sse) *sse = a;
+  if (mse) *mse = a / ((double)rows * s.d0);
+  if (out) {
+    // the loss epilogue stores (out - X) * scale; undo it on the host
+    std::vector<float> d((size_t)rows * s.ld0), x((size_t)rows * s.ld0);
+    CU(cudaMemcpyAsync(d.data(), s.DOUT + (size_t)E * s.n_max * s.ld0, sizeof(float) * d.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(x.data(), which == 0 ? s.Xtrain : s.Xtest, sizeof(float) * x.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    const double scale = 2.0 / ((double)rows * s.d0);
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < s.d0; ++c)
+        out[(size_t)r * s.d0 + c] = (float)((double)d[(size_t)r * s.ld0 + c] / scale + (double)x[(size_t)r * s.ld0 + c]);
+  }
+  if (grads) {
+    CU(cudaMemsetAsync(s.grad + (size_t)E * s.Pp, 0, sizeof(float) * s.Pp, h->stream));
+    if ((rc = run_phases_plain(h, P_BWD1, P_BWD1 + 7, E, E + 1))) return rc;
+    if ((rc = get_vec(h, s.grad + (size_t)E * s.Pp, grads))) return rc;
+  }
+  return BAE_OK;
+}
+
+int bae_debug_draws(bae_handle* h, int chain, int step, float* noise, double* scalars3) {
+  if (!h || !noise || !scalars3) return fail(BAE_ERR_INVALID, "null argument");
+  const DevState& s = h->hs;
+  CU(cudaSetDevice(h->device));
+  CU(launch_debug_draws(h->dS, chain, step, h->stage_noise, h->stage_d, h->stream));
+  h->launches++;
+  CU(cudaMemcpyAsync(noise, h->stage_noise, sizeof(float) * s.w_size, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(scalars3, h->stage_d, sizeof(double) * 3, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+
+int bae_debug_swap_uniform(bae_handle* h, int ensemble, int round, int pair, double* u) {
+  if (!h || !u) return fail(BAE_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(launch_debug_swap_u(h->dS, h->hs.chain_id_base / h->hs.n_rungs + ensemble, round, pair, h->stage_d, h->stream));
+  h->launches++;
+  CU(cudaMemcpyAsync(u, h->stage_d, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+
+int bae_read_traces(bae_handle* h, int chain, int first_step, int n, bae_trace* outp) {
+  if (!h || !outp) return fail(BAE_ERR_INVALID, "null argument");
+  const DevState& s = h->hs;
+  if (chain < 0 || chain >= s.C || first_step < 0 || n < 0 || first_step + n > s.samples)
+    return fail(BAE_ERR_INVALID, "trace range out of bounds");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(outp, s.traces + (size_t)chain * s.samples + first_step, sizeof(bae_trace) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+
+int bae_swap_counts(bae_handle* h, int64_t* num_swap, int64_t* total) {
+  if (!h || !num_swap || !total) return fail(BAE_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  long long a = 0, b = 0;
+  CU(cudaMemcpyAsync(&a, h->hs.num_swap, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(&b, h->hs.total_swap, sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *num_swap = a;
+  *total = b;
+  return BAE_OK;
+}
+
+int bae_exchange_pack(bae_handle* h, int chain, float* dev_w, double* host_scalars4) {
+  if (!h || !dev_w || !host_scalars4) return fail(BAE_ERR_INVALID, "null argument");
+  const DevState& s = h->hs;
+  if (chain < 0 || chain >= s.C) return fail(BAE_ERR_INVALID, "chain out of range");
+  CU(cudaSetDevice(h->device));
+  CU(launch_unpack(h->dS, s.theta + (size_t)chain * s.Pp, dev_w, h->stream));
+  h->launches++;
+  int alias = 1;
+  int rc = get1<int>(h, s.ch.alias, chain, &alias);
+  if (rc) return rc;
+  if (!alias) {  // detached `w`: its BatchNorm buffers live in wb
+    CU(cudaMemcpyAsync(dev_w + s.seg[SEG_BN_RM].ref_off, s.wb + (size_t)chain * s.nbuf, sizeof(float) * s.d3, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(dev_w + s.seg[SEG_BN_RV].ref_off, s.wb + (size_t)chain * s.nbuf + s.d3, sizeof(float) * s.d3, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(dev_w + s.seg[SEG_BN_NBT].ref_off, s.wb + (size_t)chain * s.nbuf + 2 * s.d3, sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  get1(h, s.ch.eta, chain, &host_scalars4[0]);
+  get1(h, s.ch.lik, chain, &host_scalars4[1]);
+  get1(h, s.ch.adapt, chain, &host_scalars4[2]);
+  get1(h, s.ch.last_sse, chain, &host_scalars4[3]);
+  return BAE_OK;
+}
+
+int bae_exchange_unpack(bae_handle* h, int chain, const float* dev_w, const double* host_scalars2) {
+  if (!h || !dev_w || !host_scalars2) return fail(BAE_ERR_INVALID, "null argument");
+  const DevState& s = h->hs;
+  if (chain < 0 || chain >= s.C) return fail(BAE_ERR_INVALID, "chain out of range");
+  CU(cudaSetDevice(h->device));
+  // buffers of the received dict go to wb; trainables go straight into the live model (reloaded next step anyway)
+  CU(cudaMemcpyAsync(s.wb + (size_t)chain * s.nbuf, dev_w + s.seg[SEG_BN_RM].ref_off, sizeof(float) * s.d3, cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(s.wb + (size_t)chain * s.nbuf + s.d3, dev_w + s.seg[SEG_BN_RV].ref_off, sizeof(float) * s.d3, cudaMemcpyDeviceToDevice, h->stream));
+  CU(cudaMemcpyAsync(s.wb + (size_t)chain * s.nbuf + 2 * s.d3, dev_w + s.seg[SEG_BN_NBT].ref_off, sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+  // keep the live buffers: pack into scratch, then copy trainable segments only
+  float* scratch = s.wcur + (size_t)chain * s.Pp;
+  CU(cudaMemsetAsync(scratch, 0, sizeof(float) * s.Pp, h->stream));
+  CU(launch_pack(h->dS, dev_w, scratch, h->stream));
+  h->launches++;
+  for (int i = 0; i < kNumSegs; ++i) {
+    const Seg& g = s.seg[i];
+    if (!g.trainable) continue;
+    CU(cudaMemcpyAsync(s.theta + (size_t)chain * s.Pp + g.pad_off, scratch + g.pad_off, sizeof(float) * g.rows * g.ld,
+                       cudaMemcpyDeviceToDevice, h->stream));
+  }
+  put1(h, s.ch.eta, chain, host_scalars2[0]);
+  put1(h, s.ch.last_sse, chain, host_scalars2[1]);
+  put1<int>(h, s.ch.alias, chain, 0);
+  return BAE_OK;
+}
+
+int bae_exchange_finish(bae_handle* h) {
+  if (!h) return fail(BAE_ERR_INVALID, "null handle");
+  const DevState& s = h->hs;
+  CU(cudaSetDevice(h->device));
+  // every chain's `w` becomes a detached dict (MAIN:602); chains that kept their own configuration
+  // snapshot their live buffers
+  std::vector<int> alias(s.C);
+  CU(cudaMemcpyAsync(alias.data(), s.ch.alias, sizeof(int) * s.C, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < s.C; ++c) {
+    if (!alias[c]) continue;
+    const float* th = s.theta + (size_t)c * s.Pp;
+    CU(cudaMemcpyAsync(s.wb + (size_t)c * s.nbuf, th + s.seg[SEG_BN_RM].pad_off, sizeof(float) * s.d3, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(s.wb + (size_t)c * s.nbuf + s.d3, th + s.seg[SEG_BN_RV].pad_off, sizeof(float) * s.d3, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(s.wb + (size_t)c * s.nbuf + 2 * s.d3, th + s.seg[SEG_BN_NBT].pad_off, sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
+    alias[c] = 0;
+  }
+  std::vector<int> zero(s.C, 0);
+  CU(cudaMemcpyAsync(s.ch.alias, zero.data(), sizeof(int) * s.C, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+
+}  // extern "C"

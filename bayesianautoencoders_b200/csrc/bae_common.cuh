@@ -1,0 +1,167 @@
+// Shared host/device definitions for the PT-Langevin sampler (sm_100a).
+// Layout, phase program and per-chain state. See DESIGN.md for the data layout in HBM.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/bae_b200.h"
+
+namespace bae {
+
+constexpr int kNumSegs = 17;
+// Sorted state_dict key order of the reference's getparameters (MAIN:228-241).
+enum SegId : int {
+  SEG_BN_BIAS = 0,  // decode.0.bias (beta)
+  SEG_BN_NBT,       // decode.0.num_batches_tracked
+  SEG_BN_RM,        // decode.0.running_mean
+  SEG_BN_RV,        // decode.0.running_var
+  SEG_BN_W,         // decode.0.weight (gamma)
+  SEG_D1_B, SEG_D1_W,  // decode.1 (layer 4)
+  SEG_D3_B, SEG_D3_W,  // decode.3 (layer 5)
+  SEG_D5_B, SEG_D5_W,  // decode.5 (layer 6)
+  SEG_E0_B, SEG_E0_W,  // encode.0 (layer 1)
+  SEG_E2_B, SEG_E2_W,  // encode.2 (layer 2)
+  SEG_E4_B, SEG_E4_W   // encode.4 (layer 3)
+};
+
+struct Seg {
+  int ref_off;    // offset in the reference flat vector
+  int pad_off;    // offset in the padded device vector (multiple of 32 floats)
+  int rows, cols; // logical shape (1-D tensors: rows = 1)
+  int ld;         // padded row pitch in floats (multiple of 4)
+  int trainable;  // 0 for the three BatchNorm buffers
+};
+
+// ---- GEMM phase descriptors ---------------------------------------------------------------------
+enum EpiKind : int {
+  EPI_SIGMOID = 0,  // C = sigmoid(acc + bias[c])
+  EPI_BIAS,         // C = acc + bias[c]                       (pre-BatchNorm z)
+  EPI_LOSS,         // o = acc + bias[c]; d = o - X; partial SSE; C = d * scale (dLoss/dOut)
+  EPI_DSIG,         // C = acc * H * (1 - H)                    (delta through a sigmoid)
+  EPI_PLAIN,        // C = acc
+  EPI_GRADW         // C = acc (weight gradient) + column sums of the A operand -> bias gradient
+};
+
+struct GemmDesc {
+  const float* A; long long sA; int lda; int aMode;  // aMode 0: A(i,k) = A[i*lda+k]; 1: A(i,k) = A[k*lda+i]
+  const float* B; long long sB; int ldb; int bMode;  // bMode 0: B(j,k) = B[j*ldb+k]; 1: B(j,k) = B[k*ldb+j]
+  float* C; long long sC; int ldc;
+  int M, N, K;
+  int epi;
+  const float* bias; long long sBias;
+  const float* aux; long long sAux; int ldaux;
+  float* gbias; long long sGb;
+  double* part; int partStride;  // [chain][partStride][2] loss partials (sum d^2, sum d)
+  float scale;
+  int needLang;  // 1: only chains whose current step is a Langevin step
+  int tm, tn;    // tiles along M and N
+  int big;       // 1: 128x128 tiles, 0: 64x64 tiles
+  int outFull;   // EPI_LOSS: optional second output with o itself (parity probe), else null
+  float* out2; long long sOut2;
+};
+
+enum PhaseKind : int {
+  PH_PROLOGUE = 0, PH_GEMM, PH_BN_FWD, PH_BN_BWD, PH_ADAM1, PH_ADAM2, PH_EPILOGUE,
+  PH_SWAP_DECIDE, PH_SWAP_GATHER, PH_SWAP_SCATTER
+};
+
+struct PhaseDesc {
+  int kind;
+  int g0, g1;   // GEMM descriptor indices (g1 = -1 if single)
+  int arg;      // BN: stats slot (0 first train pass, 1 second train pass, 2 test); rows via argRows
+  int argRows;  // BN: number of data rows
+  int needLang;
+};
+
+constexpr int kMaxGemm = 40;
+constexpr int kMaxPhase = 64;
+constexpr int kAdamChunk = 2048;   // floats per Adam work item (256 threads x 2 float4)
+constexpr int kThreads = 256;
+
+// Per-chain scalar state (structure of arrays, length C_alloc = C + 1; slot C is the eval scratch chain).
+struct ChainArrays {
+  double *eta, *lik, *prior_cur, *last_sse, *prop_sse, *mse_tr, *mse_te, *T, *adapt;
+  int *adam_t, *alias, *init_count, *nacc, *nlang, *step;
+  // per-step scratch
+  int* is_lang;
+  double *lx, *eta_noise, *u;
+  float *ss1, *sq1, *ss2, *sq2;  // Adam step_size and sqrt(bias_correction2) for the two drift calls
+};
+
+struct DevState {
+  // ---- static configuration
+  int d0, d1, d2, d3;
+  int ld0, ld1, ld2, ld3;
+  int n_train, n_test, n_max;
+  int C, C_alloc, n_rungs, chain_id_base;
+  int samples, pt_step, swap_interval, use_langevin;
+  float lr, step_w, step_eta, l_prob, sigma_sq, nu1, nu2;
+  unsigned seed_lo, seed_hi;
+  int w_size, Pp, n_adam_items, nbuf;  // nbuf = 2*d3 + 1
+  Seg seg[kNumSegs];
+  // ---- chain-batched vectors [C_alloc][Pp]
+  float *theta, *m, *v, *wcur, *grad;
+  // ---- BatchNorm side state
+  float* wb;        // [C_alloc][nbuf]   buffers of the detached `w` dict: rm[d3], rv[d3], nbt
+  float* wb_tmp;    // swap scratch
+  float* bn_mu;     // [3][C_alloc][ld3] batch mean per stats slot
+  float* bn_var;    // [3][C_alloc][ld3] biased batch variance
+  float* bn_inv;    // [C_alloc][ld3]    1/sqrt(var+eps) of the most recent forward
+  // ---- data + activations
+  float *Xtrain, *Xtest;
+  float *H1, *H2, *Z, *Y, *H4, *H5, *DOUT, *D5, *D4, *DY, *D2, *D1;
+  // ---- partial sums
+  double* loss_part;  // [3][C_alloc][loss_stride][2]
+  int loss_stride;
+  double* adam_part;  // [C_alloc][n_adam_items][3]  (sum noise^2, sum prop^2, sum wc_delta^2)
+  // ---- per-chain scalars
+  ChainArrays ch;
+  // ---- traces
+  bae_trace* traces;  // [C][samples]
+  int trace_idx_pad[13];  // padded index of the 13 traced entries (-1: beyond w_size)
+  // ---- swap
+  int* swap_src;     // [C] chain whose configuration ends at position p
+  int* swap_flag;    // [C] 1 if position p receives a different configuration
+  double* swap_tmp;  // [C][2] eta, last_sse scratch
+  long long *num_swap, *total_swap;
+  int swap_round;
+  // ---- program
+  int n_gemm, n_phase;
+  GemmDesc gemm[kMaxGemm];
+  PhaseDesc phase[kMaxPhase];
+};
+
+// ---- Philox4x32-10 ----------------------------------------------------------------------------
+// Stream ids (counter word 1 bits 8..15); low 8 bits carry the tensor id for weight noise.
+enum PhiloxStream : unsigned { STREAM_WEIGHT_NOISE = 1, STREAM_STEP_SCALARS = 2, STREAM_SWAP = 3 };
+
+struct u4 { unsigned x, y, z, w; };
+
+__host__ __device__ inline void mulhilo(unsigned a, unsigned b, unsigned& hi, unsigned& lo) {
+  unsigned long long p = (unsigned long long)a * (unsigned long long)b;
+  hi = (unsigned)(p >> 32);
+  lo = (unsigned)p;
+}
+
+__host__ __device__ inline u4 philox4x32_10(u4 c, unsigned k0, unsigned k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned hi0, lo0, hi1, lo1;
+    mulhilo(0xD2511F53u, c.x, hi0, lo0);
+    mulhilo(0xCD9E8D57u, c.z, hi1, lo1);
+    u4 n;
+    n.x = hi1 ^ c.y ^ k0;
+    n.y = lo1;
+    n.z = hi0 ^ c.w ^ k1;
+    n.w = lo0;
+    c = n;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+
+// uniform in (0,1): ((x >> 8) + 0.5) * 2^-24
+__host__ __device__ inline float u01(unsigned x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+}  // namespace bae

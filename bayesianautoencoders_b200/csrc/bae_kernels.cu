@@ -1,0 +1,1003 @@
+// Persistent PT-Langevin step kernel for sm_100a: the whole iteration of MAIN:432-592 for every
+// chain on the GPU runs as ONE cooperative launch that walks a phase program (forward GEMMs with
+// fused bias/sigmoid/loss epilogues, train-mode BatchNorm, backward GEMMs with fused sigmoid-derivative
+// and bias-gradient epilogues, Adam drift + Philox proposal noise, likelihood/prior/reverse-density
+// reduction and the Metropolis-Hastings test), separated by grid barriers.
+//
+// This file holds the FP32 CUDA-core path (tiled SGEMM; 128x128 or 64x64 tiles, 256 threads);
+// the tcgen05 3xTF32 tile engine for wide layers lives in bae_tc.cuh and plugs into the same phases.
+#include <cooperative_groups.h>
+#include <math_constants.h>
+
+#include "bae_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace bae {
+
+constexpr int BK = 16;
+constexpr float kBnEps = 1e-5f;
+constexpr float kBnMom = 0.1f;
+constexpr float kB1 = 0.9f, kB2 = 0.999f, kAdamEps = 1e-8f;
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic block-wide sum (all 256 threads call). Result valid in every thread.
+__device__ __forceinline__ double block_sum_d(double v, double* red /* >= 9 doubles */) {
+  v = warp_sum_d(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < kThreads / 32; ++i) s += red[i];
+    red[8] = s;
+  }
+  __syncthreads();
+  return red[8];
+}
+
+__device__ __forceinline__ void box_muller(float u1, float u2, float& n0, float& n1) {
+  float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  n0 = r * c;
+  n1 = r * s;
+}
+
+// Four N(0,1) draws for (chain, step, tensor seg, quad index).
+__device__ __forceinline__ void noise_quad(const DevState* S, int chain_global, int step, int seg, unsigned quad,
+                                           float (&n)[4]) {
+  u4 c;
+  c.x = quad;
+  c.y = (unsigned)seg | (STREAM_WEIGHT_NOISE << 8);
+  c.z = (unsigned)step;
+  c.w = (unsigned)chain_global;
+  u4 r = philox4x32_10(c, S->seed_lo, S->seed_hi);
+  box_muller(u01(r.x), u01(r.y), n[0], n[1]);
+  box_muller(u01(r.z), u01(r.w), n[2], n[3]);
+}
+
+__device__ __forceinline__ int find_seg(const DevState* S, int p) {
+  int s = 0;
+#pragma unroll
+  for (int i = 1; i < kNumSegs; ++i) s += (p >= S->seg[i].pad_off) ? 1 : 0;
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 tiled GEMM item: C[M x N] = A(M x K) * B(N x K)^T with a fused epilogue
+// ------------------------------------------------------------------------------------------------
+template <int BT>
+__device__ __forceinline__ void tile_load(const float* P, int ld, int mode, int extent, int K, int t0,
+                                          int k0, float4 (&r)[BT * 4 / kThreads]) {
+  constexpr int NV = BT * 4 / kThreads;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int f = threadIdx.x + i * kThreads;
+    const float* addr;
+    bool valid;
+    if (mode == 0) {  // K contiguous
+      int row = f % BT, k4 = f / BT;
+      int gr = t0 + row, gk = k0 + k4 * 4;
+      valid = (gr < extent) && (gk < K);
+      addr = P + (size_t)gr * ld + gk;
+    } else {  // tile dimension contiguous
+      int kk = f / (BT / 4), t4 = f % (BT / 4);
+      int gk = k0 + kk, gt = t0 + t4 * 4;
+      valid = (gk < K) && (gt < extent);
+      addr = P + (size_t)gk * ld + gt;
+    }
+    // plain (coherent) loads: operands are rewritten by earlier phases of the same launch, so ld.global.nc is illegal
+    r[i] = valid ? *reinterpret_cast<const float4*>(addr) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <int BT>
+__device__ __forceinline__ void tile_store(float* __restrict__ sm /*[BK][BT]*/, int mode,
+                                           const float4 (&r)[BT * 4 / kThreads]) {
+  constexpr int NV = BT * 4 / kThreads;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int f = threadIdx.x + i * kThreads;
+    if (mode == 0) {
+      int row = f % BT, k4 = f / BT;
+      sm[(k4 * 4 + 0) * BT + row] = r[i].x;
+      sm[(k4 * 4 + 1) * BT + row] = r[i].y;
+      sm[(k4 * 4 + 2) * BT + row] = r[i].z;
+      sm[(k4 * 4 + 3) * BT + row] = r[i].w;
+    } else {
+      int kk = f / (BT / 4), t4 = f % (BT / 4);
+      *reinterpret_cast<float4*>(&sm[kk * BT + t4 * 4]) = r[i];
+    }
+  }
+}
+
+template <int BM, int BN>
+__device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int tile_m, int tile_n, float* smem,
+                          double* red) {
+  constexpr int TM = BM / 16, TN = BN / 16;  // 8x8 (128) or 4x4 (64) per thread
+  constexpr int GM = TM / 4, GN = TN / 4;
+  float* As = smem;                 // [2][BK][BM]
+  float* Bs = smem + 2 * BK * BM;   // [2][BK][BN]
+  const float* A = g.A + (size_t)chain * g.sA;
+  const float* B = g.B + (size_t)chain * g.sB;
+  const int m0 = tile_m * BM, n0 = tile_n * BN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  float colsum = 0.f;
+  const bool do_colsum = (g.epi == EPI_GRADW) && (g.gbias != nullptr) && (tile_n == 0) && (threadIdx.x < BM);
+
+  float4 ra[BM * 4 / kThreads], rb[BN * 4 / kThreads];
+  const int nk = (g.K + BK - 1) / BK;
+  tile_load<BM>(A, g.lda, g.aMode, g.M, g.K, m0, 0, ra);
+  tile_load<BN>(B, g.ldb, g.bMode, g.N, g.K, n0, 0, rb);
+  __syncthreads();  // previous item's smem reads are done
+  tile_store<BM>(As, g.aMode, ra);
+  tile_store<BN>(Bs, g.bMode, rb);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int cur = kt & 1;
+    if (kt + 1 < nk) {
+      tile_load<BM>(A, g.lda, g.aMode, g.M, g.K, m0, (kt + 1) * BK, ra);
+      tile_load<BN>(B, g.ldb, g.bMode, g.N, g.K, n0, (kt + 1) * BK, rb);
+    }
+    const float* as = As + cur * BK * BM;
+    const float* bs = Bs + cur * BK * BN;
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int gi = 0; gi < GM; ++gi) {
+        float4 t = *reinterpret_cast<const float4*>(&as[k * BM + gi * 64 + ty * 4]);
+        a[gi * 4 + 0] = t.x; a[gi * 4 + 1] = t.y; a[gi * 4 + 2] = t.z; a[gi * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int hi = 0; hi < GN; ++hi) {
+        float4 t = *reinterpret_cast<const float4*>(&bs[k * BN + hi * 64 + tx * 4]);
+        b[hi * 4 + 0] = t.x; b[hi * 4 + 1] = t.y; b[hi * 4 + 2] = t.z; b[hi * 4 + 3] = t.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (do_colsum) {
+#pragma unroll
+      for (int k = 0; k < BK; ++k) colsum += as[k * BM + threadIdx.x];
+    }
+    if (kt + 1 < nk) {
+      tile_store<BM>(As + (cur ^ 1) * BK * BM, g.aMode, ra);
+      tile_store<BN>(Bs + (cur ^ 1) * BK * BN, g.bMode, rb);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue
+  float* C = g.C ? g.C + (size_t)chain * g.sC : nullptr;
+  const float* bias = g.bias ? g.bias + (size_t)chain * g.sBias : nullptr;
+  const float* aux = g.aux ? g.aux + (size_t)chain * g.sAux : nullptr;
+  float* out2 = g.out2 ? g.out2 + (size_t)chain * g.sOut2 : nullptr;
+  float l_sse = 0.f, l_sd = 0.f;
+#pragma unroll
+  for (int gi = 0; gi < GM; ++gi) {
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+      const int i = gi * 4 + ii;
+      const int r = m0 + gi * 64 + ty * 4 + ii;
+      if (r >= g.M) continue;
+#pragma unroll
+      for (int hi = 0; hi < GN; ++hi) {
+        const int c = n0 + hi * 64 + tx * 4;
+        if (c >= g.N) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = acc[i][hi * 4 + j];
+        const int nval = min(4, g.N - c);
+        float bv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
+        if (bias) {
+          float4 t = *reinterpret_cast<const float4*>(&bias[c]);  // pads are zero
+          bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+        }
+        if (aux) {
+          float4 t = *reinterpret_cast<const float4*>(&aux[(size_t)r * g.ldaux + c]);
+          av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
+        }
+        float o2[4] = {0.f, 0.f, 0.f, 0.f};
+        switch (g.epi) {
+          case EPI_SIGMOID:
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = sigmoidf_(v[j] + bv[j]);
+            break;
+          case EPI_BIAS:
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = v[j] + bv[j];
+            break;
+          case EPI_LOSS:
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float o = v[j] + bv[j];
+              o2[j] = o;
+              float d = o - av[j];
+              if (j < nval) { l_sse = fmaf(d, d, l_sse); l_sd += d; }
+              v[j] = d * g.scale;
+            }
+            break;
+          case EPI_DSIG:
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = v[j] * av[j] * (1.0f - av[j]);
+            break;
+          default:
+            break;
+        }
+        if (C) {
+          float* dst = &C[(size_t)r * g.ldc + c];
+          if (nval == 4) {
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+            for (int j = 0; j < nval; ++j) dst[j] = v[j];
+          }
+        }
+        if (out2) {
+          float* dst = &out2[(size_t)r * g.ldc + c];
+          for (int j = 0; j < nval; ++j) dst[j] = o2[j];
+        }
+      }
+    }
+  }
+  if (g.epi == EPI_LOSS) {
+    double s0 = block_sum_d((double)l_sse, red);
+    double s1 = block_sum_d((double)l_sd, red);
+    if (threadIdx.x == 0) {
+      double* p = g.part + ((size_t)chain * g.partStride + (size_t)tile_m * g.tn + tile_n) * 2;
+      p[0] = s0;
+      p[1] = s1;
+    }
+  }
+  if (do_colsum) {
+    int r = m0 + threadIdx.x;
+    if (r < g.M) (g.gbias + (size_t)chain * g.sGb)[r] = colsum;
+  }
+}
+
+__device__ void run_gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, float* smem,
+                               double* red) {
+  const int nch = c_end - c_begin;
+  const GemmDesc& ga = S->gemm[ph.g0];
+  const int ta = ga.tm * ga.tn;
+  const int tb = (ph.g1 >= 0) ? S->gemm[ph.g1].tm * S->gemm[ph.g1].tn : 0;
+  const int per_chain = ta + tb;
+  const int total = per_chain * nch;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int chain = c_begin + item / per_chain;
+    int t = item % per_chain;
+    const GemmDesc& g = (t < ta) ? ga : S->gemm[ph.g1];
+    if (t >= ta) t -= ta;
+    if (g.needLang && !S->ch.is_lang[chain]) continue;
+    const int tile_m = t / g.tn, tile_n = t % g.tn;
+    if (g.big)
+      gemm_item<128, 128>(S, g, chain, tile_m, tile_n, smem, red);
+    else
+      gemm_item<64, 64>(S, g, chain, tile_m, tile_n, smem, red);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm1d, training mode (MAIN:165): batch statistics forward, full backward
+// ------------------------------------------------------------------------------------------------
+__device__ void run_bn_fwd(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, double* red2 /*[8][32]*/) {
+  const int d3 = S->d3, ld3 = S->ld3, N = ph.argRows, slot = ph.arg;
+  const int nblk = (d3 + 31) / 32;
+  const int total = nblk * (c_end - c_begin);
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int chain = c_begin + item / nblk;
+    if (ph.needLang && !S->ch.is_lang[chain]) continue;
+    const int c = (item % nblk) * 32 + cl;
+    const bool cv = c < d3;
+    const float* Z = S->Z + (size_t)chain * S->n_max * ld3;
+    float* Y = S->Y + (size_t)chain * S->n_max * ld3;
+    double s = 0.0;
+    if (cv)
+      for (int r = rl; r < N; r += 8) s += (double)Z[(size_t)r * ld3 + c];
+    __syncthreads();
+    red2[rl * 32 + cl] = s;
+    __syncthreads();
+    double tot = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += red2[i * 32 + cl];
+    const float mean = (float)(tot / N);
+    double q = 0.0;
+    if (cv)
+      for (int r = rl; r < N; r += 8) {
+        float dz = Z[(size_t)r * ld3 + c] - mean;
+        q += (double)dz * (double)dz;
+      }
+    __syncthreads();
+    red2[rl * 32 + cl] = q;
+    __syncthreads();
+    double qt = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) qt += red2[i * 32 + cl];
+    const float var = (float)(qt / N);
+    const float inv = 1.0f / sqrtf(var + kBnEps);
+    if (cv) {
+      const float* th = S->theta + (size_t)chain * S->Pp;
+      const float gam = th[S->seg[SEG_BN_W].pad_off + c];
+      const float bet = th[S->seg[SEG_BN_BIAS].pad_off + c];
+      if (rl == 0) {
+        S->bn_mu[((size_t)slot * S->C_alloc + chain) * ld3 + c] = mean;
+        S->bn_var[((size_t)slot * S->C_alloc + chain) * ld3 + c] = var;
+        S->bn_inv[(size_t)chain * ld3 + c] = inv;
+      }
+      for (int r = rl; r < N; r += 8) {
+        float zh = (Z[(size_t)r * ld3 + c] - mean) * inv;
+        Y[(size_t)r * ld3 + c] = fmaf(zh, gam, bet);
+      }
+    }
+  }
+}
+
+__device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, double* red2) {
+  const int d3 = S->d3, ld3 = S->ld3, N = ph.argRows, slot = ph.arg;
+  const int nblk = (d3 + 31) / 32;
+  const int total = nblk * (c_end - c_begin);
+  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int chain = c_begin + item / nblk;
+    if (ph.needLang && !S->ch.is_lang[chain]) continue;
+    const int c = (item % nblk) * 32 + cl;
+    const bool cv = c < d3;
+    const float* Z = S->Z + (size_t)chain * S->n_max * ld3;
+    float* DY = S->DY + (size_t)chain * S->n_max * ld3;
+    float mean = 0.f, inv = 0.f, gam = 0.f;
+    if (cv) {
+      mean = S->bn_mu[((size_t)slot * S->C_alloc + chain) * ld3 + c];
+      inv = S->bn_inv[(size_t)chain * ld3 + c];
+      gam = S->theta[(size_t)chain * S->Pp + S->seg[SEG_BN_W].pad_off + c];
+    }
+    double s1 = 0.0, s2 = 0.0;
+    if (cv)
+      for (int r = rl; r < N; r += 8) {
+        float dy = DY[(size_t)r * ld3 + c];
+        float zh = (Z[(size_t)r * ld3 + c] - mean) * inv;
+        s1 += (double)dy;
+        s2 += (double)dy * (double)zh;
+      }
+    __syncthreads();
+    red2[rl * 32 + cl] = s1;
+    red2[256 + rl * 32 + cl] = s2;
+    __syncthreads();
+    double t1 = 0.0, t2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t1 += red2[i * 32 + cl]; t2 += red2[256 + i * 32 + cl]; }
+    if (cv) {
+      float* gr = S->grad + (size_t)chain * S->Pp;
+      if (rl == 0) {
+        gr[S->seg[SEG_BN_BIAS].pad_off + c] = (float)t1;   // d beta  = sum dy
+        gr[S->seg[SEG_BN_W].pad_off + c] = (float)t2;      // d gamma = sum dy * zhat
+      }
+      const float m1 = (float)(t1 / N) * gam;              // mean(dzhat), dzhat = dy * gamma
+      const float m2 = (float)(t2 / N) * gam;              // mean(dzhat * zhat)
+      for (int r = rl; r < N; r += 8) {
+        float dy = DY[(size_t)r * ld3 + c];
+        float zh = (Z[(size_t)r * ld3 + c] - mean) * inv;
+        DY[(size_t)r * ld3 + c] = inv * (dy * gam - m1 - zh * m2);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam drift + proposal noise (first call, MAIN:473-474 / random walk MAIN:492) and the reverse
+// drift (second call, MAIN:475-477), fused with the reductions the MH ratio needs.
+// ------------------------------------------------------------------------------------------------
+__device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, double* red) {
+  const int nit = S->n_adam_items;
+  const int total = nit * (c_end - c_begin);
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int chain = c_begin + item / nit;
+    const int it = item % nit;
+    const bool lang = S->ch.is_lang[chain] != 0;
+    const bool alias = S->ch.alias[chain] != 0;
+    double* part = S->adam_part + ((size_t)chain * nit + it) * 3;
+    if (which == 2 && !lang) {
+      if (threadIdx.x == 0) part[2] = 0.0;
+      continue;
+    }
+    const size_t base = (size_t)chain * S->Pp;
+    float* th = S->theta + base;
+    float* mm = S->m + base;
+    float* vv = S->v + base;
+    float* wc = S->wcur + base;
+    const float* gr = S->grad + base;
+    const int step = S->ch.step[chain];
+    const int cg_id = S->chain_id_base + chain;
+    const float ss = (which == 1) ? S->ch.ss1[chain] : S->ch.ss2[chain];
+    const float sq = (which == 1) ? S->ch.sq1[chain] : S->ch.sq2[chain];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < kAdamChunk / (kThreads * 4); ++u) {
+      const int p = it * kAdamChunk + (u * kThreads + threadIdx.x) * 4;
+      if (p >= S->Pp) continue;
+      const int sg = find_seg(S, p);
+      const Seg& sd = S->seg[sg];
+      if (!sd.trainable) continue;
+      const int local = p - sd.pad_off;
+      if (local >= sd.rows * sd.ld) continue;   // alignment gap between tensors
+      const int col = local % sd.ld;
+      const int nval = min(4, sd.cols - col);
+      if (nval <= 0) continue;
+      float4 t4 = *reinterpret_cast<const float4*>(&th[p]);
+      float t[4] = {t4.x, t4.y, t4.z, t4.w};
+      if (which == 1) {
+        float nz[4];
+        noise_quad(S, cg_id, step, sg, (unsigned)(local >> 2), nz);
+        float o[4];
+        if (lang) {
+          float4 g4 = *reinterpret_cast<const float4*>(&gr[p]);
+          float4 m4 = *reinterpret_cast<const float4*>(&mm[p]);
+          float4 v4 = *reinterpret_cast<const float4*>(&vv[p]);
+          float g[4] = {g4.x, g4.y, g4.z, g4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            m[j] = m[j] + (g[j] - m[j]) * (1.0f - kB1);
+            v[j] = v[j] * kB2 + (1.0f - kB2) * g[j] * g[j];
+            float denom = sqrtf(v[j]) / sq + kAdamEps;
+            o[j] = t[j] - ss * (m[j] / denom);
+          }
+          *reinterpret_cast<float4*>(&mm[p]) = make_float4(m[0], m[1], m[2], m[3]);
+          *reinterpret_cast<float4*>(&vv[p]) = make_float4(v[0], v[1], v[2], v[3]);
+          if (!alias) *reinterpret_cast<float4*>(&wc[p]) = t4;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = t[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nval) {
+            float nj = nz[j] * S->step_w;
+            o[j] = o[j] + nj;
+            a0 = fmaf(nj, nj, a0);
+            a1 = fmaf(o[j], o[j], a1);
+          } else {
+            o[j] = 0.f;
+          }
+        }
+        *reinterpret_cast<float4*>(&th[p]) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+        float4 g4 = *reinterpret_cast<const float4*>(&gr[p]);
+        float4 m4 = *reinterpret_cast<const float4*>(&mm[p]);
+        float4 v4 = *reinterpret_cast<const float4*>(&vv[p]);
+        float g[4] = {g4.x, g4.y, g4.z, g4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+        float w0[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!alias) {
+          float4 w4 = *reinterpret_cast<const float4*>(&wc[p]);
+          w0[0] = w4.x; w0[1] = w4.y; w0[2] = w4.z; w0[3] = w4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          m[j] = m[j] + (g[j] - m[j]) * (1.0f - kB1);
+          v[j] = v[j] * kB2 + (1.0f - kB2) * g[j] * g[j];
+          float denom = sqrtf(v[j]) / sq + kAdamEps;
+          float wpg = t[j] - ss * (m[j] / denom);   // w_prop_gd
+          if (!alias && j < nval) {
+            float dl = w0[j] - wpg;
+            a2 = fmaf(dl, dl, a2);
+          }
+        }
+        *reinterpret_cast<float4*>(&mm[p]) = make_float4(m[0], m[1], m[2], m[3]);
+        *reinterpret_cast<float4*>(&vv[p]) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    if (which == 1) {
+      double s0 = block_sum_d((double)a0, red);
+      double s1 = block_sum_d((double)a1, red);
+      if (threadIdx.x == 0) { part[0] = s0; part[1] = s1; }
+    } else {
+      double s2 = block_sum_d((double)a2, red);
+      if (threadIdx.x == 0) part[2] = s2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scalar prologue: branch select, tempered -> canonical switch, draws        MAIN:435-452, 500, 526
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double loglik_d(double sse, double n, double tau_sq, double temp) {
+  // MAIN:325-329: tau_sq MULTIPLIES the SSE, as written in the reference.
+  return (-(n * 0.5) * log(2.0 * CUDART_PI * tau_sq) - 0.5 * tau_sq * sse) / temp;
+}
+
+__device__ void step_scalars(const DevState* S, int chain_global, int step, double& lx, double& eta_noise, double& u) {
+  u4 c;
+  c.x = 0u;
+  c.y = 0xFFu | (STREAM_STEP_SCALARS << 8);
+  c.z = (unsigned)step;
+  c.w = (unsigned)chain_global;
+  u4 r = philox4x32_10(c, S->seed_lo, S->seed_hi);
+  lx = (double)u01(r.x);
+  float n0, n1;
+  box_muller(u01(r.y), u01(r.z), n0, n1);
+  eta_noise = (double)n0 * (double)S->step_eta;
+  u = (double)u01(r.w);
+}
+
+__device__ void run_prologue(const DevState* S, int c_begin, int c_end) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int chain = c_begin + gtid; chain < c_end; chain += gridDim.x * blockDim.x) {
+    const ChainArrays& ch = S->ch;
+    const int i = ch.step[chain];
+    if (i < S->pt_step) ch.adapt[chain] = ch.T[chain];                        // MAIN:437-438
+    if (i == S->pt_step && ch.init_count[chain] == 0) {                         // MAIN:440-445
+      ch.adapt[chain] = 1.0;
+      // evaluated on w_proposal, the chain's OWN last proposal -- it does not travel with exchanges
+      ch.lik[chain] = loglik_d(ch.prop_sse[chain], (double)S->n_train * S->d0, 1.0, 1.0);
+      ch.init_count[chain] = 1;
+    }
+    double lx, en, u;
+    step_scalars(S, S->chain_id_base + chain, i, lx, en, u);
+    ch.lx[chain] = lx;
+    ch.eta_noise[chain] = en;
+    ch.u[chain] = u;
+    const int lang = (S->use_langevin && lx < (double)S->l_prob) ? 1 : 0;       // MAIN:452
+    ch.is_lang[chain] = lang;
+    if (lang) {
+      const int t1 = ch.adam_t[chain] + 1, t2 = t1 + 1;
+      ch.ss1[chain] = (float)((double)S->lr / (1.0 - pow((double)kB1, (double)t1)));
+      ch.sq1[chain] = (float)sqrt(1.0 - pow((double)kB2, (double)t1));
+      ch.ss2[chain] = (float)((double)S->lr / (1.0 - pow((double)kB1, (double)t2)));
+      ch.sq2[chain] = (float)sqrt(1.0 - pow((double)kB2, (double)t2));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scalar epilogue: BatchNorm-buffer bookkeeping, likelihood, prior, reverse-proposal density, MH test
+// (one CTA per chain)                                                              MAIN:476-592
+// ------------------------------------------------------------------------------------------------
+__device__ void run_epilogue(const DevState* S, int c_begin, int c_end, double* red) {
+  const int d3 = S->d3, ld3 = S->ld3;
+  const ChainArrays& ch = S->ch;
+  for (int chain = c_begin + blockIdx.x; chain < c_end; chain += gridDim.x) {
+    const bool lang = ch.is_lang[chain] != 0;
+    const bool alias = ch.alias[chain] != 0;
+    const int step = ch.step[chain];
+    const int cg_id = S->chain_id_base + chain;
+    float* th = S->theta + (size_t)chain * S->Pp;
+    float* wb = S->wb + (size_t)chain * S->nbuf;   // rm[d3], rv[d3], nbt
+    float* rm = th + S->seg[SEG_BN_RM].pad_off;
+    float* rv = th + S->seg[SEG_BN_RV].pad_off;
+    float* nbt_live = th + S->seg[SEG_BN_NBT].pad_off;
+    const float* mu1 = S->bn_mu + ((size_t)0 * S->C_alloc + chain) * ld3;
+    const float* va1 = S->bn_var + ((size_t)0 * S->C_alloc + chain) * ld3;
+    const float* mu2 = S->bn_mu + ((size_t)1 * S->C_alloc + chain) * ld3;
+    const float* va2 = S->bn_var + ((size_t)1 * S->C_alloc + chain) * ld3;
+    const float* mut = S->bn_mu + ((size_t)2 * S->C_alloc + chain) * ld3;
+    const float* vat = S->bn_var + ((size_t)2 * S->C_alloc + chain) * ld3;
+    const float ub_tr = (float)S->n_train / (float)(S->n_train - 1);
+    const float ub_te = (float)S->n_test / (float)(S->n_test - 1);
+
+    // --- gather partial sums (fixed order -> deterministic)
+    double p_sse_tr = 0.0, p_sse_te = 0.0, p_noise = 0.0, p_prop = 0.0, p_wc = 0.0;
+    const int nl_tr = S->loss_stride;
+    const double* lp_tr = S->loss_part + (((size_t)1 * S->C_alloc + chain) * S->loss_stride) * 2;
+    const double* lp_te = S->loss_part + (((size_t)2 * S->C_alloc + chain) * S->loss_stride) * 2;
+    for (int i = threadIdx.x; i < nl_tr; i += kThreads) { p_sse_tr += lp_tr[i * 2]; p_sse_te += lp_te[i * 2]; }
+    const double* ap = S->adam_part + (size_t)chain * S->n_adam_items * 3;
+    for (int i = threadIdx.x; i < S->n_adam_items; i += kThreads) {
+      p_noise += ap[i * 3 + 0];
+      p_prop += ap[i * 3 + 1];
+      if (lang) p_wc += ap[i * 3 + 2];
+    }
+    // --- BatchNorm buffer bookkeeping (all sorted-key buffer entries take noise, MAIN:259-260)
+    double b_wc = 0.0, b_wp = 0.0, b_prior = 0.0;
+    for (int c = threadIdx.x; c < d3; c += kThreads) {
+      float nzm[4], nzv[4];
+      noise_quad(S, cg_id, step, SEG_BN_RM, (unsigned)(c >> 2), nzm);
+      noise_quad(S, cg_id, step, SEG_BN_RV, (unsigned)(c >> 2), nzv);
+      const float n_rm = nzm[c & 3] * S->step_w, n_rv = nzv[c & 3] * S->step_w;
+      const float base_rm = alias ? rm[c] : wb[c];
+      const float base_rv = alias ? rv[c] : wb[d3 + c];
+      float p_rm, p_rv;
+      if (lang) {
+        // first drift forward at w (MAIN:473): running stats of the loaded dict are updated
+        const float g_rm = (1.0f - kBnMom) * base_rm + kBnMom * mu1[c];
+        const float g_rv = (1.0f - kBnMom) * base_rv + kBnMom * va1[c] * ub_tr;
+        p_rm = g_rm + n_rm;                                  // w_proposal buffers (MAIN:474)
+        p_rv = g_rv + n_rv;
+        if (!alias) {
+          // second drift forward at w_proposal (MAIN:475) -> w_prop_gd buffers
+          const float q_rm = (1.0f - kBnMom) * p_rm + kBnMom * mu2[c];
+          const float q_rv = (1.0f - kBnMom) * p_rv + kBnMom * va2[c] * ub_tr;
+          const double d1 = (double)wb[c] - (double)q_rm, d2 = (double)wb[d3 + c] - (double)q_rv;
+          b_wc += d1 * d1 + d2 * d2;
+        }
+      } else {
+        p_rm = base_rm + n_rm;                               // MAIN:492
+        p_rv = base_rv + n_rv;
+      }
+      b_wp += (double)n_rm * n_rm + (double)n_rv * n_rv;
+      b_prior += (double)p_rm * p_rm + (double)p_rv * p_rv;
+      // likelihood forwards reload w_proposal (MAIN:505, 508); the test forward is the last to touch the live model
+      rm[c] = (1.0f - kBnMom) * p_rm + kBnMom * mut[c];
+      rv[c] = (1.0f - kBnMom) * p_rv + kBnMom * vat[c] * ub_te;
+      // stash proposal buffers; they become `w`'s buffers on accept
+      S->wb_tmp[(size_t)chain * S->nbuf + c] = p_rm;
+      S->wb_tmp[(size_t)chain * S->nbuf + d3 + c] = p_rv;
+    }
+    const double sse_tr = block_sum_d(p_sse_tr, red);
+    const double sse_te = block_sum_d(p_sse_te, red);
+    const double s_noise = block_sum_d(p_noise, red);
+    const double s_prop = block_sum_d(p_prop, red);
+    const double s_wc = block_sum_d(p_wc, red);
+    const double sb_wc = block_sum_d(b_wc, red);
+    const double sb_wp = block_sum_d(b_wp, red);
+    const double sb_prior = block_sum_d(b_prior, red);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // --- num_batches_tracked (int64 in the model, float in the dicts)
+      float nzn[4];
+      noise_quad(S, cg_id, step, SEG_BN_NBT, 0u, nzn);
+      const float n_nbt = nzn[0] * S->step_w;
+      const float base_nbt = alias ? nbt_live[0] : wb[2 * d3];
+      float p_nbt;
+      double nbt_wc = 0.0, nbt_wp = 0.0;
+      if (lang) {
+        const float g_nbt = truncf(base_nbt) + 1.0f;          // load (trunc) + first forward
+        p_nbt = g_nbt + n_nbt;                                // int64 + float32 -> float32 (MAIN:260)
+        nbt_wp = (double)p_nbt - (double)g_nbt;
+        if (!alias) {
+          const float q_nbt = truncf(p_nbt) + 1.0f;           // load + second forward
+          nbt_wc = (double)wb[2 * d3] - (double)q_nbt;
+        }
+      } else {
+        p_nbt = base_nbt + n_nbt;
+        nbt_wp = (double)p_nbt - (double)base_nbt;
+      }
+      nbt_live[0] = truncf(p_nbt) + 1.0f;
+      S->wb_tmp[(size_t)chain * S->nbuf + 2 * d3] = p_nbt;
+
+      const double sigma_sq = (double)S->step_w * (double)S->step_w;
+      double diff_prop = 0.0;
+      if (lang) {
+        const double first = -0.5 * (s_wc + sb_wc + nbt_wc * nbt_wc) / sigma_sq;        // MAIN:481
+        const double second = -0.5 * (s_noise + sb_wp + nbt_wp * nbt_wp) / sigma_sq;    // MAIN:482
+        diff_prop = first - second;
+      }
+      const double eta_pro = ch.eta[chain] + ch.eta_noise[chain];                         // MAIN:500
+      const double tau_pro = exp(eta_pro);
+      const double adapt = ch.adapt[chain];
+      const double n_tr = (double)S->n_train * S->d0, n_te = (double)S->n_test * S->d0;
+      const double lik_prop = loglik_d(sse_tr, n_tr, tau_pro, adapt);                     // MAIN:505
+      const double mse_tr = sse_tr / n_tr, mse_te = sse_te / n_te;
+      const double sumsq = s_prop + sb_prior + (double)p_nbt * (double)p_nbt;
+      const double prior_prop = -((double)S->w_size * 0.5) * log((double)S->sigma_sq)     // MAIN:331-336
+                                - sumsq / (2.0 * (double)S->sigma_sq)
+                                - (1.0 + (double)S->nu1) * log(tau_pro) - ((double)S->nu2 / tau_pro);
+      const double lik_cur = ch.lik[chain];
+      const double sum_value = (lik_prop - lik_cur) + (prior_prop - ch.prior_cur[chain]) + diff_prop;  // MAIN:524
+      const double log_u = log(ch.u[chain]);                                              // MAIN:526
+      const bool accept = log_u < sum_value;                                              // MAIN:532
+      if (accept) {
+        ch.nacc[chain] += 1;
+        ch.lik[chain] = lik_prop;
+        ch.prior_cur[chain] = prior_prop;
+        ch.eta[chain] = eta_pro;
+        ch.mse_tr[chain] = mse_tr;
+        ch.mse_te[chain] = mse_te;
+        ch.alias[chain] = 0;                                  // w = deepcopy(w_proposal)   MAIN:537
+      } else {
+        ch.alias[chain] = 1;                                  // w = old_w (live tensors)   MAIN:555
+      }
+      if (lang) {
+        ch.nlang[chain] += 1;
+        ch.adam_t[chain] += 2;
+      }
+      ch.last_sse[chain] = sse_tr;
+      ch.prop_sse[chain] = sse_tr;
+      if (chain < S->C && step < S->samples) {
+        bae_trace& tr = S->traces[(size_t)chain * S->samples + step];
+        tr.likelihood_proposal = lik_prop;
+        tr.likelihood = lik_cur;
+        tr.sum_value = sum_value;
+        tr.log_u = log_u;
+        tr.prior_proposal = prior_prop;
+        tr.diff_prop = diff_prop;
+        tr.mse_train = ch.mse_tr[chain];
+        tr.mse_test = ch.mse_te[chain];
+        tr.mse_train_proposal = mse_tr;
+        tr.mse_test_proposal = mse_te;
+        tr.eta = ch.eta[chain];
+        tr.accepted = accept ? 1 : 0;
+        tr.langevin = lang ? 1 : 0;
+        tr.step = step;
+        for (int k = 0; k < 13; ++k) tr.weights[k] = S->trace_idx_pad[k] >= 0 ? th[S->trace_idx_pad[k]] : 0.f;
+      }
+      ch.step[chain] = step + 1;
+      red[10] = accept ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    if (red[10] != 0.0) {   // accept: `w` buffers <- proposal buffers
+      for (int c = threadIdx.x; c < S->nbuf; c += kThreads) wb[c] = S->wb_tmp[(size_t)chain * S->nbuf + c];
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Replica exchange: sequential adjacent-pair sweep per ensemble            MAIN:962-1011, 1059-1065
+// ------------------------------------------------------------------------------------------------
+__device__ double swap_uniform(const DevState* S, int ensemble_global, int round, int pair) {
+  u4 c;
+  c.x = (unsigned)pair;
+  c.y = 0xFEu | (STREAM_SWAP << 8);
+  c.z = (unsigned)round;
+  c.w = (unsigned)ensemble_global;
+  u4 r = philox4x32_10(c, S->seed_lo, S->seed_hi);
+  return (double)u01(r.x);
+}
+
+__device__ void run_swap_decide(const DevState* S) {
+  const int n = S->n_rungs;
+  const int nens = S->C / n;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const ChainArrays& ch = S->ch;
+  const double ntr = (double)S->n_train * S->d0;
+  for (int e = gtid; e < nens; e += gridDim.x * blockDim.x) {
+    const int b = e * n;
+    // queue slots: configuration id, and the (lhood, T) slots that travel with the message (MAIN:999-1005)
+    for (int p = 0; p < n; ++p) S->swap_src[b + p] = b + p;
+    double lh_prev = ch.lik[b], T_prev = ch.adapt[b];
+    int cfg_prev = b;
+    for (int p = 0; p + 1 < n; ++p) {
+      const int cfg1 = cfg_prev, cfg2 = b + p + 1;
+      const double lhood1 = lh_prev, T1 = T_prev;
+      const double lhood2 = ch.lik[cfg2], T2 = ch.adapt[cfg2];
+      const double lhood12 = loglik_d(ch.last_sse[cfg1], ntr, exp(ch.eta[cfg1]), T2);   // MAIN:980
+      const double lhood21 = loglik_d(ch.last_sse[cfg2], ntr, exp(ch.eta[cfg2]), T1);   // MAIN:982
+      const double ex = (lhood12 - lhood1) + (lhood21 - lhood2);
+      const double prob = fmin(1.0, exp(ex));                                            // MAIN:988
+      const int round = ch.step[b] / S->swap_interval - 1;
+      const double u = swap_uniform(S, (S->chain_id_base / n) + e, round, p);
+      const bool sw = u < prob;
+      atomicAdd((unsigned long long*)S->total_swap, 1ull);
+      if (sw) {
+        atomicAdd((unsigned long long*)S->num_swap, 1ull);
+        S->swap_src[b + p] = cfg2;       // position p receives configuration 2
+        cfg_prev = cfg1;                 // configuration 1 moves on to position p+1
+        lh_prev = lhood12;               // and carries lhood12 / T1 in its message slots
+        T_prev = T1;
+      } else {
+        S->swap_src[b + p] = cfg1;
+        cfg_prev = cfg2;
+        lh_prev = lhood2;
+        T_prev = T2;
+      }
+    }
+    S->swap_src[b + n - 1] = cfg_prev;
+  }
+}
+
+// gather: wcur[p] <- theta[src[p]] (trainable + buffers view of `w`), scalars to tmp
+__device__ void run_swap_gather(const DevState* S) {
+  const int nit = (S->Pp + kAdamChunk - 1) / kAdamChunk;
+  const int total = nit * S->C;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int p = item / nit, it = item % nit;
+    const int src = S->swap_src[p];
+    if (it == 0) {
+      // buffers of the posted `w`: detached copy or the live model's buffers (MAIN:595)
+      const float* sth = S->theta + (size_t)src * S->Pp;
+      const bool al = S->ch.alias[src] != 0;
+      for (int c = threadIdx.x; c < S->nbuf; c += kThreads) {
+        float v;
+        if (al) {
+          if (c < S->d3) v = sth[S->seg[SEG_BN_RM].pad_off + c];
+          else if (c < 2 * S->d3) v = sth[S->seg[SEG_BN_RV].pad_off + c - S->d3];
+          else v = sth[S->seg[SEG_BN_NBT].pad_off];
+        } else {
+          v = S->wb[(size_t)src * S->nbuf + c];
+        }
+        S->wb_tmp[(size_t)p * S->nbuf + c] = v;
+      }
+      if (threadIdx.x == 0) {
+        S->swap_tmp[p * 2 + 0] = S->ch.eta[src];
+        S->swap_tmp[p * 2 + 1] = S->ch.last_sse[src];
+      }
+    }
+    if (src == p) continue;
+    const float4* s4 = reinterpret_cast<const float4*>(S->theta + (size_t)src * S->Pp + (size_t)it * kAdamChunk);
+    float4* d4 = reinterpret_cast<float4*>(S->wcur + (size_t)p * S->Pp + (size_t)it * kAdamChunk);
+    const int nv = min(kAdamChunk, S->Pp - it * kAdamChunk) / 4;
+    for (int i = threadIdx.x; i < nv; i += kThreads) d4[i] = s4[i];
+  }
+}
+
+__device__ void run_swap_scatter(const DevState* S) {
+  const int nit = (S->Pp + kAdamChunk - 1) / kAdamChunk;
+  const int total = nit * S->C;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int p = item / nit, it = item % nit;
+    const int src = S->swap_src[p];
+    if (it == 0) {
+      for (int c = threadIdx.x; c < S->nbuf; c += kThreads) S->wb[(size_t)p * S->nbuf + c] = S->wb_tmp[(size_t)p * S->nbuf + c];
+      if (threadIdx.x == 0) {
+        S->ch.eta[p] = S->swap_tmp[p * 2 + 0];       // MAIN:603
+        S->ch.last_sse[p] = S->swap_tmp[p * 2 + 1];
+        S->ch.alias[p] = 0;                          // MAIN:602: w = dictfromlist(...) is a detached dict
+      }
+    }
+    if (src == p) continue;
+    // only trainable entries move into the live model; its BatchNorm buffers are reloaded from `w` next step
+    const float4* s4 = reinterpret_cast<const float4*>(S->wcur + (size_t)p * S->Pp + (size_t)it * kAdamChunk);
+    float* dbase = S->theta + (size_t)p * S->Pp;
+    const int nv = min(kAdamChunk, S->Pp - it * kAdamChunk) / 4;
+    for (int i = threadIdx.x; i < nv; i += kThreads) {
+      const int pidx = it * kAdamChunk + i * 4;
+      const int sg = find_seg(S, pidx);
+      if (!S->seg[sg].trainable) continue;
+      *reinterpret_cast<float4*>(dbase + pidx) = s4[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The persistent program kernel
+// ------------------------------------------------------------------------------------------------
+__device__ void run_phase(const DevState* S, int pi, int c_begin, int c_end, int force_swap, float* smem,
+                          double* red) {
+  const PhaseDesc& ph = S->phase[pi];
+  if (ph.kind >= PH_SWAP_DECIDE && !force_swap) {
+    // inside bae_run: exchange only after every swap_interval-th iteration (MAIN:594); all chains share the step count
+    const int st = S->ch.step[0];
+    if (st == 0 || (st % S->swap_interval) != 0) return;
+  }
+  switch (ph.kind) {
+    case PH_PROLOGUE: run_prologue(S, c_begin, c_end); break;
+    case PH_GEMM: run_gemm_phase(S, ph, c_begin, c_end, smem, red); break;
+    case PH_BN_FWD: run_bn_fwd(S, ph, c_begin, c_end, reinterpret_cast<double*>(smem)); break;
+    case PH_BN_BWD: run_bn_bwd(S, ph, c_begin, c_end, reinterpret_cast<double*>(smem)); break;
+    case PH_ADAM1: run_adam(S, 1, c_begin, c_end, red); break;
+    case PH_ADAM2: run_adam(S, 2, c_begin, c_end, red); break;
+    case PH_EPILOGUE: run_epilogue(S, c_begin, c_end, red); break;
+    case PH_SWAP_DECIDE: run_swap_decide(S); break;
+    case PH_SWAP_GATHER: run_swap_gather(S); break;
+    case PH_SWAP_SCATTER: run_swap_scatter(S); break;
+    default: break;
+  }
+}
+
+// Cooperative launch: walks phases [ph_begin, ph_end) `n_rep` times with a grid barrier after each.
+__global__ void __launch_bounds__(kThreads, 2)
+bae_program_kernel(const DevState* __restrict__ S, int ph_begin, int ph_end, int n_rep, int c_begin, int c_end,
+                   int force_swap) {
+  __shared__ __align__(16) float smem[2 * BK * 128 * 2];   // 32 KB: A and B double buffers (128-wide tiles)
+  __shared__ double red[16];
+  cg::grid_group grid = cg::this_grid();
+  for (int rep = 0; rep < n_rep; ++rep) {
+    for (int pi = ph_begin; pi < ph_end; ++pi) {
+      run_phase(S, pi, c_begin, c_end, force_swap, smem, red);
+      grid.sync();
+    }
+  }
+}
+
+// Plain launch of ONE phase (no grid barrier): used for per-phase profiling and the parity probe.
+__global__ void __launch_bounds__(kThreads, 2)
+bae_phase_kernel(const DevState* __restrict__ S, int pi, int c_begin, int c_end) {
+  __shared__ __align__(16) float smem[2 * BK * 128 * 2];
+  __shared__ double red[16];
+  run_phase(S, pi, c_begin, c_end, 1, smem, red);
+}
+
+// Writes the proposal noise of (chain, step) in REFERENCE order, plus the three step scalars.
+__global__ void bae_debug_draws_kernel(const DevState* __restrict__ S, int chain, int step, float* noise,
+                                       double* scalars) {
+  const int cg_id = S->chain_id_base + chain;
+  for (int sg = 0; sg < kNumSegs; ++sg) {
+    const Seg& sd = S->seg[sg];
+    const int n = sd.rows * sd.cols;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+      const int r = e / sd.cols, c = e % sd.cols;
+      const int local = r * sd.ld + c;
+      float nz[4];
+      noise_quad(S, cg_id, step, sg, (unsigned)(local >> 2), nz);
+      noise[sd.ref_off + e] = nz[local & 3] * S->step_w;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double lx, en, u;
+    step_scalars(S, cg_id, step, lx, en, u);
+    scalars[0] = lx;
+    scalars[1] = en;
+    scalars[2] = u;
+  }
+}
+
+__global__ void bae_debug_swap_u_kernel(const DevState* __restrict__ S, int ensemble_global, int round, int pair,
+                                        double* out) {
+  out[0] = swap_uniform(S, ensemble_global, round, pair);
+}
+
+// ---- reference-order <-> padded-order packing -----------------------------------------------------
+__global__ void bae_pack_kernel(const DevState* __restrict__ S, const float* ref_vec, float* pad_vec) {
+  for (int sg = 0; sg < kNumSegs; ++sg) {
+    const Seg& sd = S->seg[sg];
+    const int n = sd.rows * sd.cols;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+      const int r = e / sd.cols, c = e % sd.cols;
+      pad_vec[sd.pad_off + r * sd.ld + c] = ref_vec[sd.ref_off + e];
+    }
+  }
+}
+
+__global__ void bae_unpack_kernel(const DevState* __restrict__ S, const float* pad_vec, float* ref_vec) {
+  for (int sg = 0; sg < kNumSegs; ++sg) {
+    const Seg& sd = S->seg[sg];
+    const int n = sd.rows * sd.cols;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+      const int r = e / sd.cols, c = e % sd.cols;
+      ref_vec[sd.ref_off + e] = pad_vec[sd.pad_off + r * sd.ld + c];
+    }
+  }
+}
+
+}  // namespace bae
+
+// ---- launch wrappers used by bae_api.cu ----------------------------------------------------------
+namespace bae {
+
+int max_coop_blocks_per_sm() {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel, kThreads, 0);
+  return nb;
+}
+
+cudaError_t launch_program(const DevState* dS, int grid, int ph_begin, int ph_end, int n_rep, int c_begin, int c_end,
+                           int force_swap, cudaStream_t st) {
+  void* args[] = {(void*)&dS, (void*)&ph_begin, (void*)&ph_end, (void*)&n_rep, (void*)&c_begin, (void*)&c_end,
+                  (void*)&force_swap};
+  return cudaLaunchCooperativeKernel((void*)bae_program_kernel, dim3(grid), dim3(kThreads), args, 0, st);
+}
+
+cudaError_t launch_phase(const DevState* dS, int grid, int pi, int c_begin, int c_end, cudaStream_t st) {
+  bae_phase_kernel<<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_debug_draws(const DevState* dS, int chain, int step, float* noise, double* scalars, cudaStream_t st) {
+  bae_debug_draws_kernel<<<64, 256, 0, st>>>(dS, chain, step, noise, scalars);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_debug_swap_u(const DevState* dS, int ens, int round, int pair, double* out, cudaStream_t st) {
+  bae_debug_swap_u_kernel<<<1, 1, 0, st>>>(dS, ens, round, pair, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const DevState* dS, const float* ref_vec, float* pad_vec, cudaStream_t st) {
+  bae_pack_kernel<<<64, 256, 0, st>>>(dS, ref_vec, pad_vec);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpack(const DevState* dS, const float* pad_vec, float* ref_vec, cudaStream_t st) {
+  bae_unpack_kernel<<<64, 256, 0, st>>>(dS, pad_vec, ref_vec);
+  return cudaGetLastError();
+}
+
+}  // namespace bae

@@ -1,0 +1,151 @@
+/*
+ * bae_b200.h -- C-ABI of the B200-native parallel-tempering Langevin sampler over autoencoder weights.
+ *
+ * The reference (sydney-machine-learning/BayesianAutoencoders) has no FFI; its boundary for this path
+ * is the Python method surface of Bayesian/bayes_autoenc_langevincheck.py ("MAIN"):
+ *   Model.evaluate_proposal / langevin_gradient / addnoiseandcopy / getparameters   MAIN:188-262
+ *   ptReplica.run / likelihood_func / prior_likelihood                              MAIN:304-336, 348-603
+ *   ParallelTempering.swap_procedure / run_chains / default_beta_ladder             MAIN:867-1090
+ * The entry points below are what a ctypes binding of that surface calls (INTEGRATION.md shows the
+ * binding). Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative bae_status, with a per-thread message available from bae_last_error(); the caller owns
+ * every host buffer, the library owns every device buffer; calls on one handle must be serialised by
+ * the caller; one handle drives one GPU.
+ *
+ * Flat parameter vectors crossing this boundary are in the reference's `getparameters` order
+ * (sorted state_dict keys, BatchNorm buffers included, MAIN:228-241), length bae_w_size().
+ */
+#ifndef BAE_B200_H
+#define BAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bae_handle bae_handle;
+
+enum bae_status {
+  BAE_OK = 0,
+  BAE_ERR_INVALID = -1,   /* bad argument */
+  BAE_ERR_CUDA = -2,      /* CUDA runtime/driver error (message has the CUDA string) */
+  BAE_ERR_NO_DEVICE = -3, /* no usable sm_100 device: there is NO CPU fallback */
+  BAE_ERR_STATE = -4      /* call sequence error (e.g. step before data upload) */
+};
+
+/* Hyper-parameters and shapes. Defaults in comments are the reference's values. */
+typedef struct bae_config {
+  int32_t dims[4];        /* in_shape, in_one, in_two, enc_shape                 MAIN:76-79,84-87,97-100 */
+  int32_t n_train;        /* rows of the training matrix                          MAIN:833 */
+  int32_t n_test;         /* rows of the test matrix                              MAIN:834 */
+  int32_t n_chains;       /* chains resident on this handle (multiple of n_rungs) */
+  int32_t n_rungs;        /* ladder length = chains per ensemble (num_chains)     MAIN:64 */
+  int32_t chain_id_base;  /* global id of local chain 0 (keys the Philox streams; multi-GPU sharding) */
+  int32_t samples;        /* iterations per chain (NumSamples)                    MAIN:846 */
+  int32_t pt_switch_step; /* int(pt_samples * samples): tempered -> canonical     MAIN:429,437-445 */
+  int32_t swap_interval;  /* 5                                                    MAIN:69 */
+  int32_t use_langevin;   /* 1                                                    MAIN:61 */
+  float lr;               /* Adam lr 0.01                                         MAIN:80,89,101,178 */
+  float step_w;           /* proposal sigma 0.005                                 MAIN:81,88,102 */
+  float step_eta;         /* 0.2                                                  MAIN:387 */
+  float l_prob;           /* 0.9                                                  MAIN:286 */
+  float sigma_squared;    /* 25                                                   MAIN:396 */
+  float nu_1;             /* 0                                                    MAIN:397 */
+  float nu_2;             /* 3                                                    MAIN:398 */
+  uint64_t seed;          /* Philox4x32-10 key */
+  int32_t gemm_path;      /* 0 = auto, 1 = FP32 CUDA-core tiles only, 2 = tcgen05 3xTF32 where widths allow */
+  int32_t reserved;
+} bae_config;
+
+/* Per-step record, one per (chain, iteration): what MAIN:520-592 stores into its trace arrays. */
+typedef struct bae_trace {
+  double likelihood_proposal; /* MAIN:520 */
+  double likelihood;          /* MAIN:521 (value before the accept update) */
+  double sum_value;           /* MAIN:524,530 */
+  double log_u;               /* MAIN:526-527 */
+  double prior_proposal;      /* MAIN:511 */
+  double diff_prop;           /* MAIN:485,491 */
+  double mse_train;           /* MAIN:542/557 (accepted value carried forward) */
+  double mse_test;            /* MAIN:543/558 */
+  double mse_train_proposal;  /* msetrain of this step's proposal, MAIN:505 */
+  double mse_test_proposal;   /* MAIN:508 */
+  double eta;                 /* eta after the step */
+  float weights[13];          /* MAIN:564-592: live-model entries 0,100,10000,5000,2000,...,11000 */
+  int32_t accepted;           /* MAIN:532 */
+  int32_t langevin;           /* MAIN:452 */
+  int32_t step;
+} bae_trace;
+
+/* Scalars of one chain (checkpoint / parity injection). */
+typedef struct bae_chain_scalars {
+  double eta, likelihood, prior_current, last_sse_train, mse_train, mse_test, temperature, adapttemp;
+  int32_t adam_t, w_is_alias, init_count, num_accepted, langevin_count, step;
+  double prop_sse_train; /* SSE of this chain's own last proposal (used by the i == pt re-evaluation, MAIN:442) */
+} bae_chain_scalars;
+
+const char* bae_last_error(void);
+int bae_version(void);
+
+/* Lifecycle. `device` is a CUDA ordinal. Fails with BAE_ERR_NO_DEVICE when no sm_100 GPU is present. */
+int bae_create(const bae_config* cfg, int device, bae_handle** out);
+int bae_destroy(bae_handle* h);
+int bae_w_size(const bae_handle* h);       /* len(getparameters())            MAIN:352 */
+int bae_n_trainable(const bae_handle* h);
+
+/* Row-major float32 matrices, n_train x dims[0] and n_test x dims[0] (ParallelTempering.traindata/testdata, MAIN:833-834). */
+int bae_upload_data(bae_handle* h, const float* train, const float* test);
+/* Per-chain temperatures (assign_temperatures, MAIN:922-935), length n_chains. */
+int bae_set_ladder(bae_handle* h, const double* temperatures);
+
+/* run() prologue for one chain (MAIN:349-401): theta_init = torch-default-initialised state_dict (flat),
+ * w0 = the float64 np.random.randn(w_size) start vector. Computes eta0, prior_current, likelihood. */
+int bae_init_chain(bae_handle* h, int chain, const float* theta_init, const double* w0);
+
+/* Full state of one chain. Any pointer may be NULL. theta/w/m/v: w_size floats, reference order.
+ * `w` is meaningful only when scalars->w_is_alias == 0 (otherwise w IS theta, MAIN:449/555). */
+int bae_get_state(bae_handle* h, int chain, float* theta, float* w, float* m, float* v, bae_chain_scalars* s);
+int bae_set_state(bae_handle* h, int chain, const float* theta, const float* w, const float* m, const float* v,
+                  const bae_chain_scalars* s);
+
+/* n_steps iterations of MAIN:432-592 for every chain on the handle: ONE persistent cooperative kernel
+ * launch (forward/backward, Adam drift, noise, likelihood, prior, reverse-proposal density, MH test). */
+int bae_step(bae_handle* h, int n_steps);
+/* One exchange round (MAIN:594-603 + 962-1011 + 1059-1065) for every ensemble resident on the handle. */
+int bae_swap_local(bae_handle* h);
+/* Steps with an exchange round after every swap_interval-th iteration, like run_chains (MAIN:1035-1072). */
+int bae_run(bae_handle* h, int n_steps);
+int bae_synchronize(bae_handle* h);
+
+/* Parity probe (Model.evaluate_proposal + MSELoss.backward, MAIN:188-226): forward (and backward when
+ * grads != NULL) of `w` (w_size floats, or NULL for the chain's live model) on the train (which=0) or test
+ * (which=1) matrix. Does not disturb the chain state. out: n x dims[0] or NULL. */
+int bae_eval(bae_handle* h, int chain, int which, const float* w, double* sse, double* mse, float* grads, float* out);
+
+/* The draws iteration `step` of global chain id (chain_id_base + chain) consumes: noise = w_size fp32
+ * normals * step_w in reference order (MAIN:260), scalars = {lx, eta_noise, u} (MAIN:447,500,526). */
+int bae_debug_draws(bae_handle* h, int chain, int step, float* noise, double* scalars3);
+/* Swap uniform of (ensemble, round, pair) (MAIN:994). */
+int bae_debug_swap_uniform(bae_handle* h, int ensemble, int round, int pair, double* u);
+
+/* Trace ring: records of iterations [first_step, first_step+n) of one chain. */
+int bae_read_traces(bae_handle* h, int chain, int first_step, int n, bae_trace* out);
+int bae_swap_counts(bae_handle* h, int64_t* num_swap, int64_t* total_swap_proposals);
+
+/* Multi-GPU ladder sharding (one process per GPU): export / import the exchange view of a chain
+ * ([vec(w), eta, likelihood, adapttemp, last_sse], MAIN:595-596) as DEVICE buffers usable with NCCL. */
+int bae_exchange_pack(bae_handle* h, int chain, float* dev_w /*w_size*/, double* host_scalars4);
+int bae_exchange_unpack(bae_handle* h, int chain, const float* dev_w, const double* host_scalars2 /*eta,last_sse*/);
+/* Marks `w` as a detached copy for every chain, as MAIN:602 does after each exchange round. */
+int bae_exchange_finish(bae_handle* h);
+
+/* Introspection for the benchmark: kernels launched so far by this handle, last step-kernel time (ms). */
+int64_t bae_launch_count(const bae_handle* h);
+int bae_last_step_ms(bae_handle* h, float* ms);
+int bae_gemm_path(const bae_handle* h);  /* 1 = FP32 CUDA cores, 2 = tcgen05 3xTF32 */
+void* bae_stream(bae_handle* h);         /* cudaStream_t the handle launches on */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BAE_B200_H */
