@@ -5,13 +5,16 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>
+
 #include "bae_common.cuh"
 
 namespace bae {
-int max_coop_blocks_per_sm();
-cudaError_t launch_program(const DevState* dS, int grid, int ph_begin, int ph_end, int n_rep, int c_begin, int c_end,
-                           int force_swap, cudaStream_t st);
-cudaError_t launch_phase(const DevState* dS, int grid, int pi, int c_begin, int c_end, cudaStream_t st);
+int max_coop_blocks_per_sm(int use_tc);
+cudaError_t launch_program(const DevState* dS, int use_tc, int grid, int ph_begin, int ph_end, int n_rep, int c_begin,
+                           int c_end, int force_swap, cudaStream_t st);
+cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, cudaStream_t st);
+cudaError_t launch_split(const float* src, float* hi, float* lo, size_t n, cudaStream_t st);
 cudaError_t launch_debug_draws(const DevState* dS, int chain, int step, float* noise, double* scalars, cudaStream_t st);
 cudaError_t launch_debug_swap_u(const DevState* dS, int ens, int round, int pair, double* out, cudaStream_t st);
 cudaError_t launch_pack(const DevState* dS, const float* ref_vec, float* pad_vec, cudaStream_t st);
@@ -56,6 +59,9 @@ struct bae_handle {
   std::vector<void*> allocs;
   int grid = 0;
   bool data_loaded = false;
+  std::vector<CUtensorMap> tmaps_host;
+  std::vector<float> ones_col;
+  std::string tmap_error;
   float* stage_ref = nullptr;    // [w_size] device staging, reference order
   float* stage_noise = nullptr;  // [w_size]
   double* stage_d = nullptr;     // small device scratch for doubles
@@ -119,10 +125,24 @@ static void build_layout(DevState& s) {
   }
 }
 
-static GemmDesc make_gemm(const DevState& s, int M, int N, int K) {
+static GemmDesc make_gemm(const DevState& s, int M, int N, int K, int b_nmajor = 0) {
   GemmDesc g;
   memset(&g, 0, sizeof(g));
   g.M = M; g.N = N; g.K = K;
+  g.biasCol = -1;
+  if (s.tc) {
+    // tcgen05 tiles: 128 x BN, BN <= 256 chosen so the N tiles are balanced
+    // long contractions (weight gradients, K = rows) use narrower tiles so that the hi*hi term can rotate over
+    // three TMEM accumulators (shorter truncating accumulation chains); see bae_tc.cuh
+    const int maxbn = (K > 1024) ? 128 : 256;
+    g.tcMain = (K > 1024) ? 3 : 1;
+    g.tm = (M + 127) / 128;
+    g.tn = (N + maxbn - 1) / maxbn;
+    const int align = b_nmajor ? 32 : 16;
+    g.tcBN = round_up((N + g.tn - 1) / g.tn, align);
+    g.tcBBytes = g.tcBN * 128;   // K-major: BN rows x 128 B; N-major: BN/32 chunks x 4096 B
+    return g;
+  }
   g.big = (M >= 128 && N > 64) ? 1 : 0;
   const int bt = g.big ? 128 : 64;
   g.tm = (M + bt - 1) / bt;
@@ -130,18 +150,100 @@ static GemmDesc make_gemm(const DevState& s, int M, int N, int K) {
   return g;
 }
 
+// ---- TMA tensor maps (driver entry point fetched at run time: no link dependency on libcuda) ----------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// K-major operand: element (row, k) at ptr[chain*cs + row*ld + k]; box = 32 k x box_rows rows
+static int tmap_kmajor(CUtensorMap* out, const float* ptr, int K, int rows, int ld, int nchain, long long cs, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)std::max(1, nchain)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(cs > 0 ? cs : (long long)rows * ld) * 4};
+  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+// MN-major operand: element (t, k) at ptr[chain*cs + k*ld + t]; one box = [32 k][32 t] (a 4 KB swizzled chunk);
+// the producer issues one TMA per 32-wide chunk of the tile dimension.
+static int tmap_mnmajor(CUtensorMap* out, const float* ptr, int extent, int K, int ld, int nchain, long long cs, int /*box_chunks*/) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[3] = {(cuuint64_t)extent, (cuuint64_t)K, (cuuint64_t)std::max(1, nchain)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(cs > 0 ? cs : (long long)K * ld) * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 static void build_program(bae_handle* h) {
   DevState& s = h->hs;
   const long long P = s.Pp;
   const long long a1 = (long long)s.n_max * s.ld1, a2 = (long long)s.n_max * s.ld2, a3 = (long long)s.n_max * s.ld3,
                   a0 = (long long)s.n_max * s.ld0;
-  auto W = [&](int seg) { return s.theta + s.seg[seg].pad_off; };
+  const bool tcm = s.tc != 0;
+  auto W = [&](int seg) { return (tcm ? s.theta_hi : s.theta) + s.seg[seg].pad_off; };   // GEMM operand view of theta
+  auto Wl = [&](int seg) { return s.theta_lo + s.seg[seg].pad_off; };
+  auto Wraw = [&](int seg) { return s.theta + s.seg[seg].pad_off; };
   auto G = [&](int seg) { return s.grad + s.seg[seg].pad_off; };
+  // lo twin of an activation / delta / data array (tcgen05 path only)
+  auto LO = [&](const float* p) -> float* {
+    if (!tcm || !p) return nullptr;
+    if (p == s.H1) return s.H1l; if (p == s.H2) return s.H2l; if (p == s.Y) return s.Yl; if (p == s.H4) return s.H4l;
+    if (p == s.H5) return s.H5l; if (p == s.DOUT) return s.DOUTl; if (p == s.D5) return s.D5l; if (p == s.D4) return s.D4l;
+    if (p == s.DY) return s.DYl; if (p == s.D2) return s.D2l; if (p == s.D1) return s.D1l;
+    if (p == s.Xtrain_hi) return s.Xtrain_lo; if (p == s.Xtest_hi) return s.Xtest_lo;
+    return nullptr;
+  };
+  h->tmaps_host.clear();
+  h->tmap_error.clear();
+  // registers the four tensor maps of a GEMM; Al/Bl are the lo twins of g.A / g.B
+  auto add_maps = [&](GemmDesc& g, const float* Al, const float* Bl) {
+    if (!tcm) return;
+    const int nchA = g.sA ? s.C_alloc : 1, nchB = g.sB ? s.C_alloc : 1;
+    const float* ptrs[4] = {g.A, Al, g.B, Bl};
+    for (int i = 0; i < 4; ++i) {
+      CUtensorMap tm;
+      memset(&tm, 0, sizeof(tm));
+      int rc;
+      if (i < 2) {
+        rc = g.aMode == 0 ? tmap_kmajor(&tm, ptrs[i], g.K, g.M, g.lda, nchA, g.sA, 128)
+                          : tmap_mnmajor(&tm, ptrs[i], g.M, g.K, g.lda, nchA, g.sA, 4);
+      } else {
+        rc = g.bMode == 0 ? tmap_kmajor(&tm, ptrs[i], g.K, g.N, g.ldb, nchB, g.sB, g.tcBN)
+                          : tmap_mnmajor(&tm, ptrs[i], g.N, g.K, g.ldb, nchB, g.sB, g.tcBN / 32);
+      }
+      if (rc != 0 && h->tmap_error.empty())
+        h->tmap_error = "cuTensorMapEncodeTiled failed (CUresult " + std::to_string(rc) + ") for GEMM operand " + std::to_string(i);
+      g.tmIdx[i] = (int)h->tmaps_host.size();
+      h->tmaps_host.push_back(tm);
+    }
+    g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)g.aMode << 15) | ((unsigned)g.bMode << 16) |
+              ((unsigned)(g.tcBN >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+  };
   int ng = 0;
   // ---- forward descriptors for (train, first pass), (train, second pass), (test)
   int fwd_base[3];
   for (int pass = 0; pass < 3; ++pass) {
-    const float* X = (pass == 2) ? s.Xtest : s.Xtrain;
+    const float* Xraw = (pass == 2) ? s.Xtest : s.Xtrain;
+    const float* X = tcm ? ((pass == 2) ? s.Xtest_hi : s.Xtrain_hi) : Xraw;
     const int N = (pass == 2) ? s.n_test : s.n_train;
     const int need = (pass == 0) ? 1 : 0;
     fwd_base[pass] = ng;
@@ -154,62 +256,66 @@ static void build_program(bae_handle* h) {
         {s.H4, a2, s.ld2, SEG_D3_W, SEG_D3_B, s.H5, a1, s.ld1, s.d2, s.d1, EPI_SIGMOID},
         {s.H5, a1, s.ld1, SEG_D5_W, SEG_D5_B, s.DOUT, a0, s.ld0, s.d1, s.d0, EPI_LOSS}};
     for (int l = 0; l < 6; ++l) {
-      GemmDesc g = make_gemm(s, N, ls[l].dout, ls[l].din);
+      GemmDesc g = make_gemm(s, N, ls[l].dout, ls[l].din, 0);
       g.A = ls[l].A; g.sA = ls[l].sA; g.lda = ls[l].lda; g.aMode = 0;
       g.B = W(ls[l].wseg); g.sB = P; g.ldb = s.seg[ls[l].wseg].ld; g.bMode = 0;
       g.C = ls[l].C; g.sC = ls[l].sC; g.ldc = ls[l].ldc;
+      g.Cl = (ls[l].epi == EPI_BIAS) ? nullptr : LO(ls[l].C);   // z stays a plain FP32 array (BatchNorm input)
       g.epi = ls[l].epi;
-      g.bias = W(ls[l].bseg); g.sBias = P;
+      g.bias = Wraw(ls[l].bseg); g.sBias = P;
       g.needLang = need;
       if (ls[l].epi == EPI_LOSS) {
-        g.aux = X; g.sAux = 0; g.ldaux = s.ld0;
+        g.aux = Xraw; g.sAux = 0; g.ldaux = s.ld0; g.auxl = nullptr;
         g.scale = 2.0f / ((float)N * (float)s.d0);   // d MSELoss / d out (mean over all N*d0 elements, MAIN:150,223)
         g.part = s.loss_part + (size_t)pass * s.C_alloc * s.loss_stride * 2;
         g.partStride = s.loss_stride;
       }
+      add_maps(g, LO(ls[l].A), tcm ? Wl(ls[l].wseg) : nullptr);
       s.gemm[ng++] = g;
     }
   }
   // ---- backward descriptors (shared by both drift calls)
   const int N = s.n_train;
-  int bwd_base = ng;
+  const float* Xtr = tcm ? s.Xtrain_hi : s.Xtrain;
   struct BL { float* dOut; long long sD; int ldd; int dout; const float* Ain; long long sAin; int ldain; int din;
               int wseg, bseg; float* dIn; long long sDin; int lddin; const float* Hin; int epi_x; };
   const BL bl[6] = {
-      // layer 6: dOut = DOUT [N x d0], input H5
       {s.DOUT, a0, s.ld0, s.d0, s.H5, a1, s.ld1, s.d1, SEG_D5_W, SEG_D5_B, s.D5, a1, s.ld1, s.H5, EPI_DSIG},
       {s.D5, a1, s.ld1, s.d1, s.H4, a2, s.ld2, s.d2, SEG_D3_W, SEG_D3_B, s.D4, a2, s.ld2, s.H4, EPI_DSIG},
       {s.D4, a2, s.ld2, s.d2, s.Y, a3, s.ld3, s.d3, SEG_D1_W, SEG_D1_B, s.DY, a3, s.ld3, nullptr, EPI_PLAIN},
       {s.DY, a3, s.ld3, s.d3, s.H2, a2, s.ld2, s.d2, SEG_E4_W, -1 /* encode.4.bias gradient is exactly 0 */, s.D2, a2, s.ld2, s.H2, EPI_DSIG},
       {s.D2, a2, s.ld2, s.d2, s.H1, a1, s.ld1, s.d1, SEG_E2_W, SEG_E2_B, s.D1, a1, s.ld1, s.H1, EPI_DSIG},
-      {s.D1, a1, s.ld1, s.d1, s.Xtrain, 0, s.ld0, s.d0, SEG_E0_W, SEG_E0_B, nullptr, 0, 0, nullptr, EPI_PLAIN}};
+      {s.D1, a1, s.ld1, s.d1, Xtr, 0, s.ld0, s.d0, SEG_E0_W, SEG_E0_B, nullptr, 0, 0, nullptr, EPI_PLAIN}};
   int bw_idx[6], bx_idx[6];
   for (int l = 0; l < 6; ++l) {
-    // dW[o,i] = sum_n dOut[n,o] * Ain[n,i]
-    GemmDesc g = make_gemm(s, bl[l].dout, bl[l].din, N);
+    // dW[o,i] = sum_n dOut[n,o] * Ain[n,i]; on the tcgen05 path a ones column appended to Ain yields the bias gradient
+    const bool ones = tcm && bl[l].bseg >= 0;
+    GemmDesc g = make_gemm(s, bl[l].dout, bl[l].din + (ones ? 1 : 0), N, 1);
     g.A = bl[l].dOut; g.sA = bl[l].sD; g.lda = bl[l].ldd; g.aMode = 1;
     g.B = bl[l].Ain; g.sB = bl[l].sAin; g.ldb = bl[l].ldain; g.bMode = 1;
     g.C = G(bl[l].wseg); g.sC = P; g.ldc = s.seg[bl[l].wseg].ld;
     g.epi = EPI_GRADW;
     if (bl[l].bseg >= 0) { g.gbias = G(bl[l].bseg); g.sGb = P; }
+    if (ones) g.biasCol = bl[l].din;
     g.needLang = 1;
+    add_maps(g, LO(bl[l].dOut), LO(bl[l].Ain));
     bw_idx[l] = ng;
     s.gemm[ng++] = g;
     bx_idx[l] = -1;
     if (bl[l].dIn) {
       // dIn[n,i] = sum_o dOut[n,o] * W[o,i]   (x sigmoid' of the layer input)
-      GemmDesc x = make_gemm(s, N, bl[l].din, bl[l].dout);
+      GemmDesc x = make_gemm(s, N, bl[l].din, bl[l].dout, 1);
       x.A = bl[l].dOut; x.sA = bl[l].sD; x.lda = bl[l].ldd; x.aMode = 0;
       x.B = W(bl[l].wseg); x.sB = P; x.ldb = s.seg[bl[l].wseg].ld; x.bMode = 1;
-      x.C = bl[l].dIn; x.sC = bl[l].sDin; x.ldc = bl[l].lddin;
+      x.C = bl[l].dIn; x.sC = bl[l].sDin; x.ldc = bl[l].lddin; x.Cl = LO(bl[l].dIn);
       x.epi = bl[l].epi_x;
-      if (bl[l].Hin) { x.aux = bl[l].Hin; x.sAux = bl[l].sDin; x.ldaux = bl[l].lddin; }
+      if (bl[l].Hin) { x.aux = bl[l].Hin; x.sAux = bl[l].sDin; x.ldaux = bl[l].lddin; x.auxl = LO(bl[l].Hin); }
       x.needLang = 1;
+      add_maps(x, LO(bl[l].dOut), tcm ? Wl(bl[l].wseg) : nullptr);
       bx_idx[l] = ng;
       s.gemm[ng++] = x;
     }
   }
-  (void)bwd_base;
   s.n_gemm = ng;
   // ---- phases
   auto set = [&](int pi, int kind, int g0, int g1, int arg, int rows, int need) {
@@ -289,7 +395,20 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   DevState& s = h->hs;
   memset(&s, 0, sizeof(s));
   s.d0 = cfg->dims[0]; s.d1 = cfg->dims[1]; s.d2 = cfg->dims[2]; s.d3 = cfg->dims[3];
-  s.ld0 = round_up(s.d0, 4); s.ld1 = round_up(s.d1, 4); s.ld2 = round_up(s.d2, 4); s.ld3 = round_up(s.d3, 4);
+  {
+    // tcgen05 path only where the layers are real dense contractions (Madelon-like widths); narrow layers
+    // (Coil-2000's 50-85, Swiss Roll's 2-10) stay on the FP32 CUDA-core tiles.
+    const int dmin = std::min(std::min(s.d0, s.d1), std::min(s.d2, s.d3));
+    const bool eligible = dmin >= 128 && cfg->n_train >= 128 && cfg->n_test >= 128;
+    if (cfg->gemm_path == 2 && !eligible)
+      return fail(BAE_ERR_INVALID, "gemm_path=2 (tcgen05) needs every layer width >= 128 and >= 128 rows");
+    s.tc = (cfg->gemm_path == 2 || (cfg->gemm_path == 0 && eligible)) ? 1 : 0;
+    if (s.tc && !get_encode()) return fail(BAE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  }
+  // row pitches: multiple of 4 floats; the tcgen05 path reserves one extra column (ones column, bias gradients)
+  const int extra = s.tc ? 1 : 0;
+  s.ld0 = round_up(s.d0 + extra, 4); s.ld1 = round_up(s.d1 + extra, 4); s.ld2 = round_up(s.d2 + extra, 4);
+  s.ld3 = round_up(s.d3 + extra, 4);
   s.n_train = cfg->n_train; s.n_test = cfg->n_test; s.n_max = std::max(cfg->n_train, cfg->n_test);
   s.C = cfg->n_chains; s.C_alloc = s.C + 1; s.n_rungs = cfg->n_rungs; s.chain_id_base = cfg->chain_id_base;
   s.samples = cfg->samples; s.pt_step = cfg->pt_switch_step; s.swap_interval = cfg->swap_interval;
@@ -315,6 +434,22 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     GemmDesc t2 = make_gemm(s, std::min(s.n_train, s.n_test), s.d0, s.d1);
     s.loss_stride = std::max(s.loss_stride, t2.tm * t2.tn);
   }
+  if (s.tc) {
+    CU(dalloc(h, &s.theta_hi, CA * P)); CU(dalloc(h, &s.theta_lo, CA * P));
+    CU(dalloc(h, &s.Xtrain_hi, (size_t)s.n_train * s.ld0)); CU(dalloc(h, &s.Xtrain_lo, (size_t)s.n_train * s.ld0));
+    CU(dalloc(h, &s.Xtest_hi, (size_t)s.n_test * s.ld0)); CU(dalloc(h, &s.Xtest_lo, (size_t)s.n_test * s.ld0));
+    CU(dalloc(h, &s.H1l, CA * nm * s.ld1)); CU(dalloc(h, &s.H2l, CA * nm * s.ld2)); CU(dalloc(h, &s.Yl, CA * nm * s.ld3));
+    CU(dalloc(h, &s.H4l, CA * nm * s.ld2)); CU(dalloc(h, &s.H5l, CA * nm * s.ld1)); CU(dalloc(h, &s.DOUTl, CA * nm * s.ld0));
+    CU(dalloc(h, &s.D5l, CA * nm * s.ld1)); CU(dalloc(h, &s.D4l, CA * nm * s.ld2)); CU(dalloc(h, &s.DYl, CA * nm * s.ld3));
+    CU(dalloc(h, &s.D2l, CA * nm * s.ld2)); CU(dalloc(h, &s.D1l, CA * nm * s.ld1));
+    // ones column (index d) of every activation that is the B operand of a weight-gradient GEMM
+    std::vector<float> ones(CA * nm, 1.0f);
+    struct OC { float* p; int ld, d; };
+    const OC oc[5] = {{s.H1, s.ld1, s.d1}, {s.H2, s.ld2, s.d2}, {s.Y, s.ld3, s.d3}, {s.H4, s.ld2, s.d2}, {s.H5, s.ld1, s.d1}};
+    for (const OC& o : oc)
+      CU(cudaMemcpy2DAsync(o.p + o.d, (size_t)o.ld * 4, ones.data(), 4, 4, CA * nm, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
   CU(dalloc(h, &s.loss_part, 3 * CA * (size_t)s.loss_stride * 2));
   CU(dalloc(h, &s.adam_part, CA * (size_t)s.n_adam_items * 3));
   ChainArrays& c = s.ch;
@@ -336,9 +471,17 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     h->dS = reinterpret_cast<DevState*>(q);
   }
   build_program(h);
+  if (s.tc) {
+    if (!h->tmap_error.empty()) return fail(BAE_ERR_CUDA, h->tmap_error);
+    void* q = nullptr;
+    CU(cudaMalloc(&q, h->tmaps_host.size() * sizeof(CUtensorMap)));
+    h->allocs.push_back(q);
+    CU(cudaMemcpyAsync(q, h->tmaps_host.data(), h->tmaps_host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
+    s.tmaps = q;
+  }
   int rc = upload_state(h);
   if (rc) return rc;
-  const int bps = max_coop_blocks_per_sm();
+  const int bps = max_coop_blocks_per_sm(s.tc);
   if (bps < 1) return fail(BAE_ERR_CUDA, "step kernel cannot be made resident (occupancy 0)");
   h->grid = prop.multiProcessorCount * bps;
   CU(cudaStreamSynchronize(h->stream));
@@ -360,7 +503,7 @@ int bae_destroy(bae_handle* h) {
 
 int bae_w_size(const bae_handle* h) { return h ? h->hs.w_size : BAE_ERR_INVALID; }
 int bae_n_trainable(const bae_handle* h) { return h ? h->hs.w_size - h->hs.nbuf : BAE_ERR_INVALID; }
-int bae_gemm_path(const bae_handle* h) { return h ? 1 : BAE_ERR_INVALID; }
+int bae_gemm_path(const bae_handle* h) { return h ? (h->hs.tc ? 2 : 1) : BAE_ERR_INVALID; }
 void* bae_stream(bae_handle* h) { return h ? (void*)h->stream : nullptr; }
 int64_t bae_launch_count(const bae_handle* h) { return h ? h->launches : 0; }
 
@@ -378,6 +521,15 @@ int bae_upload_data(bae_handle* h, const float* train, const float* test) {
                        cudaMemcpyHostToDevice, h->stream));
   CU(cudaMemcpy2DAsync(s.Xtest, (size_t)s.ld0 * 4, test, (size_t)s.d0 * 4, (size_t)s.d0 * 4, s.n_test,
                        cudaMemcpyHostToDevice, h->stream));
+  if (s.tc) {
+    // TF32 (hi, lo) operand copies; the hi copy carries the ones column at index d0 (bias gradient of encode.0)
+    CU(launch_split(s.Xtrain, s.Xtrain_hi, s.Xtrain_lo, (size_t)s.n_train * s.ld0, h->stream));
+    CU(launch_split(s.Xtest, s.Xtest_hi, s.Xtest_lo, (size_t)s.n_test * s.ld0, h->stream));
+    h->launches += 2;
+    if (h->ones_col.size() < (size_t)s.n_max) h->ones_col.assign(s.n_max, 1.0f);
+    CU(cudaMemcpy2DAsync(s.Xtrain_hi + s.d0, (size_t)s.ld0 * 4, h->ones_col.data(), 4, 4, s.n_train, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpy2DAsync(s.Xtest_hi + s.d0, (size_t)s.ld0 * 4, h->ones_col.data(), 4, 4, s.n_test, cudaMemcpyHostToDevice, h->stream));
+  }
   h->data_loaded = true;
   return BAE_OK;
 }
@@ -400,6 +552,11 @@ static int put_vec(bae_handle* h, const float* host_ref, float* dev_pad_chain) {
   CU(cudaMemsetAsync(dev_pad_chain, 0, sizeof(float) * s.Pp, h->stream));
   CU(launch_pack(h->dS, h->stage_ref, dev_pad_chain, h->stream));
   h->launches++;
+  if (s.tc && dev_pad_chain >= s.theta && dev_pad_chain < s.theta + (size_t)s.C_alloc * s.Pp) {
+    const size_t off = dev_pad_chain - s.theta;   // keep the TF32 operand copies of theta in step
+    CU(launch_split(dev_pad_chain, s.theta_hi + off, s.theta_lo + off, (size_t)s.Pp, h->stream));
+    h->launches++;
+  }
   CU(cudaStreamSynchronize(h->stream));
   return BAE_OK;
 }
@@ -428,7 +585,7 @@ static int get1(bae_handle* h, const T* dev_arr, int idx, T* v) {
 
 static int run_phases_plain(bae_handle* h, int p_begin, int p_end, int c_begin, int c_end) {
   for (int p = p_begin; p < p_end; ++p) {
-    CU(launch_phase(h->dS, h->grid, p, c_begin, c_end, h->stream));
+    CU(launch_phase(h->dS, h->hs.tc, h->grid, p, c_begin, c_end, h->stream));
     h->launches++;
   }
   return BAE_OK;
@@ -603,12 +760,12 @@ static int coop_launch(bae_handle* h, int p_begin, int p_end, int n_rep, int for
           CU(cudaStreamSynchronize(h->stream));
           if (st == 0 || st % h->hs.swap_interval != 0) continue;
         }
-        CU(launch_phase(h->dS, h->grid, p, 0, h->hs.C, h->stream));
+        CU(launch_phase(h->dS, h->hs.tc, h->grid, p, 0, h->hs.C, h->stream));
         h->launches++;
       }
     }
   } else {
-    CU(launch_program(h->dS, h->grid, p_begin, p_end, n_rep, 0, h->hs.C, force_swap, h->stream));
+    CU(launch_program(h->dS, h->hs.tc, h->grid, p_begin, p_end, n_rep, 0, h->hs.C, force_swap, h->stream));
     h->launches++;
   }
   CU(cudaEventRecord(h->ev1, h->stream));
@@ -656,6 +813,10 @@ int bae_eval(bae_handle* h, int chain, int which, const float* w, double* sse, d
     if ((rc = put_vec(h, w, th))) return rc;
   } else {
     CU(cudaMemcpyAsync(th, s.theta + (size_t)chain * s.Pp, sizeof(float) * s.Pp, cudaMemcpyDeviceToDevice, h->stream));
+    if (s.tc) {
+      CU(cudaMemcpyAsync(s.theta_hi + (size_t)E * s.Pp, s.theta_hi + (size_t)chain * s.Pp, sizeof(float) * s.Pp, cudaMemcpyDeviceToDevice, h->stream));
+      CU(cudaMemcpyAsync(s.theta_lo + (size_t)E * s.Pp, s.theta_lo + (size_t)chain * s.Pp, sizeof(float) * s.Pp, cudaMemcpyDeviceToDevice, h->stream));
+    }
   }
   const int pass = which == 0 ? 0 : 2;
   const int rows = which == 0 ? s.n_train : s.n_test;
@@ -669,6 +830,12 @@ int bae_eval(bae_handle* h, int chain, int which, const float* w, double* sse, d
     CU(cudaMemcpyAsync(d.data(), s.DOUT + (size_t)E * s.n_max * s.ld0, sizeof(float) * d.size(), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(x.data(), which == 0 ? s.Xtrain : s.Xtest, sizeof(float) * x.size(), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
+    if (s.tc) {
+      std::vector<float> dl(d.size());
+      CU(cudaMemcpyAsync(dl.data(), s.DOUTl + (size_t)E * s.n_max * s.ld0, sizeof(float) * dl.size(), cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+      for (size_t i = 0; i < d.size(); ++i) d[i] += dl[i];
+    }
     const double scale = 2.0 / ((double)rows * s.d0);
     for (int r = 0; r < rows; ++r)
       for (int c = 0; c < s.d0; ++c)
@@ -769,6 +936,11 @@ int bae_exchange_unpack(bae_handle* h, int chain, const float* dev_w, const doub
     CU(cudaMemcpyAsync(s.theta + (size_t)chain * s.Pp + g.pad_off, scratch + g.pad_off, sizeof(float) * g.rows * g.ld,
                        cudaMemcpyDeviceToDevice, h->stream));
   }
+  if (s.tc) {
+    const size_t off = (size_t)chain * s.Pp;
+    CU(launch_split(s.theta + off, s.theta_hi + off, s.theta_lo + off, (size_t)s.Pp, h->stream));
+    h->launches++;
+  }
   put1(h, s.ch.eta, chain, host_scalars2[0]);
   put1(h, s.ch.last_sse, chain, host_scalars2[1]);
   put1<int>(h, s.ch.alias, chain, 0);
@@ -796,6 +968,42 @@ int bae_exchange_finish(bae_handle* h) {
   CU(cudaMemcpyAsync(s.ch.alias, zero.data(), sizeof(int) * s.C, cudaMemcpyHostToDevice, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return BAE_OK;
+}
+
+
+// Debug probe: copy a per-chain device array (padded layout, hi part on the tcgen05 path) to the host.
+// `chain` may be n_chains (the parity-probe scratch slot). Returns the row pitch in *ld.
+int bae_debug_buffer(bae_handle* h, const char* name, int chain, float* out, int64_t n_floats, int* ld, int lo_part) {
+  if (!h || !name || !out) return fail(BAE_ERR_INVALID, "null argument");
+  const DevState& s = h->hs;
+  if (chain < 0 || chain > s.C) return fail(BAE_ERR_INVALID, "chain out of range");
+  CU(cudaSetDevice(h->device));
+  struct E { const char* n; const float* hi; const float* lo; int ld; };
+  const E tab[] = {{"H1", s.H1, s.H1l, s.ld1}, {"H2", s.H2, s.H2l, s.ld2}, {"Z", s.Z, nullptr, s.ld3}, {"Y", s.Y, s.Yl, s.ld3},
+                   {"H4", s.H4, s.H4l, s.ld2}, {"H5", s.H5, s.H5l, s.ld1}, {"DOUT", s.DOUT, s.DOUTl, s.ld0},
+                   {"D5", s.D5, s.D5l, s.ld1}, {"D4", s.D4, s.D4l, s.ld2}, {"DY", s.DY, s.DYl, s.ld3},
+                   {"D2", s.D2, s.D2l, s.ld2}, {"D1", s.D1, s.D1l, s.ld1}};
+  for (const E& e : tab) {
+    if (strcmp(e.n, name) != 0) continue;
+    const float* src = lo_part ? e.lo : e.hi;
+    if (!src) return fail(BAE_ERR_INVALID, "no such part");
+    const size_t per = (size_t)s.n_max * e.ld;
+    if ((size_t)n_floats > per) return fail(BAE_ERR_INVALID, "too many floats");
+    CU(cudaMemcpyAsync(out, src + (size_t)chain * per, sizeof(float) * n_floats, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (ld) *ld = e.ld;
+    return BAE_OK;
+  }
+  if (strcmp(name, "grad") == 0 || strcmp(name, "theta") == 0 || strcmp(name, "theta_hi") == 0 || strcmp(name, "theta_lo") == 0) {
+    const float* src = name[0] == 'g' ? s.grad : (strcmp(name, "theta") == 0 ? s.theta : (name[6] == 'h' ? s.theta_hi : s.theta_lo));
+    if (!src) return fail(BAE_ERR_INVALID, "no such array");
+    if (n_floats > s.Pp) return fail(BAE_ERR_INVALID, "too many floats");
+    CU(cudaMemcpyAsync(out, src + (size_t)chain * s.Pp, sizeof(float) * n_floats, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (ld) *ld = 0;
+    return BAE_OK;
+  }
+  return fail(BAE_ERR_INVALID, "unknown buffer name");
 }
 
 }  // extern "C"

@@ -56,8 +56,15 @@ struct GemmDesc {
   int needLang;  // 1: only chains whose current step is a Langevin step
   int tm, tn;    // tiles along M and N
   int big;       // 1: 128x128 tiles, 0: 64x64 tiles
-  int outFull;   // EPI_LOSS: optional second output with o itself (parity probe), else null
-  float* out2; long long sOut2;
+  // ---- tcgen05 path (3xTF32): operands and outputs are (hi, lo) pairs; A/B/C/aux above hold the hi part
+  float* Cl;            // lo part of the output (null: store the plain FP32 value to C)
+  const float* auxl;    // lo part of aux (null: aux is a plain FP32 array)
+  int tcBN;             // tile width (multiple of 16; multiple of 32 when B is N-major), <= 256
+  int tcBBytes;         // bytes of one B tile (hi or lo) per K block
+  int tcMain;           // TMEM accumulators the hi*hi term rotates over; (tcMain + 1) * tcBN <= 512 columns
+  int tmIdx[4];         // tensor maps: A_hi, A_lo, B_hi, B_lo
+  unsigned idesc;       // tcgen05 instruction descriptor
+  int biasCol;          // EPI_GRADW: output column that holds the bias gradient (ones column trick), or -1
 };
 
 enum PhaseKind : int {
@@ -125,6 +132,12 @@ struct DevState {
   double* swap_tmp;  // [C][2] eta, last_sse scratch
   long long *num_swap, *total_swap;
   int swap_round;
+  // ---- tcgen05 path
+  int tc;             // 1: GEMM phases run on the tensor cores (3xTF32), activations stored as (hi, lo)
+  void* tmaps;        // CUtensorMap array in global memory (64-byte aligned)
+  float *theta_hi, *theta_lo;
+  float *Xtrain_hi, *Xtrain_lo, *Xtest_hi, *Xtest_lo;
+  float *H1l, *H2l, *Yl, *H4l, *H5l, *DOUTl, *D5l, *D4l, *DYl, *D2l, *D1l;
   // ---- program
   int n_gemm, n_phase;
   GemmDesc gemm[kMaxGemm];

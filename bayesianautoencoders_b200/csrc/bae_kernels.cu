@@ -10,6 +10,7 @@
 #include <math_constants.h>
 
 #include "bae_common.cuh"
+#include "bae_tc.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -191,7 +192,6 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
   float* C = g.C ? g.C + (size_t)chain * g.sC : nullptr;
   const float* bias = g.bias ? g.bias + (size_t)chain * g.sBias : nullptr;
   const float* aux = g.aux ? g.aux + (size_t)chain * g.sAux : nullptr;
-  float* out2 = g.out2 ? g.out2 + (size_t)chain * g.sOut2 : nullptr;
   float l_sse = 0.f, l_sd = 0.f;
 #pragma unroll
   for (int gi = 0; gi < GM; ++gi) {
@@ -217,7 +217,6 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
           float4 t = *reinterpret_cast<const float4*>(&aux[(size_t)r * g.ldaux + c]);
           av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
         }
-        float o2[4] = {0.f, 0.f, 0.f, 0.f};
         switch (g.epi) {
           case EPI_SIGMOID:
 #pragma unroll
@@ -231,7 +230,6 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float o = v[j] + bv[j];
-              o2[j] = o;
               float d = o - av[j];
               if (j < nval) { l_sse = fmaf(d, d, l_sse); l_sd += d; }
               v[j] = d * g.scale;
@@ -251,10 +249,6 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
           } else {
             for (int j = 0; j < nval; ++j) dst[j] = v[j];
           }
-        }
-        if (out2) {
-          float* dst = &out2[(size_t)r * g.ldc + c];
-          for (int j = 0; j < nval; ++j) dst[j] = o2[j];
         }
       }
     }
@@ -344,9 +338,18 @@ __device__ void run_bn_fwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
         S->bn_var[((size_t)slot * S->C_alloc + chain) * ld3 + c] = var;
         S->bn_inv[(size_t)chain * ld3 + c] = inv;
       }
+      float* Yl = S->tc ? S->Yl + (size_t)chain * S->n_max * ld3 : nullptr;
       for (int r = rl; r < N; r += 8) {
         float zh = (Z[(size_t)r * ld3 + c] - mean) * inv;
-        Y[(size_t)r * ld3 + c] = fmaf(zh, gam, bet);
+        float y = fmaf(zh, gam, bet);
+        if (Yl) {
+          float hi, lo;
+          tc::split_tf32(y, hi, lo);
+          Y[(size_t)r * ld3 + c] = hi;
+          Yl[(size_t)r * ld3 + c] = lo;
+        } else {
+          Y[(size_t)r * ld3 + c] = y;
+        }
       }
     }
   }
@@ -364,6 +367,7 @@ __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
     const bool cv = c < d3;
     const float* Z = S->Z + (size_t)chain * S->n_max * ld3;
     float* DY = S->DY + (size_t)chain * S->n_max * ld3;
+    float* DYl = S->tc ? S->DYl + (size_t)chain * S->n_max * ld3 : nullptr;
     float mean = 0.f, inv = 0.f, gam = 0.f;
     if (cv) {
       mean = S->bn_mu[((size_t)slot * S->C_alloc + chain) * ld3 + c];
@@ -374,6 +378,7 @@ __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
     if (cv)
       for (int r = rl; r < N; r += 8) {
         float dy = DY[(size_t)r * ld3 + c];
+        if (DYl) dy += DYl[(size_t)r * ld3 + c];
         float zh = (Z[(size_t)r * ld3 + c] - mean) * inv;
         s1 += (double)dy;
         s2 += (double)dy * (double)zh;
@@ -395,8 +400,17 @@ __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
       const float m2 = (float)(t2 / N) * gam;              // mean(dzhat * zhat)
       for (int r = rl; r < N; r += 8) {
         float dy = DY[(size_t)r * ld3 + c];
+        if (DYl) dy += DYl[(size_t)r * ld3 + c];
         float zh = (Z[(size_t)r * ld3 + c] - mean) * inv;
-        DY[(size_t)r * ld3 + c] = inv * (dy * gam - m1 - zh * m2);
+        float dz = inv * (dy * gam - m1 - zh * m2);
+        if (DYl) {
+          float hi, lo;
+          tc::split_tf32(dz, hi, lo);
+          DY[(size_t)r * ld3 + c] = hi;
+          DYl[(size_t)r * ld3 + c] = lo;
+        } else {
+          DY[(size_t)r * ld3 + c] = dz;
+        }
       }
     }
   }
@@ -479,6 +493,13 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
           }
         }
         *reinterpret_cast<float4*>(&th[p]) = make_float4(o[0], o[1], o[2], o[3]);
+        if (S->tc) {
+          float h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tc::split_tf32(o[j], h[j], l[j]);
+          *reinterpret_cast<float4*>(&S->theta_hi[base + p]) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(&S->theta_lo[base + p]) = make_float4(l[0], l[1], l[2], l[3]);
+        }
       } else {
         float4 g4 = *reinterpret_cast<const float4*>(&gr[p]);
         float4 m4 = *reinterpret_cast<const float4*>(&mm[p]);
@@ -851,7 +872,15 @@ __device__ void run_swap_scatter(const DevState* S) {
       const int pidx = it * kAdamChunk + i * 4;
       const int sg = find_seg(S, pidx);
       if (!S->seg[sg].trainable) continue;
-      *reinterpret_cast<float4*>(dbase + pidx) = s4[i];
+      const float4 val = s4[i];
+      *reinterpret_cast<float4*>(dbase + pidx) = val;
+      if (S->tc) {
+        float4 h, l;
+        tc::split_tf32(val.x, h.x, l.x); tc::split_tf32(val.y, h.y, l.y);
+        tc::split_tf32(val.z, h.z, l.z); tc::split_tf32(val.w, h.w, l.w);
+        *reinterpret_cast<float4*>(S->theta_hi + (size_t)p * S->Pp + pidx) = h;
+        *reinterpret_cast<float4*>(S->theta_lo + (size_t)p * S->Pp + pidx) = l;
+      }
     }
   }
 }
@@ -903,6 +932,59 @@ bae_phase_kernel(const DevState* __restrict__ S, int pi, int c_begin, int c_end)
   __shared__ __align__(16) float smem[2 * BK * 128 * 2];
   __shared__ double red[16];
   run_phase(S, pi, c_begin, c_end, 1, smem, red);
+}
+
+// ---- tensor-core variants: GEMM phases go through the tcgen05 tile engine (1 CTA per SM, ~193 KB smem ring)
+__device__ void run_phase_tc(const DevState* S, int pi, int c_begin, int c_end, int force_swap, tc::Smem& tsm,
+                             tc::Ring& ring, float* smem_small, double* red) {
+  const PhaseDesc& ph = S->phase[pi];
+  if (ph.kind == PH_GEMM) {
+    tc::gemm_phase(S, ph, c_begin, c_end, tsm, ring);
+  } else {
+    run_phase(S, pi, c_begin, c_end, force_swap, smem_small, red);
+    tc::fence_proxy_async();   // theta_hi/lo, Y, dZ written with generic stores are read by TMA next
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, int n_rep, int c_begin, int c_end,
+                      int force_swap) {
+  extern __shared__ uint8_t dyn_smem[];
+  __shared__ __align__(16) float smem_small[1024];   // BatchNorm column reductions (512 doubles)
+  __shared__ double red[16];
+  tc::Smem tsm;
+  tc::Ring ring;
+  tc::setup(tsm, dyn_smem);
+  cg::grid_group grid = cg::this_grid();
+  for (int rep = 0; rep < n_rep; ++rep) {
+    for (int pi = ph_begin; pi < ph_end; ++pi) {
+      run_phase_tc(S, pi, c_begin, c_end, force_swap, tsm, ring, smem_small, red);
+      grid.sync();
+    }
+  }
+  tc::teardown(tsm);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_end) {
+  extern __shared__ uint8_t dyn_smem[];
+  __shared__ __align__(16) float smem_small[1024];
+  __shared__ double red[16];
+  tc::Smem tsm;
+  tc::Ring ring;
+  tc::setup(tsm, dyn_smem);
+  run_phase_tc(S, pi, c_begin, c_end, 1, tsm, ring, smem_small, red);
+  tc::teardown(tsm);
+}
+
+// value -> (hi, lo) TF32 split of n floats
+__global__ void bae_split_kernel(const float* __restrict__ src, float* hi, float* lo, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float h, l;
+    tc::split_tf32(src[i], h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
 }
 
 // Writes the proposal noise of (chain, step) in REFERENCE order, plus the three step scalars.
@@ -962,21 +1044,37 @@ __global__ void bae_unpack_kernel(const DevState* __restrict__ S, const float* p
 // ---- launch wrappers used by bae_api.cu ----------------------------------------------------------
 namespace bae {
 
-int max_coop_blocks_per_sm() {
+int max_coop_blocks_per_sm(int use_tc) {
   int nb = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel, kThreads, 0);
+  if (use_tc) {
+    cudaFuncSetAttribute(bae_program_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    cudaFuncSetAttribute(bae_phase_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel_tc, kThreads, tc::kSmemBytes);
+  } else {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel, kThreads, 0);
+  }
   return nb;
 }
 
-cudaError_t launch_program(const DevState* dS, int grid, int ph_begin, int ph_end, int n_rep, int c_begin, int c_end,
-                           int force_swap, cudaStream_t st) {
+cudaError_t launch_program(const DevState* dS, int use_tc, int grid, int ph_begin, int ph_end, int n_rep, int c_begin,
+                           int c_end, int force_swap, cudaStream_t st) {
   void* args[] = {(void*)&dS, (void*)&ph_begin, (void*)&ph_end, (void*)&n_rep, (void*)&c_begin, (void*)&c_end,
                   (void*)&force_swap};
+  if (use_tc)
+    return cudaLaunchCooperativeKernel((void*)bae_program_kernel_tc, dim3(grid), dim3(kThreads), args, tc::kSmemBytes, st);
   return cudaLaunchCooperativeKernel((void*)bae_program_kernel, dim3(grid), dim3(kThreads), args, 0, st);
 }
 
-cudaError_t launch_phase(const DevState* dS, int grid, int pi, int c_begin, int c_end, cudaStream_t st) {
-  bae_phase_kernel<<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end);
+cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, cudaStream_t st) {
+  if (use_tc)
+    bae_phase_kernel_tc<<<grid, kThreads, tc::kSmemBytes, st>>>(dS, pi, c_begin, c_end);
+  else
+    bae_phase_kernel<<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_split(const float* src, float* hi, float* lo, size_t n, cudaStream_t st) {
+  bae_split_kernel<<<256, 256, 0, st>>>(src, hi, lo, n);
   return cudaGetLastError();
 }
 

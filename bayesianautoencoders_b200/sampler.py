@@ -236,6 +236,15 @@ class DeviceSampler:
         N.check(self.lib.bae_debug_draws(self._h, int(chain), int(step), noise.ctypes.data, sc.ctypes.data))
         return dict(noise=noise, lx=sc[0], eta_noise=sc[1], u=sc[2])
 
+    def debug_buffer(self, name, chain, rows, lo_part=False):
+        """Raw [rows, ld] view of a per-chain device array (debug probe)."""
+        ld = C.c_int()
+        probe = np.zeros(4, np.float32)
+        N.check(self.lib.bae_debug_buffer(self._h, name.encode(), int(chain), probe.ctypes.data, 4, C.byref(ld), int(lo_part)))
+        out = np.zeros((rows, ld.value), np.float32)
+        N.check(self.lib.bae_debug_buffer(self._h, name.encode(), int(chain), out.ctypes.data, out.size, C.byref(ld), int(lo_part)))
+        return out
+
     def debug_swap_uniform(self, ensemble, rnd, pair):
         u = C.c_double()
         N.check(self.lib.bae_debug_swap_uniform(self._h, int(ensemble), int(rnd), int(pair), C.byref(u)))

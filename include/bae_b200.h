@@ -139,6 +139,10 @@ int bae_exchange_unpack(bae_handle* h, int chain, const float* dev_w, const doub
 /* Marks `w` as a detached copy for every chain, as MAIN:602 does after each exchange round. */
 int bae_exchange_finish(bae_handle* h);
 
+/* Debug probe: raw copy of a per-chain device array ("H1","H2","Z","Y","H4","H5","DOUT","D5","D4","DY","D2","D1",
+ * "grad","theta","theta_hi","theta_lo") in the padded device layout; chain may be n_chains (probe scratch slot). */
+int bae_debug_buffer(bae_handle* h, const char* name, int chain, float* out, int64_t n_floats, int* ld, int lo_part);
+
 /* Introspection for the benchmark: kernels launched so far by this handle, last step-kernel time (ms). */
 int64_t bae_launch_count(const bae_handle* h);
 int bae_last_step_ms(bae_handle* h, float* ms);
