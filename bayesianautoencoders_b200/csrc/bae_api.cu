@@ -199,31 +199,21 @@ static void build_program(bae_handle* h) {
   const long long a1 = (long long)s.n_max * s.ld1, a2 = (long long)s.n_max * s.ld2, a3 = (long long)s.n_max * s.ld3,
                   a0 = (long long)s.n_max * s.ld0;
   const bool tcm = s.tc != 0;
-  auto W = [&](int seg) { return (tcm ? s.theta_hi : s.theta) + s.seg[seg].pad_off; };   // GEMM operand view of theta
-  auto Wl = [&](int seg) { return s.theta_lo + s.seg[seg].pad_off; };
-  auto Wraw = [&](int seg) { return s.theta + s.seg[seg].pad_off; };
+  auto W = [&](int seg) { return s.theta + s.seg[seg].pad_off; };
+  auto Wraw = W;
   auto G = [&](int seg) { return s.grad + s.seg[seg].pad_off; };
-  // lo twin of an activation / delta / data array (tcgen05 path only)
-  auto LO = [&](const float* p) -> float* {
-    if (!tcm || !p) return nullptr;
-    if (p == s.H1) return s.H1l; if (p == s.H2) return s.H2l; if (p == s.Y) return s.Yl; if (p == s.H4) return s.H4l;
-    if (p == s.H5) return s.H5l; if (p == s.DOUT) return s.DOUTl; if (p == s.D5) return s.D5l; if (p == s.D4) return s.D4l;
-    if (p == s.DY) return s.DYl; if (p == s.D2) return s.D2l; if (p == s.D1) return s.D1l;
-    if (p == s.Xtrain_hi) return s.Xtrain_lo; if (p == s.Xtest_hi) return s.Xtest_lo;
-    return nullptr;
-  };
   h->tmaps_host.clear();
   h->tmap_error.clear();
-  // registers the four tensor maps of a GEMM; Al/Bl are the lo twins of g.A / g.B
-  auto add_maps = [&](GemmDesc& g, const float* Al, const float* Bl) {
+  // registers the two tensor maps (A, B) of a GEMM
+  auto add_maps = [&](GemmDesc& g) {
     if (!tcm) return;
     const int nchA = g.sA ? s.C_alloc : 1, nchB = g.sB ? s.C_alloc : 1;
-    const float* ptrs[4] = {g.A, Al, g.B, Bl};
-    for (int i = 0; i < 4; ++i) {
+    const float* ptrs[2] = {g.A, g.B};
+    for (int i = 0; i < 2; ++i) {
       CUtensorMap tm;
       memset(&tm, 0, sizeof(tm));
       int rc;
-      if (i < 2) {
+      if (i < 1) {
         rc = g.aMode == 0 ? tmap_kmajor(&tm, ptrs[i], g.K, g.M, g.lda, nchA, g.sA, 128)
                           : tmap_mnmajor(&tm, ptrs[i], g.M, g.K, g.lda, nchA, g.sA, 4);
       } else {
@@ -243,7 +233,7 @@ static void build_program(bae_handle* h) {
   int fwd_base[3];
   for (int pass = 0; pass < 3; ++pass) {
     const float* Xraw = (pass == 2) ? s.Xtest : s.Xtrain;
-    const float* X = tcm ? ((pass == 2) ? s.Xtest_hi : s.Xtrain_hi) : Xraw;
+    const float* X = Xraw;
     const int N = (pass == 2) ? s.n_test : s.n_train;
     const int need = (pass == 0) ? 1 : 0;
     fwd_base[pass] = ng;
@@ -260,23 +250,22 @@ static void build_program(bae_handle* h) {
       g.A = ls[l].A; g.sA = ls[l].sA; g.lda = ls[l].lda; g.aMode = 0;
       g.B = W(ls[l].wseg); g.sB = P; g.ldb = s.seg[ls[l].wseg].ld; g.bMode = 0;
       g.C = ls[l].C; g.sC = ls[l].sC; g.ldc = ls[l].ldc;
-      g.Cl = (ls[l].epi == EPI_BIAS) ? nullptr : LO(ls[l].C);   // z stays a plain FP32 array (BatchNorm input)
       g.epi = ls[l].epi;
       g.bias = Wraw(ls[l].bseg); g.sBias = P;
       g.needLang = need;
       if (ls[l].epi == EPI_LOSS) {
-        g.aux = Xraw; g.sAux = 0; g.ldaux = s.ld0; g.auxl = nullptr;
+        g.aux = Xraw; g.sAux = 0; g.ldaux = s.ld0;
         g.scale = 2.0f / ((float)N * (float)s.d0);   // d MSELoss / d out (mean over all N*d0 elements, MAIN:150,223)
         g.part = s.loss_part + (size_t)pass * s.C_alloc * s.loss_stride * 2;
         g.partStride = s.loss_stride;
       }
-      add_maps(g, LO(ls[l].A), tcm ? Wl(ls[l].wseg) : nullptr);
+      add_maps(g);
       s.gemm[ng++] = g;
     }
   }
   // ---- backward descriptors (shared by both drift calls)
   const int N = s.n_train;
-  const float* Xtr = tcm ? s.Xtrain_hi : s.Xtrain;
+  const float* Xtr = s.Xtrain;
   struct BL { float* dOut; long long sD; int ldd; int dout; const float* Ain; long long sAin; int ldain; int din;
               int wseg, bseg; float* dIn; long long sDin; int lddin; const float* Hin; int epi_x; };
   const BL bl[6] = {
@@ -298,7 +287,7 @@ static void build_program(bae_handle* h) {
     if (bl[l].bseg >= 0) { g.gbias = G(bl[l].bseg); g.sGb = P; }
     if (ones) g.biasCol = bl[l].din;
     g.needLang = 1;
-    add_maps(g, LO(bl[l].dOut), LO(bl[l].Ain));
+    add_maps(g);
     bw_idx[l] = ng;
     s.gemm[ng++] = g;
     bx_idx[l] = -1;
@@ -307,11 +296,11 @@ static void build_program(bae_handle* h) {
       GemmDesc x = make_gemm(s, N, bl[l].din, bl[l].dout, 1);
       x.A = bl[l].dOut; x.sA = bl[l].sD; x.lda = bl[l].ldd; x.aMode = 0;
       x.B = W(bl[l].wseg); x.sB = P; x.ldb = s.seg[bl[l].wseg].ld; x.bMode = 1;
-      x.C = bl[l].dIn; x.sC = bl[l].sDin; x.ldc = bl[l].lddin; x.Cl = LO(bl[l].dIn);
+      x.C = bl[l].dIn; x.sC = bl[l].sDin; x.ldc = bl[l].lddin;
       x.epi = bl[l].epi_x;
-      if (bl[l].Hin) { x.aux = bl[l].Hin; x.sAux = bl[l].sDin; x.ldaux = bl[l].lddin; x.auxl = LO(bl[l].Hin); }
+      if (bl[l].Hin) { x.aux = bl[l].Hin; x.sAux = bl[l].sDin; x.ldaux = bl[l].lddin; }
       x.needLang = 1;
-      add_maps(x, LO(bl[l].dOut), tcm ? Wl(bl[l].wseg) : nullptr);
+      add_maps(x);
       bx_idx[l] = ng;
       s.gemm[ng++] = x;
     }
@@ -435,13 +424,6 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     s.loss_stride = std::max(s.loss_stride, t2.tm * t2.tn);
   }
   if (s.tc) {
-    CU(dalloc(h, &s.theta_hi, CA * P)); CU(dalloc(h, &s.theta_lo, CA * P));
-    CU(dalloc(h, &s.Xtrain_hi, (size_t)s.n_train * s.ld0)); CU(dalloc(h, &s.Xtrain_lo, (size_t)s.n_train * s.ld0));
-    CU(dalloc(h, &s.Xtest_hi, (size_t)s.n_test * s.ld0)); CU(dalloc(h, &s.Xtest_lo, (size_t)s.n_test * s.ld0));
-    CU(dalloc(h, &s.H1l, CA * nm * s.ld1)); CU(dalloc(h, &s.H2l, CA * nm * s.ld2)); CU(dalloc(h, &s.Yl, CA * nm * s.ld3));
-    CU(dalloc(h, &s.H4l, CA * nm * s.ld2)); CU(dalloc(h, &s.H5l, CA * nm * s.ld1)); CU(dalloc(h, &s.DOUTl, CA * nm * s.ld0));
-    CU(dalloc(h, &s.D5l, CA * nm * s.ld1)); CU(dalloc(h, &s.D4l, CA * nm * s.ld2)); CU(dalloc(h, &s.DYl, CA * nm * s.ld3));
-    CU(dalloc(h, &s.D2l, CA * nm * s.ld2)); CU(dalloc(h, &s.D1l, CA * nm * s.ld1));
     // ones column (index d) of every activation that is the B operand of a weight-gradient GEMM
     std::vector<float> ones(CA * nm, 1.0f);
     struct OC { float* p; int ld, d; };
@@ -522,13 +504,10 @@ int bae_upload_data(bae_handle* h, const float* train, const float* test) {
   CU(cudaMemcpy2DAsync(s.Xtest, (size_t)s.ld0 * 4, test, (size_t)s.d0 * 4, (size_t)s.d0 * 4, s.n_test,
                        cudaMemcpyHostToDevice, h->stream));
   if (s.tc) {
-    // TF32 (hi, lo) operand copies; the hi copy carries the ones column at index d0 (bias gradient of encode.0)
-    CU(launch_split(s.Xtrain, s.Xtrain_hi, s.Xtrain_lo, (size_t)s.n_train * s.ld0, h->stream));
-    CU(launch_split(s.Xtest, s.Xtest_hi, s.Xtest_lo, (size_t)s.n_test * s.ld0, h->stream));
-    h->launches += 2;
+    // ones column at index d0: the weight-gradient GEMM of encode.0 reads it to produce the bias gradient
     if (h->ones_col.size() < (size_t)s.n_max) h->ones_col.assign(s.n_max, 1.0f);
-    CU(cudaMemcpy2DAsync(s.Xtrain_hi + s.d0, (size_t)s.ld0 * 4, h->ones_col.data(), 4, 4, s.n_train, cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpy2DAsync(s.Xtest_hi + s.d0, (size_t)s.ld0 * 4, h->ones_col.data(), 4, 4, s.n_test, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpy2DAsync(s.Xtrain + s.d0, (size_t)s.ld0 * 4, h->ones_col.data(), 4, 4, s.n_train, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpy2DAsync(s.Xtest + s.d0, (size_t)s.ld0 * 4, h->ones_col.data(), 4, 4, s.n_test, cudaMemcpyHostToDevice, h->stream));
   }
   h->data_loaded = true;
   return BAE_OK;
@@ -552,11 +531,6 @@ static int put_vec(bae_handle* h, const float* host_ref, float* dev_pad_chain) {
   CU(cudaMemsetAsync(dev_pad_chain, 0, sizeof(float) * s.Pp, h->stream));
   CU(launch_pack(h->dS, h->stage_ref, dev_pad_chain, h->stream));
   h->launches++;
-  if (s.tc && dev_pad_chain >= s.theta && dev_pad_chain < s.theta + (size_t)s.C_alloc * s.Pp) {
-    const size_t off = dev_pad_chain - s.theta;   // keep the TF32 operand copies of theta in step
-    CU(launch_split(dev_pad_chain, s.theta_hi + off, s.theta_lo + off, (size_t)s.Pp, h->stream));
-    h->launches++;
-  }
   CU(cudaStreamSynchronize(h->stream));
   return BAE_OK;
 }
@@ -813,10 +787,6 @@ int bae_eval(bae_handle* h, int chain, int which, const float* w, double* sse, d
     if ((rc = put_vec(h, w, th))) return rc;
   } else {
     CU(cudaMemcpyAsync(th, s.theta + (size_t)chain * s.Pp, sizeof(float) * s.Pp, cudaMemcpyDeviceToDevice, h->stream));
-    if (s.tc) {
-      CU(cudaMemcpyAsync(s.theta_hi + (size_t)E * s.Pp, s.theta_hi + (size_t)chain * s.Pp, sizeof(float) * s.Pp, cudaMemcpyDeviceToDevice, h->stream));
-      CU(cudaMemcpyAsync(s.theta_lo + (size_t)E * s.Pp, s.theta_lo + (size_t)chain * s.Pp, sizeof(float) * s.Pp, cudaMemcpyDeviceToDevice, h->stream));
-    }
   }
   const int pass = which == 0 ? 0 : 2;
   const int rows = which == 0 ? s.n_train : s.n_test;
@@ -830,12 +800,7 @@ int bae_eval(bae_handle* h, int chain, int which, const float* w, double* sse, d
     CU(cudaMemcpyAsync(d.data(), s.DOUT + (size_t)E * s.n_max * s.ld0, sizeof(float) * d.size(), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(x.data(), which == 0 ? s.Xtrain : s.Xtest, sizeof(float) * x.size(), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    if (s.tc) {
-      std::vector<float> dl(d.size());
-      CU(cudaMemcpyAsync(dl.data(), s.DOUTl + (size_t)E * s.n_max * s.ld0, sizeof(float) * dl.size(), cudaMemcpyDeviceToHost, h->stream));
-      CU(cudaStreamSynchronize(h->stream));
-      for (size_t i = 0; i < d.size(); ++i) d[i] += dl[i];
-    }
+
     const double scale = 2.0 / ((double)rows * s.d0);
     for (int r = 0; r < rows; ++r)
       for (int c = 0; c < s.d0; ++c)
@@ -936,11 +901,7 @@ int bae_exchange_unpack(bae_handle* h, int chain, const float* dev_w, const doub
     CU(cudaMemcpyAsync(s.theta + (size_t)chain * s.Pp + g.pad_off, scratch + g.pad_off, sizeof(float) * g.rows * g.ld,
                        cudaMemcpyDeviceToDevice, h->stream));
   }
-  if (s.tc) {
-    const size_t off = (size_t)chain * s.Pp;
-    CU(launch_split(s.theta + off, s.theta_hi + off, s.theta_lo + off, (size_t)s.Pp, h->stream));
-    h->launches++;
-  }
+
   put1(h, s.ch.eta, chain, host_scalars2[0]);
   put1(h, s.ch.last_sse, chain, host_scalars2[1]);
   put1<int>(h, s.ch.alias, chain, 0);
@@ -979,10 +940,10 @@ int bae_debug_buffer(bae_handle* h, const char* name, int chain, float* out, int
   if (chain < 0 || chain > s.C) return fail(BAE_ERR_INVALID, "chain out of range");
   CU(cudaSetDevice(h->device));
   struct E { const char* n; const float* hi; const float* lo; int ld; };
-  const E tab[] = {{"H1", s.H1, s.H1l, s.ld1}, {"H2", s.H2, s.H2l, s.ld2}, {"Z", s.Z, nullptr, s.ld3}, {"Y", s.Y, s.Yl, s.ld3},
-                   {"H4", s.H4, s.H4l, s.ld2}, {"H5", s.H5, s.H5l, s.ld1}, {"DOUT", s.DOUT, s.DOUTl, s.ld0},
-                   {"D5", s.D5, s.D5l, s.ld1}, {"D4", s.D4, s.D4l, s.ld2}, {"DY", s.DY, s.DYl, s.ld3},
-                   {"D2", s.D2, s.D2l, s.ld2}, {"D1", s.D1, s.D1l, s.ld1}};
+  const E tab[] = {{"H1", s.H1, nullptr, s.ld1}, {"H2", s.H2, nullptr, s.ld2}, {"Z", s.Z, nullptr, s.ld3}, {"Y", s.Y, nullptr, s.ld3},
+                   {"H4", s.H4, nullptr, s.ld2}, {"H5", s.H5, nullptr, s.ld1}, {"DOUT", s.DOUT, nullptr, s.ld0},
+                   {"D5", s.D5, nullptr, s.ld1}, {"D4", s.D4, nullptr, s.ld2}, {"DY", s.DY, nullptr, s.ld3},
+                   {"D2", s.D2, nullptr, s.ld2}, {"D1", s.D1, nullptr, s.ld1}};
   for (const E& e : tab) {
     if (strcmp(e.n, name) != 0) continue;
     const float* src = lo_part ? e.lo : e.hi;
@@ -994,8 +955,8 @@ int bae_debug_buffer(bae_handle* h, const char* name, int chain, float* out, int
     if (ld) *ld = e.ld;
     return BAE_OK;
   }
-  if (strcmp(name, "grad") == 0 || strcmp(name, "theta") == 0 || strcmp(name, "theta_hi") == 0 || strcmp(name, "theta_lo") == 0) {
-    const float* src = name[0] == 'g' ? s.grad : (strcmp(name, "theta") == 0 ? s.theta : (name[6] == 'h' ? s.theta_hi : s.theta_lo));
+  if (strcmp(name, "grad") == 0 || strcmp(name, "theta") == 0) {
+    const float* src = name[0] == 'g' ? s.grad : s.theta;
     if (!src) return fail(BAE_ERR_INVALID, "no such array");
     if (n_floats > s.Pp) return fail(BAE_ERR_INVALID, "too many floats");
     CU(cudaMemcpyAsync(out, src + (size_t)chain * s.Pp, sizeof(float) * n_floats, cudaMemcpyDeviceToHost, h->stream));

@@ -56,13 +56,11 @@ struct GemmDesc {
   int needLang;  // 1: only chains whose current step is a Langevin step
   int tm, tn;    // tiles along M and N
   int big;       // 1: 128x128 tiles, 0: 64x64 tiles
-  // ---- tcgen05 path (3xTF32): operands and outputs are (hi, lo) pairs; A/B/C/aux above hold the hi part
-  float* Cl;            // lo part of the output (null: store the plain FP32 value to C)
-  const float* auxl;    // lo part of aux (null: aux is a plain FP32 array)
+  // ---- tcgen05 path (3xTF32 with the hi/lo split done in shared memory)
   int tcBN;             // tile width (multiple of 16; multiple of 32 when B is N-major), <= 256
   int tcBBytes;         // bytes of one B tile (hi or lo) per K block
   int tcMain;           // TMEM accumulators the hi*hi term rotates over; (tcMain + 1) * tcBN <= 512 columns
-  int tmIdx[4];         // tensor maps: A_hi, A_lo, B_hi, B_lo
+  int tmIdx[2];         // tensor maps: A, B
   unsigned idesc;       // tcgen05 instruction descriptor
   int biasCol;          // EPI_GRADW: output column that holds the bias gradient (ones column trick), or -1
 };
@@ -133,11 +131,8 @@ struct DevState {
   long long *num_swap, *total_swap;
   int swap_round;
   // ---- tcgen05 path
-  int tc;             // 1: GEMM phases run on the tensor cores (3xTF32), activations stored as (hi, lo)
+  int tc;             // 1: GEMM phases run on the tensor cores (3xTF32); row pitches reserve a ones column
   void* tmaps;        // CUtensorMap array in global memory (64-byte aligned)
-  float *theta_hi, *theta_lo;
-  float *Xtrain_hi, *Xtrain_lo, *Xtest_hi, *Xtest_lo;
-  float *H1l, *H2l, *Yl, *H4l, *H5l, *DOUTl, *D5l, *D4l, *DYl, *D2l, *D1l;
   // ---- program
   int n_gemm, n_phase;
   GemmDesc gemm[kMaxGemm];

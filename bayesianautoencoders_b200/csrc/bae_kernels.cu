@@ -338,18 +338,9 @@ __device__ void run_bn_fwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
         S->bn_var[((size_t)slot * S->C_alloc + chain) * ld3 + c] = var;
         S->bn_inv[(size_t)chain * ld3 + c] = inv;
       }
-      float* Yl = S->tc ? S->Yl + (size_t)chain * S->n_max * ld3 : nullptr;
       for (int r = rl; r < N; r += 8) {
         float zh = (Z[(size_t)r * ld3 + c] - mean) * inv;
-        float y = fmaf(zh, gam, bet);
-        if (Yl) {
-          float hi, lo;
-          tc::split_tf32(y, hi, lo);
-          Y[(size_t)r * ld3 + c] = hi;
-          Yl[(size_t)r * ld3 + c] = lo;
-        } else {
-          Y[(size_t)r * ld3 + c] = y;
-        }
+        Y[(size_t)r * ld3 + c] = fmaf(zh, gam, bet);
       }
     }
   }
@@ -367,7 +358,6 @@ __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
     const bool cv = c < d3;
     const float* Z = S->Z + (size_t)chain * S->n_max * ld3;
     float* DY = S->DY + (size_t)chain * S->n_max * ld3;
-    float* DYl = S->tc ? S->DYl + (size_t)chain * S->n_max * ld3 : nullptr;
     float mean = 0.f, inv = 0.f, gam = 0.f;
     if (cv) {
       mean = S->bn_mu[((size_t)slot * S->C_alloc + chain) * ld3 + c];
@@ -378,7 +368,6 @@ __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
     if (cv)
       for (int r = rl; r < N; r += 8) {
         float dy = DY[(size_t)r * ld3 + c];
-        if (DYl) dy += DYl[(size_t)r * ld3 + c];
         float zh = (Z[(size_t)r * ld3 + c] - mean) * inv;
         s1 += (double)dy;
         s2 += (double)dy * (double)zh;
@@ -400,17 +389,8 @@ __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
       const float m2 = (float)(t2 / N) * gam;              // mean(dzhat * zhat)
       for (int r = rl; r < N; r += 8) {
         float dy = DY[(size_t)r * ld3 + c];
-        if (DYl) dy += DYl[(size_t)r * ld3 + c];
         float zh = (Z[(size_t)r * ld3 + c] - mean) * inv;
-        float dz = inv * (dy * gam - m1 - zh * m2);
-        if (DYl) {
-          float hi, lo;
-          tc::split_tf32(dz, hi, lo);
-          DY[(size_t)r * ld3 + c] = hi;
-          DYl[(size_t)r * ld3 + c] = lo;
-        } else {
-          DY[(size_t)r * ld3 + c] = dz;
-        }
+        DY[(size_t)r * ld3 + c] = inv * (dy * gam - m1 - zh * m2);
       }
     }
   }
@@ -493,13 +473,6 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
           }
         }
         *reinterpret_cast<float4*>(&th[p]) = make_float4(o[0], o[1], o[2], o[3]);
-        if (S->tc) {
-          float h[4], l[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) tc::split_tf32(o[j], h[j], l[j]);
-          *reinterpret_cast<float4*>(&S->theta_hi[base + p]) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(&S->theta_lo[base + p]) = make_float4(l[0], l[1], l[2], l[3]);
-        }
       } else {
         float4 g4 = *reinterpret_cast<const float4*>(&gr[p]);
         float4 m4 = *reinterpret_cast<const float4*>(&mm[p]);
@@ -872,15 +845,7 @@ __device__ void run_swap_scatter(const DevState* S) {
       const int pidx = it * kAdamChunk + i * 4;
       const int sg = find_seg(S, pidx);
       if (!S->seg[sg].trainable) continue;
-      const float4 val = s4[i];
-      *reinterpret_cast<float4*>(dbase + pidx) = val;
-      if (S->tc) {
-        float4 h, l;
-        tc::split_tf32(val.x, h.x, l.x); tc::split_tf32(val.y, h.y, l.y);
-        tc::split_tf32(val.z, h.z, l.z); tc::split_tf32(val.w, h.w, l.w);
-        *reinterpret_cast<float4*>(S->theta_hi + (size_t)p * S->Pp + pidx) = h;
-        *reinterpret_cast<float4*>(S->theta_lo + (size_t)p * S->Pp + pidx) = l;
-      }
+      *reinterpret_cast<float4*>(dbase + pidx) = s4[i];
     }
   }
 }
@@ -942,7 +907,7 @@ __device__ void run_phase_tc(const DevState* S, int pi, int c_begin, int c_end, 
     tc::gemm_phase(S, ph, c_begin, c_end, tsm, ring);
   } else {
     run_phase(S, pi, c_begin, c_end, force_swap, smem_small, red);
-    tc::fence_proxy_async();   // theta_hi/lo, Y, dZ written with generic stores are read by TMA next
+    tc::fence_proxy_async();   // theta, Y, dZ written with generic stores are read by TMA in the next phase
   }
 }
 

@@ -2,13 +2,16 @@
 //
 //   D[128 x BN] (FP32, TMEM) += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi        per 8-wide K step
 //
-// Operands are stored in HBM as (hi, lo) pairs: hi = value with the low 13 mantissa bits cleared (an exact
-// TF32 number), lo = value - hi (exact in FP32). Three kind::tf32 MMAs recover ~FP32 products; the
-// accumulator lives in TMEM in FP32. Tiles are staged by TMA (128-byte swizzle) into a 2-stage shared-memory
-// ring; one elected thread issues tcgen05.mma; four epilogue warps drain TMEM with tcgen05.ld and apply
-// the fused epilogue (bias/sigmoid/loss/sigmoid-derivative/gradient routing), writing (hi, lo) pairs back.
+// Operands live in HBM as plain FP32. The tensor core reads a 32-bit container and ignores the low 13
+// mantissa bits (measured: tests/cuda/tc_selftest.cu), so the raw tile IS the `hi` operand; two converter
+// warps compute lo = x - trunc_tf32(x) (exact in FP32) into a second shared-memory tile. Three kind::tf32
+// MMAs per K step then recover ~FP32 products with FP32 accumulation in TMEM. Raw tiles are staged by TMA
+// (128-byte swizzle) into a 2-stage shared-memory ring; one elected thread issues tcgen05.mma; four epilogue
+// warps drain TMEM with tcgen05.ld and apply the fused epilogue (bias / sigmoid / loss / sigmoid-derivative /
+// gradient routing).
 //
-// Warp roles inside the 256-thread CTA: warp 0 = TMA producer, warp 1 = MMA issuer, warps 4-7 = epilogue.
+// Warp roles inside the 256-thread CTA: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-3 = hi/lo
+// converters, warps 4-7 = epilogue.
 #pragma once
 #include <cuda.h>
 
@@ -24,6 +27,7 @@ constexpr int kATileBytes = kBM * kBK * 4;     // 16 KB
 constexpr int kBTileBytes = 256 * kBK * 4;     // 32 KB (BN <= 256)
 constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;  // A_hi, A_lo, B_hi, B_lo = 96 KB
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+// stage layout: [A raw 16 KB][A lo 16 KB][B raw 32 KB][B lo 32 KB]
 constexpr int kTmemCols = 512;                 // (tcMain + 1) accumulators of BN columns each, single-buffered
 
 struct Ring {
@@ -33,8 +37,9 @@ struct Ring {
 
 struct Smem {
   uint8_t* tiles;        // 1024-byte aligned, kStages * kStageBytes
-  uint64_t* full;        // [kStages]
-  uint64_t* empty;       // [kStages]
+  uint64_t* full;        // [kStages] TMA bytes landed
+  uint64_t* conv;        // [kStages] lo tiles written by the converter warps
+  uint64_t* empty;       // [kStages] MMAs that read the stage have completed
   uint64_t* tmem_full;   // [2]
   uint64_t* tmem_empty;  // [2]
   uint32_t* tmem_base;   // TMEM base address written by tcgen05.alloc
@@ -139,13 +144,14 @@ __device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem) {
   sm.tiles = reinterpret_cast<uint8_t*>(base);
   uint8_t* tail = sm.tiles + kStages * kStageBytes;
   sm.full = reinterpret_cast<uint64_t*>(tail);
-  sm.empty = sm.full + kStages;
+  sm.conv = sm.full + kStages;
+  sm.empty = sm.conv + kStages;
   sm.tmem_full = sm.empty + kStages;
   sm.tmem_empty = sm.tmem_full + 2;
   sm.tmem_base = reinterpret_cast<uint32_t*>(sm.tmem_empty + 2);
   sm.red = reinterpret_cast<double*>(tail + 128);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.conv[i], 2); mbar_init(&sm.empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -203,7 +209,7 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
         const int nkb = (g.K + kBK - 1) / kBK;
         const int m0 = it.tile_m * kBM, n0 = it.tile_n * g.tcBN;
         const int ca = g.sA ? it.chain : 0, cb = g.sB ? it.chain : 0;
-        const uint32_t bytes = 2u * kATileBytes + 2u * (uint32_t)g.tcBBytes;
+        const uint32_t bytes = (uint32_t)kATileBytes + (uint32_t)g.tcBBytes;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&sm.empty[ring.stage], ring.phase ^ 1);
           uint8_t* st = sm.tiles + ring.stage * kStageBytes;
@@ -211,25 +217,19 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
           const int k0 = kb * kBK;
           if (g.aMode == 0) {
             tma_load_3d(st, &maps[g.tmIdx[0]], &sm.full[ring.stage], k0, m0, ca);
-            tma_load_3d(st + kATileBytes, &maps[g.tmIdx[1]], &sm.full[ring.stage], k0, m0, ca);
           } else {
             // MN-major: one [32 K-rows][32 floats] box per 32-wide chunk of the tile dimension
 #pragma unroll
-            for (int c = 0; c < kBM / 32; ++c) {
+            for (int c = 0; c < kBM / 32; ++c)
               tma_load_3d(st + c * 4096, &maps[g.tmIdx[0]], &sm.full[ring.stage], m0 + c * 32, k0, ca);
-              tma_load_3d(st + kATileBytes + c * 4096, &maps[g.tmIdx[1]], &sm.full[ring.stage], m0 + c * 32, k0, ca);
-            }
           }
           uint8_t* sb = st + 2 * kATileBytes;
           if (g.bMode == 0) {
-            tma_load_3d(sb, &maps[g.tmIdx[2]], &sm.full[ring.stage], k0, n0, cb);
-            tma_load_3d(sb + kBTileBytes, &maps[g.tmIdx[3]], &sm.full[ring.stage], k0, n0, cb);
+            tma_load_3d(sb, &maps[g.tmIdx[1]], &sm.full[ring.stage], k0, n0, cb);
           } else {
             const int nch = g.tcBN / 32;
-            for (int c = 0; c < nch; ++c) {
-              tma_load_3d(sb + c * 4096, &maps[g.tmIdx[2]], &sm.full[ring.stage], n0 + c * 32, k0, cb);
-              tma_load_3d(sb + kBTileBytes + c * 4096, &maps[g.tmIdx[3]], &sm.full[ring.stage], n0 + c * 32, k0, cb);
-            }
+            for (int c = 0; c < nch; ++c)
+              tma_load_3d(sb + c * 4096, &maps[g.tmIdx[1]], &sm.full[ring.stage], n0 + c * 32, k0, cb);
           }
           if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
         }
@@ -253,6 +253,7 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
         const uint32_t astep = g.aMode ? 1024u : 32u, bstep = g.bMode ? 1024u : 32u;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&sm.full[ring.stage], ring.phase);
+          mbar_wait(&sm.conv[ring.stage], ring.phase);
           fence_after_sync();
           const uint32_t sa = smem_u32(sm.tiles + ring.stage * kStageBytes);
           const uint32_t sb = sa + 2 * kATileBytes;
@@ -274,6 +275,42 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
         ring.acc_phase ^= 1;
       }
     }
+  } else if (warp == 2 || warp == 3) {
+    // ================= hi/lo converters: lo = x - trunc_tf32(x), element-wise on the swizzled tile bytes =================
+    const int ct = threadIdx.x - 64;   // 0..63
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      Item it;
+      if (!decode_item(S, ph, c_begin, item, it)) continue;
+      const GemmDesc& g = *it.g;
+      const int nkb = (g.K + kBK - 1) / kBK;
+      const int nB4 = g.tcBBytes / 16;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&sm.full[ring.stage], ring.phase);
+        uint8_t* st = sm.tiles + ring.stage * kStageBytes;
+        const float4* ar = reinterpret_cast<const float4*>(st);
+        float4* al = reinterpret_cast<float4*>(st + kATileBytes);
+        const float4* br = reinterpret_cast<const float4*>(st + 2 * kATileBytes);
+        float4* bl = reinterpret_cast<float4*>(st + 2 * kATileBytes + kBTileBytes);
+#pragma unroll 8
+        for (int i = ct; i < kATileBytes / 16; i += 64) {
+          const float4 v = ar[i];
+          float4 l, h;
+          split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+          al[i] = l;
+        }
+#pragma unroll 8
+        for (int i = ct; i < nB4; i += 64) {
+          const float4 v = br[i];
+          float4 l, h;
+          split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+          bl[i] = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> tensor-core (async proxy) reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.conv[ring.stage]);
+        if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
+      }
+    }
   } else if (warp >= 4) {
     // ================= epilogue: TMEM -> registers -> fused epilogue -> HBM (hi, lo) =================
     const int q = warp & 3;
@@ -287,10 +324,8 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
       const int m0 = it.tile_m * kBM, n0 = it.tile_n * g.tcBN;
       const int r = m0 + q * 32 + lane;
       float* C = g.C ? g.C + (size_t)chain * g.sC : nullptr;
-      float* Cl = g.Cl ? g.Cl + (size_t)chain * g.sC : nullptr;
       const float* bias = g.bias ? g.bias + (size_t)chain * g.sBias : nullptr;
       const float* aux = g.aux ? g.aux + (size_t)chain * g.sAux : nullptr;
-      const float* auxl = g.auxl ? g.auxl + (size_t)chain * g.sAux : nullptr;
       float* gbias = g.gbias ? g.gbias + (size_t)chain * g.sGb : nullptr;
       mbar_wait(&sm.tmem_full[0], ring.acc_phase);
       fence_after_sync();
@@ -324,10 +359,6 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
             if (aux) {
               float4 t = *reinterpret_cast<const float4*>(&aux[(size_t)r * g.ldaux + c]);
               av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
-              if (auxl) {
-                float4 u = *reinterpret_cast<const float4*>(&auxl[(size_t)r * g.ldaux + c]);
-                av[0] += u.x; av[1] += u.y; av[2] += u.z; av[3] += u.w;
-              }
             }
             switch (g.epi) {
               case EPI_SIGMOID:
@@ -363,23 +394,9 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
               continue;
             }
             if (!C) continue;
-            if (Cl) {
-              float h[4], l[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) split_tf32(v[j], h[j], l[j]);
-              float* dh = &C[(size_t)r * g.ldc + c];
-              float* dl = &Cl[(size_t)r * g.ldc + c];
-              if (nval == 4) {
-                *reinterpret_cast<float4*>(dh) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(dl) = make_float4(l[0], l[1], l[2], l[3]);
-              } else {
-                for (int j = 0; j < nval; ++j) { dh[j] = h[j]; dl[j] = l[j]; }
-              }
-            } else {
-              float* dst = &C[(size_t)r * g.ldc + c];
-              if (nval == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-              else for (int j = 0; j < nval; ++j) dst[j] = v[j];
-            }
+            float* dst = &C[(size_t)r * g.ldc + c];
+            if (nval == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            else for (int j = 0; j < nval; ++j) dst[j] = v[j];
           }
         }
       }

@@ -70,6 +70,83 @@ probe_kernel(const CUtensorMap* maps, int aMode, int bMode, unsigned idesc, floa
   teardown(sm);
 }
 
+
+// 3xTF32 with the RAW fp32 operand standing in for `hi`: correct only if the tensor core ignores the low 13 mantissa bits.
+__global__ void __launch_bounds__(256, 1)
+probe3x_kernel(const CUtensorMap* maps, unsigned idesc, float* C) {
+  extern __shared__ uint8_t dyn[];
+  Smem sm;
+  setup(sm, dyn);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem = *sm.tmem_base;
+  uint8_t* s0 = sm.tiles;   // A_raw[2], A_lo[2], B_raw[2], B_lo[2], 16 KB each
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(&sm.full[0], 8 * 16384);
+    for (int o = 0; o < 4; ++o)
+      for (int kb = 0; kb < 2; ++kb) tma_load_3d(s0 + (o * 2 + kb) * 16384, &maps[o], &sm.full[0], kb * 32, 0, 0);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_wait(&sm.full[0], 0);
+    fence_after_sync();
+    for (int kb = 0; kb < 2; ++kb)
+      for (int kk = 0; kk < 4; ++kk) {
+        uint64_t ar = make_desc(smem_u32(s0 + (0 * 2 + kb) * 16384) + kk * 32, false);
+        uint64_t al = make_desc(smem_u32(s0 + (1 * 2 + kb) * 16384) + kk * 32, false);
+        uint64_t br = make_desc(smem_u32(s0 + (2 * 2 + kb) * 16384) + kk * 32, false);
+        uint64_t bl = make_desc(smem_u32(s0 + (3 * 2 + kb) * 16384) + kk * 32, false);
+        umma_tf32(tmem, al, br, idesc, (kb | kk) ? 1u : 0u);
+        umma_tf32(tmem, ar, bl, idesc, 1u);
+        umma_tf32(tmem, ar, br, idesc, 1u);
+      }
+    umma_commit(&sm.tmem_full[0]);
+  }
+  if (warp >= 4) {
+    const int q = warp & 3;
+    mbar_wait(&sm.tmem_full[0], 0);
+    fence_after_sync();
+    const int r = q * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+      for (int j = 0; j < 32; ++j) C[r * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    fence_before_sync();
+  }
+  __syncthreads();
+  teardown(sm);
+}
+
+static int test_raw_as_hi(EncodeTiledFn enc) {
+  std::vector<float> A(M * K), B(N * K), Al(M * K), Bl(N * K);
+  srand(7);
+  auto tf = [](float x) { unsigned u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; };
+  for (int i = 0; i < M * K; ++i) { A[i] = (rand() % 2000001 - 1000000) / 1000000.0f * 1.2345f; Al[i] = A[i] - tf(A[i]); }
+  for (int i = 0; i < N * K; ++i) { B[i] = (rand() % 2000001 - 1000000) / 1000000.0f * 0.789f; Bl[i] = B[i] - tf(B[i]); }
+  std::vector<double> ref(M * N, 0.0);
+  for (int i = 0; i < M; ++i) for (int j = 0; j < N; ++j) { double s = 0; for (int k = 0; k < K; ++k) s += (double)A[i * K + k] * B[j * K + k]; ref[i * N + j] = s; }
+  float* d[4]; float* dC; CUtensorMap* dM; CUtensorMap hm[4];
+  const std::vector<float>* src[4] = {&A, &Al, &B, &Bl};
+  for (int o = 0; o < 4; ++o) {
+    CK(cudaMalloc(&d[o], M * K * 4)); CK(cudaMemcpy(d[o], src[o]->data(), M * K * 4, cudaMemcpyHostToDevice));
+    cuuint64_t dims[3] = {K, 128, 1}; cuuint64_t str[2] = {K * 4, (cuuint64_t)128 * K * 4}; cuuint32_t box[3] = {32, 128, 1}; cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(&hm[o], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, d[o], dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("encode failed\n"); return 1; }
+  }
+  CK(cudaMalloc(&dC, M * N * 4)); CK(cudaMalloc(&dM, sizeof(hm))); CK(cudaMemcpy(dM, hm, sizeof(hm), cudaMemcpyHostToDevice));
+  CK(cudaFuncSetAttribute(probe3x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+  probe3x_kernel<<<1, 256, kSmemBytes>>>(dM, idesc, dC);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> Ch(M * N);
+  CK(cudaMemcpy(Ch.data(), dC, M * N * 4, cudaMemcpyDeviceToHost));
+  double maxerr = 0, maxref = 0;
+  for (int i = 0; i < M * N; ++i) { maxerr = fmax(maxerr, fabs(Ch[i] - ref[i])); maxref = fmax(maxref, fabs(ref[i])); }
+  printf("raw-as-hi 3xTF32: max |err| %.3e, max |ref| %.3e, ratio %.2e  (%s)\n", maxerr, maxref, maxerr / maxref,
+         maxerr / maxref < 3e-6 ? "tensor core truncates the low 13 bits: raw operand usable as hi" : "NOT truncating: explicit hi needed");
+  return 0;
+}
+
 int main() {
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qr;
@@ -125,6 +202,7 @@ int main() {
     if (maxerr > 1e-3 * maxref) bad++;
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dDa); cudaFree(dDb); cudaFree(dM);
   }
+  test_raw_as_hi(enc);
   printf(bad ? "SELFTEST FAILED (%d)\n" : "SELFTEST OK\n", bad);
   return bad ? 2 : 0;
 }
