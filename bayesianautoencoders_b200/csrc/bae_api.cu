@@ -134,13 +134,13 @@ static GemmDesc make_gemm(const DevState& s, int M, int N, int K, int b_nmajor =
     // tcgen05 tiles: 128 x BN, BN <= 256 chosen so the N tiles are balanced
     // long contractions (weight gradients, K = rows) use narrower tiles so that the hi*hi term can rotate over
     // three TMEM accumulators (shorter truncating accumulation chains); see bae_tc.cuh
-    const int maxbn = (K > 1024) ? 128 : 256;
+    const int align = b_nmajor ? 32 : 16;
+    const int maxbn = ((K > 1024) ? 128 : 240) / align * align;
     g.tcMain = (K > 1024) ? 3 : 1;
     g.tm = (M + 127) / 128;
     g.tn = (N + maxbn - 1) / maxbn;
-    const int align = b_nmajor ? 32 : 16;
     g.tcBN = round_up((N + g.tn - 1) / g.tn, align);
-    g.tcBBytes = g.tcBN * 128;   // K-major: BN rows x 128 B; N-major: BN/32 chunks x 4096 B
+    g.tcBBytes = g.tcBN * 64;    // K-major: BN rows x 64 B; N-major: BN/32 chunks x 2048 B
     return g;
   }
   g.big = (M >= 128 && N > 64) ? 1 : 0;
@@ -166,27 +166,27 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// K-major operand: element (row, k) at ptr[chain*cs + row*ld + k]; box = 32 k x box_rows rows
+// K-major operand: element (row, k) at ptr[chain*cs + row*ld + k]; box = 16 k x box_rows rows
 static int tmap_kmajor(CUtensorMap* out, const float* ptr, int K, int rows, int ld, int nchain, long long cs, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return -1;
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)std::max(1, nchain)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(cs > 0 ? cs : (long long)rows * ld) * 4};
-  cuuint32_t box[3] = {32, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {16, (cuuint32_t)box_rows, 1};   // 16 floats of K per pipeline stage (64-byte rows)
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-// MN-major operand: element (t, k) at ptr[chain*cs + k*ld + t]; one box = [32 k][32 t] (a 4 KB swizzled chunk);
+// MN-major operand: element (t, k) at ptr[chain*cs + k*ld + t]; one box = [16 k][32 t] (a 2 KB swizzled chunk);
 // the producer issues one TMA per 32-wide chunk of the tile dimension.
 static int tmap_mnmajor(CUtensorMap* out, const float* ptr, int extent, int K, int ld, int nchain, long long cs, int /*box_chunks*/) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return -1;
   cuuint64_t dims[3] = {(cuuint64_t)extent, (cuuint64_t)K, (cuuint64_t)std::max(1, nchain)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(cs > 0 ? cs : (long long)K * ld) * 4};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t box[3] = {32, 16, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -446,6 +446,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   CU(dalloc(h, &s.num_swap, 1)); CU(dalloc(h, &s.total_swap, 1));
   CU(dalloc(h, &h->stage_ref, (size_t)s.w_size + 8)); CU(dalloc(h, &h->stage_noise, (size_t)s.w_size + 8));
   CU(dalloc(h, &h->stage_d, 64));
+  if (getenv("BAE_TC_TRACE") && getenv("BAE_TC_TRACE")[0] == '1') CU(dalloc(h, &s.dbg, 4096));
   {
     void* q = nullptr;
     CU(cudaMalloc(&q, sizeof(DevState)));
@@ -965,6 +966,18 @@ int bae_debug_buffer(bae_handle* h, const char* name, int chain, float* out, int
     return BAE_OK;
   }
   return fail(BAE_ERR_INVALID, "unknown buffer name");
+}
+
+
+// Debug: timeline trace of CTA 0 (needs BAE_TC_TRACE=1 at create time): 4096 int64 values.
+int bae_debug_trace(bae_handle* h, long long* out, int clear) {
+  if (!h || !out) return fail(BAE_ERR_INVALID, "null argument");
+  if (!h->hs.dbg) return fail(BAE_ERR_STATE, "tracing not enabled (BAE_TC_TRACE=1)");
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(out, h->hs.dbg, 4096 * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (clear) CU(cudaMemset(h->hs.dbg, 0, 4096 * sizeof(long long)));
+  return BAE_OK;
 }
 
 }  // extern "C"

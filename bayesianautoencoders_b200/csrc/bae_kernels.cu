@@ -17,6 +17,9 @@ namespace cg = cooperative_groups;
 namespace bae {
 
 constexpr int BK = 16;
+// The phase helpers below run on the first 256 threads of a CTA (the tcgen05 kernels carry extra role warps),
+// so they synchronise on a named barrier instead of __syncthreads().
+#define BLOCK_SYNC() asm volatile("bar.sync 2, 256;" ::: "memory")
 constexpr float kBnEps = 1e-5f;
 constexpr float kBnMom = 0.1f;
 constexpr float kB1 = 0.9f, kB2 = 0.999f, kAdamEps = 1e-8f;
@@ -36,15 +39,15 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 __device__ __forceinline__ double block_sum_d(double v, double* red /* >= 9 doubles */) {
   v = warp_sum_d(v);
   int w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  __syncthreads();
+  BLOCK_SYNC();
   if (l == 0) red[w] = v;
-  __syncthreads();
+  BLOCK_SYNC();
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int i = 0; i < kThreads / 32; ++i) s += red[i];
     red[8] = s;
   }
-  __syncthreads();
+  BLOCK_SYNC();
   return red[8];
 }
 
@@ -147,10 +150,10 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
   const int nk = (g.K + BK - 1) / BK;
   tile_load<BM>(A, g.lda, g.aMode, g.M, g.K, m0, 0, ra);
   tile_load<BN>(B, g.ldb, g.bMode, g.N, g.K, n0, 0, rb);
-  __syncthreads();  // previous item's smem reads are done
+  BLOCK_SYNC();  // previous item's smem reads are done
   tile_store<BM>(As, g.aMode, ra);
   tile_store<BN>(Bs, g.bMode, rb);
-  __syncthreads();
+  BLOCK_SYNC();
   for (int kt = 0; kt < nk; ++kt) {
     const int cur = kt & 1;
     if (kt + 1 < nk) {
@@ -185,7 +188,7 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
       tile_store<BM>(As + (cur ^ 1) * BK * BM, g.aMode, ra);
       tile_store<BN>(Bs + (cur ^ 1) * BK * BN, g.bMode, rb);
     }
-    __syncthreads();
+    BLOCK_SYNC();
   }
 
   // ---- epilogue
@@ -308,9 +311,9 @@ __device__ void run_bn_fwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
     double s = 0.0;
     if (cv)
       for (int r = rl; r < N; r += 8) s += (double)Z[(size_t)r * ld3 + c];
-    __syncthreads();
+    BLOCK_SYNC();
     red2[rl * 32 + cl] = s;
-    __syncthreads();
+    BLOCK_SYNC();
     double tot = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) tot += red2[i * 32 + cl];
@@ -321,9 +324,9 @@ __device__ void run_bn_fwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
         float dz = Z[(size_t)r * ld3 + c] - mean;
         q += (double)dz * (double)dz;
       }
-    __syncthreads();
+    BLOCK_SYNC();
     red2[rl * 32 + cl] = q;
-    __syncthreads();
+    BLOCK_SYNC();
     double qt = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) qt += red2[i * 32 + cl];
@@ -372,10 +375,10 @@ __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
         s1 += (double)dy;
         s2 += (double)dy * (double)zh;
       }
-    __syncthreads();
+    BLOCK_SYNC();
     red2[rl * 32 + cl] = s1;
     red2[256 + rl * 32 + cl] = s2;
-    __syncthreads();
+    BLOCK_SYNC();
     double t1 = 0.0, t2 = 0.0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { t1 += red2[i * 32 + cl]; t2 += red2[256 + i * 32 + cl]; }
@@ -532,8 +535,8 @@ __device__ void step_scalars(const DevState* S, int chain_global, int step, doub
 }
 
 __device__ void run_prologue(const DevState* S, int c_begin, int c_end) {
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  for (int chain = c_begin + gtid; chain < c_end; chain += gridDim.x * blockDim.x) {
+  const int gtid = blockIdx.x * kThreads + threadIdx.x;
+  for (int chain = c_begin + gtid; chain < c_end; chain += gridDim.x * kThreads) {
     const ChainArrays& ch = S->ch;
     const int i = ch.step[chain];
     if (i < S->pt_step) ch.adapt[chain] = ch.T[chain];                        // MAIN:437-438
@@ -642,7 +645,7 @@ __device__ void run_epilogue(const DevState* S, int c_begin, int c_end, double* 
     const double sb_wc = block_sum_d(b_wc, red);
     const double sb_wp = block_sum_d(b_wp, red);
     const double sb_prior = block_sum_d(b_prior, red);
-    __syncthreads();
+    BLOCK_SYNC();
     if (threadIdx.x == 0) {
       // --- num_batches_tracked (int64 in the model, float in the dicts)
       float nzn[4];
@@ -725,11 +728,11 @@ __device__ void run_epilogue(const DevState* S, int c_begin, int c_end, double* 
       ch.step[chain] = step + 1;
       red[10] = accept ? 1.0 : 0.0;
     }
-    __syncthreads();
+    BLOCK_SYNC();
     if (red[10] != 0.0) {   // accept: `w` buffers <- proposal buffers
       for (int c = threadIdx.x; c < S->nbuf; c += kThreads) wb[c] = S->wb_tmp[(size_t)chain * S->nbuf + c];
     }
-    __syncthreads();
+    BLOCK_SYNC();
   }
 }
 
@@ -749,10 +752,10 @@ __device__ double swap_uniform(const DevState* S, int ensemble_global, int round
 __device__ void run_swap_decide(const DevState* S) {
   const int n = S->n_rungs;
   const int nens = S->C / n;
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gtid = blockIdx.x * kThreads + threadIdx.x;
   const ChainArrays& ch = S->ch;
   const double ntr = (double)S->n_train * S->d0;
-  for (int e = gtid; e < nens; e += gridDim.x * blockDim.x) {
+  for (int e = gtid; e < nens; e += gridDim.x * kThreads) {
     const int b = e * n;
     // queue slots: configuration id, and the (lhood, T) slots that travel with the message (MAIN:999-1005)
     for (int p = 0; p < n; ++p) S->swap_src[b + p] = b + p;
@@ -853,6 +856,7 @@ __device__ void run_swap_scatter(const DevState* S) {
 // ------------------------------------------------------------------------------------------------
 // The persistent program kernel
 // ------------------------------------------------------------------------------------------------
+template <bool kSimtGemm>
 __device__ void run_phase(const DevState* S, int pi, int c_begin, int c_end, int force_swap, float* smem,
                           double* red) {
   const PhaseDesc& ph = S->phase[pi];
@@ -863,7 +867,9 @@ __device__ void run_phase(const DevState* S, int pi, int c_begin, int c_end, int
   }
   switch (ph.kind) {
     case PH_PROLOGUE: run_prologue(S, c_begin, c_end); break;
-    case PH_GEMM: run_gemm_phase(S, ph, c_begin, c_end, smem, red); break;
+    case PH_GEMM:
+      if constexpr (kSimtGemm) run_gemm_phase(S, ph, c_begin, c_end, smem, red);
+      break;
     case PH_BN_FWD: run_bn_fwd(S, ph, c_begin, c_end, reinterpret_cast<double*>(smem)); break;
     case PH_BN_BWD: run_bn_bwd(S, ph, c_begin, c_end, reinterpret_cast<double*>(smem)); break;
     case PH_ADAM1: run_adam(S, 1, c_begin, c_end, red); break;
@@ -885,7 +891,7 @@ bae_program_kernel(const DevState* __restrict__ S, int ph_begin, int ph_end, int
   cg::grid_group grid = cg::this_grid();
   for (int rep = 0; rep < n_rep; ++rep) {
     for (int pi = ph_begin; pi < ph_end; ++pi) {
-      run_phase(S, pi, c_begin, c_end, force_swap, smem, red);
+      run_phase<true>(S, pi, c_begin, c_end, force_swap, smem, red);
       grid.sync();
     }
   }
@@ -896,7 +902,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 bae_phase_kernel(const DevState* __restrict__ S, int pi, int c_begin, int c_end) {
   __shared__ __align__(16) float smem[2 * BK * 128 * 2];
   __shared__ double red[16];
-  run_phase(S, pi, c_begin, c_end, 1, smem, red);
+  run_phase<true>(S, pi, c_begin, c_end, 1, smem, red);
 }
 
 // ---- tensor-core variants: GEMM phases go through the tcgen05 tile engine (1 CTA per SM, ~193 KB smem ring)
@@ -906,12 +912,12 @@ __device__ void run_phase_tc(const DevState* S, int pi, int c_begin, int c_end, 
   if (ph.kind == PH_GEMM) {
     tc::gemm_phase(S, ph, c_begin, c_end, tsm, ring);
   } else {
-    run_phase(S, pi, c_begin, c_end, force_swap, smem_small, red);
+    if (threadIdx.x < kThreads) run_phase<false>(S, pi, c_begin, c_end, force_swap, smem_small, red);
     tc::fence_proxy_async();   // theta, Y, dZ written with generic stores are read by TMA in the next phase
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(tc::kThreadsTc, 1)
 bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, int n_rep, int c_begin, int c_end,
                       int force_swap) {
   extern __shared__ uint8_t dyn_smem[];
@@ -930,7 +936,7 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
   tc::teardown(tsm);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(tc::kThreadsTc, 1)
 bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_end) {
   extern __shared__ uint8_t dyn_smem[];
   __shared__ __align__(16) float smem_small[1024];
@@ -1014,7 +1020,7 @@ int max_coop_blocks_per_sm(int use_tc) {
   if (use_tc) {
     cudaFuncSetAttribute(bae_program_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     cudaFuncSetAttribute(bae_phase_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel_tc, kThreads, tc::kSmemBytes);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel_tc, tc::kThreadsTc, tc::kSmemBytes);
   } else {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel, kThreads, 0);
   }
@@ -1026,13 +1032,13 @@ cudaError_t launch_program(const DevState* dS, int use_tc, int grid, int ph_begi
   void* args[] = {(void*)&dS, (void*)&ph_begin, (void*)&ph_end, (void*)&n_rep, (void*)&c_begin, (void*)&c_end,
                   (void*)&force_swap};
   if (use_tc)
-    return cudaLaunchCooperativeKernel((void*)bae_program_kernel_tc, dim3(grid), dim3(kThreads), args, tc::kSmemBytes, st);
+    return cudaLaunchCooperativeKernel((void*)bae_program_kernel_tc, dim3(grid), dim3(tc::kThreadsTc), args, tc::kSmemBytes, st);
   return cudaLaunchCooperativeKernel((void*)bae_program_kernel, dim3(grid), dim3(kThreads), args, 0, st);
 }
 
 cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, cudaStream_t st) {
   if (use_tc)
-    bae_phase_kernel_tc<<<grid, kThreads, tc::kSmemBytes, st>>>(dS, pi, c_begin, c_end);
+    bae_phase_kernel_tc<<<grid, tc::kThreadsTc, tc::kSmemBytes, st>>>(dS, pi, c_begin, c_end);
   else
     bae_phase_kernel<<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end);
   return cudaGetLastError();

@@ -5,13 +5,13 @@
 // Operands live in HBM as plain FP32. The tensor core reads a 32-bit container and ignores the low 13
 // mantissa bits (measured: tests/cuda/tc_selftest.cu), so the raw tile IS the `hi` operand; two converter
 // warps compute lo = x - trunc_tf32(x) (exact in FP32) into a second shared-memory tile. Three kind::tf32
-// MMAs per K step then recover ~FP32 products with FP32 accumulation in TMEM. Raw tiles are staged by TMA
-// (128-byte swizzle) into a 2-stage shared-memory ring; one elected thread issues tcgen05.mma; four epilogue
-// warps drain TMEM with tcgen05.ld and apply the fused epilogue (bias / sigmoid / loss / sigmoid-derivative /
-// gradient routing).
+// MMAs per K step then recover ~FP32 products with FP32 accumulation in TMEM. Raw tiles (16 floats of K per
+// stage) are staged by TMA into a 4-stage shared-memory ring; one elected thread issues tcgen05.mma; eight
+// epilogue warps drain TMEM with tcgen05.ld and apply the fused epilogue (bias / sigmoid / loss /
+// sigmoid-derivative / gradient routing) with coalesced, shared-memory-transposed loads and stores.
 //
-// Warp roles inside the 256-thread CTA: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-3 = hi/lo
-// converters, warps 4-7 = epilogue.
+// Warp roles inside the 384-thread CTA: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-3 = hi/lo
+// converters, warps 4-11 = epilogue (two warps per TMEM lane quarter, alternating 32-column chunks).
 #pragma once
 #include <cuda.h>
 
@@ -20,14 +20,21 @@
 namespace bae {
 namespace tc {
 
-constexpr int kStages = 2;
+constexpr int kThreadsTc = 384;
+constexpr int kStages = 4;
 constexpr int kBM = 128;
-constexpr int kBK = 32;                        // floats per K block = one 128-byte swizzle row
-constexpr int kATileBytes = kBM * kBK * 4;     // 16 KB
-constexpr int kBTileBytes = 256 * kBK * 4;     // 32 KB (BN <= 256)
-constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;  // A_hi, A_lo, B_hi, B_lo = 96 KB
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-// stage layout: [A raw 16 KB][A lo 16 KB][B raw 32 KB][B lo 32 KB]
+constexpr int kBK = 16;                        // floats of K per stage (64-byte rows: SWIZZLE_64B for K-major tiles)
+constexpr int kMaxBN = 240;
+constexpr int kATileBytes = kBM * kBK * 4;     // 8 KB
+constexpr int kBTileBytes = kMaxBN * kBK * 4;  // 15 KB
+constexpr int kMnChunkBytes = kBK * 128;       // MN-major chunk: [16 K-rows][32 floats]
+constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;  // A raw, A lo, B raw, B lo = 46 KB
+constexpr int kEpiPitch = 36;                  // floats; 144-byte rows keep float4 accesses conflict-free
+constexpr int kEpiWarps = 8;
+constexpr int kConvWarps = 10;                 // warps 2..11 convert; warps 4..11 then run the epilogue of the tile
+constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch * 4;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
+// stage layout: [A raw 8 KB][A lo 8 KB][B raw 15 KB][B lo 15 KB]
 constexpr int kTmemCols = 512;                 // (tcMain + 1) accumulators of BN columns each, single-buffered
 
 struct Ring {
@@ -43,7 +50,8 @@ struct Smem {
   uint64_t* tmem_full;   // [2]
   uint64_t* tmem_empty;  // [2]
   uint32_t* tmem_base;   // TMEM base address written by tcgen05.alloc
-  double* red;           // [8] epilogue reduction scratch
+  double* red;           // [16] epilogue reduction scratch
+  float* epi_stage;      // [8 warps][32][kEpiPitch] epilogue transpose tiles
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -122,15 +130,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptor, Blackwell version field = 1.
-//   K-major  tile: rows of 128 B (32 floats of K), SWIZZLE_128B (16-byte chunks), 8-row groups 1024 B apart (SBO).
-//   MN-major tile: chunks of [32 K-rows][128 B of MN]. 32-bit MN-major operands only exist in the
+// Shared-memory matrix descriptor, Blackwell version field = 1 (layouts verified by tests/cuda/tc_selftest.cu).
+//   K-major  tile: rows of 64 B (16 floats of K), SWIZZLE_64B, 8-row groups 512 B apart (SBO).
+//   MN-major tile: chunks of [16 K-rows][128 B of MN]. 32-bit MN-major operands only exist in the
 //                  SWIZZLE_128B_BASE32B layout (32-byte chunks XOR row%4; TMA mode SWIZZLE_128B_ATOM_32B):
-//                  4-K-row groups 512 B apart (SBO), MN chunks 4096 B apart (LBO).
+//                  4-K-row groups 512 B apart (SBO), MN chunks 2048 B apart (LBO).
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
-  const uint64_t lbo = mn_major ? (4096u >> 4) : 1u;
-  const uint64_t sbo = mn_major ? (512u >> 4) : (1024u >> 4);
-  const uint64_t layout = mn_major ? 1ull : 2ull;   // SWIZZLE_128B_BASE32B : SWIZZLE_128B
+  const uint64_t lbo = mn_major ? ((uint32_t)kMnChunkBytes >> 4) : 1u;
+  const uint64_t sbo = 512u >> 4;
+  const uint64_t layout = mn_major ? 1ull : 4ull;   // SWIZZLE_128B_BASE32B : SWIZZLE_64B
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 
@@ -149,10 +157,11 @@ __device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem) {
   sm.tmem_full = sm.empty + kStages;
   sm.tmem_empty = sm.tmem_full + 2;
   sm.tmem_base = reinterpret_cast<uint32_t*>(sm.tmem_empty + 2);
-  sm.red = reinterpret_cast<double*>(tail + 128);
+  sm.red = reinterpret_cast<double*>(tail + 128);          // 16 doubles
+  sm.epi_stage = reinterpret_cast<float*>(tail + 256);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.conv[i], 2); mbar_init(&sm.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], 4); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.conv[i], kConvWarps); mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x / 32 == 2) tmem_alloc(sm.tmem_base, kTmemCols);
@@ -165,6 +174,15 @@ __device__ __forceinline__ void teardown(Smem& sm) {
   fence_before_sync();
   __syncthreads();
   if (threadIdx.x / 32 == 2) tmem_dealloc(*sm.tmem_base, kTmemCols);
+}
+
+// Timeline trace (debug): CTA 0 appends (tag, clock) pairs per role; 4 roles x 1024 entries.
+__device__ __forceinline__ void trace(const DevState* S, int role, int& n, int tag) {
+  if (S->dbg && blockIdx.x == 0 && n < 511) {
+    S->dbg[role * 1024 + 2 * n] = tag;
+    S->dbg[role * 1024 + 2 * n + 1] = clock64();
+    ++n;
+  }
 }
 
 // Decode the work item of a GEMM phase (same arithmetic in every role).
@@ -202,6 +220,7 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
+      int ntr = 0;
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         Item it;
         if (!decode_item(S, ph, c_begin, item, it)) continue;
@@ -212,16 +231,17 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
         const uint32_t bytes = (uint32_t)kATileBytes + (uint32_t)g.tcBBytes;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&sm.empty[ring.stage], ring.phase ^ 1);
+          trace(S, 0, ntr, kb);
           uint8_t* st = sm.tiles + ring.stage * kStageBytes;
           mbar_expect_tx(&sm.full[ring.stage], bytes);
           const int k0 = kb * kBK;
           if (g.aMode == 0) {
             tma_load_3d(st, &maps[g.tmIdx[0]], &sm.full[ring.stage], k0, m0, ca);
           } else {
-            // MN-major: one [32 K-rows][32 floats] box per 32-wide chunk of the tile dimension
+            // MN-major: one [16 K-rows][32 floats] box per 32-wide chunk of the tile dimension
 #pragma unroll
             for (int c = 0; c < kBM / 32; ++c)
-              tma_load_3d(st + c * 4096, &maps[g.tmIdx[0]], &sm.full[ring.stage], m0 + c * 32, k0, ca);
+              tma_load_3d(st + c * kMnChunkBytes, &maps[g.tmIdx[0]], &sm.full[ring.stage], m0 + c * 32, k0, ca);
           }
           uint8_t* sb = st + 2 * kATileBytes;
           if (g.bMode == 0) {
@@ -229,7 +249,7 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
           } else {
             const int nch = g.tcBN / 32;
             for (int c = 0; c < nch; ++c)
-              tma_load_3d(sb + c * 4096, &maps[g.tmIdx[1]], &sm.full[ring.stage], n0 + c * 32, k0, cb);
+              tma_load_3d(sb + c * kMnChunkBytes, &maps[g.tmIdx[1]], &sm.full[ring.stage], n0 + c * 32, k0, cb);
           }
           if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
         }
@@ -238,6 +258,7 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
+      int ntr = 0;
       const uint32_t tmem = *sm.tmem_base;
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         Item it;
@@ -254,10 +275,11 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&sm.full[ring.stage], ring.phase);
           mbar_wait(&sm.conv[ring.stage], ring.phase);
+          trace(S, 1, ntr, kb);
           fence_after_sync();
           const uint32_t sa = smem_u32(sm.tiles + ring.stage * kStageBytes);
           const uint32_t sb = sa + 2 * kATileBytes;
-          const int nkk = min(4, (g.K - kb * kBK + 7) / 8);
+          const int nkk = min(kBK / 8, (g.K - kb * kBK + 7) / 8);
           for (int kk = 0; kk < nkk; ++kk) {
             const uint64_t a_hi = make_desc(sa + kk * astep, g.aMode != 0);
             const uint64_t a_lo = make_desc(sa + kATileBytes + kk * astep, g.aMode != 0);
@@ -271,55 +293,59 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
           umma_commit(&sm.empty[ring.stage]);   // frees the smem slot when these MMAs have read it
           if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
         }
+        trace(S, 1, ntr, 1000);
         umma_commit(&sm.tmem_full[0]);   // accumulators complete -> epilogue
         ring.acc_phase ^= 1;
       }
     }
-  } else if (warp == 2 || warp == 3) {
-    // ================= hi/lo converters: lo = x - trunc_tf32(x), element-wise on the swizzled tile bytes =================
-    const int ct = threadIdx.x - 64;   // 0..63
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
-      Item it;
-      if (!decode_item(S, ph, c_begin, item, it)) continue;
-      const GemmDesc& g = *it.g;
-      const int nkb = (g.K + kBK - 1) / kBK;
-      const int nB4 = g.tcBBytes / 16;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&sm.full[ring.stage], ring.phase);
-        uint8_t* st = sm.tiles + ring.stage * kStageBytes;
-        const float4* ar = reinterpret_cast<const float4*>(st);
-        float4* al = reinterpret_cast<float4*>(st + kATileBytes);
-        const float4* br = reinterpret_cast<const float4*>(st + 2 * kATileBytes);
-        float4* bl = reinterpret_cast<float4*>(st + 2 * kATileBytes + kBTileBytes);
-#pragma unroll 8
-        for (int i = ct; i < kATileBytes / 16; i += 64) {
-          const float4 v = ar[i];
-          float4 l, h;
-          split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-          al[i] = l;
-        }
-#pragma unroll 8
-        for (int i = ct; i < nB4; i += 64) {
-          const float4 v = br[i];
-          float4 l, h;
-          split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-          bl[i] = l;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> tensor-core (async proxy) reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.conv[ring.stage]);
-        if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
-      }
-    }
-  } else if (warp >= 4) {
-    // ================= epilogue: TMEM -> registers -> fused epilogue -> HBM (hi, lo) =================
-    const int q = warp & 3;
-    const int et = threadIdx.x - 128;   // 0..127
+  } else {
+    // ================= warps 2..11: hi/lo conversion of every K block of the tile, then (warps 4..11) the epilogue ====
+    // lo = x - trunc_tf32(x), element-wise on the swizzled tile bytes (position independent)
+    const int ct = threadIdx.x - 64;   // 0..319
+    constexpr int kConvThreads = kConvWarps * 32;
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int eg = (warp - 4) >> 2;       // 0/1: which alternating 32-column chunks this warp drains
+    const int ew = warp - 4;              // 0..7 (epilogue warps)
+    const int et = threadIdx.x - 128;     // 0..255 (epilogue threads)
     const uint32_t tmem = *sm.tmem_base;
+    int ntr = 0;
     for (int item = blockIdx.x; item < total; item += gridDim.x) {
       Item it;
       if (!decode_item(S, ph, c_begin, item, it)) continue;
       const GemmDesc& g = *it.g;
+      {
+        const int nkb = (g.K + kBK - 1) / kBK;
+        const int nB4 = g.tcBBytes / 16;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&sm.full[ring.stage], ring.phase);
+          if (ct == 0) trace(S, 2, ntr, kb);
+          uint8_t* st = sm.tiles + ring.stage * kStageBytes;
+          const float4* ar = reinterpret_cast<const float4*>(st);
+          float4* al = reinterpret_cast<float4*>(st + kATileBytes);
+          const float4* br = reinterpret_cast<const float4*>(st + 2 * kATileBytes);
+          float4* bl = reinterpret_cast<float4*>(st + 2 * kATileBytes + kBTileBytes);
+#pragma unroll
+          for (int i = ct; i < kATileBytes / 16; i += kConvThreads) {
+            const float4 v = ar[i];
+            float4 l, h;
+            split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+            al[i] = l;
+          }
+#pragma unroll 3
+          for (int i = ct; i < nB4; i += kConvThreads) {
+            const float4 v = br[i];
+            float4 l, h;
+            split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+            bl[i] = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> tensor-core (async proxy) reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.conv[ring.stage]);
+          if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
+        }
+      }
+      if (warp < 4) continue;
+      // ---------------- epilogue: TMEM -> registers -> fused epilogue -> HBM ----------------
       const int chain = it.chain;
       const int m0 = it.tile_m * kBM, n0 = it.tile_n * g.tcBN;
       const int r = m0 + q * 32 + lane;
@@ -328,13 +354,17 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
       const float* aux = g.aux ? g.aux + (size_t)chain * g.sAux : nullptr;
       float* gbias = g.gbias ? g.gbias + (size_t)chain * g.sGb : nullptr;
       mbar_wait(&sm.tmem_full[0], ring.acc_phase);
+      if (et == 0) trace(S, 3, ntr, 0);
       fence_after_sync();
       const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16);
       const int nacc = min(g.tcMain, (g.K + kBK - 1) / kBK);   // main accumulators that were written
       float l_sse = 0.f, l_sd = 0.f;
       const int n_end = min(g.N, n0 + g.tcBN);   // this tile owns output columns [n0, n_end)
       const int ncols = n_end - n0;
-      for (int c0 = 0; c0 < ncols; c0 += 32) {
+      float* stg = sm.epi_stage + ew * (32 * kEpiPitch);   // this warp's 32 x 32 staging tile (pitch 36 floats)
+      const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;  // coalesced view: 4 rows x 128 B per instruction
+      const int r0 = m0 + q * 32;
+      for (int c0 = eg * 32; c0 < ncols; c0 += 64) {
         uint32_t raw[32], part[32];
         tmem_ld32(tbase + c0, raw);
         for (int a = 1; a <= nacc; ++a) {   // a == nacc: the cross-term accumulator
@@ -342,67 +372,87 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
 #pragma unroll
           for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(part[j]));
         }
-        if (r < g.M) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        const int cbase = n0 + c0;
+        // ---- aux tile (sigmoid outputs / data), loaded coalesced and transposed through shared memory
+        if (aux) {
+          float4 t[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = r0 + i * 4 + sub_r, cc = cbase + sub_c;
+            t[i] = (rr < g.M && cc < n_end) ? *reinterpret_cast<const float4*>(&aux[(size_t)rr * g.ldaux + cc])
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(&stg[(i * 4 + sub_r) * kEpiPitch + sub_c]) = t[i];
+          __syncwarp();
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const int c = n0 + c0 + j4 * 4;
-            const int nval = min(4, n_end - c);
-            if (nval <= 0) continue;
-            float v[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[j] = __uint_as_float(raw[j4 * 4 + j]);
-            float bv[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
-            if (bias) {
-              float4 t = *reinterpret_cast<const float4*>(&bias[c]);
-              bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+            const float4 a4 = *reinterpret_cast<const float4*>(&stg[lane * kEpiPitch + j4 * 4]);
+            if (g.epi == EPI_LOSS) {
+              part[j4 * 4 + 0] = __float_as_uint(a4.x); part[j4 * 4 + 1] = __float_as_uint(a4.y);
+              part[j4 * 4 + 2] = __float_as_uint(a4.z); part[j4 * 4 + 3] = __float_as_uint(a4.w);
+            } else {   // EPI_DSIG
+              v[j4 * 4 + 0] *= a4.x * (1.0f - a4.x); v[j4 * 4 + 1] *= a4.y * (1.0f - a4.y);
+              v[j4 * 4 + 2] *= a4.z * (1.0f - a4.z); v[j4 * 4 + 3] *= a4.w * (1.0f - a4.w);
             }
-            if (aux) {
-              float4 t = *reinterpret_cast<const float4*>(&aux[(size_t)r * g.ldaux + c]);
-              av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
+          }
+          __syncwarp();
+        }
+        if (bias) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            if (cbase + j4 * 4 < n_end) {
+              const float4 b4 = *reinterpret_cast<const float4*>(&bias[cbase + j4 * 4]);   // warp-uniform address
+              v[j4 * 4 + 0] += b4.x; v[j4 * 4 + 1] += b4.y; v[j4 * 4 + 2] += b4.z; v[j4 * 4 + 3] += b4.w;
             }
-            switch (g.epi) {
-              case EPI_SIGMOID:
+          }
+        }
+        if (g.epi == EPI_SIGMOID) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = 1.0f / (1.0f + expf(-(v[j] + bv[j])));
-                break;
-              case EPI_BIAS:
+          for (int j = 0; j < 32; ++j) v[j] = 1.0f / (1.0f + expf(-v[j]));
+        } else if (g.epi == EPI_LOSS) {
+          const bool rv = (r < g.M);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = v[j] + bv[j];
-                break;
-              case EPI_LOSS:
+          for (int j = 0; j < 32; ++j) {
+            const float dd = v[j] - __uint_as_float(part[j]);
+            if (rv && cbase + j < n_end) { l_sse = fmaf(dd, dd, l_sse); l_sd += dd; }
+            v[j] = dd * g.scale;
+          }
+        }
+        // ---- transpose through shared memory and store coalesced
+        if (C) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float dd = (v[j] + bv[j]) - av[j];
-                  if (j < nval) { l_sse = fmaf(dd, dd, l_sse); l_sd += dd; }
-                  v[j] = dd * g.scale;
-                }
-                break;
-              case EPI_DSIG:
+          for (int j4 = 0; j4 < 8; ++j4)
+            *reinterpret_cast<float4*>(&stg[lane * kEpiPitch + j4 * 4]) = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+          __syncwarp();
+          const int lim = (g.epi == EPI_GRADW && g.biasCol >= 0) ? min(n_end, g.biasCol) : n_end;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = v[j] * av[j] * (1.0f - av[j]);
-                break;
-              default:
-                break;
-            }
-            if (g.epi == EPI_GRADW && g.biasCol >= 0) {
-              // the ones column appended to the activation operand makes column biasCol the bias gradient
+          for (int i = 0; i < 8; ++i) {
+            const int rr = r0 + i * 4 + sub_r, cc = cbase + sub_c;
+            if (rr >= g.M || cc >= n_end) continue;
+            const float4 o = *reinterpret_cast<const float4*>(&stg[(i * 4 + sub_r) * kEpiPitch + sub_c]);
+            float* dst = &C[(size_t)rr * g.ldc + cc];
+            if (cc + 4 <= lim) {
+              *reinterpret_cast<float4*>(dst) = o;
+            } else {
+              const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                if (c + j == g.biasCol) gbias[r] = v[j];
-                else if (c + j < g.biasCol) C[(size_t)r * g.ldc + c + j] = v[j];
+                if (cc + j < lim) dst[j] = ov[j];
+                else if (g.epi == EPI_GRADW && cc + j == g.biasCol) gbias[rr] = ov[j];   // ones-column trick
               }
-              continue;
             }
-            if (!C) continue;
-            float* dst = &C[(size_t)r * g.ldc + c];
-            if (nval == 4) *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-            else for (int j = 0; j < nval; ++j) dst[j] = v[j];
           }
+          __syncwarp();
         }
       }
       // release the accumulator stage
       fence_before_sync();
       __syncwarp();
+      if (et == 0) trace(S, 3, ntr, 1);
       if (lane == 0) mbar_arrive(&sm.tmem_empty[0]);
       ring.acc_phase ^= 1;
       if (g.epi == EPI_LOSS) {
@@ -412,13 +462,15 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
           s0 += __shfl_xor_sync(0xffffffffu, s0, o);
           s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (lane == 0) { sm.red[q * 2] = s0; sm.red[q * 2 + 1] = s1; }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (lane == 0) { sm.red[ew * 2] = s0; sm.red[ew * 2 + 1] = s1; }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (et == 0) {
           double* p = g.part + ((size_t)chain * g.partStride + (size_t)it.tile_m * g.tn + it.tile_n) * 2;
-          p[0] = sm.red[0] + sm.red[2] + sm.red[4] + sm.red[6];
-          p[1] = sm.red[1] + sm.red[3] + sm.red[5] + sm.red[7];
+          double a0 = 0.0, a1 = 0.0;
+          for (int w = 0; w < kEpiWarps; ++w) { a0 += sm.red[w * 2]; a1 += sm.red[w * 2 + 1]; }
+          p[0] = a0;
+          p[1] = a1;
         }
       }
     }

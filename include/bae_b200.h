@@ -143,6 +143,8 @@ int bae_exchange_finish(bae_handle* h);
  * "grad","theta","theta_hi","theta_lo") in the padded device layout; chain may be n_chains (probe scratch slot). */
 int bae_debug_buffer(bae_handle* h, const char* name, int chain, float* out, int64_t n_floats, int* ld, int lo_part);
 
+int bae_debug_trace(bae_handle* h, long long* out4096, int clear);   /* CTA-0 role timeline, BAE_TC_TRACE=1 */
+
 /* Introspection for the benchmark: kernels launched so far by this handle, last step-kernel time (ms). */
 int64_t bae_launch_count(const bae_handle* h);
 int bae_last_step_ms(bae_handle* h, float* ms);

@@ -116,6 +116,105 @@ probe3x_kernel(const CUtensorMap* maps, unsigned idesc, float* C) {
   teardown(sm);
 }
 
+
+// ---- BK = 16 staging (64-byte K rows): K-major uses SWIZZLE_64B, MN-major uses [16 K-rows][128 B] chunks (BASE32B swizzle)
+__device__ __forceinline__ uint64_t make_desc16(uint32_t saddr, bool mn_major) {
+  const uint64_t lbo = mn_major ? (2048u >> 4) : 1u;
+  const uint64_t sbo = 512u >> 4;                      // K-major: 8 rows x 64 B; MN-major: 4 K-rows x 128 B
+  const uint64_t layout = mn_major ? 1ull : 4ull;      // SWIZZLE_128B_BASE32B : SWIZZLE_64B
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+__global__ void __launch_bounds__(256, 1)
+probe16_kernel(const CUtensorMap* maps, int aMode, int bMode, unsigned idesc, float* C) {
+  extern __shared__ uint8_t dyn[];
+  Smem sm;
+  setup(sm, dyn);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem = *sm.tmem_base;
+  uint8_t* sA = sm.tiles;              // [4 k-blocks of 16][8 KB]
+  uint8_t* sB = sm.tiles + 4 * 8192;   // [4 k-blocks][8 KB]
+  if (warp == 0 && lane == 0) {
+    mbar_expect_tx(&sm.full[0], 8 * 8192);
+    for (int kb = 0; kb < 4; ++kb) {
+      if (aMode == 0) tma_load_3d(sA + kb * 8192, &maps[0], &sm.full[0], kb * 16, 0, 0);
+      else for (int c = 0; c < 4; ++c) tma_load_3d(sA + kb * 8192 + c * 2048, &maps[0], &sm.full[0], c * 32, kb * 16, 0);
+      if (bMode == 0) tma_load_3d(sB + kb * 8192, &maps[1], &sm.full[0], kb * 16, 0, 0);
+      else for (int c = 0; c < 4; ++c) tma_load_3d(sB + kb * 8192 + c * 2048, &maps[1], &sm.full[0], c * 32, kb * 16, 0);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_wait(&sm.full[0], 0);
+    fence_after_sync();
+    const uint32_t astep = aMode ? 1024u : 32u, bstep = bMode ? 1024u : 32u;
+    for (int kb = 0; kb < 4; ++kb)
+      for (int kk = 0; kk < 2; ++kk) {
+        uint64_t a = make_desc16(smem_u32(sA + kb * 8192) + kk * astep, aMode != 0);
+        uint64_t b = make_desc16(smem_u32(sB + kb * 8192) + kk * bstep, bMode != 0);
+        umma_tf32(tmem, a, b, idesc, (kb | kk) ? 1u : 0u);
+      }
+    umma_commit(&sm.tmem_full[0]);
+  }
+  if (warp >= 4) {
+    const int q = warp & 3;
+    mbar_wait(&sm.tmem_full[0], 0);
+    fence_after_sync();
+    const int r = q * 32 + lane;
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+      for (int j = 0; j < 32; ++j) C[r * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    fence_before_sync();
+  }
+  __syncthreads();
+  teardown(sm);
+}
+
+static int test_bk16(EncodeTiledFn enc) {
+  std::vector<float> A(M * K), B(N * K);
+  srand(3);
+  auto tf = [](float x) { unsigned u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; memcpy(&x, &u, 4); return x; };
+  for (auto& x : A) x = tf((rand() % 2001 - 1000) / 1000.0f);
+  for (auto& x : B) x = tf((rand() % 2001 - 1000) / 1000.0f);
+  std::vector<double> ref(M * N, 0.0);
+  for (int i = 0; i < M; ++i) for (int j = 0; j < N; ++j) { double s = 0; for (int k = 0; k < K; ++k) s += (double)A[i * K + k] * B[j * K + k]; ref[i * N + j] = s; }
+  CK(cudaFuncSetAttribute(probe16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  int bad = 0;
+  for (int aMode = 0; aMode < 2; ++aMode) for (int bMode = 0; bMode < 2; ++bMode) {
+    std::vector<float> As(M * K), Bs(N * K);
+    for (int i = 0; i < M; ++i) for (int k = 0; k < K; ++k) As[aMode ? k * M + i : i * K + k] = A[i * K + k];
+    for (int j = 0; j < N; ++j) for (int k = 0; k < K; ++k) Bs[bMode ? k * N + j : j * K + k] = B[j * K + k];
+    float *dA, *dB, *dC; CUtensorMap* dM;
+    CK(cudaMalloc(&dA, As.size() * 4)); CK(cudaMalloc(&dB, Bs.size() * 4)); CK(cudaMalloc(&dC, M * N * 4)); CK(cudaMalloc(&dM, 2 * sizeof(CUtensorMap)));
+    CK(cudaMemcpy(dA, As.data(), As.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, Bs.data(), Bs.size() * 4, cudaMemcpyHostToDevice));
+    CUtensorMap hm[2];
+    for (int o = 0; o < 2; ++o) {
+      const int mode = o ? bMode : aMode; const int rows = o ? N : M; float* p = o ? dB : dA;
+      cuuint64_t dims[3]; cuuint64_t str[2]; cuuint32_t box[3]; cuuint32_t es[3] = {1, 1, 1};
+      if (mode == 0) { dims[0] = K; dims[1] = rows; dims[2] = 1; str[0] = K * 4; str[1] = (cuuint64_t)rows * K * 4; box[0] = 16; box[1] = 128; box[2] = 1; }
+      else { dims[0] = rows; dims[1] = K; dims[2] = 1; str[0] = rows * 4; str[1] = (cuuint64_t)rows * K * 4; box[0] = 32; box[1] = 16; box[2] = 1; }
+      CUresult r = enc(&hm[o], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, p, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       mode ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
+    }
+    CK(cudaMemcpy(dM, hm, sizeof(hm), cudaMemcpyHostToDevice));
+    unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)aMode << 15) | ((unsigned)bMode << 16) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+    probe16_kernel<<<1, 256, kSmemBytes>>>(dM, aMode, bMode, idesc, dC);
+    CK(cudaDeviceSynchronize());
+    std::vector<float> Ch(M * N);
+    CK(cudaMemcpy(Ch.data(), dC, M * N * 4, cudaMemcpyDeviceToHost));
+    double maxerr = 0, maxref = 0;
+    for (int i = 0; i < M * N; ++i) { maxerr = fmax(maxerr, fabs(Ch[i] - ref[i])); maxref = fmax(maxref, fabs(ref[i])); }
+    printf("BK16 aMode %d bMode %d: max |err| %.3e (max |ref| %.3e)\n", aMode, bMode, maxerr, maxref);
+    if (maxerr > 1e-3 * maxref) bad++;
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dM);
+  }
+  return bad;
+}
+
 static int test_raw_as_hi(EncodeTiledFn enc) {
   std::vector<float> A(M * K), B(N * K), Al(M * K), Bl(N * K);
   srand(7);
@@ -203,6 +302,7 @@ int main() {
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dDa); cudaFree(dDb); cudaFree(dM);
   }
   test_raw_as_hi(enc);
+  bad += test_bk16(enc);
   printf(bad ? "SELFTEST FAILED (%d)\n" : "SELFTEST OK\n", bad);
   return bad ? 2 : 0;
 }
