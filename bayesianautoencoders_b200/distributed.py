@@ -1,0 +1,196 @@
+"""Multi-GPU parallel tempering: the temperature ladder sharded across ranks (one process per GPU).
+
+Each ensemble's ladder of `n_rungs` temperatures is cut into `world_size` contiguous blocks; rank r owns
+rungs [r*L, (r+1)*L) of EVERY ensemble (L = n_rungs / world_size). Between exchange rounds the chains are
+independent, so no collective is on the data path. One exchange round (MAIN:594-603, 962-1011, 1059-1065):
+
+  1. all_gather of 4 doubles per chain (eta, stored likelihood, adapttemp, SSE of `w`)   -- <= 32 B / chain
+  2. every rank runs the SAME deterministic sequential sweep (pairs 0-1, 1-2, ... per ensemble) with the
+     same Philox swap uniforms -> identical permutation everywhere, no second collective for agreement
+  3. configurations whose destination is on another rank travel once (send/recv of the fp32 vector);
+     local moves are device copies
+  4. every chain's `w` becomes a detached dict (MAIN:602)
+
+The sweep arithmetic restates `run_swap_decide` of csrc/bae_kernels.cu on the host in float64.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+_M0, _M1, _W0, _W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(c, k):
+    """Philox4x32-10; c: 4 ints, k: 2 ints -> 4 ints (same generator as csrc/bae_common.cuh)."""
+    c = [int(x) & 0xFFFFFFFF for x in c]
+    k = [int(x) & 0xFFFFFFFF for x in k]
+    for _ in range(10):
+        p0, p1 = _M0 * c[0], _M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k[1]) & 0xFFFFFFFF,
+             p0 & 0xFFFFFFFF]
+        k = [(k[0] + _W0) & 0xFFFFFFFF, (k[1] + _W1) & 0xFFFFFFFF]
+    return c
+
+
+def swap_uniform(seed, ensemble_global, rnd, pair):
+    """The uniform `swap_procedure` draws for (ensemble, round, pair): bit-identical to the device stream."""
+    r = philox4x32_10([pair, 0xFE | (3 << 8), rnd, ensemble_global], [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF])
+    return float(np.float32((np.float32(r[0] >> 8) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)))
+
+
+def loglik(sse, n, tau_sq, temp):
+    return (-(n * 0.5) * math.log(2.0 * math.pi * tau_sq) - 0.5 * tau_sq * sse) / temp
+
+
+def sweep(table, n_elems, uniforms):
+    """Sequential adjacent-pair sweep over ONE ensemble (MAIN:1059-1065 with the message-slot quirk of
+    MAIN:999-1005). table: [n_rungs, 4] = (eta, stored likelihood, adapttemp, SSE of w) by ladder position.
+    Returns (src, n_swapped): src[p] = position whose configuration ends at p."""
+    n = table.shape[0]
+    src = list(range(n))
+    cfg_prev, lh_prev, T_prev = 0, table[0, 1], table[0, 2]
+    swapped = 0
+    for p in range(n - 1):
+        cfg1, cfg2 = cfg_prev, p + 1
+        lhood1, T1 = lh_prev, T_prev
+        lhood2, T2 = table[cfg2, 1], table[cfg2, 2]
+        lhood12 = loglik(table[cfg1, 3], n_elems, math.exp(table[cfg1, 0]), T2)
+        lhood21 = loglik(table[cfg2, 3], n_elems, math.exp(table[cfg2, 0]), T1)
+        ex = (lhood12 - lhood1) + (lhood21 - lhood2)
+        prob = 1.0 if ex >= 0 else math.exp(ex)
+        if uniforms[p] < prob:
+            swapped += 1
+            src[p] = cfg2
+            cfg_prev, lh_prev, T_prev = cfg1, lhood12, T1
+        else:
+            src[p] = cfg1
+            cfg_prev, lh_prev, T_prev = cfg2, lhood2, T2
+    src[n - 1] = cfg_prev
+    return src, swapped
+
+
+class ShardedLadder:
+    """Exchange rounds for a ladder sharded over `world_size` ranks. `transport` supplies the chain state:
+
+      transport.scalars(local_chain) -> (eta, likelihood, adapttemp, last_sse)
+      transport.pack(local_chain)    -> torch tensor [w_size] (fp32, on the rank's device) of the posted `w`
+      transport.unpack(local_chain, tensor, eta, last_sse)
+      transport.finish()             -> detach every chain's `w` (MAIN:602)
+
+    Local chain index = ensemble * L + (rung - rank * L).
+    """
+
+    def __init__(self, dist, rank, world_size, n_ensembles, n_rungs, n_elems, seed, transport):
+        if n_rungs % world_size:
+            raise ValueError("n_rungs must be a multiple of world_size")
+        self.dist, self.rank, self.world = dist, rank, world_size
+        self.E, self.R, self.L = n_ensembles, n_rungs, n_rungs // world_size
+        self.n_elems, self.seed, self.t = n_elems, seed, transport
+        self.round = 0
+        self.num_swap = 0
+        self.total_swap_proposals = 0
+        self.vectors_sent = 0
+
+    def owner(self, rung):
+        return rung // self.L
+
+    def local_index(self, ensemble, rung):
+        return ensemble * self.L + (rung - self.rank * self.L)
+
+    def gather_table(self):
+        import torch
+        loc = torch.tensor([self.t.scalars(c) for c in range(self.E * self.L)], dtype=torch.float64)   # [E*L, 4]
+        dev = self.t.collective_device()
+        loc = loc.to(dev)
+        out = [torch.empty_like(loc) for _ in range(self.world)]
+        self.dist.all_gather(out, loc)
+        tab = np.zeros((self.E, self.R, 4))
+        for r, part in enumerate(out):
+            tab[:, r * self.L:(r + 1) * self.L, :] = part.cpu().numpy().reshape(self.E, self.L, 4)
+        return tab
+
+    def exchange(self):
+        """One exchange round. Returns the per-ensemble permutations (identical on every rank)."""
+        import torch
+        tab = self.gather_table()
+        perms = []
+        for e in range(self.E):
+            u = [swap_uniform(self.seed, e, self.round, p) for p in range(self.R - 1)]
+            src, nsw = sweep(tab[e], self.n_elems, u)
+            perms.append(src)
+            self.num_swap += nsw
+            self.total_swap_proposals += self.R - 1
+        # data movement: each configuration moves once, from position src[p] to position p
+        sends, recvs, local_moves = [], [], []
+        for e in range(self.E):
+            for p, s in enumerate(perms[e]):
+                if s == p:
+                    continue
+                po, so = self.owner(p), self.owner(s)
+                if po == self.rank and so == self.rank:
+                    local_moves.append((e, s, p))
+                elif so == self.rank:
+                    sends.append((e, s, p, po))
+                elif po == self.rank:
+                    recvs.append((e, s, p, so))
+        staged = {}
+        for e, s, p in local_moves:
+            staged[(e, p)] = self.t.pack(self.local_index(e, s)).clone()
+        ops, bufs = [], {}
+        for e, s, p, dst in sends:
+            buf = self.t.pack(self.local_index(e, s)).clone()
+            bufs[("s", e, p)] = buf
+            ops.append(self.dist.P2POp(self.dist.isend, buf, dst))
+            self.vectors_sent += 1
+        for e, s, p, frm in recvs:
+            buf = torch.empty_like(self.t.pack(self.local_index(e, p)))
+            bufs[("r", e, p)] = buf
+            ops.append(self.dist.P2POp(self.dist.irecv, buf, frm))
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+        for e, s, p in local_moves:
+            self.t.unpack(self.local_index(e, p), staged[(e, p)], tab[e, s, 0], tab[e, s, 3])
+        for e, s, p, frm in recvs:
+            self.t.unpack(self.local_index(e, p), bufs[("r", e, p)], tab[e, s, 0], tab[e, s, 3])
+        self.t.finish()
+        self.round += 1
+        return perms
+
+
+class DeviceTransport:
+    """`ShardedLadder` transport over a `DeviceSampler` (CUDA tensors, NCCL)."""
+
+    def __init__(self, sampler, device):
+        import torch
+        self.s = sampler
+        self.dev = torch.device("cuda", device)
+        self._buf = torch.empty(sampler.w_size, dtype=torch.float32, device=self.dev)
+        self._sc = np.zeros(4, np.float64)
+
+    def collective_device(self):
+        return self.dev
+
+    def scalars(self, chain):
+        st = self.s.get_state(chain, vectors=False)
+        return (st["eta"], st["likelihood"], st["adapttemp"], st["last_sse_train"])
+
+    def pack(self, chain):
+        from . import _native as N
+        N.check(self.s.lib.bae_exchange_pack(self.s._h, int(chain), self._buf.data_ptr(), self._sc.ctypes.data))
+        self.s.synchronize()
+        return self._buf
+
+    def unpack(self, chain, tensor, eta, last_sse):
+        from . import _native as N
+        import torch
+        torch.cuda.synchronize(self.dev)
+        sc = np.array([eta, last_sse], np.float64)
+        N.check(self.s.lib.bae_exchange_unpack(self.s._h, int(chain), tensor.data_ptr(), sc.ctypes.data))
+        self.s.synchronize()
+
+    def finish(self):
+        from . import _native as N
+        N.check(self.s.lib.bae_exchange_finish(self.s._h))

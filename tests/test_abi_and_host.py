@@ -1,0 +1,150 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol the header declares, struct layouts match,
+the library refuses to run without a GPU (no CPU fallback), and the host-side mirror logic (parameter
+plumbing, ladder, result files, R-hat) matches the reference's definitions."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as entry
+from oracle import bae_oracle as bo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    entry.build()
+    from bayesianautoencoders_b200 import _native
+    return _native.load()
+
+
+def test_every_header_symbol_is_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "bae_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(bae_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/bae_b200.h but not exported"
+    from bayesianautoencoders_b200 import _native
+    assert set(_native.EXPORTS) <= set(names)
+
+
+def test_struct_layouts_match_header():
+    from bayesianautoencoders_b200 import _native as N
+    assert C.sizeof(N.Trace) == 152            # 11 doubles + 13 floats + 3 ints
+    assert C.sizeof(N.ChainScalars) == 96      # 8 doubles + 6 ints + 1 double
+    assert C.sizeof(N.Config) == 96
+    assert N.Config.seed.offset % 8 == 0
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from bayesianautoencoders_b200 import BaeError, DeviceSampler
+    with pytest.raises(BaeError, match="no CUDA device|no CPU fallback"):
+        DeviceSampler((3, 10, 5, 2), np.zeros((10, 3), np.float32), np.zeros((10, 3), np.float32), 1, 1, 10, [1.0])
+
+
+def test_invalid_config_is_rejected_before_touching_the_device(lib):
+    from bayesianautoencoders_b200 import _native as N
+    cfg = N.Config()
+    h = C.c_void_p()
+    assert lib.bae_create(C.byref(cfg), 0, C.byref(h)) == -1      # dims are zero
+    assert b"dims" in lib.bae_last_error()
+    for i, d in enumerate((3, 10, 5, 2)):
+        cfg.dims[i] = d
+    cfg.n_train, cfg.n_test, cfg.n_chains, cfg.n_rungs, cfg.samples, cfg.swap_interval = 10, 10, 6, 4, 5, 5
+    assert lib.bae_create(C.byref(cfg), 0, C.byref(h)) == -1      # 6 chains is not a multiple of 4 rungs
+    assert lib.bae_create(None, 0, C.byref(h)) == -1
+    assert lib.bae_destroy(None) == 0
+
+
+def test_model_parameter_plumbing_matches_reference_order():
+    """getparameters = sorted-key order incl. BatchNorm buffers (MAIN:228-241); dictfromlist rounds to fp32
+    (MAIN:243-251); load_state_dict truncates num_batches_tracked (int64 buffer)."""
+    from bayesianautoencoders_b200 import Model, SORTED_KEYS
+    dims4 = (6, 5, 4, 3)
+    m = Model(dims4)
+    L = bo.Layout(dims4)
+    assert m.w_size == L.w_size
+    assert list(SORTED_KEYS) == list(bo.SORTED_KEYS)
+    vec = np.arange(L.w_size, dtype=np.float64) * 0.37 + 0.123456789123
+    d = m.dictfromlist(vec)
+    assert list(d.keys()) == bo.SORTED_KEYS
+    for k in bo.SORTED_KEYS:
+        assert d[k].dtype == np.float32 and d[k].shape == (L.shapes[k] if L.shapes[k] else ())
+        np.testing.assert_array_equal(d[k].reshape(-1), vec[L.slice(k)].astype(np.float32))
+    flat = m.getparameters(d)
+    np.testing.assert_array_equal(flat, vec.astype(np.float32).astype(np.float64))
+    m.loadparameters(d)
+    assert m.getparameters()[L.nbt_index] == np.trunc(np.float32(vec[L.nbt_index]))
+    sd = m.state_dict()
+    assert list(sd.keys())[0] == "encode.0.weight" and "decode.0.num_batches_tracked" in sd
+    w2 = m.addnoiseandcopy(d, 0, 0.005, rng=np.random.default_rng(1))
+    assert list(w2.keys()) == list(d.keys())
+    assert abs(float(np.std(m.getparameters(w2) - flat)) - 0.005) < 1e-3
+
+
+def test_ladder_matches_reference_formula():
+    from bayesianautoencoders_b200 import ParallelTempering
+    pt = ParallelTempering(True, 8, 2, 48000, 5, None, 10, 0.5, 0.005, dims4=(3, 10, 5, 2),
+                           traindata=np.zeros((4, 3)), testdata=np.zeros((4, 3)))
+    pt.assign_temperatures()
+    np.testing.assert_allclose(pt.temperatures, 2.0 ** (np.arange(8) / 7.0), rtol=1e-12)     # MAIN:914, 924-926
+    np.testing.assert_allclose(pt.temperatures, bo.temperature_ladder(8, 2), rtol=1e-15)
+    assert pt.NumSamples == 6000                                                               # MAIN:846
+    for bad in ((0, 8, 2), (2, 8, 1), (2, 0, 2)):
+        with pytest.raises(ValueError):
+            pt.default_beta_ladder(*bad)
+    with pytest.raises(ValueError):
+        pt.default_beta_ladder(2, None, None)
+
+
+def test_replica_files_names_and_formats(tmp_path):
+    """MAIN:631-696: 22 text files per temperature, names `<stat>_<temperature>.txt`, printf formats."""
+    from bayesianautoencoders_b200 import write_replica_files
+    from bayesianautoencoders_b200.sampler import TRACE_DTYPE
+    n = 7
+    tr = np.zeros(n, dtype=TRACE_DTYPE)
+    rng = np.random.default_rng(0)
+    for k in ("sum_value", "likelihood", "likelihood_proposal", "log_u"):
+        tr[k] = rng.standard_normal(n) * 100
+    tr["mse_train"] = rng.random(n)
+    tr["mse_test"] = rng.random(n)
+    tr["weights"] = rng.standard_normal((n, 13))
+    files = write_replica_files(str(tmp_path), 1.1040895136738123, tr, 37.9)
+    names = sorted(os.path.basename(f) for f in files)
+    t = "1.1040895136738123"
+    expect = ["sum_value_", "likelihood_value_", "likelihood_value_proposal", "mse_test_chain_", "mse_train_chain_",
+              "acc_test_chain_", "acc_train_chain_", "u_value_", "accept_percentage"] + \
+             [f"weight[{i}]_" for i in (0, 100, 10000, 5000, 2000, 3000, 4000, 6000, 7000, 8000, 9000, 11000)]
+    assert sorted(set(names)) == sorted(e + t + ".txt" for e in expect)
+    got = np.loadtxt(tmp_path / f"mse_train_chain_{t}.txt")
+    np.testing.assert_allclose(got, tr["mse_train"], atol=5e-6)                 # %1.5f
+    line = open(tmp_path / f"sum_value_{t}.txt").readline().strip()
+    assert re.fullmatch(r"-?\d+\.\d{2}", line)                                  # %1.2f
+    assert re.fullmatch(r"-?\d+\.\d{4}", open(tmp_path / f"likelihood_value_{t}.txt").readline().strip())
+    np.testing.assert_allclose(np.loadtxt(tmp_path / f"acc_train_chain_{t}.txt"), np.sqrt(tr["mse_train"]), atol=5e-3)
+    assert open(tmp_path / f"accept_percentage{t}.txt").read() == "37"         # '%d' % accept_ratio
+    # weight[5000] is written twice by the reference (arrays 3 and 7, same values): column 7 wins
+    np.testing.assert_allclose(np.loadtxt(tmp_path / f"weight[5000]_{t}.txt"), tr["weights"][:, 7], atol=5e-3)
+
+
+def test_gelman_rubin_matches_direct_formulas():
+    """GR:690-735 restated independently on a small example."""
+    from bayesianautoencoders_b200 import gelman_rubin
+    rng = np.random.default_rng(3)
+    data = rng.standard_normal((5, 400, 3)) + np.array([0.0, 1.0, -2.0])
+    r = gelman_rubin(data)
+    m, n = 5, 400
+    means = data.mean(axis=1)
+    B_on_n = means.var(axis=0)
+    W = data.var(axis=1).mean(axis=0)
+    Vhat = (n / (n - 1)) * W + B_on_n + B_on_n / m
+    np.testing.assert_allclose(r["simple"], Vhat / W, rtol=1e-12)
+    assert np.all(np.abs(r["simple"] - 1) < 0.05) and np.all(np.abs(r["advanced"] - 1) < 0.08)
+    shifted = data + np.arange(5)[:, None, None] * 3.0        # chains that disagree -> R-hat >> 1
+    assert np.all(gelman_rubin(shifted)["simple"] > 3)
