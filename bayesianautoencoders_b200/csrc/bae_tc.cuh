@@ -21,32 +21,35 @@ namespace bae {
 namespace tc {
 
 constexpr int kThreadsTc = 384;
-constexpr int kStages = 4;
+constexpr int kStages = 5;                     // raw-tile ring fed by TMA
+constexpr int kLoStages = 3;                   // lo-tile ring written by the converter warps
 constexpr int kBM = 128;
 constexpr int kBK = 16;                        // floats of K per stage (64-byte rows: SWIZZLE_64B for K-major tiles)
 constexpr int kMaxBN = 240;
 constexpr int kATileBytes = kBM * kBK * 4;     // 8 KB
 constexpr int kBTileBytes = kMaxBN * kBK * 4;  // 15 KB
 constexpr int kMnChunkBytes = kBK * 128;       // MN-major chunk: [16 K-rows][32 floats]
-constexpr int kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;  // A raw, A lo, B raw, B lo = 46 KB
+constexpr int kStageBytes = kATileBytes + kBTileBytes;          // one raw stage (A, B) or one lo stage = 23 KB
 constexpr int kEpiPitch = 36;                  // floats; 144-byte rows keep float4 accesses conflict-free
 constexpr int kEpiWarps = 8;
 constexpr int kConvWarps = 10;                 // warps 2..11 convert; warps 4..11 then run the epilogue of the tile
 constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch * 4;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiBytes;
-// stage layout: [A raw 8 KB][A lo 8 KB][B raw 15 KB][B lo 15 KB]
+constexpr int kSmemBytes = (kStages + kLoStages) * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kEpiBytes;
+// stage layout: [A 8 KB][B 15 KB]; kStages raw stages followed by kLoStages lo stages
 constexpr int kTmemCols = 512;                 // (tcMain + 1) accumulators of BN columns each, single-buffered
 
 struct Ring {
-  uint32_t stage = 0, phase = 0;     // shared-memory ring (producer / MMA)
+  uint32_t stage = 0, phase = 0;     // raw-tile ring (producer / converters / MMA)
+  uint32_t lo = 0, lo_phase = 0;     // lo-tile ring (converters / MMA)
   uint32_t acc_phase = 0;            // TMEM accumulator hand-off parity (MMA / epilogue), one tile in flight
 };
 
 struct Smem {
-  uint8_t* tiles;        // 1024-byte aligned, kStages * kStageBytes
+  uint8_t* tiles;        // 1024-byte aligned, (kStages + kLoStages) * kStageBytes
   uint64_t* full;        // [kStages] TMA bytes landed
-  uint64_t* conv;        // [kStages] lo tiles written by the converter warps
-  uint64_t* empty;       // [kStages] MMAs that read the stage have completed
+  uint64_t* empty;       // [kStages] MMAs that read the raw stage have completed
+  uint64_t* conv;        // [kLoStages] lo tiles written by the converter warps
+  uint64_t* lo_empty;    // [kLoStages] MMAs that read the lo stage have completed
   uint64_t* tmem_full;   // [2]
   uint64_t* tmem_empty;  // [2]
   uint32_t* tmem_base;   // TMEM base address written by tcgen05.alloc
@@ -150,17 +153,19 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 __device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem) {
   uintptr_t base = (reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023;
   sm.tiles = reinterpret_cast<uint8_t*>(base);
-  uint8_t* tail = sm.tiles + kStages * kStageBytes;
+  uint8_t* tail = sm.tiles + (kStages + kLoStages) * kStageBytes;
   sm.full = reinterpret_cast<uint64_t*>(tail);
-  sm.conv = sm.full + kStages;
-  sm.empty = sm.conv + kStages;
-  sm.tmem_full = sm.empty + kStages;
+  sm.empty = sm.full + kStages;
+  sm.conv = sm.empty + kStages;
+  sm.lo_empty = sm.conv + kLoStages;
+  sm.tmem_full = sm.lo_empty + kLoStages;
   sm.tmem_empty = sm.tmem_full + 2;
   sm.tmem_base = reinterpret_cast<uint32_t*>(sm.tmem_empty + 2);
-  sm.red = reinterpret_cast<double*>(tail + 128);          // 16 doubles
-  sm.epi_stage = reinterpret_cast<float*>(tail + 256);
+  sm.red = reinterpret_cast<double*>(tail + 256);          // 16 doubles
+  sm.epi_stage = reinterpret_cast<float*>(tail + 512);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.conv[i], kConvWarps); mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < kLoStages; ++i) { mbar_init(&sm.conv[i], kConvWarps); mbar_init(&sm.lo_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -243,7 +248,7 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
             for (int c = 0; c < kBM / 32; ++c)
               tma_load_3d(st + c * kMnChunkBytes, &maps[g.tmIdx[0]], &sm.full[ring.stage], m0 + c * 32, k0, ca);
           }
-          uint8_t* sb = st + 2 * kATileBytes;
+          uint8_t* sb = st + kATileBytes;
           if (g.bMode == 0) {
             tma_load_3d(sb, &maps[g.tmIdx[1]], &sm.full[ring.stage], k0, n0, cb);
           } else {
@@ -274,24 +279,28 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
         const uint32_t astep = g.aMode ? 1024u : 32u, bstep = g.bMode ? 1024u : 32u;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&sm.full[ring.stage], ring.phase);
-          mbar_wait(&sm.conv[ring.stage], ring.phase);
+          mbar_wait(&sm.conv[ring.lo], ring.lo_phase);
           trace(S, 1, ntr, kb);
           fence_after_sync();
           const uint32_t sa = smem_u32(sm.tiles + ring.stage * kStageBytes);
-          const uint32_t sb = sa + 2 * kATileBytes;
+          const uint32_t sb = sa + kATileBytes;
+          const uint32_t la = smem_u32(sm.tiles + (kStages + ring.lo) * kStageBytes);
+          const uint32_t lb = la + kATileBytes;
           const int nkk = min(kBK / 8, (g.K - kb * kBK + 7) / 8);
           for (int kk = 0; kk < nkk; ++kk) {
             const uint64_t a_hi = make_desc(sa + kk * astep, g.aMode != 0);
-            const uint64_t a_lo = make_desc(sa + kATileBytes + kk * astep, g.aMode != 0);
+            const uint64_t a_lo = make_desc(la + kk * astep, g.aMode != 0);
             const uint64_t b_hi = make_desc(sb + kk * bstep, g.bMode != 0);
-            const uint64_t b_lo = make_desc(sb + kBTileBytes + kk * bstep, g.bMode != 0);
+            const uint64_t b_lo = make_desc(lb + kk * bstep, g.bMode != 0);
             const uint32_t d_main = tmem + (uint32_t)((kb % g.tcMain) * g.tcBN);
             umma_tf32(d_cross, a_lo, b_hi, g.idesc, (kb | kk) ? 1u : 0u);
             umma_tf32(d_cross, a_hi, b_lo, g.idesc, 1u);
             umma_tf32(d_main, a_hi, b_hi, g.idesc, (kb >= g.tcMain || kk) ? 1u : 0u);
           }
-          umma_commit(&sm.empty[ring.stage]);   // frees the smem slot when these MMAs have read it
+          umma_commit(&sm.empty[ring.stage]);   // frees the raw slot when these MMAs have read it
+          umma_commit(&sm.lo_empty[ring.lo]);   // ... and the lo slot
           if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
+          if (++ring.lo == kLoStages) { ring.lo = 0; ring.lo_phase ^= 1; }
         }
         trace(S, 1, ntr, 1000);
         umma_commit(&sm.tmem_full[0]);   // accumulators complete -> epilogue
@@ -318,12 +327,14 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
         const int nB4 = g.tcBBytes / 16;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&sm.full[ring.stage], ring.phase);
+          mbar_wait(&sm.lo_empty[ring.lo], ring.lo_phase ^ 1);
           if (ct == 0) trace(S, 2, ntr, kb);
-          uint8_t* st = sm.tiles + ring.stage * kStageBytes;
+          const uint8_t* st = sm.tiles + ring.stage * kStageBytes;
+          uint8_t* lt = sm.tiles + (kStages + ring.lo) * kStageBytes;
           const float4* ar = reinterpret_cast<const float4*>(st);
-          float4* al = reinterpret_cast<float4*>(st + kATileBytes);
-          const float4* br = reinterpret_cast<const float4*>(st + 2 * kATileBytes);
-          float4* bl = reinterpret_cast<float4*>(st + 2 * kATileBytes + kBTileBytes);
+          float4* al = reinterpret_cast<float4*>(lt);
+          const float4* br = reinterpret_cast<const float4*>(st + kATileBytes);
+          float4* bl = reinterpret_cast<float4*>(lt + kATileBytes);
 #pragma unroll
           for (int i = ct; i < kATileBytes / 16; i += kConvThreads) {
             const float4 v = ar[i];
@@ -340,8 +351,9 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> tensor-core (async proxy) reads
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.conv[ring.stage]);
+          if (lane == 0) mbar_arrive(&sm.conv[ring.lo]);
           if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
+          if (++ring.lo == kLoStages) { ring.lo = 0; ring.lo_phase ^= 1; }
         }
       }
       if (warp < 4) continue;
@@ -364,6 +376,18 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
       float* stg = sm.epi_stage + ew * (32 * kEpiPitch);   // this warp's 32 x 32 staging tile (pitch 36 floats)
       const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;  // coalesced view: 4 rows x 128 B per instruction
       const int r0 = m0 + q * 32;
+      // aux tile loads (sigmoid outputs / data) are coalesced (4 rows x 128 B per instruction) and issued one
+      // chunk ahead so that their L2 latency overlaps the TMEM drain and the math of the current chunk
+      float4 t[8];
+      auto load_aux = [&](int c0n) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = r0 + i * 4 + sub_r, cc = n0 + c0n + sub_c;
+          t[i] = (c0n < ncols && rr < g.M && cc < n_end) ? *reinterpret_cast<const float4*>(&aux[(size_t)rr * g.ldaux + cc])
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      if (aux) load_aux(eg * 32);
       for (int c0 = eg * 32; c0 < ncols; c0 += 64) {
         uint32_t raw[32], part[32];
         tmem_ld32(tbase + c0, raw);
@@ -376,18 +400,13 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
         const int cbase = n0 + c0;
+        if (et == 0) trace(S, 3, ntr, 10);
         // ---- aux tile (sigmoid outputs / data), loaded coalesced and transposed through shared memory
         if (aux) {
-          float4 t[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = r0 + i * 4 + sub_r, cc = cbase + sub_c;
-            t[i] = (rr < g.M && cc < n_end) ? *reinterpret_cast<const float4*>(&aux[(size_t)rr * g.ldaux + cc])
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
 #pragma unroll
           for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(&stg[(i * 4 + sub_r) * kEpiPitch + sub_c]) = t[i];
           __syncwarp();
+          load_aux(c0 + 64);   // prefetch the next chunk of this warp
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
             const float4 a4 = *reinterpret_cast<const float4*>(&stg[lane * kEpiPitch + j4 * 4]);
@@ -401,6 +420,7 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
           }
           __syncwarp();
         }
+        if (et == 0) trace(S, 3, ntr, 11);
         if (bias) {
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
@@ -422,6 +442,7 @@ __device__ void gemm_phase(const DevState* S, const PhaseDesc& ph, int c_begin, 
             v[j] = dd * g.scale;
           }
         }
+        if (et == 0) trace(S, 3, ntr, 12);
         // ---- transpose through shared memory and store coalesced
         if (C) {
 #pragma unroll
