@@ -15,6 +15,7 @@ cudaError_t launch_program(const DevState* dS, int use_tc, int grid, int ph_begi
                            int c_end, int force_swap, cudaStream_t st);
 cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, cudaStream_t st);
 cudaError_t launch_split(const float* src, float* hi, float* lo, size_t n, cudaStream_t st);
+cudaError_t launch_grad_reduce(const DevState* dS, int chain, cudaStream_t st);
 cudaError_t launch_debug_draws(const DevState* dS, int chain, int step, float* noise, double* scalars, cudaStream_t st);
 cudaError_t launch_debug_swap_u(const DevState* dS, int ens, int round, int pair, double* out, cudaStream_t st);
 cudaError_t launch_pack(const DevState* dS, const float* ref_vec, float* pad_vec, cudaStream_t st);
@@ -58,6 +59,7 @@ struct bae_handle {
   DevState* dS = nullptr;
   std::vector<void*> allocs;
   int grid = 0;
+  int grid_hint = 296;    // CTAs of the persistent kernel (used to size K splits before the grid is known)
   bool data_loaded = false;
   std::vector<CUtensorMap> tmaps_host;
   std::vector<float> ones_col;
@@ -130,6 +132,7 @@ static GemmDesc make_gemm(const DevState& s, int M, int N, int K, int b_nmajor =
   memset(&g, 0, sizeof(g));
   g.M = M; g.N = N; g.K = K;
   g.biasCol = -1;
+  g.ksplit = 1;
   if (s.tc) {
     // tcgen05 tiles: 128 x BN, BN <= 256 chosen so the N tiles are balanced
     // long contractions (weight gradients, K = rows) use narrower tiles so that the hi*hi term can rotate over
@@ -148,6 +151,15 @@ static GemmDesc make_gemm(const DevState& s, int M, int N, int K, int b_nmajor =
   g.tm = (M + bt - 1) / bt;
   g.tn = (N + bt - 1) / bt;
   return g;
+}
+
+// FP32 path, weight-gradient GEMMs: few chains / few output tiles but a long contraction (K = rows). Split K over
+// work items so the phase fills the grid; the copies are summed in fixed order (deterministic) by the Adam phase.
+static int fp32_ksplit(const DevState& s, int grid_hint, const GemmDesc& g, int rows) {
+  const int tiles = g.tm * g.tn * s.C;
+  const int nk = (rows + 15) / 16;
+  const int ks = (2 * grid_hint + tiles - 1) / tiles;
+  return std::max(1, std::min(std::min(ks, 16), nk / 8));
 }
 
 // ---- TMA tensor maps (driver entry point fetched at run time: no link dependency on libcuda) ----------
@@ -285,6 +297,13 @@ static void build_program(bae_handle* h) {
     g.C = G(bl[l].wseg); g.sC = P; g.ldc = s.seg[bl[l].wseg].ld;
     g.epi = EPI_GRADW;
     if (bl[l].bseg >= 0) { g.gbias = G(bl[l].bseg); g.sGb = P; }
+    if (!tcm) {
+      const int ks = fp32_ksplit(s, h->grid_hint, g, N);
+      g.ksplit = ks;
+      s.seg_ksplit[bl[l].wseg] = ks;
+      if (bl[l].bseg >= 0) s.seg_ksplit[bl[l].bseg] = ks;
+      s.max_ksplit = std::max(s.max_ksplit, ks);
+    }
     if (ones) g.biasCol = bl[l].din;
     g.needLang = 1;
     add_maps(g);
@@ -408,7 +427,15 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   build_layout(s);
   const size_t CA = s.C_alloc, P = s.Pp;
   CU(dalloc(h, &s.theta, CA * P)); CU(dalloc(h, &s.m, CA * P)); CU(dalloc(h, &s.v, CA * P));
-  CU(dalloc(h, &s.wcur, CA * P)); CU(dalloc(h, &s.grad, CA * P));
+  CU(dalloc(h, &s.wcur, CA * P));
+  for (int i = 0; i < kNumSegs; ++i) s.seg_ksplit[i] = 1;
+  s.max_ksplit = 1;
+  if (!s.tc) {
+    const int dd[7] = {s.d0, s.d1, s.d2, s.d3, s.d2, s.d1, s.d0};
+    for (int l = 0; l < 6; ++l)
+      s.max_ksplit = std::max(s.max_ksplit, fp32_ksplit(s, h->grid_hint, make_gemm(s, dd[l + 1], dd[l], s.n_train, 1), s.n_train));
+  }
+  CU(dalloc(h, &s.grad, (size_t)s.max_ksplit * CA * P));   // K-split copies of the gradient (copy 0 is the result)
   CU(dalloc(h, &s.wb, CA * s.nbuf)); CU(dalloc(h, &s.wb_tmp, CA * s.nbuf));
   CU(dalloc(h, &s.bn_mu, 3 * CA * s.ld3)); CU(dalloc(h, &s.bn_var, 3 * CA * s.ld3)); CU(dalloc(h, &s.bn_inv, CA * s.ld3));
   CU(dalloc(h, &s.Xtrain, (size_t)s.n_train * s.ld0)); CU(dalloc(h, &s.Xtest, (size_t)s.n_test * s.ld0));
@@ -808,8 +835,10 @@ int bae_eval(bae_handle* h, int chain, int which, const float* w, double* sse, d
         out[(size_t)r * s.d0 + c] = (float)((double)d[(size_t)r * s.ld0 + c] / scale + (double)x[(size_t)r * s.ld0 + c]);
   }
   if (grads) {
-    CU(cudaMemsetAsync(s.grad + (size_t)E * s.Pp, 0, sizeof(float) * s.Pp, h->stream));
+    for (int k = 0; k < s.max_ksplit; ++k)
+      CU(cudaMemsetAsync(s.grad + ((size_t)k * s.C_alloc + E) * s.Pp, 0, sizeof(float) * s.Pp, h->stream));
     if ((rc = run_phases_plain(h, P_BWD1, P_BWD1 + 7, E, E + 1))) return rc;
+    if (s.max_ksplit > 1) CU(launch_grad_reduce(h->dS, E, h->stream));
     if ((rc = get_vec(h, s.grad + (size_t)E * s.Pp, grads))) return rc;
   }
   return BAE_OK;

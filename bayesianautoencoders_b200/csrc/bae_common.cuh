@@ -56,6 +56,8 @@ struct GemmDesc {
   int needLang;  // 1: only chains whose current step is a Langevin step
   int tm, tn;    // tiles along M and N
   int big;       // 1: 128x128 tiles, 0: 64x64 tiles
+  int ksplit;    // FP32 path, weight-gradient GEMMs: K (= rows) split over this many work items; split s writes
+                 // gradient copy s (stride = C_alloc * Pp floats), summed in fixed order by the Adam phase
   // ---- tcgen05 path (3xTF32 with the hi/lo split done in shared memory)
   int tcBN;             // tile width (multiple of 16; multiple of 32 when B is N-major), <= 256
   int tcBBytes;         // bytes of one B tile (hi or lo) per K block
@@ -104,6 +106,8 @@ struct DevState {
   unsigned seed_lo, seed_hi;
   int w_size, Pp, n_adam_items, nbuf;  // nbuf = 2*d3 + 1
   Seg seg[kNumSegs];
+  int seg_ksplit[kNumSegs];   // gradient copies to sum per tensor (1 = written directly)
+  int max_ksplit;
   // ---- chain-batched vectors [C_alloc][Pp]
   float *theta, *m, *v, *wcur, *grad;
   // ---- BatchNorm side state

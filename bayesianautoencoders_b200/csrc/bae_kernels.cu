@@ -128,7 +128,7 @@ __device__ __forceinline__ void tile_store(float* __restrict__ sm /*[BK][BT]*/, 
 }
 
 template <int BM, int BN>
-__device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int tile_m, int tile_n, float* smem,
+__device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int tile_m, int tile_n, int split, float* smem,
                           double* red) {
   constexpr int TM = BM / 16, TN = BN / 16;  // 8x8 (128) or 4x4 (64) per thread
   constexpr int GM = TM / 4, GN = TN / 4;
@@ -147,9 +147,14 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
   const bool do_colsum = (g.epi == EPI_GRADW) && (g.gbias != nullptr) && (tile_n == 0) && (threadIdx.x < BM);
 
   float4 ra[BM * 4 / kThreads], rb[BN * 4 / kThreads];
-  const int nk = (g.K + BK - 1) / BK;
-  tile_load<BM>(A, g.lda, g.aMode, g.M, g.K, m0, 0, ra);
-  tile_load<BN>(B, g.ldb, g.bMode, g.N, g.K, n0, 0, rb);
+  const int nk_all = (g.K + BK - 1) / BK;
+  const int kt0 = (int)(((long long)nk_all * split) / g.ksplit);          // this item's K-tile range
+  const int nk = (int)(((long long)nk_all * (split + 1)) / g.ksplit) - kt0;
+  A += (size_t)kt0 * BK * (g.aMode ? g.lda : 1);
+  B += (size_t)kt0 * BK * (g.bMode ? g.ldb : 1);
+  const int Krem = g.K - kt0 * BK;   // loads are bounded against the remaining K
+  tile_load<BM>(A, g.lda, g.aMode, g.M, Krem, m0, 0, ra);
+  tile_load<BN>(B, g.ldb, g.bMode, g.N, Krem, n0, 0, rb);
   BLOCK_SYNC();  // previous item's smem reads are done
   tile_store<BM>(As, g.aMode, ra);
   tile_store<BN>(Bs, g.bMode, rb);
@@ -157,8 +162,8 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
   for (int kt = 0; kt < nk; ++kt) {
     const int cur = kt & 1;
     if (kt + 1 < nk) {
-      tile_load<BM>(A, g.lda, g.aMode, g.M, g.K, m0, (kt + 1) * BK, ra);
-      tile_load<BN>(B, g.ldb, g.bMode, g.N, g.K, n0, (kt + 1) * BK, rb);
+      tile_load<BM>(A, g.lda, g.aMode, g.M, Krem, m0, (kt + 1) * BK, ra);
+      tile_load<BN>(B, g.ldb, g.bMode, g.N, Krem, n0, (kt + 1) * BK, rb);
     }
     const float* as = As + cur * BK * BM;
     const float* bs = Bs + cur * BK * BN;
@@ -192,7 +197,8 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
   }
 
   // ---- epilogue
-  float* C = g.C ? g.C + (size_t)chain * g.sC : nullptr;
+  const size_t split_off = (size_t)split * S->C_alloc * S->Pp;   // gradient copy of this K split (0 when ksplit == 1)
+  float* C = g.C ? g.C + (size_t)chain * g.sC + split_off : nullptr;
   const float* bias = g.bias ? g.bias + (size_t)chain * g.sBias : nullptr;
   const float* aux = g.aux ? g.aux + (size_t)chain * g.sAux : nullptr;
   float l_sse = 0.f, l_sd = 0.f;
@@ -267,7 +273,7 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
   }
   if (do_colsum) {
     int r = m0 + threadIdx.x;
-    if (r < g.M) (g.gbias + (size_t)chain * g.sGb)[r] = colsum;
+    if (r < g.M) (g.gbias + (size_t)chain * g.sGb + split_off)[r] = colsum;
   }
 }
 
@@ -275,8 +281,8 @@ __device__ void run_gemm_phase(const DevState* S, const PhaseDesc& ph, int c_beg
                                double* red) {
   const int nch = c_end - c_begin;
   const GemmDesc& ga = S->gemm[ph.g0];
-  const int ta = ga.tm * ga.tn;
-  const int tb = (ph.g1 >= 0) ? S->gemm[ph.g1].tm * S->gemm[ph.g1].tn : 0;
+  const int ta = ga.tm * ga.tn * ga.ksplit;
+  const int tb = (ph.g1 >= 0) ? S->gemm[ph.g1].tm * S->gemm[ph.g1].tn * S->gemm[ph.g1].ksplit : 0;
   const int per_chain = ta + tb;
   const int total = per_chain * nch;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
@@ -285,11 +291,13 @@ __device__ void run_gemm_phase(const DevState* S, const PhaseDesc& ph, int c_beg
     const GemmDesc& g = (t < ta) ? ga : S->gemm[ph.g1];
     if (t >= ta) t -= ta;
     if (g.needLang && !S->ch.is_lang[chain]) continue;
+    const int split = t % g.ksplit;
+    t /= g.ksplit;
     const int tile_m = t / g.tn, tile_n = t % g.tn;
     if (g.big)
-      gemm_item<128, 128>(S, g, chain, tile_m, tile_n, smem, red);
+      gemm_item<128, 128>(S, g, chain, tile_m, tile_n, split, smem, red);
     else
-      gemm_item<64, 64>(S, g, chain, tile_m, tile_n, smem, red);
+      gemm_item<64, 64>(S, g, chain, tile_m, tile_n, split, smem, red);
   }
 }
 
@@ -298,38 +306,41 @@ __device__ void run_gemm_phase(const DevState* S, const PhaseDesc& ph, int c_beg
 // ------------------------------------------------------------------------------------------------
 __device__ void run_bn_fwd(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, double* red2 /*[8][32]*/) {
   const int d3 = S->d3, ld3 = S->ld3, N = ph.argRows, slot = ph.arg;
-  const int nblk = (d3 + 31) / 32;
+  // a CTA covers `cpb` columns with 256/cpb row lanes each (narrow bottlenecks such as Swiss Roll's 2 columns
+  // still use every thread)
+  int cpb = 32;
+  while (cpb > 1 && (cpb >> 1) >= d3) cpb >>= 1;
+  const int rln = kThreads / cpb;
+  const int nblk = (d3 + cpb - 1) / cpb;
   const int total = nblk * (c_end - c_begin);
-  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
     const int chain = c_begin + item / nblk;
     if (ph.needLang && !S->ch.is_lang[chain]) continue;
-    const int c = (item % nblk) * 32 + cl;
+    const int c = (item % nblk) * cpb + cl;
     const bool cv = c < d3;
     const float* Z = S->Z + (size_t)chain * S->n_max * ld3;
     float* Y = S->Y + (size_t)chain * S->n_max * ld3;
     double s = 0.0;
     if (cv)
-      for (int r = rl; r < N; r += 8) s += (double)Z[(size_t)r * ld3 + c];
+      for (int r = rl; r < N; r += rln) s += (double)Z[(size_t)r * ld3 + c];
     BLOCK_SYNC();
-    red2[rl * 32 + cl] = s;
+    red2[rl * cpb + cl] = s;
     BLOCK_SYNC();
     double tot = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) tot += red2[i * 32 + cl];
+    for (int i = 0; i < rln; ++i) tot += red2[i * cpb + cl];
     const float mean = (float)(tot / N);
     double q = 0.0;
     if (cv)
-      for (int r = rl; r < N; r += 8) {
+      for (int r = rl; r < N; r += rln) {
         float dz = Z[(size_t)r * ld3 + c] - mean;
         q += (double)dz * (double)dz;
       }
     BLOCK_SYNC();
-    red2[rl * 32 + cl] = q;
+    red2[rl * cpb + cl] = q;
     BLOCK_SYNC();
     double qt = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) qt += red2[i * 32 + cl];
+    for (int i = 0; i < rln; ++i) qt += red2[i * cpb + cl];
     const float var = (float)(qt / N);
     const float inv = 1.0f / sqrtf(var + kBnEps);
     if (cv) {
@@ -341,7 +352,7 @@ __device__ void run_bn_fwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
         S->bn_var[((size_t)slot * S->C_alloc + chain) * ld3 + c] = var;
         S->bn_inv[(size_t)chain * ld3 + c] = inv;
       }
-      for (int r = rl; r < N; r += 8) {
+      for (int r = rl; r < N; r += rln) {
         float zh = (Z[(size_t)r * ld3 + c] - mean) * inv;
         Y[(size_t)r * ld3 + c] = fmaf(zh, gam, bet);
       }
@@ -351,13 +362,16 @@ __device__ void run_bn_fwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
 
 __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, double* red2) {
   const int d3 = S->d3, ld3 = S->ld3, N = ph.argRows, slot = ph.arg;
-  const int nblk = (d3 + 31) / 32;
+  int cpb = 32;
+  while (cpb > 1 && (cpb >> 1) >= d3) cpb >>= 1;
+  const int rln = kThreads / cpb;
+  const int nblk = (d3 + cpb - 1) / cpb;
   const int total = nblk * (c_end - c_begin);
-  const int cl = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
     const int chain = c_begin + item / nblk;
     if (ph.needLang && !S->ch.is_lang[chain]) continue;
-    const int c = (item % nblk) * 32 + cl;
+    const int c = (item % nblk) * cpb + cl;
     const bool cv = c < d3;
     const float* Z = S->Z + (size_t)chain * S->n_max * ld3;
     float* DY = S->DY + (size_t)chain * S->n_max * ld3;
@@ -369,19 +383,18 @@ __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
     }
     double s1 = 0.0, s2 = 0.0;
     if (cv)
-      for (int r = rl; r < N; r += 8) {
+      for (int r = rl; r < N; r += rln) {
         float dy = DY[(size_t)r * ld3 + c];
         float zh = (Z[(size_t)r * ld3 + c] - mean) * inv;
         s1 += (double)dy;
         s2 += (double)dy * (double)zh;
       }
     BLOCK_SYNC();
-    red2[rl * 32 + cl] = s1;
-    red2[256 + rl * 32 + cl] = s2;
+    red2[rl * cpb + cl] = s1;
+    red2[256 + rl * cpb + cl] = s2;
     BLOCK_SYNC();
     double t1 = 0.0, t2 = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { t1 += red2[i * 32 + cl]; t2 += red2[256 + i * 32 + cl]; }
+    for (int i = 0; i < rln; ++i) { t1 += red2[i * cpb + cl]; t2 += red2[256 + i * cpb + cl]; }
     if (cv) {
       float* gr = S->grad + (size_t)chain * S->Pp;
       if (rl == 0) {
@@ -390,13 +403,25 @@ __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
       }
       const float m1 = (float)(t1 / N) * gam;              // mean(dzhat), dzhat = dy * gamma
       const float m2 = (float)(t2 / N) * gam;              // mean(dzhat * zhat)
-      for (int r = rl; r < N; r += 8) {
+      for (int r = rl; r < N; r += rln) {
         float dy = DY[(size_t)r * ld3 + c];
         float zh = (Z[(size_t)r * ld3 + c] - mean) * inv;
         DY[(size_t)r * ld3 + c] = inv * (dy * gam - m1 - zh * m2);
       }
     }
   }
+}
+
+// Gradient of 4 consecutive entries: fixed-order sum of the K-split copies written by the weight-gradient GEMMs.
+__device__ __forceinline__ float4 load_grad4(const DevState* S, const float* gr, int p, int sg) {
+  float4 g4 = *reinterpret_cast<const float4*>(&gr[p]);
+  const int ks = S->seg_ksplit[sg];
+  const size_t stride = (size_t)S->C_alloc * S->Pp;
+  for (int s2 = 1; s2 < ks; ++s2) {
+    const float4 t = *reinterpret_cast<const float4*>(&gr[p + s2 * stride]);
+    g4.x += t.x; g4.y += t.y; g4.z += t.z; g4.w += t.w;
+  }
+  return g4;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -446,7 +471,7 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
         noise_quad(S, cg_id, step, sg, (unsigned)(local >> 2), nz);
         float o[4];
         if (lang) {
-          float4 g4 = *reinterpret_cast<const float4*>(&gr[p]);
+          float4 g4 = load_grad4(S, gr, p, sg);
           float4 m4 = *reinterpret_cast<const float4*>(&mm[p]);
           float4 v4 = *reinterpret_cast<const float4*>(&vv[p]);
           float g[4] = {g4.x, g4.y, g4.z, g4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -477,7 +502,7 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
         }
         *reinterpret_cast<float4*>(&th[p]) = make_float4(o[0], o[1], o[2], o[3]);
       } else {
-        float4 g4 = *reinterpret_cast<const float4*>(&gr[p]);
+        float4 g4 = load_grad4(S, gr, p, sg);
         float4 m4 = *reinterpret_cast<const float4*>(&mm[p]);
         float4 v4 = *reinterpret_cast<const float4*>(&vv[p]);
         float g[4] = {g4.x, g4.y, g4.z, g4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -948,6 +973,23 @@ bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_e
   tc::teardown(tsm);
 }
 
+// Parity probe: fold the K-split gradient copies of one chain into copy 0.
+__global__ void bae_grad_reduce_kernel(const DevState* __restrict__ S, int chain) {
+  float* gr = S->grad + (size_t)chain * S->Pp;
+  const size_t stride = (size_t)S->C_alloc * S->Pp;
+  for (int sg = 0; sg < kNumSegs; ++sg) {
+    const Seg& sd = S->seg[sg];
+    const int ks = S->seg_ksplit[sg];
+    if (ks <= 1) continue;
+    const int n = sd.rows * sd.ld;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+      float a = gr[sd.pad_off + e];
+      for (int s2 = 1; s2 < ks; ++s2) a += gr[sd.pad_off + e + s2 * stride];
+      gr[sd.pad_off + e] = a;
+    }
+  }
+}
+
 // value -> (hi, lo) TF32 split of n floats
 __global__ void bae_split_kernel(const float* __restrict__ src, float* hi, float* lo, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -1041,6 +1083,11 @@ cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c
     bae_phase_kernel_tc<<<grid, tc::kThreadsTc, tc::kSmemBytes, st>>>(dS, pi, c_begin, c_end);
   else
     bae_phase_kernel<<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grad_reduce(const DevState* dS, int chain, cudaStream_t st) {
+  bae_grad_reduce_kernel<<<64, 256, 0, st>>>(dS, chain);
   return cudaGetLastError();
 }
 
