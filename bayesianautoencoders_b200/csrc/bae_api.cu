@@ -6,6 +6,7 @@
 #include <vector>
 
 #include <cuda.h>
+#include <cuda_profiler_api.h>
 
 #include "bae_common.cuh"
 
@@ -127,6 +128,15 @@ static void build_layout(DevState& s) {
   }
 }
 
+static int tc_max_bn() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BAE_TC_MAXBN");
+    v = e ? std::max(32, std::min(240, atoi(e) / 16 * 16)) : 240;
+  }
+  return v;
+}
+
 static GemmDesc make_gemm(const DevState& s, int M, int N, int K, int b_nmajor = 0) {
   GemmDesc g;
   memset(&g, 0, sizeof(g));
@@ -134,16 +144,14 @@ static GemmDesc make_gemm(const DevState& s, int M, int N, int K, int b_nmajor =
   g.biasCol = -1;
   g.ksplit = 1;
   if (s.tc) {
-    // tcgen05 tiles: 128 x BN, BN <= 256 chosen so the N tiles are balanced
-    // long contractions (weight gradients, K = rows) use narrower tiles so that the hi*hi term can rotate over
-    // three TMEM accumulators (shorter truncating accumulation chains); see bae_tc.cuh
-    const int align = b_nmajor ? 32 : 16;
-    const int maxbn = ((K > 1024) ? 128 : 240) / align * align;
-    g.tcMain = (K > 1024) ? 3 : 1;
+    // tcgen05 tiles: 128 x BN, BN <= 240 (a multiple of 16) chosen so the N tiles are balanced. An N-major B
+    // operand is loaded in 32-column chunks, so its tile in shared memory may be wider than the MMA's N.
+    const int maxbn = b_nmajor ? std::min(tc_max_bn(), 224) : tc_max_bn();   // 7 chunks x 2 KB fit the 15 KB B slot
     g.tm = (M + 127) / 128;
     g.tn = (N + maxbn - 1) / maxbn;
-    g.tcBN = round_up((N + g.tn - 1) / g.tn, align);
-    g.tcBBytes = g.tcBN * 64;    // K-major: BN rows x 64 B; N-major: BN/32 chunks x 2048 B
+    g.tcBN = round_up((N + g.tn - 1) / g.tn, 16);
+    g.tcBBytes = b_nmajor ? round_up(g.tcBN, 32) / 32 * 2048 : g.tcBN * 64;   // chunks of [16 k][32 n] : rows of 64 B
+    g.tcMain = 1;
     return g;
   }
   g.big = (M >= 128 && N > 64) ? 1 : 0;
@@ -155,7 +163,14 @@ static GemmDesc make_gemm(const DevState& s, int M, int N, int K, int b_nmajor =
 
 // FP32 path, weight-gradient GEMMs: few chains / few output tiles but a long contraction (K = rows). Split K over
 // work items so the phase fills the grid; the copies are summed in fixed order (deterministic) by the Adam phase.
-static int fp32_ksplit(const DevState& s, int grid_hint, const GemmDesc& g, int rows) {
+static int grad_ksplit(const DevState& s, int grid_hint, const GemmDesc& g, int rows) {
+  if (s.tc) {
+    // tcgen05 path: the tensor core truncates when it adds into its accumulator, so keep every accumulation chain
+    // at the length of a forward layer's (<= ~640 rows, 40 K blocks); extra splits also balance the phase
+    const char* e = getenv("BAE_TC_KSPLIT_ROWS");
+    const int per = e ? std::max(64, atoi(e)) : 640;
+    return std::max(1, std::min(16, (rows + per - 1) / per));
+  }
   const int tiles = g.tm * g.tn * s.C;
   const int nk = (rows + 15) / 16;
   const int ks = (2 * grid_hint + tiles - 1) / tiles;
@@ -297,8 +312,8 @@ static void build_program(bae_handle* h) {
     g.C = G(bl[l].wseg); g.sC = P; g.ldc = s.seg[bl[l].wseg].ld;
     g.epi = EPI_GRADW;
     if (bl[l].bseg >= 0) { g.gbias = G(bl[l].bseg); g.sGb = P; }
-    if (!tcm) {
-      const int ks = fp32_ksplit(s, h->grid_hint, g, N);
+    {
+      const int ks = grad_ksplit(s, h->grid_hint, g, N);
       g.ksplit = ks;
       s.seg_ksplit[bl[l].wseg] = ks;
       if (bl[l].bseg >= 0) s.seg_ksplit[bl[l].bseg] = ks;
@@ -430,10 +445,10 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   CU(dalloc(h, &s.wcur, CA * P));
   for (int i = 0; i < kNumSegs; ++i) s.seg_ksplit[i] = 1;
   s.max_ksplit = 1;
-  if (!s.tc) {
+  {
     const int dd[7] = {s.d0, s.d1, s.d2, s.d3, s.d2, s.d1, s.d0};
     for (int l = 0; l < 6; ++l)
-      s.max_ksplit = std::max(s.max_ksplit, fp32_ksplit(s, h->grid_hint, make_gemm(s, dd[l + 1], dd[l], s.n_train, 1), s.n_train));
+      s.max_ksplit = std::max(s.max_ksplit, grad_ksplit(s, h->grid_hint, make_gemm(s, dd[l + 1], dd[l], s.n_train, 1), s.n_train));
   }
   CU(dalloc(h, &s.grad, (size_t)s.max_ksplit * CA * P));   // K-split copies of the gradient (copy 0 is the result)
   CU(dalloc(h, &s.wb, CA * s.nbuf)); CU(dalloc(h, &s.wb_tmp, CA * s.nbuf));
@@ -474,6 +489,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   CU(dalloc(h, &h->stage_ref, (size_t)s.w_size + 8)); CU(dalloc(h, &h->stage_noise, (size_t)s.w_size + 8));
   CU(dalloc(h, &h->stage_d, 64));
   if (getenv("BAE_TC_TRACE") && getenv("BAE_TC_TRACE")[0] == '1') CU(dalloc(h, &s.dbg, 4096));
+  s.dbg_flags = getenv("BAE_TC_DBGFLAGS") ? atoi(getenv("BAE_TC_DBGFLAGS")) : 0;
   {
     void* q = nullptr;
     CU(cudaMalloc(&q, sizeof(DevState)));
@@ -1006,6 +1022,12 @@ int bae_debug_trace(bae_handle* h, long long* out, int clear) {
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaMemcpy(out, h->hs.dbg, 4096 * sizeof(long long), cudaMemcpyDeviceToHost));
   if (clear) CU(cudaMemset(h->hs.dbg, 0, 4096 * sizeof(long long)));
+  return BAE_OK;
+}
+
+// Debug: cudaProfilerStart / cudaProfilerStop around a region (ncu --profile-from-start off).
+int bae_debug_profiler(int on) {
+  CU(on ? cudaProfilerStart() : cudaProfilerStop());
   return BAE_OK;
 }
 

@@ -17,9 +17,11 @@ namespace cg = cooperative_groups;
 namespace bae {
 
 constexpr int BK = 16;
-// The phase helpers below run on the first 256 threads of a CTA (the tcgen05 kernels carry extra role warps),
-// so they synchronise on a named barrier instead of __syncthreads().
+// The phase helpers below run on 256 threads of a CTA: all of them in the FP32 kernels, the two epilogue warpgroups
+// (threads 128..383, the ones holding the large register budget) in the tcgen05 kernels. They index themselves with
+// TID (a permutation of 0..255 in both cases) and synchronise on a named barrier instead of __syncthreads().
 #define BLOCK_SYNC() asm volatile("bar.sync 2, 256;" ::: "memory")
+#define TID (threadIdx.x & 255)
 constexpr float kBnEps = 1e-5f;
 constexpr float kBnMom = 0.1f;
 constexpr float kB1 = 0.9f, kB2 = 0.999f, kAdamEps = 1e-8f;
@@ -38,11 +40,11 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // Deterministic block-wide sum (all 256 threads call). Result valid in every thread.
 __device__ __forceinline__ double block_sum_d(double v, double* red /* >= 9 doubles */) {
   v = warp_sum_d(v);
-  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  int w = TID >> 5, l = TID & 31;
   BLOCK_SYNC();
   if (l == 0) red[w] = v;
   BLOCK_SYNC();
-  if (threadIdx.x == 0) {
+  if (TID == 0) {
     double s = 0.0;
     for (int i = 0; i < kThreads / 32; ++i) s += red[i];
     red[8] = s;
@@ -88,7 +90,7 @@ __device__ __forceinline__ void tile_load(const float* P, int ld, int mode, int 
   constexpr int NV = BT * 4 / kThreads;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    int f = threadIdx.x + i * kThreads;
+    int f = TID + i * kThreads;
     const float* addr;
     bool valid;
     if (mode == 0) {  // K contiguous
@@ -113,7 +115,7 @@ __device__ __forceinline__ void tile_store(float* __restrict__ sm /*[BK][BT]*/, 
   constexpr int NV = BT * 4 / kThreads;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    int f = threadIdx.x + i * kThreads;
+    int f = TID + i * kThreads;
     if (mode == 0) {
       int row = f % BT, k4 = f / BT;
       sm[(k4 * 4 + 0) * BT + row] = r[i].x;
@@ -137,14 +139,14 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
   const float* A = g.A + (size_t)chain * g.sA;
   const float* B = g.B + (size_t)chain * g.sB;
   const int m0 = tile_m * BM, n0 = tile_n * BN;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int tx = TID & 15, ty = TID >> 4;
   float acc[TM][TN];
 #pragma unroll
   for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
   float colsum = 0.f;
-  const bool do_colsum = (g.epi == EPI_GRADW) && (g.gbias != nullptr) && (tile_n == 0) && (threadIdx.x < BM);
+  const bool do_colsum = (g.epi == EPI_GRADW) && (g.gbias != nullptr) && (tile_n == 0) && (TID < BM);
 
   float4 ra[BM * 4 / kThreads], rb[BN * 4 / kThreads];
   const int nk_all = (g.K + BK - 1) / BK;
@@ -187,7 +189,7 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
     }
     if (do_colsum) {
 #pragma unroll
-      for (int k = 0; k < BK; ++k) colsum += as[k * BM + threadIdx.x];
+      for (int k = 0; k < BK; ++k) colsum += as[k * BM + TID];
     }
     if (kt + 1 < nk) {
       tile_store<BM>(As + (cur ^ 1) * BK * BM, g.aMode, ra);
@@ -265,14 +267,14 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
   if (g.epi == EPI_LOSS) {
     double s0 = block_sum_d((double)l_sse, red);
     double s1 = block_sum_d((double)l_sd, red);
-    if (threadIdx.x == 0) {
+    if (TID == 0) {
       double* p = g.part + ((size_t)chain * g.partStride + (size_t)tile_m * g.tn + tile_n) * 2;
       p[0] = s0;
       p[1] = s1;
     }
   }
   if (do_colsum) {
-    int r = m0 + threadIdx.x;
+    int r = m0 + TID;
     if (r < g.M) (g.gbias + (size_t)chain * g.sGb + split_off)[r] = colsum;
   }
 }
@@ -313,7 +315,7 @@ __device__ void run_bn_fwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
   const int rln = kThreads / cpb;
   const int nblk = (d3 + cpb - 1) / cpb;
   const int total = nblk * (c_end - c_begin);
-  const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
+  const int cl = TID % cpb, rl = TID / cpb;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
     const int chain = c_begin + item / nblk;
     if (ph.needLang && !S->ch.is_lang[chain]) continue;
@@ -367,7 +369,7 @@ __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
   const int rln = kThreads / cpb;
   const int nblk = (d3 + cpb - 1) / cpb;
   const int total = nblk * (c_end - c_begin);
-  const int cl = threadIdx.x % cpb, rl = threadIdx.x / cpb;
+  const int cl = TID % cpb, rl = TID / cpb;
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
     const int chain = c_begin + item / nblk;
     if (ph.needLang && !S->ch.is_lang[chain]) continue;
@@ -438,7 +440,7 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
     const bool alias = S->ch.alias[chain] != 0;
     double* part = S->adam_part + ((size_t)chain * nit + it) * 3;
     if (which == 2 && !lang) {
-      if (threadIdx.x == 0) part[2] = 0.0;
+      if (TID == 0) part[2] = 0.0;
       continue;
     }
     const size_t base = (size_t)chain * S->Pp;
@@ -454,7 +456,7 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
     for (int u = 0; u < kAdamChunk / (kThreads * 4); ++u) {
-      const int p = it * kAdamChunk + (u * kThreads + threadIdx.x) * 4;
+      const int p = it * kAdamChunk + (u * kThreads + TID) * 4;
       if (p >= S->Pp) continue;
       const int sg = find_seg(S, p);
       const Seg& sd = S->seg[sg];
@@ -529,10 +531,10 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
     if (which == 1) {
       double s0 = block_sum_d((double)a0, red);
       double s1 = block_sum_d((double)a1, red);
-      if (threadIdx.x == 0) { part[0] = s0; part[1] = s1; }
+      if (TID == 0) { part[0] = s0; part[1] = s1; }
     } else {
       double s2 = block_sum_d((double)a2, red);
-      if (threadIdx.x == 0) part[2] = s2;
+      if (TID == 0) part[2] = s2;
     }
   }
 }
@@ -560,7 +562,7 @@ __device__ void step_scalars(const DevState* S, int chain_global, int step, doub
 }
 
 __device__ void run_prologue(const DevState* S, int c_begin, int c_end) {
-  const int gtid = blockIdx.x * kThreads + threadIdx.x;
+  const int gtid = blockIdx.x * kThreads + TID;
   for (int chain = c_begin + gtid; chain < c_end; chain += gridDim.x * kThreads) {
     const ChainArrays& ch = S->ch;
     const int i = ch.step[chain];
@@ -619,16 +621,16 @@ __device__ void run_epilogue(const DevState* S, int c_begin, int c_end, double* 
     const int nl_tr = S->loss_stride;
     const double* lp_tr = S->loss_part + (((size_t)1 * S->C_alloc + chain) * S->loss_stride) * 2;
     const double* lp_te = S->loss_part + (((size_t)2 * S->C_alloc + chain) * S->loss_stride) * 2;
-    for (int i = threadIdx.x; i < nl_tr; i += kThreads) { p_sse_tr += lp_tr[i * 2]; p_sse_te += lp_te[i * 2]; }
+    for (int i = TID; i < nl_tr; i += kThreads) { p_sse_tr += lp_tr[i * 2]; p_sse_te += lp_te[i * 2]; }
     const double* ap = S->adam_part + (size_t)chain * S->n_adam_items * 3;
-    for (int i = threadIdx.x; i < S->n_adam_items; i += kThreads) {
+    for (int i = TID; i < S->n_adam_items; i += kThreads) {
       p_noise += ap[i * 3 + 0];
       p_prop += ap[i * 3 + 1];
       if (lang) p_wc += ap[i * 3 + 2];
     }
     // --- BatchNorm buffer bookkeeping (all sorted-key buffer entries take noise, MAIN:259-260)
     double b_wc = 0.0, b_wp = 0.0, b_prior = 0.0;
-    for (int c = threadIdx.x; c < d3; c += kThreads) {
+    for (int c = TID; c < d3; c += kThreads) {
       float nzm[4], nzv[4];
       noise_quad(S, cg_id, step, SEG_BN_RM, (unsigned)(c >> 2), nzm);
       noise_quad(S, cg_id, step, SEG_BN_RV, (unsigned)(c >> 2), nzv);
@@ -671,7 +673,7 @@ __device__ void run_epilogue(const DevState* S, int c_begin, int c_end, double* 
     const double sb_wp = block_sum_d(b_wp, red);
     const double sb_prior = block_sum_d(b_prior, red);
     BLOCK_SYNC();
-    if (threadIdx.x == 0) {
+    if (TID == 0) {
       // --- num_batches_tracked (int64 in the model, float in the dicts)
       float nzn[4];
       noise_quad(S, cg_id, step, SEG_BN_NBT, 0u, nzn);
@@ -755,7 +757,7 @@ __device__ void run_epilogue(const DevState* S, int c_begin, int c_end, double* 
     }
     BLOCK_SYNC();
     if (red[10] != 0.0) {   // accept: `w` buffers <- proposal buffers
-      for (int c = threadIdx.x; c < S->nbuf; c += kThreads) wb[c] = S->wb_tmp[(size_t)chain * S->nbuf + c];
+      for (int c = TID; c < S->nbuf; c += kThreads) wb[c] = S->wb_tmp[(size_t)chain * S->nbuf + c];
     }
     BLOCK_SYNC();
   }
@@ -777,7 +779,7 @@ __device__ double swap_uniform(const DevState* S, int ensemble_global, int round
 __device__ void run_swap_decide(const DevState* S) {
   const int n = S->n_rungs;
   const int nens = S->C / n;
-  const int gtid = blockIdx.x * kThreads + threadIdx.x;
+  const int gtid = blockIdx.x * kThreads + TID;
   const ChainArrays& ch = S->ch;
   const double ntr = (double)S->n_train * S->d0;
   for (int e = gtid; e < nens; e += gridDim.x * kThreads) {
@@ -826,7 +828,7 @@ __device__ void run_swap_gather(const DevState* S) {
       // buffers of the posted `w`: detached copy or the live model's buffers (MAIN:595)
       const float* sth = S->theta + (size_t)src * S->Pp;
       const bool al = S->ch.alias[src] != 0;
-      for (int c = threadIdx.x; c < S->nbuf; c += kThreads) {
+      for (int c = TID; c < S->nbuf; c += kThreads) {
         float v;
         if (al) {
           if (c < S->d3) v = sth[S->seg[SEG_BN_RM].pad_off + c];
@@ -837,7 +839,7 @@ __device__ void run_swap_gather(const DevState* S) {
         }
         S->wb_tmp[(size_t)p * S->nbuf + c] = v;
       }
-      if (threadIdx.x == 0) {
+      if (TID == 0) {
         S->swap_tmp[p * 2 + 0] = S->ch.eta[src];
         S->swap_tmp[p * 2 + 1] = S->ch.last_sse[src];
       }
@@ -846,7 +848,7 @@ __device__ void run_swap_gather(const DevState* S) {
     const float4* s4 = reinterpret_cast<const float4*>(S->theta + (size_t)src * S->Pp + (size_t)it * kAdamChunk);
     float4* d4 = reinterpret_cast<float4*>(S->wcur + (size_t)p * S->Pp + (size_t)it * kAdamChunk);
     const int nv = min(kAdamChunk, S->Pp - it * kAdamChunk) / 4;
-    for (int i = threadIdx.x; i < nv; i += kThreads) d4[i] = s4[i];
+    for (int i = TID; i < nv; i += kThreads) d4[i] = s4[i];
   }
 }
 
@@ -857,8 +859,8 @@ __device__ void run_swap_scatter(const DevState* S) {
     const int p = item / nit, it = item % nit;
     const int src = S->swap_src[p];
     if (it == 0) {
-      for (int c = threadIdx.x; c < S->nbuf; c += kThreads) S->wb[(size_t)p * S->nbuf + c] = S->wb_tmp[(size_t)p * S->nbuf + c];
-      if (threadIdx.x == 0) {
+      for (int c = TID; c < S->nbuf; c += kThreads) S->wb[(size_t)p * S->nbuf + c] = S->wb_tmp[(size_t)p * S->nbuf + c];
+      if (TID == 0) {
         S->ch.eta[p] = S->swap_tmp[p * 2 + 0];       // MAIN:603
         S->ch.last_sse[p] = S->swap_tmp[p * 2 + 1];
         S->ch.alias[p] = 0;                          // MAIN:602: w = dictfromlist(...) is a detached dict
@@ -869,7 +871,7 @@ __device__ void run_swap_scatter(const DevState* S) {
     const float4* s4 = reinterpret_cast<const float4*>(S->wcur + (size_t)p * S->Pp + (size_t)it * kAdamChunk);
     float* dbase = S->theta + (size_t)p * S->Pp;
     const int nv = min(kAdamChunk, S->Pp - it * kAdamChunk) / 4;
-    for (int i = threadIdx.x; i < nv; i += kThreads) {
+    for (int i = TID; i < nv; i += kThreads) {
       const int pidx = it * kAdamChunk + i * 4;
       const int sg = find_seg(S, pidx);
       if (!S->seg[sg].trainable) continue;
@@ -930,16 +932,24 @@ bae_phase_kernel(const DevState* __restrict__ S, int pi, int c_begin, int c_end)
   run_phase<true>(S, pi, c_begin, c_end, 1, smem, red);
 }
 
-// ---- tensor-core variants: GEMM phases go through the tcgen05 tile engine (1 CTA per SM, ~193 KB smem ring)
-__device__ void run_phase_tc(const DevState* S, int pi, int c_begin, int c_end, int force_swap, tc::Smem& tsm,
-                             tc::Ring& ring, float* smem_small, double* red) {
+// ---- tensor-core variants: GEMM phases go through the tcgen05 tile engine (1 CTA of 512 threads per SM).
+// Warpgroups 1 and 2 (threads 128..383, 192 registers each) run the GEMM epilogues and every non-GEMM phase;
+// warpgroups 0 and 3 (64 registers) hold the TMA producer, the MMA issuer and the hi/lo converters.
+__device__ __forceinline__ void run_phase_tc_back(const DevState* S, int pi, int c_begin, int c_end, int force_swap,
+                                                  tc::Smem& tsm, tc::Ring& ring, float* smem_small, double* red) {
   const PhaseDesc& ph = S->phase[pi];
-  if (ph.kind == PH_GEMM) {
-    tc::gemm_phase(S, ph, c_begin, c_end, tsm, ring);
-  } else {
-    if (threadIdx.x < kThreads) run_phase<false>(S, pi, c_begin, c_end, force_swap, smem_small, red);
-    tc::fence_proxy_async();   // theta, Y, dZ written with generic stores are read by TMA in the next phase
-  }
+  if (ph.kind == PH_GEMM)
+    tc::gemm_phase_epilogue(S, ph, c_begin, c_end, tsm, ring);
+  else
+    run_phase<false>(S, pi, c_begin, c_end, force_swap, smem_small, red);
+  // generic-proxy stores of this phase (activations, theta, Y, dZ) are read by TMA (async proxy) in later phases
+  tc::fence_proxy_async();
+}
+
+__device__ __forceinline__ void run_phase_tc_front(const DevState* S, int pi, int c_begin, int c_end, tc::Smem& tsm,
+                                                   tc::Ring& ring) {
+  const PhaseDesc& ph = S->phase[pi];
+  if (ph.kind == PH_GEMM) tc::gemm_phase_front(S, ph, c_begin, c_end, tsm, ring);
 }
 
 __global__ void __launch_bounds__(tc::kThreadsTc, 1)
@@ -952,10 +962,22 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
   tc::Ring ring;
   tc::setup(tsm, dyn_smem);
   cg::grid_group grid = cg::this_grid();
-  for (int rep = 0; rep < n_rep; ++rep) {
-    for (int pi = ph_begin; pi < ph_end; ++pi) {
-      run_phase_tc(S, pi, c_begin, c_end, force_swap, tsm, ring, smem_small, red);
-      grid.sync();
+  const int wg = threadIdx.x >> 7;
+  if (wg == 1 || wg == 2) {
+    tc::regs_inc<tc::kRegsEpi>();
+    for (int rep = 0; rep < n_rep; ++rep) {
+      for (int pi = ph_begin; pi < ph_end; ++pi) {
+        run_phase_tc_back(S, pi, c_begin, c_end, force_swap, tsm, ring, smem_small, red);
+        grid.sync();
+      }
+    }
+  } else {
+    tc::regs_dec<tc::kRegsLean>();
+    for (int rep = 0; rep < n_rep; ++rep) {
+      for (int pi = ph_begin; pi < ph_end; ++pi) {
+        run_phase_tc_front(S, pi, c_begin, c_end, tsm, ring);
+        grid.sync();
+      }
     }
   }
   tc::teardown(tsm);
@@ -969,7 +991,14 @@ bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_e
   tc::Smem tsm;
   tc::Ring ring;
   tc::setup(tsm, dyn_smem);
-  run_phase_tc(S, pi, c_begin, c_end, 1, tsm, ring, smem_small, red);
+  const int wg = threadIdx.x >> 7;
+  if (wg == 1 || wg == 2) {
+    tc::regs_inc<tc::kRegsEpi>();
+    run_phase_tc_back(S, pi, c_begin, c_end, 1, tsm, ring, smem_small, red);
+  } else {
+    tc::regs_dec<tc::kRegsLean>();
+    run_phase_tc_front(S, pi, c_begin, c_end, tsm, ring);
+  }
   tc::teardown(tsm);
 }
 

@@ -16,6 +16,7 @@ ap.add_argument("--chains", type=int, default=64)
 ap.add_argument("--rounds", type=int, default=1)
 ap.add_argument("--steps-per-round", type=int, default=5)
 ap.add_argument("--gemm-path", type=int, default=0)
+ap.add_argument("--profile-round", type=int, default=-1, help="cudaProfilerStart/Stop around this round (ncu --profile-from-start off)")
 a = ap.parse_args()
 dims4, ntr, nte = SHAPES[a.shape]
 train, test = synth(dims4, ntr, nte)
@@ -26,8 +27,12 @@ rng = np.random.default_rng(0)
 for j in range(a.chains):
     s.init_chain(j, default_theta_init(dims4, rng), rng.standard_normal(s.w_size))
 for r in range(a.rounds):
+    if r == a.profile_round:
+        s.synchronize(); s.lib.bae_debug_profiler(1)
     s.run(a.steps_per_round)
     s.synchronize()
+    if r == a.profile_round:
+        s.lib.bae_debug_profiler(0)
     print("round", r, "ms", s.last_ms(), flush=True)
 tr = s.traces(0, 0, a.rounds * a.steps_per_round)
 print("accepted", tr["accepted"].tolist(), "langevin", tr["langevin"].tolist())
