@@ -82,7 +82,7 @@ struct PhaseDesc {
 
 constexpr int kMaxGemm = 40;
 constexpr int kMaxPhase = 64;
-constexpr int kAdamChunk = 2048;   // floats per Adam work item (256 threads x 2 float4)
+constexpr int kAdamChunk = 8192;   // floats per Adam work item (256 threads x 8 float4)
 constexpr int kThreads = 256;
 
 // Per-chain scalar state (structure of arrays, length C_alloc = C + 1; slot C is the eval scratch chain).

@@ -74,10 +74,23 @@ __device__ __forceinline__ void noise_quad(const DevState* S, int chain_global, 
   box_muller(u01(r.z), u01(r.w), n[2], n[3]);
 }
 
+// Tensor table of the flat parameter vector in shared memory (filled once per kernel): the tcgen05 kernels run with the
+// shared-memory carve-out at its maximum, i.e. without an L1 to cache the table in global memory.
+struct SegLite { int pad_off, span, cols, ld, trainable, ksplit; };   // span = rows * ld
+__shared__ SegLite sh_seg[kNumSegs];
+
+__device__ __forceinline__ void load_seg_table(const DevState* S) {
+  for (int i = threadIdx.x; i < kNumSegs; i += blockDim.x) {
+    const Seg& g = S->seg[i];
+    sh_seg[i] = SegLite{g.pad_off, g.rows * g.ld, g.cols, g.ld, g.trainable, S->seg_ksplit[i]};
+  }
+  __syncthreads();
+}
+
 __device__ __forceinline__ int find_seg(const DevState* S, int p) {
   int s = 0;
 #pragma unroll
-  for (int i = 1; i < kNumSegs; ++i) s += (p >= S->seg[i].pad_off) ? 1 : 0;
+  for (int i = 1; i < kNumSegs; ++i) s += (p >= sh_seg[i].pad_off) ? 1 : 0;
   return s;
 }
 
@@ -415,10 +428,8 @@ __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
 }
 
 // Gradient of 4 consecutive entries: fixed-order sum of the K-split copies written by the weight-gradient GEMMs.
-__device__ __forceinline__ float4 load_grad4(const DevState* S, const float* gr, int p, int sg) {
+__device__ __forceinline__ float4 load_grad4(const float* __restrict__ gr, int p, int ks, size_t stride) {
   float4 g4 = *reinterpret_cast<const float4*>(&gr[p]);
-  const int ks = S->seg_ksplit[sg];
-  const size_t stride = (size_t)S->C_alloc * S->Pp;
   for (int s2 = 1; s2 < ks; ++s2) {
     const float4 t = *reinterpret_cast<const float4*>(&gr[p + s2 * stride]);
     g4.x += t.x; g4.y += t.y; g4.z += t.z; g4.w += t.w;
@@ -433,6 +444,9 @@ __device__ __forceinline__ float4 load_grad4(const DevState* S, const float* gr,
 __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, double* red) {
   const int nit = S->n_adam_items;
   const int total = nit * (c_end - c_begin);
+  const int Pp = S->Pp;
+  const float step_w = S->step_w;
+  const size_t gstride = (size_t)S->C_alloc * Pp;   // distance between the K-split copies of the gradient
   for (int item = blockIdx.x; item < total; item += gridDim.x) {
     const int chain = c_begin + item / nit;
     const int it = item % nit;
@@ -443,37 +457,35 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
       if (TID == 0) part[2] = 0.0;
       continue;
     }
-    const size_t base = (size_t)chain * S->Pp;
-    float* th = S->theta + base;
-    float* mm = S->m + base;
-    float* vv = S->v + base;
-    float* wc = S->wcur + base;
-    const float* gr = S->grad + base;
+    const size_t base = (size_t)chain * Pp;
+    float* __restrict__ th = S->theta + base;
+    float* __restrict__ mm = S->m + base;
+    float* __restrict__ vv = S->v + base;
+    float* __restrict__ wc = S->wcur + base;
+    const float* __restrict__ gr = S->grad + base;
     const int step = S->ch.step[chain];
     const int cg_id = S->chain_id_base + chain;
     const float ss = (which == 1) ? S->ch.ss1[chain] : S->ch.ss2[chain];
     const float sq = (which == 1) ? S->ch.sq1[chain] : S->ch.sq2[chain];
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
+#pragma unroll 2
     for (int u = 0; u < kAdamChunk / (kThreads * 4); ++u) {
       const int p = it * kAdamChunk + (u * kThreads + TID) * 4;
-      if (p >= S->Pp) continue;
+      if (p >= Pp) continue;
       const int sg = find_seg(S, p);
-      const Seg& sd = S->seg[sg];
+      const SegLite sd = sh_seg[sg];
       if (!sd.trainable) continue;
       const int local = p - sd.pad_off;
-      if (local >= sd.rows * sd.ld) continue;   // alignment gap between tensors
+      if (local >= sd.span) continue;   // alignment gap between tensors
       const int col = local % sd.ld;
       const int nval = min(4, sd.cols - col);
       if (nval <= 0) continue;
       float4 t4 = *reinterpret_cast<const float4*>(&th[p]);
       float t[4] = {t4.x, t4.y, t4.z, t4.w};
       if (which == 1) {
-        float nz[4];
-        noise_quad(S, cg_id, step, sg, (unsigned)(local >> 2), nz);
         float o[4];
         if (lang) {
-          float4 g4 = load_grad4(S, gr, p, sg);
+          float4 g4 = load_grad4(gr, p, sd.ksplit, gstride);
           float4 m4 = *reinterpret_cast<const float4*>(&mm[p]);
           float4 v4 = *reinterpret_cast<const float4*>(&vv[p]);
           float g[4] = {g4.x, g4.y, g4.z, g4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -491,10 +503,12 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[j] = t[j];
         }
+        float nz[4];
+        noise_quad(S, cg_id, step, sg, (unsigned)(local >> 2), nz);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if (j < nval) {
-            float nj = nz[j] * S->step_w;
+            float nj = nz[j] * step_w;
             o[j] = o[j] + nj;
             a0 = fmaf(nj, nj, a0);
             a1 = fmaf(o[j], o[j], a1);
@@ -504,7 +518,7 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
         }
         *reinterpret_cast<float4*>(&th[p]) = make_float4(o[0], o[1], o[2], o[3]);
       } else {
-        float4 g4 = load_grad4(S, gr, p, sg);
+        float4 g4 = load_grad4(gr, p, sd.ksplit, gstride);
         float4 m4 = *reinterpret_cast<const float4*>(&mm[p]);
         float4 v4 = *reinterpret_cast<const float4*>(&vv[p]);
         float g[4] = {g4.x, g4.y, g4.z, g4.w}, m[4] = {m4.x, m4.y, m4.z, m4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
@@ -915,6 +929,7 @@ bae_program_kernel(const DevState* __restrict__ S, int ph_begin, int ph_end, int
                    int force_swap) {
   __shared__ __align__(16) float smem[2 * BK * 128 * 2];   // 32 KB: A and B double buffers (128-wide tiles)
   __shared__ double red[16];
+  load_seg_table(S);
   cg::grid_group grid = cg::this_grid();
   for (int rep = 0; rep < n_rep; ++rep) {
     for (int pi = ph_begin; pi < ph_end; ++pi) {
@@ -929,6 +944,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 bae_phase_kernel(const DevState* __restrict__ S, int pi, int c_begin, int c_end) {
   __shared__ __align__(16) float smem[2 * BK * 128 * 2];
   __shared__ double red[16];
+  load_seg_table(S);
   run_phase<true>(S, pi, c_begin, c_end, 1, smem, red);
 }
 
@@ -961,6 +977,7 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
   tc::Smem tsm;
   tc::Ring ring;
   tc::setup(tsm, dyn_smem);
+  load_seg_table(S);
   cg::grid_group grid = cg::this_grid();
   const int wg = threadIdx.x >> 7;
   if (wg == 1 || wg == 2) {
@@ -991,6 +1008,7 @@ bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_e
   tc::Smem tsm;
   tc::Ring ring;
   tc::setup(tsm, dyn_smem);
+  load_seg_table(S);
   const int wg = threadIdx.x >> 7;
   if (wg == 1 || wg == 2) {
     tc::regs_inc<tc::kRegsEpi>();
