@@ -319,6 +319,227 @@ __device__ void run_gemm_phase(const DevState* S, const PhaseDesc& ph, int c_beg
 // ------------------------------------------------------------------------------------------------
 // BatchNorm1d, training mode (MAIN:165): batch statistics forward, full backward
 // ------------------------------------------------------------------------------------------------
+// ---- BatchNorm phases for wide bottlenecks (d3 >= 16): a work item is (chain, 16 columns). 4 float4 column groups x
+// 64 row lanes; every thread keeps 8 rows (8 or 16 float4 loads) in flight, because only 256 threads per SM run these
+// phases and the tcgen05 kernels have no L1. The passes over a [rows x 16] slab (128 KB) after the first hit L2.
+constexpr int kBnCols = 16, kBnLanes = kThreads / 4, kBnUnroll = 8;
+
+// Sum of v over the 64 row lanes for each of this thread's 4 columns (result in every thread). red2: >= 128 doubles.
+__device__ __forceinline__ void bn_colsum4(double (&v)[4], double* red2) {
+  const int lane = TID & 31, w = TID >> 5, c4 = TID & 3;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 4);
+    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 8);
+    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+  }
+  BLOCK_SYNC();
+  if (lane < 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red2[w * kBnCols + c4 * 4 + k] = v[k];
+  }
+  BLOCK_SYNC();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; ++i) t += red2[i * kBnCols + c4 * 4 + k];
+    v[k] = t;
+  }
+}
+
+__device__ void run_bn_fwd_wide(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, double* red2) {
+  const int d3 = S->d3, ld3 = S->ld3, N = ph.argRows, slot = ph.arg;
+  const int nblk = (d3 + kBnCols - 1) / kBnCols;
+  const int total = nblk * (c_end - c_begin);
+  const int c4 = TID & 3, rl = TID >> 2;
+  const int off_g = sh_seg[SEG_BN_W].pad_off, off_b = sh_seg[SEG_BN_BIAS].pad_off;
+  const size_t slab = (size_t)S->n_max * ld3;
+  const bool need = ph.needLang != 0;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int chain = c_begin + item / nblk;
+    if (need && !S->ch.is_lang[chain]) continue;
+    const int c0 = (item % nblk) * kBnCols + c4 * 4;
+    const bool cv = c0 < d3;   // a float4 may reach past d3 (pad / ones column: read, never written)
+    const float* __restrict__ Z = S->Z + (size_t)chain * slab + c0;
+    float* __restrict__ Y = S->Y + (size_t)chain * slab + c0;
+    double a[4] = {0.0, 0.0, 0.0, 0.0};
+    if (cv)
+      for (int base = rl; base < N; base += kBnLanes * kBnUnroll) {
+        float4 z[kBnUnroll];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+          const int r = base + u * kBnLanes;
+          z[u] = (r < N) ? *reinterpret_cast<const float4*>(Z + (size_t)r * ld3) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) { a[0] += (double)z[u].x; a[1] += (double)z[u].y; a[2] += (double)z[u].z; a[3] += (double)z[u].w; }
+      }
+    bn_colsum4(a, red2);
+    const float mean[4] = {(float)(a[0] / N), (float)(a[1] / N), (float)(a[2] / N), (float)(a[3] / N)};
+    double q[4] = {0.0, 0.0, 0.0, 0.0};
+    if (cv)
+      for (int base = rl; base < N; base += kBnLanes * kBnUnroll) {
+        float4 z[kBnUnroll];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+          const int r = base + u * kBnLanes;
+          z[u] = (r < N) ? *reinterpret_cast<const float4*>(Z + (size_t)r * ld3)
+                         : make_float4(mean[0], mean[1], mean[2], mean[3]);
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+          const float d0 = z[u].x - mean[0], d1 = z[u].y - mean[1], d2 = z[u].z - mean[2], d3_ = z[u].w - mean[3];
+          q[0] += (double)d0 * (double)d0; q[1] += (double)d1 * (double)d1;
+          q[2] += (double)d2 * (double)d2; q[3] += (double)d3_ * (double)d3_;
+        }
+      }
+    bn_colsum4(q, red2);
+    if (!cv) continue;
+    const float* th = S->theta + (size_t)chain * S->Pp;
+    float var[4], inv[4], gam[4], bet[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      var[k] = (float)(q[k] / N);
+      inv[k] = 1.0f / sqrtf(var[k] + kBnEps);
+      const bool ok = c0 + k < d3;
+      gam[k] = ok ? th[off_g + c0 + k] : 0.f;
+      bet[k] = ok ? th[off_b + c0 + k] : 0.f;
+      if (rl == 0 && ok) {
+        S->bn_mu[((size_t)slot * S->C_alloc + chain) * ld3 + c0 + k] = mean[k];
+        S->bn_var[((size_t)slot * S->C_alloc + chain) * ld3 + c0 + k] = var[k];
+        S->bn_inv[(size_t)chain * ld3 + c0 + k] = inv[k];
+      }
+    }
+    const bool full4 = c0 + 4 <= d3;
+    for (int base = rl; base < N; base += kBnLanes * kBnUnroll) {
+      float4 z[kBnUnroll];
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const int r = base + u * kBnLanes;
+        if (r < N) z[u] = *reinterpret_cast<const float4*>(Z + (size_t)r * ld3);
+      }
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const int r = base + u * kBnLanes;
+        if (r >= N) continue;
+        const float y[4] = {fmaf((z[u].x - mean[0]) * inv[0], gam[0], bet[0]), fmaf((z[u].y - mean[1]) * inv[1], gam[1], bet[1]),
+                            fmaf((z[u].z - mean[2]) * inv[2], gam[2], bet[2]), fmaf((z[u].w - mean[3]) * inv[3], gam[3], bet[3])};
+        float* yp = Y + (size_t)r * ld3;
+        if (full4) {
+          *reinterpret_cast<float4*>(yp) = make_float4(y[0], y[1], y[2], y[3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (c0 + k < d3) yp[k] = y[k];
+        }
+      }
+    }
+  }
+}
+
+__device__ void run_bn_bwd_wide(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, double* red2) {
+  const int d3 = S->d3, ld3 = S->ld3, N = ph.argRows, slot = ph.arg;
+  const int nblk = (d3 + kBnCols - 1) / kBnCols;
+  const int total = nblk * (c_end - c_begin);
+  const int c4 = TID & 3, rl = TID >> 2;
+  const int off_g = sh_seg[SEG_BN_W].pad_off, off_b = sh_seg[SEG_BN_BIAS].pad_off;
+  const size_t slab = (size_t)S->n_max * ld3;
+  const bool need = ph.needLang != 0;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int chain = c_begin + item / nblk;
+    if (need && !S->ch.is_lang[chain]) continue;
+    const int c0 = (item % nblk) * kBnCols + c4 * 4;
+    const bool cv = c0 < d3;
+    const float* __restrict__ Z = S->Z + (size_t)chain * slab + c0;
+    float* DY = S->DY + (size_t)chain * slab + c0;
+    float mean[4] = {0.f, 0.f, 0.f, 0.f}, inv[4] = {0.f, 0.f, 0.f, 0.f}, gam[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cv) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (c0 + k < d3) {
+          mean[k] = S->bn_mu[((size_t)slot * S->C_alloc + chain) * ld3 + c0 + k];
+          inv[k] = S->bn_inv[(size_t)chain * ld3 + c0 + k];
+          gam[k] = S->theta[(size_t)chain * S->Pp + off_g + c0 + k];
+        }
+    }
+    double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+    if (cv)
+      for (int base = rl; base < N; base += kBnLanes * kBnUnroll) {
+        float4 dy[kBnUnroll], z[kBnUnroll];
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+          const int r = base + u * kBnLanes;
+          if (r < N) {
+            dy[u] = *reinterpret_cast<const float4*>(DY + (size_t)r * ld3);
+            z[u] = *reinterpret_cast<const float4*>(Z + (size_t)r * ld3);
+          } else {
+            dy[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            z[u] = dy[u];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kBnUnroll; ++u) {
+          const float d[4] = {dy[u].x, dy[u].y, dy[u].z, dy[u].w};
+          const float zz[4] = {z[u].x, z[u].y, z[u].z, z[u].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float zh = (zz[k] - mean[k]) * inv[k];
+            s1[k] += (double)d[k];
+            s2[k] += (double)d[k] * (double)zh;
+          }
+        }
+      }
+    bn_colsum4(s1, red2);
+    bn_colsum4(s2, red2);
+    if (!cv) continue;
+    float* gr = S->grad + (size_t)chain * S->Pp;
+    float m1[4], m2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (rl == 0 && c0 + k < d3) {
+        gr[off_b + c0 + k] = (float)s1[k];   // d beta  = sum dy
+        gr[off_g + c0 + k] = (float)s2[k];   // d gamma = sum dy * zhat
+      }
+      m1[k] = (float)(s1[k] / N) * gam[k];   // mean(dzhat), dzhat = dy * gamma
+      m2[k] = (float)(s2[k] / N) * gam[k];   // mean(dzhat * zhat)
+    }
+    const bool full4 = c0 + 4 <= d3;
+    for (int base = rl; base < N; base += kBnLanes * kBnUnroll) {
+      float4 dy[kBnUnroll], z[kBnUnroll];
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const int r = base + u * kBnLanes;
+        if (r < N) {
+          dy[u] = *reinterpret_cast<const float4*>(DY + (size_t)r * ld3);
+          z[u] = *reinterpret_cast<const float4*>(Z + (size_t)r * ld3);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const int r = base + u * kBnLanes;
+        if (r >= N) continue;
+        const float d[4] = {dy[u].x, dy[u].y, dy[u].z, dy[u].w};
+        const float zz[4] = {z[u].x, z[u].y, z[u].z, z[u].w};
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float zh = (zz[k] - mean[k]) * inv[k];
+          o[k] = inv[k] * (d[k] * gam[k] - m1[k] - zh * m2[k]);
+        }
+        float* dp = DY + (size_t)r * ld3;
+        if (full4) {
+          *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (c0 + k < d3) dp[k] = o[k];
+        }
+      }
+    }
+  }
+}
+
 __device__ void run_bn_fwd(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, double* red2 /*[8][32]*/) {
   const int d3 = S->d3, ld3 = S->ld3, N = ph.argRows, slot = ph.arg;
   // a CTA covers `cpb` columns with 256/cpb row lanes each (narrow bottlenecks such as Swiss Roll's 2 columns
@@ -911,8 +1132,14 @@ __device__ void run_phase(const DevState* S, int pi, int c_begin, int c_end, int
     case PH_GEMM:
       if constexpr (kSimtGemm) run_gemm_phase(S, ph, c_begin, c_end, smem, red);
       break;
-    case PH_BN_FWD: run_bn_fwd(S, ph, c_begin, c_end, reinterpret_cast<double*>(smem)); break;
-    case PH_BN_BWD: run_bn_bwd(S, ph, c_begin, c_end, reinterpret_cast<double*>(smem)); break;
+    case PH_BN_FWD:
+      if (S->d3 >= kBnCols) run_bn_fwd_wide(S, ph, c_begin, c_end, reinterpret_cast<double*>(smem));
+      else run_bn_fwd(S, ph, c_begin, c_end, reinterpret_cast<double*>(smem));
+      break;
+    case PH_BN_BWD:
+      if (S->d3 >= kBnCols) run_bn_bwd_wide(S, ph, c_begin, c_end, reinterpret_cast<double*>(smem));
+      else run_bn_bwd(S, ph, c_begin, c_end, reinterpret_cast<double*>(smem));
+      break;
     case PH_ADAM1: run_adam(S, 1, c_begin, c_end, red); break;
     case PH_ADAM2: run_adam(S, 2, c_begin, c_end, red); break;
     case PH_EPILOGUE: run_epilogue(S, c_begin, c_end, red); break;
@@ -986,6 +1213,11 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
       for (int pi = ph_begin; pi < ph_end; ++pi) {
         run_phase_tc_back(S, pi, c_begin, c_end, force_swap, tsm, ring, smem_small, red);
         grid.sync();
+        if (S->dbg && blockIdx.x == 0 && threadIdx.x == 128 && rep == 1) {   // debug: phase end times of the 2nd iteration
+          long long t;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+          S->dbg[3584 + pi - ph_begin] = t;
+        }
       }
     }
   } else {

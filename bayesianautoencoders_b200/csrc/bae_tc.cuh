@@ -56,17 +56,22 @@ struct Ring {
   uint32_t kbc = 0;                  // running K-block count of this CTA modulo kConvGroups
 };
 
+// Carve-up of the dynamic shared memory. Only the base pointer is kept in a register; every other address is the
+// base plus a compile-time offset (the persistent kernel keeps this struct live across all phases, and nothing there
+// may spill: with the carve-out at its maximum there is no L1 behind local memory).
 struct Smem {
-  uint8_t* tiles;        // 1024-byte aligned, 2 * kStages * kStageBytes
-  uint64_t* full;        // [kStages] TMA bytes of the raw pair landed
-  uint64_t* conv;        // [kStages] lo pair written by a converter group (which had waited for `full`)
-  uint64_t* empty;       // [kStages] the MMAs that read the stage have completed
-  uint64_t* tmem_full;   // [2]
-  uint64_t* tmem_empty;  // [2]
-  uint32_t* tmem_base;   // TMEM base address written by tcgen05.alloc
-  double* red;           // [16] epilogue reduction scratch
-  float* epi_stage;      // [8 warps][32][kEpiPitch] epilogue transpose tiles
+  uint8_t* tiles;        // 1024-byte aligned, 2 * kStages * kStageBytes, followed by barriers and epilogue staging
+  static constexpr int kTail = 2 * kStages * kStageBytes;
+  __device__ __forceinline__ uint64_t* full() const { return reinterpret_cast<uint64_t*>(tiles + kTail); }            // [kStages] TMA bytes landed
+  __device__ __forceinline__ uint64_t* conv() const { return full() + kStages; }        // [kStages] lo pair written
+  __device__ __forceinline__ uint64_t* empty() const { return conv() + kStages; }       // [kStages] MMAs of the stage completed
+  __device__ __forceinline__ uint64_t* tmem_full() const { return empty() + kStages; }  // [2]
+  __device__ __forceinline__ uint64_t* tmem_empty() const { return tmem_full() + 2; }   // [2]
+  __device__ __forceinline__ uint32_t* tmem_base() const { return reinterpret_cast<uint32_t*>(tmem_empty() + 2); }   // TMEM base address
+  __device__ __forceinline__ double* red() const { return reinterpret_cast<double*>(tiles + kTail + 256); }           // [16] reduction scratch
+  __device__ __forceinline__ float* epi_stage() const { return reinterpret_cast<float*>(tiles + kTail + 512); }       // [8][32][kEpiPitch]
 };
+static_assert((3 * kStages + 4) * 8 + 4 <= 256, "barrier area");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -224,21 +229,12 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 __device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem) {
   uintptr_t base = (reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023;
   sm.tiles = reinterpret_cast<uint8_t*>(base);
-  uint8_t* tail = sm.tiles + 2 * kStages * kStageBytes;
-  sm.full = reinterpret_cast<uint64_t*>(tail);
-  sm.conv = sm.full + kStages;
-  sm.empty = sm.conv + kStages;
-  sm.tmem_full = sm.empty + kStages;
-  sm.tmem_empty = sm.tmem_full + 2;
-  sm.tmem_base = reinterpret_cast<uint32_t*>(sm.tmem_empty + 2);
-  sm.red = reinterpret_cast<double*>(tail + 256);          // 16 doubles
-  sm.epi_stage = reinterpret_cast<float*>(tail + 512);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full[i], 1); mbar_init(&sm.conv[i], kConvGroupWarps); mbar_init(&sm.empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full[i], 1); mbar_init(&sm.tmem_empty[i], kEpiWarps); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full()[i], 1); mbar_init(&sm.conv()[i], kConvGroupWarps); mbar_init(&sm.empty()[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full()[i], 1); mbar_init(&sm.tmem_empty()[i], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (threadIdx.x / 32 == 2) tmem_alloc(sm.tmem_base, kTmemCols);
+  if (threadIdx.x / 32 == 2) tmem_alloc(sm.tmem_base(), kTmemCols);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -247,7 +243,7 @@ __device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem) {
 __device__ __forceinline__ void teardown(Smem& sm) {
   fence_before_sync();
   __syncthreads();
-  if (threadIdx.x / 32 == 2) tmem_dealloc(*sm.tmem_base, kTmemCols);
+  if (threadIdx.x / 32 == 2) tmem_dealloc(*sm.tmem_base(), kTmemCols);
 }
 
 // Timeline trace (debug): CTA 0 appends (tag, clock) pairs per role; 4 roles x 1024 entries.
@@ -321,28 +317,28 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const CUtensorMap* mapA = &maps[g.tmIdx[0]];
         const CUtensorMap* mapB = &maps[g.tmIdx[1]];
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&sm.empty[ring.stage], ring.phase ^ 1);
+          mbar_wait(&sm.empty()[ring.stage], ring.phase ^ 1);
           if (elect_one()) {
             trace(dbg, 0, ntr, kb);
             uint8_t* st = sm.tiles + ring.stage * kStageBytes;
-            mbar_expect_tx(&sm.full[ring.stage], bytes);
+            mbar_expect_tx(&sm.full()[ring.stage], bytes);
             const int k0 = (kb0 + kb) * kBK;
             if (dbgf & 64) {
             } else if (aMode == 0) {
-              tma_load_3d(st, mapA, &sm.full[ring.stage], k0, m0, ca);
+              tma_load_3d(st, mapA, &sm.full()[ring.stage], k0, m0, ca);
             } else {
               // MN-major: one [16 K-rows][32 floats] box per 32-wide chunk of the tile dimension
 #pragma unroll
               for (int c = 0; c < kBM / 32; ++c)
-                tma_load_3d(st + c * kMnChunkBytes, mapA, &sm.full[ring.stage], m0 + c * 32, k0, ca);
+                tma_load_3d(st + c * kMnChunkBytes, mapA, &sm.full()[ring.stage], m0 + c * 32, k0, ca);
             }
             uint8_t* sb = st + kATileBytes;
             if (dbgf & 32) {
             } else if (bMode == 0) {
-              tma_load_3d(sb, mapB, &sm.full[ring.stage], k0, n0, cb);
+              tma_load_3d(sb, mapB, &sm.full()[ring.stage], k0, n0, cb);
             } else {
               for (int c = 0; c < nchB; ++c)
-                tma_load_3d(sb + c * kMnChunkBytes, mapB, &sm.full[ring.stage], n0 + c * 32, k0, cb);
+                tma_load_3d(sb + c * kMnChunkBytes, mapB, &sm.full()[ring.stage], n0 + c * 32, k0, cb);
             }
           }
           __syncwarp();
@@ -355,12 +351,12 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     {
       int ntr = 0;
       const int dbgf = S->dbg_flags;
-      const uint32_t tmem = *sm.tmem_base;
+      const uint32_t tmem = *sm.tmem_base();
       for (int item = blockIdx.x; item < total; item += gridDim.x) {
         Item it;
         if (!decode_item(S, ph, c_begin, item, it)) continue;
         const GemmDesc& g = *it.g;
-        mbar_wait(&sm.tmem_empty[0], ring.acc_phase ^ 1);   // the epilogue warps have drained the previous tile
+        mbar_wait(&sm.tmem_empty()[0], ring.acc_phase ^ 1);   // the epilogue warps have drained the previous tile
         fence_after_sync();
         const uint32_t d_main = tmem, d_cross = tmem + (uint32_t)g.tcBN;
         const bool amn = g.aMode != 0, bmn = g.bMode != 0;
@@ -371,7 +367,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const uint64_t dA = make_desc(smem_u32(sm.tiles), amn), dB = make_desc(smem_u32(sm.tiles) + kATileBytes, bmn);
         for (int kb = 0; kb < nkb; ++kb) {
           // `conv` is signalled by converter warps that had themselves waited for the TMA bytes (`full`)
-          mbar_wait(&sm.conv[ring.stage], ring.phase);
+          mbar_wait(&sm.conv()[ring.stage], ring.phase);
           fence_after_sync();
           if (elect_one()) {
             trace(dbg, 1, ntr, kb);
@@ -389,10 +385,10 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
                 umma_tf32(d_cross, ah + astep, bl + bstep, idesc, 1u);
               }
             }
-            umma_commit(&sm.empty[ring.stage]);   // frees the stage (raw and lo pairs) when these MMAs have read it
+            umma_commit(&sm.empty()[ring.stage]);   // frees the stage (raw and lo pairs) when these MMAs have read it
             if (kb == nkb - 1) {
               trace(dbg, 1, ntr, 1000);
-              umma_commit(&sm.tmem_full[0]);      // accumulators complete -> epilogue
+              umma_commit(&sm.tmem_full()[0]);      // accumulators complete -> epilogue
             }
           }
           __syncwarp();
@@ -420,8 +416,8 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         if ((int)kbc == grp) {
           // Parity waits cannot tell phases two apart: a group that runs ahead of the producer would see the `full`
           // phase of K block k - 4 as the one of k + 4. Waiting for the stage's previous MMAs first pins the phase.
-          mbar_wait(&sm.empty[ring.stage], ring.phase ^ 1);
-          mbar_wait(&sm.full[ring.stage], ring.phase);
+          mbar_wait(&sm.empty()[ring.stage], ring.phase ^ 1);
+          mbar_wait(&sm.full()[ring.stage], ring.phase);
           const uint32_t src = tiles_s + ring.stage * kStageBytes;
           const uint32_t dst = src + kStages * kStageBytes;
           int i = 0;
@@ -448,7 +444,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> tensor-core (async proxy) reads
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.conv[ring.stage]);
+          if (lane == 0) mbar_arrive(&sm.conv()[ring.stage]);
         }
         if (++kbc == (uint32_t)kConvGroups) kbc = 0;
         if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
@@ -469,8 +465,8 @@ __device__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int 
   const int eg = (warp - 4) >> 2;       // 0/1: which alternating 32-column chunks this warp owns
   const int ew = warp - 4;              // 0..7
   const int et = threadIdx.x - 128;     // 0..255
-  const uint32_t tmem = *sm.tmem_base;
-  const uint32_t stg_s = smem_u32(sm.epi_stage + ew * (32 * kEpiPitch));   // this warp's 32 x 32 staging tile (pitch 36 floats)
+  const uint32_t tmem = *sm.tmem_base();
+  const uint32_t stg_s = smem_u32(sm.epi_stage() + ew * (32 * kEpiPitch));   // this warp's 32 x 32 staging tile (pitch 36 floats)
   const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;  // coalesced view: 4 rows x 128 B per instruction
   long long* dbg = (blockIdx.x == 0) ? S->dbg : nullptr;
   const int dbgf = S->dbg_flags;
@@ -487,7 +483,7 @@ __device__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int 
 
     // ---- drain: both accumulators of this warp's chunks -> registers, then TMEM goes back to the MMA issuer.
     // Only the few scalars above are live here: the 128 accumulator registers leave no room for more.
-    mbar_wait(&sm.tmem_full[0], ring.acc_phase);
+    mbar_wait(&sm.tmem_full()[0], ring.acc_phase);
     if (et == 0) trace(dbg, 3, ntr, 0);
     fence_after_sync();
     uint32_t acc[4][32];
@@ -514,7 +510,7 @@ __device__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int 
     }
     fence_before_sync();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.tmem_empty[0]);
+    if (lane == 0) mbar_arrive(&sm.tmem_empty()[0]);
     ring.acc_phase ^= 1;
     if (et == 0) trace(dbg, 3, ntr, 1);
 
@@ -609,12 +605,12 @@ __device__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int 
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (lane == 0) { sm.red[ew * 2] = s0; sm.red[ew * 2 + 1] = s1; }
+      if (lane == 0) { sm.red()[ew * 2] = s0; sm.red()[ew * 2 + 1] = s1; }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (et == 0) {
         double* p = g.part + ((size_t)chain * g.partStride + (size_t)it.tile_m * g.tn + it.tile_n) * 2;
         double a0 = 0.0, a1 = 0.0;
-        for (int w = 0; w < kEpiWarps; ++w) { a0 += sm.red[w * 2]; a1 += sm.red[w * 2 + 1]; }
+        for (int w = 0; w < kEpiWarps; ++w) { a0 += sm.red()[w * 2]; a1 += sm.red()[w * 2 + 1]; }
         p[0] = a0;
         p[1] = a1;
       }
