@@ -61,6 +61,22 @@ def measured_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
+def ncu_traffic(shape, cpg, gemm_path):
+    """DRAM bytes (read + write) of one launch of the persistent kernel from the committed `ncu --set full` capture
+    (profiles/r1_program_kernel_traffic.json), scaled to this run's chains x iterations per launch; None if no capture fits."""
+    p = os.path.join(ROOT, "profiles", "r1_program_kernel_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        if d["shape"] != shape or d["gemm_path"] != gemm_path:
+            return None
+        per_chain_iter = (d["dram_bytes_read"] + d["dram_bytes_write"]) / (d["chains"] * d["iterations"])
+        return {"bytes_per_launch": per_chain_iter * cpg * SWAP_INTERVAL, "bytes_per_chain_iteration": per_chain_iter,
+                "source": d["source"]}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -212,10 +228,32 @@ def run_gpu(args):
     dims4, n_train, n_test = SHAPES[shape]
     train, test = synth(dims4, n_train, n_test)
     cpg = args.chains_per_gpu
-    temps = np.tile(bo.temperature_ladder(N_RUNGS, 2), cpg // N_RUNGS)
     L = bo.Layout(dims4)
-    s = DeviceSampler(dims4, train, test, cpg, N_RUNGS, SAMPLES, temps, swap_interval=SWAP_INTERVAL,
-                      seed=0xBAE5EED, device=local, chain_id_base=rank * cpg, gemm_path=args.gemm_path)
+    sharded = world > 1 and args.ladder == "sharded"
+    n_ens = cpg // N_RUNGS
+    if sharded:
+        # BASELINE.json configs[3]: every ensemble's ladder has 8 x world rungs (64 at 8 GPUs) and is cut into contiguous
+        # blocks of 8 rungs per GPU; the exchange sweep crosses GPU boundaries (scalar all-gather + weight vectors over NCCL)
+        from bayesianautoencoders_b200.distributed import DeviceTransport, ShardedLadder
+        t_all = bo.temperature_ladder(N_RUNGS * world, 2)
+        temps = np.tile(t_all[rank * N_RUNGS:(rank + 1) * N_RUNGS], n_ens)
+        s = DeviceSampler(dims4, train, test, cpg, 1, SAMPLES, temps, swap_interval=SWAP_INTERVAL,
+                          seed=0xBAE5EED, device=local, chain_id_base=rank * cpg, gemm_path=args.gemm_path)
+        ladder = ShardedLadder(dist, rank, world, n_ens, N_RUNGS * world, train.size, 0xBAE5EED, DeviceTransport(s, local))
+    else:
+        temps = np.tile(bo.temperature_ladder(N_RUNGS, 2), n_ens)
+        s = DeviceSampler(dims4, train, test, cpg, N_RUNGS, SAMPLES, temps, swap_interval=SWAP_INTERVAL,
+                          seed=0xBAE5EED, device=local, chain_id_base=rank * cpg, gemm_path=args.gemm_path)
+        ladder = None
+
+    def pt_round():
+        """One bench step: 5 iterations of every resident chain + one exchange sweep."""
+        if ladder is None:
+            s.run(SWAP_INTERVAL)          # exchange phases run inside the persistent kernel
+        else:
+            s.step(SWAP_INTERVAL)
+            s.synchronize()
+            ladder.exchange()             # NCCL: 32 B/chain all-gather + boundary-crossing weight vectors
     rng = np.random.default_rng(100 + rank)
     for j in range(cpg):
         s.init_chain(j, default_theta_init(dims4, rng), rng.standard_normal(L.w_size))
@@ -228,7 +266,7 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        s.run(SWAP_INTERVAL)
+        pt_round()
     barrier()
     clocks = ClockSampler(local)
     if rank == 0:
@@ -238,7 +276,7 @@ def run_gpu(args):
     kernel_ms = []
     ev0.record(stream)
     for _ in range(args.steps):
-        s.run(SWAP_INTERVAL)
+        pt_round()
     ev1.record(stream)
     s.synchronize()
     barrier()
@@ -256,7 +294,7 @@ def run_gpu(args):
     # per-launch duration of the dominant (persistent step) kernel, measured live with CUDA events
     per_launch = []
     for _ in range(min(3, args.steps)):
-        s.run(SWAP_INTERVAL)
+        pt_round()
         per_launch.append(s.last_ms())
         iters_done += SWAP_INTERVAL
     kernel_ms = float(np.mean(per_launch))
@@ -283,7 +321,7 @@ def run_gpu(args):
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         s.upload_data(pin_train.numpy(), pin_test.numpy())
-        s.run(SWAP_INTERVAL)
+        pt_round()
         d2h = 0
         for j in range(cpg):
             tr = s.traces(j, iters_done, SWAP_INTERVAL)   # device -> host read of the step's results
@@ -313,7 +351,11 @@ def run_gpu(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(shape, cpg), "shape": shape, "dims": list(dims4), "n_train": n_train,
                        "n_test": n_test, "chains_per_gpu": cpg, "n_rungs": N_RUNGS, "swap_interval": SWAP_INTERVAL,
-                       "parallelism": f"{world} GPU(s) x {cpg} chains, whole ensembles per GPU (no data-path collective)",
+                       "parallelism": (f"{world} GPUs x {cpg} chains: {n_ens} ensembles, each ladder of {N_RUNGS * world} rungs cut into "
+                                       f"{N_RUNGS}-rung blocks per GPU; per round one 32 B/chain all-gather + the weight vectors of "
+                                       f"configurations that cross a GPU boundary over NCCL ({ladder.vectors_sent} vectors sent by rank 0)"
+                                       if sharded else
+                                       f"{world} GPU(s) x {cpg} chains, whole ensembles per GPU (no data-path collective)"),
                        "l2_policy": "working set per step (chain state + activations) exceeds the 126 MB L2 many times over; no flush needed",
                        "gemm_path": kind},
             "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons", []),
@@ -322,8 +364,10 @@ def run_gpu(args):
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved_tf / peaks["bf16_sustained"], "traffic": None,
-                         "kernel": "bae_program_kernel (persistent step kernel)", "kernel_ms_per_launch": kernel_ms,
+                         "frac": achieved_tf / peaks["bf16_sustained"], "traffic": ncu_traffic(shape, cpg, gemm_path),
+                         "kernel": ("bae_program_kernel_tc" if gemm_path == 2 else "bae_program_kernel") + " (persistent step kernel, "
+                                   "one cooperative launch = 5 iterations of all resident chains" + ("" if sharded else " + exchange sweep") + ")",
+                         "kernel_ms_per_launch": kernel_ms,
                          "algorithmic_gflop_per_launch": flops_per_launch / 1e9,
                          "peak_source": peaks["source"] + " bf16 dense sustained (MEASURED_PEAKS.json); kind::tf32 dense is 1/2 of it, a 3-way split 1/6",
                          "mma_kind": kind},
@@ -347,6 +391,8 @@ def main():
     ap.add_argument("--gemm-path", type=int, default=0)
     ap.add_argument("--ref-iters", type=int, default=2, help="iterations per replica process in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ladder", default="sharded", choices=["sharded", "local"],
+                    help="N > 1: 'sharded' cuts every ladder across the GPUs (NCCL exchange), 'local' keeps whole ensembles per GPU")
     args = ap.parse_args()
     if args.chains_per_gpu % N_RUNGS:
         raise SystemExit("--chains-per-gpu must be a multiple of 8")

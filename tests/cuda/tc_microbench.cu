@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(512, 1) k_mma(int N, int nmma, int pattern, lo
   Smem sm;
   setup(sm, dyn);
   const int warp = threadIdx.x >> 5;
-  const uint32_t tmem = *sm.tmem_base;
+  const uint32_t tmem = *sm.tmem_base();
   // zero the operand area (generic writes -> async proxy)
   for (int i = threadIdx.x; i < 4 * kStageBytes / 16; i += blockDim.x) reinterpret_cast<float4*>(sm.tiles)[i] = make_float4(1.f, 1.f, 1.f, 1.f);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -61,11 +61,11 @@ __global__ void __launch_bounds__(512, 1) k_mma(int N, int nmma, int pattern, lo
           else umma_tf32(tmem, make_desc(sa + kk, false), make_desc(sb + kk, false), idesc, i > 2 ? 1u : 0u);
         }
       }
-      umma_commit(&sm.tmem_full[0]);
+      umma_commit(&sm.tmem_full()[0]);
     }
     __syncwarp();
     long long t1 = clock64();
-    mbar_wait(&sm.tmem_full[0], 0);
+    mbar_wait(&sm.tmem_full()[0], 0);
     long long t2 = clock64();
     if (threadIdx.x == 32) { out[0] = t1 - t0; out[1] = t2 - t0; }
   }
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(512, 1) k_mma_seq(int N, int nblk, long long* 
   Smem sm;
   setup(sm, dyn);
   const int warp = threadIdx.x >> 5;
-  const uint32_t tmem = *sm.tmem_base;
+  const uint32_t tmem = *sm.tmem_base();
   for (int i = threadIdx.x; i < 4 * kStageBytes / 16; i += blockDim.x) reinterpret_cast<float4*>(sm.tiles)[i] = make_float4(1.f, 1.f, 1.f, 1.f);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
@@ -123,11 +123,11 @@ __global__ void __launch_bounds__(512, 1) k_mma_seq(int N, int nblk, long long* 
           for (int i = 0; i < 12; ++i) umma_tf32((b & 1) ? dc : dm, ah + 2 * (i & 1), bh + 2 * (i & 1), idesc, 1u);
         }
       }
-      umma_commit(&sm.tmem_full[0]);
+      umma_commit(&sm.tmem_full()[0]);
     }
     __syncwarp();
     long long t1 = clock64();
-    mbar_wait(&sm.tmem_full[0], 0);
+    mbar_wait(&sm.tmem_full()[0], 0);
     long long t2 = clock64();
     if (threadIdx.x == 32) { out[0] = t1 - t0; out[1] = t2 - t0; }
   }
@@ -189,11 +189,11 @@ __global__ void __launch_bounds__(512, 1) k_mbar(int iters, long long* out) {
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       if (elect_one()) {
-        umma_tf32(*sm.tmem_base, make_desc(sa, false), make_desc(sb, false), idesc, 0u);
-        umma_commit(&sm.tmem_full[0]);
+        umma_tf32(*sm.tmem_base(), make_desc(sa, false), make_desc(sb, false), idesc, 0u);
+        umma_commit(&sm.tmem_full()[0]);
       }
       __syncwarp();
-      mbar_wait(&sm.tmem_full[0], ph);
+      mbar_wait(&sm.tmem_full()[0], ph);
       ph ^= 1;
       fence_after_sync();
     }
@@ -218,13 +218,13 @@ __global__ void __launch_bounds__(512, 1) k_tma(const CUtensorMap* maps, int nB,
     for (int i = 0; i < iters; ++i) {
       long long t0 = clock64();
       if (elect_one()) {
-        mbar_expect_tx(&sm.full[0], bytes);
-        tma_load_3d(sm.tiles, &maps[0], &sm.full[0], (i % 8) * 16, 0, 0);
-        tma_load_3d(sm.tiles + kATileBytes, &maps[1], &sm.full[0], (i % 8) * 16, 0, 0);
+        mbar_expect_tx(&sm.full()[0], bytes);
+        tma_load_3d(sm.tiles, &maps[0], &sm.full()[0], (i % 8) * 16, 0, 0);
+        tma_load_3d(sm.tiles + kATileBytes, &maps[1], &sm.full()[0], (i % 8) * 16, 0, 0);
       }
       __syncwarp();
       long long t1 = clock64();
-      mbar_wait(&sm.full[0], ph);
+      mbar_wait(&sm.full()[0], ph);
       ph ^= 1;
       long long t2 = clock64();
       issue += t1 - t0;
@@ -235,11 +235,11 @@ __global__ void __launch_bounds__(512, 1) k_tma(const CUtensorMap* maps, int nB,
     uint32_t phs = 0;
     for (int i = 0; i < iters + 4; ++i) {
       const int st = i & 3;
-      if (i >= 4) { mbar_wait(&sm.full[st], (phs >> st) & 1); phs ^= 1u << st; }
+      if (i >= 4) { mbar_wait(&sm.full()[st], (phs >> st) & 1); phs ^= 1u << st; }
       if (i < iters && elect_one()) {
-        mbar_expect_tx(&sm.full[st], bytes);
-        tma_load_3d(sm.tiles + st * kStageBytes, &maps[0], &sm.full[st], (i % 8) * 16, 0, 0);
-        tma_load_3d(sm.tiles + st * kStageBytes + kATileBytes, &maps[1], &sm.full[st], (i % 8) * 16, 0, 0);
+        mbar_expect_tx(&sm.full()[st], bytes);
+        tma_load_3d(sm.tiles + st * kStageBytes, &maps[0], &sm.full()[st], (i % 8) * 16, 0, 0);
+        tma_load_3d(sm.tiles + st * kStageBytes + kATileBytes, &maps[1], &sm.full()[st], (i % 8) * 16, 0, 0);
       }
       __syncwarp();
     }
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(512, 1) k_ldtm(int nw, int chunks, long long* 
   Smem sm;
   setup(sm, dyn);
   const int warp = threadIdx.x >> 5;
-  const uint32_t tmem = *sm.tmem_base;
+  const uint32_t tmem = *sm.tmem_base();
   __syncthreads();
   long long t0 = clock64();
   float acc = 0.f;
@@ -301,11 +301,11 @@ __global__ void __launch_bounds__(512, 1) k_conv(int nthreads, int n4, int iters
     uint32_t ph = 0;
     while (!stop) {
       if (elect_one()) {
-        for (int i = 0; i < 12; ++i) umma_tf32(*sm.tmem_base, make_desc(sa + (i & 1) * 32, false), make_desc(sb + (i & 1) * 32, false), idesc, 1u);
-        umma_commit(&sm.tmem_full[0]);
+        for (int i = 0; i < 12; ++i) umma_tf32(*sm.tmem_base(), make_desc(sa + (i & 1) * 32, false), make_desc(sb + (i & 1) * 32, false), idesc, 1u);
+        umma_commit(&sm.tmem_full()[0]);
       }
       __syncwarp();
-      mbar_wait(&sm.tmem_full[0], ph);
+      mbar_wait(&sm.tmem_full()[0], ph);
       ph ^= 1;
       n += 12;
     }
