@@ -905,8 +905,24 @@ int bae_swap_counts(bae_handle* h, int64_t* num_swap, int64_t* total) {
   return BAE_OK;
 }
 
+// (eta, stored likelihood, adapttemp, SSE of `w`) of every resident chain: the rows a rank contributes to the
+// all-gather of an exchange round (MAIN:594-597 posts these scalars next to the weights). out: [n_chains][4].
+int bae_exchange_table(bae_handle* h, double* out) {
+  if (!h || !out) return fail(BAE_ERR_INVALID, "null argument");
+  const DevState& s = h->hs;
+  CU(cudaSetDevice(h->device));
+  std::vector<double> col((size_t)4 * s.C);
+  const double* src[4] = {s.ch.eta, s.ch.lik, s.ch.adapt, s.ch.last_sse};
+  for (int k = 0; k < 4; ++k)
+    CU(cudaMemcpyAsync(col.data() + (size_t)k * s.C, src[k], sizeof(double) * s.C, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < s.C; ++c)
+    for (int k = 0; k < 4; ++k) out[(size_t)c * 4 + k] = col[(size_t)k * s.C + c];
+  return BAE_OK;
+}
+
 int bae_exchange_pack(bae_handle* h, int chain, float* dev_w, double* host_scalars4) {
-  if (!h || !dev_w || !host_scalars4) return fail(BAE_ERR_INVALID, "null argument");
+  if (!h || !dev_w) return fail(BAE_ERR_INVALID, "null argument");
   const DevState& s = h->hs;
   if (chain < 0 || chain >= s.C) return fail(BAE_ERR_INVALID, "chain out of range");
   CU(cudaSetDevice(h->device));
@@ -920,10 +936,12 @@ int bae_exchange_pack(bae_handle* h, int chain, float* dev_w, double* host_scala
     CU(cudaMemcpyAsync(dev_w + s.seg[SEG_BN_RV].ref_off, s.wb + (size_t)chain * s.nbuf + s.d3, sizeof(float) * s.d3, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaMemcpyAsync(dev_w + s.seg[SEG_BN_NBT].ref_off, s.wb + (size_t)chain * s.nbuf + 2 * s.d3, sizeof(float), cudaMemcpyDeviceToDevice, h->stream));
   }
-  get1(h, s.ch.eta, chain, &host_scalars4[0]);
-  get1(h, s.ch.lik, chain, &host_scalars4[1]);
-  get1(h, s.ch.adapt, chain, &host_scalars4[2]);
-  get1(h, s.ch.last_sse, chain, &host_scalars4[3]);
+  if (host_scalars4) {   // optional: bae_exchange_table reads them for all chains at once
+    get1(h, s.ch.eta, chain, &host_scalars4[0]);
+    get1(h, s.ch.lik, chain, &host_scalars4[1]);
+    get1(h, s.ch.adapt, chain, &host_scalars4[2]);
+    get1(h, s.ch.last_sse, chain, &host_scalars4[3]);
+  }
   return BAE_OK;
 }
 

@@ -40,6 +40,20 @@ def swap_uniform(seed, ensemble_global, rnd, pair):
     return float(np.float32((np.float32(r[0] >> 8) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)))
 
 
+def swap_uniforms(seed, ensembles, rnd, n_pairs):
+    """All swap uniforms of one exchange round, [len(ensembles), n_pairs] (vectorised Philox, same values as swap_uniform)."""
+    E = len(ensembles)
+    c = [np.tile(np.arange(n_pairs, dtype=np.uint64), (E, 1)), np.full((E, n_pairs), 0xFE | (3 << 8), np.uint64),
+         np.full((E, n_pairs), rnd, np.uint64), np.repeat(np.asarray(ensembles, np.uint64)[:, None], n_pairs, 1)]
+    k = [np.uint64(seed & 0xFFFFFFFF), np.uint64((seed >> 32) & 0xFFFFFFFF)]
+    m32 = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = np.uint64(_M0) * c[0], np.uint64(_M1) * c[2]
+        c = [((p1 >> np.uint64(32)) ^ c[1] ^ k[0]) & m32, p1 & m32, ((p0 >> np.uint64(32)) ^ c[3] ^ k[1]) & m32, p0 & m32]
+        k = [(k[0] + np.uint64(_W0)) & m32, (k[1] + np.uint64(_W1)) & m32]
+    return ((c[0] >> np.uint64(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+
+
 def loglik(sse, n, tau_sq, temp):
     return (-(n * 0.5) * math.log(2.0 * math.pi * tau_sq) - 0.5 * tau_sq * sse) / temp
 
@@ -101,7 +115,10 @@ class ShardedLadder:
 
     def gather_table(self):
         import torch
-        loc = torch.tensor([self.t.scalars(c) for c in range(self.E * self.L)], dtype=torch.float64)   # [E*L, 4]
+        if hasattr(self.t, "table"):
+            loc = torch.from_numpy(np.ascontiguousarray(self.t.table(), dtype=np.float64))                  # [E*L, 4], one read
+        else:
+            loc = torch.tensor([self.t.scalars(c) for c in range(self.E * self.L)], dtype=torch.float64)   # [E*L, 4]
         dev = self.t.collective_device()
         loc = loc.to(dev)
         out = [torch.empty_like(loc) for _ in range(self.world)]
@@ -113,11 +130,17 @@ class ShardedLadder:
 
     def exchange(self):
         """One exchange round. Returns the per-ensemble permutations (identical on every rank)."""
+        import contextlib
+        with (self.t.ordering() if hasattr(self.t, "ordering") else contextlib.nullcontext()):
+            return self._exchange()
+
+    def _exchange(self):
         import torch
         tab = self.gather_table()
         perms = []
+        uni = swap_uniforms(self.seed, list(range(self.E)), self.round, self.R - 1)
         for e in range(self.E):
-            u = [swap_uniform(self.seed, e, self.round, p) for p in range(self.R - 1)]
+            u = [float(x) for x in uni[e]]
             src, nsw = sweep(tab[e], self.n_elems, u)
             perms.append(src)
             self.num_swap += nsw
@@ -169,6 +192,13 @@ class DeviceTransport:
         self.dev = torch.device("cuda", device)
         self._buf = torch.empty(sampler.w_size, dtype=torch.float32, device=self.dev)
         self._sc = np.zeros(4, np.float64)
+        # the library's stream as torch's current stream during an exchange: packs, clones, NCCL sends and unpacks are
+        # then ordered on the device without host synchronisation
+        self._stream = torch.cuda.ExternalStream(sampler.lib.bae_stream(sampler._h), device=self.dev)
+
+    def ordering(self):
+        import torch
+        return torch.cuda.stream(self._stream)
 
     def collective_device(self):
         return self.dev
@@ -177,19 +207,21 @@ class DeviceTransport:
         st = self.s.get_state(chain, vectors=False)
         return (st["eta"], st["likelihood"], st["adapttemp"], st["last_sse_train"])
 
+    def table(self):
+        from . import _native as N
+        out = np.zeros((self.s.n_chains, 4), np.float64)
+        N.check(self.s.lib.bae_exchange_table(self.s._h, out.ctypes.data))
+        return out
+
     def pack(self, chain):
         from . import _native as N
-        N.check(self.s.lib.bae_exchange_pack(self.s._h, int(chain), self._buf.data_ptr(), self._sc.ctypes.data))
-        self.s.synchronize()
+        N.check(self.s.lib.bae_exchange_pack(self.s._h, int(chain), self._buf.data_ptr(), None))
         return self._buf
 
     def unpack(self, chain, tensor, eta, last_sse):
         from . import _native as N
-        import torch
-        torch.cuda.synchronize(self.dev)
         sc = np.array([eta, last_sse], np.float64)
         N.check(self.s.lib.bae_exchange_unpack(self.s._h, int(chain), tensor.data_ptr(), sc.ctypes.data))
-        self.s.synchronize()
 
     def finish(self):
         from . import _native as N

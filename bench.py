@@ -200,7 +200,10 @@ def run_reference(args):
     return 0
 
 
-def workload_name(shape, cpg):
+def workload_name(shape, cpg, world=1, sharded=False):
+    if sharded:
+        return (f"{shape} shape, {cpg * world} chains = {cpg // N_RUNGS} ensembles x {N_RUNGS * world}-rung geometric ladder (Tmax 2) "
+                f"sharded over {world} GPUs ({cpg} chains per GPU), {SWAP_INTERVAL} iterations + 1 exchange sweep per bench step")
     return (f"{shape} shape, {cpg} chains per GPU = {cpg // N_RUNGS} ensembles x {N_RUNGS}-rung geometric ladder (Tmax 2), "
             f"{SWAP_INTERVAL} iterations + 1 exchange sweep per bench step")
 
@@ -246,6 +249,8 @@ def run_gpu(args):
                           seed=0xBAE5EED, device=local, chain_id_base=rank * cpg, gemm_path=args.gemm_path)
         ladder = None
 
+    exch_s = []
+
     def pt_round():
         """One bench step: 5 iterations of every resident chain + one exchange sweep."""
         if ladder is None:
@@ -253,7 +258,9 @@ def run_gpu(args):
         else:
             s.step(SWAP_INTERVAL)
             s.synchronize()
+            t_x = time.perf_counter()
             ladder.exchange()             # NCCL: 32 B/chain all-gather + boundary-crossing weight vectors
+            exch_s.append(time.perf_counter() - t_x)
     rng = np.random.default_rng(100 + rank)
     for j in range(cpg):
         s.init_chain(j, default_theta_init(dims4, rng), rng.standard_normal(L.w_size))
@@ -268,6 +275,7 @@ def run_gpu(args):
     for _ in range(args.warmup):
         pt_round()
     barrier()
+    exch_s.clear()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -349,8 +357,8 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(shape, cpg), "shape": shape, "dims": list(dims4), "n_train": n_train,
-                       "n_test": n_test, "chains_per_gpu": cpg, "n_rungs": N_RUNGS, "swap_interval": SWAP_INTERVAL,
+            "config": {"workload": workload_name(shape, cpg, world, sharded), "shape": shape, "dims": list(dims4), "n_train": n_train,
+                       "n_test": n_test, "chains_per_gpu": cpg, "n_rungs": N_RUNGS * (world if sharded else 1), "swap_interval": SWAP_INTERVAL,
                        "parallelism": (f"{world} GPUs x {cpg} chains: {n_ens} ensembles, each ladder of {N_RUNGS * world} rungs cut into "
                                        f"{N_RUNGS}-rung blocks per GPU; per round one 32 B/chain all-gather + the weight vectors of "
                                        f"configurations that cross a GPU boundary over NCCL ({ladder.vectors_sent} vectors sent by rank 0)"
@@ -363,6 +371,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
+            "exchange_ms_per_round": (1000.0 * float(np.median(exch_s)) if exch_s else None),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": achieved_tf / peaks["bf16_sustained"], "traffic": ncu_traffic(shape, cpg, gemm_path),
                          "kernel": ("bae_program_kernel_tc" if gemm_path == 2 else "bae_program_kernel") + " (persistent step kernel, "

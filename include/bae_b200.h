@@ -134,6 +134,7 @@ int bae_swap_counts(bae_handle* h, int64_t* num_swap, int64_t* total_swap_propos
 
 /* Multi-GPU ladder sharding (one process per GPU): export / import the exchange view of a chain
  * ([vec(w), eta, likelihood, adapttemp, last_sse], MAIN:595-596) as DEVICE buffers usable with NCCL. */
+int bae_exchange_table(bae_handle* h, double* out_nchains_x4);   /* eta, likelihood, adapttemp, SSE of w for every chain (MAIN:594-597) */
 int bae_exchange_pack(bae_handle* h, int chain, float* dev_w /*w_size*/, double* host_scalars4);
 int bae_exchange_unpack(bae_handle* h, int chain, const float* dev_w, const double* host_scalars2 /*eta,last_sse*/);
 /* Marks `w` as a detached copy for every chain, as MAIN:602 does after each exchange round. */
