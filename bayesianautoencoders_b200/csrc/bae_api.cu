@@ -972,6 +972,21 @@ int bae_exchange_unpack(bae_handle* h, int chain, const float* dev_w, const doub
   return BAE_OK;
 }
 
+// All moves of an exchange round that stay on this GPU, in one gather + one scatter pass of the device's own swap
+// phases: position p receives the configuration of local chain src[p] (src[p] == p: keeps its own, or will be
+// overwritten by bae_exchange_unpack with a configuration from another rank). Like bae_exchange_finish, every
+// chain's `w` ends as a detached dict (MAIN:602).
+int bae_exchange_local(bae_handle* h, const int* src) {
+  if (!h || !src) return fail(BAE_ERR_INVALID, "null argument");
+  const DevState& s = h->hs;
+  for (int c = 0; c < s.C; ++c)
+    if (src[c] < 0 || src[c] >= s.C) return fail(BAE_ERR_INVALID, "source chain out of range");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(s.swap_src, src, sizeof(int) * s.C, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));   // `src` is caller-owned pageable memory
+  return run_phases_plain(h, P_SWAP + 1, P_SWAP + 3, 0, s.C);
+}
+
 int bae_exchange_finish(bae_handle* h) {
   if (!h) return fail(BAE_ERR_INVALID, "null handle");
   const DevState& s = h->hs;

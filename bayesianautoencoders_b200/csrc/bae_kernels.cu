@@ -775,6 +775,182 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
 }
 
 // ------------------------------------------------------------------------------------------------
+// Adam phases of the tcgen05 kernels: same arithmetic as run_adam, but the inputs (theta, the K-split copies of the
+// gradient, m, v) are streamed into the idle GEMM stage buffers by the bulk-copy engine (cp.async.bulk + mbarrier,
+// three 2048-float sub-chunks in flight per SM). Only 256 threads per SM run this phase and there is no L1; with the
+// loads off the threads' registers the phase is bound by HBM instead of by load latency.
+// ------------------------------------------------------------------------------------------------
+constexpr int kAdamSub = 2048;                       // floats per staged sub-chunk (256 threads x 2 float4)
+constexpr int kAdamArrays = 7;                       // theta, grad x 4 copies, m, v
+constexpr int kAdamStages = 3;
+constexpr int kAdamStageBytes = kAdamArrays * kAdamSub * 4;   // 56 KB
+static_assert(kAdamStages * kAdamStageBytes <= 2 * tc::kStages * tc::kStageBytes, "Adam staging fits the GEMM tile area");
+static_assert(kAdamChunk % kAdamSub == 0, "sub-chunks tile a work item");
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t bar_s) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_s), "l"(src), "r"(bytes), "r"(bar_s) : "memory");
+}
+
+__device__ void run_adam_tc(const DevState* S, int which, int c_begin, int c_end, double* red, const tc::Smem& tsm) {
+  const int nit = S->n_adam_items;
+  const int total = nit * (c_end - c_begin);
+  const int Pp = S->Pp;
+  const float step_w = S->step_w;
+  const size_t gstride = (size_t)S->C_alloc * Pp;   // distance between the K-split copies of the gradient
+  const int ncopy = min(S->max_ksplit, 4);
+  constexpr int kSubs = kAdamChunk / kAdamSub;
+  const uint32_t stage_s = tc::smem_u32(tsm.tiles);
+  uint64_t* bars = tsm.full() + 3 * tc::kStages + 8;       // three spare mbarriers behind the GEMM ones
+  const uint32_t bar_s = tc::smem_u32(bars);
+  if (TID == 0) {
+    for (int i = 0; i < kAdamStages; ++i) tc::mbar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  BLOCK_SYNC();
+  // flat sequence of (item, sub-chunk) units of this CTA; unit u lives in stage u % 3
+  const int my_items = (total > (int)blockIdx.x) ? (total - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int units = my_items * kSubs;
+  auto unit_item = [&](int u) { return (int)blockIdx.x + (u / kSubs) * (int)gridDim.x; };
+  auto issue = [&](int u) {   // one thread: the bulk copies of unit u
+    const int item = unit_item(u), sub = u % kSubs;
+    const int chain = c_begin + item / nit, it = item % nit;
+    const bool lang = S->ch.is_lang[chain] != 0;
+    const uint32_t st = stage_s + (u % kAdamStages) * kAdamStageBytes, bar = bar_s + (u % kAdamStages) * 8;
+    const size_t off = (size_t)chain * Pp + (size_t)it * kAdamChunk + (size_t)sub * kAdamSub;
+    const bool gmv = (which == 2) ? lang : lang;   // random-walk chains only need theta
+    const int narr = gmv ? (3 + ncopy) : 1;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(narr * kAdamSub * 4)) : "memory");
+    bulk_g2s(st, S->theta + off, kAdamSub * 4, bar);
+    if (gmv) {
+      bulk_g2s(st + 1 * kAdamSub * 4, S->m + off, kAdamSub * 4, bar);
+      bulk_g2s(st + 2 * kAdamSub * 4, S->v + off, kAdamSub * 4, bar);
+      for (int k = 0; k < ncopy; ++k) bulk_g2s(st + (3 + k) * kAdamSub * 4, S->grad + off + k * gstride, kAdamSub * 4, bar);
+    }
+  };
+  if (TID == 0)
+    for (int u = 0; u < min(units, kAdamStages); ++u) issue(u);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int u = 0; u < units; ++u) {
+    const int item = unit_item(u), sub = u % kSubs;
+    const int chain = c_begin + item / nit, it = item % nit;
+    const bool lang = S->ch.is_lang[chain] != 0;
+    const bool alias = S->ch.alias[chain] != 0;
+    const int stg = u % kAdamStages;
+    tc::mbar_wait(&bars[stg], (uint32_t)((u / kAdamStages) & 1));
+    const bool active = !(which == 2 && !lang);
+    if (active) {
+      const size_t base = (size_t)chain * Pp;
+      float* __restrict__ th = S->theta + base;
+      float* __restrict__ mm = S->m + base;
+      float* __restrict__ vv = S->v + base;
+      float* __restrict__ wc = S->wcur + base;
+      const int step = S->ch.step[chain];
+      const int cg_id = S->chain_id_base + chain;
+      const float ss = (which == 1) ? S->ch.ss1[chain] : S->ch.ss2[chain];
+      const float sq = (which == 1) ? S->ch.sq1[chain] : S->ch.sq2[chain];
+      const uint32_t sb = stage_s + stg * kAdamStageBytes;
+#pragma unroll
+      for (int e = 0; e < kAdamSub / (kThreads * 4); ++e) {
+        const int q = (e * kThreads + TID) * 4;                      // float index inside the sub-chunk
+        const int p = it * kAdamChunk + sub * kAdamSub + q;
+        const int sg = find_seg(S, p);
+        const SegLite sd = sh_seg[sg];
+        const int local = p - sd.pad_off;
+        if (!sd.trainable || local >= sd.span) continue;             // BatchNorm buffer, or the alignment gap between tensors
+        const int nval = (sd.cols == sd.ld) ? 4 : min(4, sd.cols - local % sd.ld);
+        if (nval <= 0) continue;
+        const float4 t4 = tc::lds128(sb + q * 4);
+        float t[4] = {t4.x, t4.y, t4.z, t4.w};
+        float g[4] = {0.f, 0.f, 0.f, 0.f}, m[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (lang) {
+          const float4 m4 = tc::lds128(sb + (1 * kAdamSub + q) * 4), v4 = tc::lds128(sb + (2 * kAdamSub + q) * 4);
+          m[0] = m4.x; m[1] = m4.y; m[2] = m4.z; m[3] = m4.w;
+          v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+          const int ks = sd.ksplit;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < ks) {
+              const float4 x = tc::lds128(sb + ((3 + k) * kAdamSub + q) * 4);
+              g[0] += x.x; g[1] += x.y; g[2] += x.z; g[3] += x.w;
+            }
+          for (int k = 4; k < ks; ++k) {   // more than four K splits (very long data sets): the rest straight from HBM
+            const float4 x = *reinterpret_cast<const float4*>(S->grad + base + p + k * gstride);
+            g[0] += x.x; g[1] += x.y; g[2] += x.z; g[3] += x.w;
+          }
+        }
+        if (which == 1) {
+          float o[4];
+          if (lang) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              m[j] = m[j] + (g[j] - m[j]) * (1.0f - kB1);
+              v[j] = v[j] * kB2 + (1.0f - kB2) * g[j] * g[j];
+              float denom = sqrtf(v[j]) / sq + kAdamEps;
+              o[j] = t[j] - ss * (m[j] / denom);
+            }
+            *reinterpret_cast<float4*>(&mm[p]) = make_float4(m[0], m[1], m[2], m[3]);
+            *reinterpret_cast<float4*>(&vv[p]) = make_float4(v[0], v[1], v[2], v[3]);
+            if (!alias) *reinterpret_cast<float4*>(&wc[p]) = t4;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = t[j];
+          }
+          float nz[4];
+          noise_quad(S, cg_id, step, sg, (unsigned)(local >> 2), nz);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j < nval) {
+              float nj = nz[j] * step_w;
+              o[j] = o[j] + nj;
+              a0 = fmaf(nj, nj, a0);
+              a1 = fmaf(o[j], o[j], a1);
+            } else {
+              o[j] = 0.f;
+            }
+          }
+          *reinterpret_cast<float4*>(&th[p]) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+          float w0[4] = {0.f, 0.f, 0.f, 0.f};
+          if (!alias) {
+            const float4 w4 = *reinterpret_cast<const float4*>(&wc[p]);
+            w0[0] = w4.x; w0[1] = w4.y; w0[2] = w4.z; w0[3] = w4.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            m[j] = m[j] + (g[j] - m[j]) * (1.0f - kB1);
+            v[j] = v[j] * kB2 + (1.0f - kB2) * g[j] * g[j];
+            float denom = sqrtf(v[j]) / sq + kAdamEps;
+            float wpg = t[j] - ss * (m[j] / denom);   // w_prop_gd
+            if (!alias && j < nval) {
+              float dl = w0[j] - wpg;
+              a2 = fmaf(dl, dl, a2);
+            }
+          }
+          *reinterpret_cast<float4*>(&mm[p]) = make_float4(m[0], m[1], m[2], m[3]);
+          *reinterpret_cast<float4*>(&vv[p]) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    }
+    // every thread is done reading the stage: refill it; at the end of an item, reduce its partial sums
+    BLOCK_SYNC();
+    if (TID == 0 && u + kAdamStages < units) issue(u + kAdamStages);
+    if (sub == kSubs - 1) {
+      double* part = S->adam_part + ((size_t)chain * nit + it) * 3;
+      if (which == 1) {
+        double s0 = block_sum_d((double)a0, red);
+        double s1 = block_sum_d((double)a1, red);
+        if (TID == 0) { part[0] = s0; part[1] = s1; }
+      } else {
+        double s2 = active ? block_sum_d((double)a2, red) : 0.0;
+        if (TID == 0) part[2] = s2;
+      }
+      a0 = a1 = a2 = 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Scalar prologue: branch select, tempered -> canonical switch, draws        MAIN:435-452, 500, 526
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double loglik_d(double sse, double n, double tau_sq, double temp) {
@@ -1183,6 +1359,8 @@ __device__ __forceinline__ void run_phase_tc_back(const DevState* S, int pi, int
   const PhaseDesc& ph = S->phase[pi];
   if (ph.kind == PH_GEMM)
     tc::gemm_phase_epilogue(S, ph, c_begin, c_end, tsm, ring);
+  else if (ph.kind == PH_ADAM1 || ph.kind == PH_ADAM2)
+    run_adam_tc(S, ph.kind == PH_ADAM1 ? 1 : 2, c_begin, c_end, red, tsm);
   else
     run_phase<false>(S, pi, c_begin, c_end, force_swap, smem_small, red);
   // generic-proxy stores of this phase (activations, theta, Y, dZ) are read by TMA (async proxy) in later phases

@@ -158,27 +158,37 @@ class ShardedLadder:
                     sends.append((e, s, p, po))
                 elif po == self.rank:
                     recvs.append((e, s, p, so))
+        batched = hasattr(self.t, "apply_local")
         staged = {}
-        for e, s, p in local_moves:
-            staged[(e, p)] = self.t.pack(self.local_index(e, s)).clone()
+        if not batched:
+            for e, s, p in local_moves:
+                staged[(e, p)] = self.t.pack(self.local_index(e, s)).clone()
         ops, bufs = [], {}
-        for e, s, p, dst in sends:
+        for e, s, p, dst in sends:       # packed BEFORE any local move can overwrite the source chain
             buf = self.t.pack(self.local_index(e, s)).clone()
             bufs[("s", e, p)] = buf
             ops.append(self.dist.P2POp(self.dist.isend, buf, dst))
             self.vectors_sent += 1
         for e, s, p, frm in recvs:
-            buf = torch.empty_like(self.t.pack(self.local_index(e, p)))
+            buf = torch.empty_like(self.t.pack(self.local_index(e, p))) if not batched else self.t.empty_vector()
             bufs[("r", e, p)] = buf
             ops.append(self.dist.P2POp(self.dist.irecv, buf, frm))
+        if batched:
+            # every same-GPU move (and the detach of all chains, MAIN:602) in one gather + one scatter pass on the device
+            src = np.arange(self.E * self.L, dtype=np.int32)
+            for e, s, p in local_moves:
+                src[self.local_index(e, p)] = self.local_index(e, s)
+            self.t.apply_local(src)
         if ops:
             for req in self.dist.batch_isend_irecv(ops):
                 req.wait()
-        for e, s, p in local_moves:
-            self.t.unpack(self.local_index(e, p), staged[(e, p)], tab[e, s, 0], tab[e, s, 3])
+        if not batched:
+            for e, s, p in local_moves:
+                self.t.unpack(self.local_index(e, p), staged[(e, p)], tab[e, s, 0], tab[e, s, 3])
         for e, s, p, frm in recvs:
             self.t.unpack(self.local_index(e, p), bufs[("r", e, p)], tab[e, s, 0], tab[e, s, 3])
-        self.t.finish()
+        if not batched:
+            self.t.finish()
         self.round += 1
         return perms
 
@@ -226,3 +236,12 @@ class DeviceTransport:
     def finish(self):
         from . import _native as N
         N.check(self.s.lib.bae_exchange_finish(self.s._h))
+
+    def empty_vector(self):
+        import torch
+        return torch.empty(self.s.w_size, dtype=torch.float32, device=self.dev)
+
+    def apply_local(self, src):
+        from . import _native as N
+        src = np.ascontiguousarray(src, dtype=np.int32)
+        N.check(self.s.lib.bae_exchange_local(self.s._h, src.ctypes.data))

@@ -138,6 +138,7 @@ int bae_exchange_table(bae_handle* h, double* out_nchains_x4);   /* eta, likelih
 int bae_exchange_pack(bae_handle* h, int chain, float* dev_w /*w_size*/, double* host_scalars4);
 int bae_exchange_unpack(bae_handle* h, int chain, const float* dev_w, const double* host_scalars2 /*eta,last_sse*/);
 /* Marks `w` as a detached copy for every chain, as MAIN:602 does after each exchange round. */
+int bae_exchange_local(bae_handle* h, const int* src_chain /*[n_chains]*/);   /* every same-GPU move of a round + detach (MAIN:602), one gather/scatter pass */
 int bae_exchange_finish(bae_handle* h);
 
 /* Debug probe: raw copy of a per-chain device array ("H1","H2","Z","Y","H4","H5","DOUT","D5","D4","DY","D2","D1",

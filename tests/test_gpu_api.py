@@ -132,3 +132,55 @@ def test_full_size_configs_run_and_are_deterministic(shape, ntr, nte, chains):
         s.close()
     for j in range(chains):
         assert runs[0][j].tobytes() == runs[1][j].tobytes()
+
+
+def test_exchange_local_matches_pack_unpack():
+    """`bae_exchange_local` (all same-GPU moves of a ladder-sharded exchange round in one gather/scatter pass) must leave the
+    chains in the same state as the per-vector `bae_exchange_pack` / `_unpack` / `_finish` path (MAIN:594-603)."""
+    import ctypes as C
+    from bayesianautoencoders_b200 import DeviceSampler, default_theta_init
+    from bayesianautoencoders_b200 import _native as N
+    import torch
+    dims4 = (12, 10, 8, 6)
+    train, test = synth_data(dims4, 200, 80)
+    n = 6
+    src = np.array([2, 0, 1, 3, 5, 4], np.int32)     # position p receives the configuration of chain src[p]
+
+    def make():
+        s = DeviceSampler(dims4, train, test, n, 1, 20, np.linspace(1.0, 2.0, n), swap_interval=5, seed=77)
+        rng = np.random.default_rng(5)
+        for j in range(n):
+            s.init_chain(j, default_theta_init(dims4, rng), rng.standard_normal(s.w_size))
+        s.step(5)
+        s.synchronize()
+        return s
+
+    a, b = make(), make()
+    # reference path: stage every moved vector, then unpack, then detach
+    tab = np.zeros((n, 4)); N.check(b.lib.bae_exchange_table(b._h, tab.ctypes.data))
+    bufs = {}
+    for p in range(n):
+        if src[p] != p:
+            t = torch.empty(b.w_size, dtype=torch.float32, device="cuda")
+            N.check(b.lib.bae_exchange_pack(b._h, int(src[p]), t.data_ptr(), None))
+            b.synchronize()
+            bufs[p] = t
+    for p, t in bufs.items():
+        sc = np.array([tab[src[p], 0], tab[src[p], 3]], np.float64)
+        N.check(b.lib.bae_exchange_unpack(b._h, p, t.data_ptr(), sc.ctypes.data))
+    N.check(b.lib.bae_exchange_finish(b._h))
+    b.synchronize()
+    # batched path
+    N.check(a.lib.bae_exchange_local(a._h, src.ctypes.data))
+    a.synchronize()
+    for p in range(n):
+        sa, sb = a.get_state(p), b.get_state(p)
+        for k in ("theta", "w", "m", "v"):
+            np.testing.assert_array_equal(sa[k], sb[k], err_msg=f"{k} of chain {p}")
+        for k in ("eta", "likelihood", "adapttemp", "last_sse_train"):
+            assert sa[k] == sb[k], (k, p)
+    # and the chains keep running identically afterwards
+    a.step(3); b.step(3); a.synchronize(); b.synchronize()
+    for p in range(n):
+        np.testing.assert_array_equal(a.get_state(p)["theta"], b.get_state(p)["theta"])
+    a.close(); b.close()
