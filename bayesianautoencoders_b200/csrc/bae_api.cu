@@ -972,6 +972,39 @@ int bae_exchange_unpack(bae_handle* h, int chain, const float* dev_w, const doub
   return BAE_OK;
 }
 
+// Host-side restatement of run_swap_decide for ONE ensemble (MAIN:962-1011, 1059-1065, with the message-slot quirk of
+// MAIN:999-1005): the sweep every rank of a ladder-sharded run executes on the all-gathered table. No GPU involved.
+// table: [n_rungs][4] = (eta, stored likelihood, adapttemp, SSE of `w`) by ladder position; uniforms: [n_rungs - 1].
+// src_out[p] = position whose configuration ends at position p.
+int bae_host_sweep(const double* table, int n_rungs, double n_elems, const float* uniforms, int* src_out, int* n_swapped) {
+  if (!table || !uniforms || !src_out || n_rungs < 1) return fail(BAE_ERR_INVALID, "bad argument");
+  auto loglik = [&](double sse, double tau_sq, double temp) {
+    return (-(n_elems * 0.5) * std::log(2.0 * 3.14159265358979323846 * tau_sq) - 0.5 * tau_sq * sse) / temp;
+  };
+  int cfg_prev = 0, swapped = 0;
+  double lh_prev = table[1], T_prev = table[2];
+  for (int p = 0; p + 1 < n_rungs; ++p) {
+    const int cfg1 = cfg_prev, cfg2 = p + 1;
+    const double lhood1 = lh_prev, T1 = T_prev;
+    const double lhood2 = table[cfg2 * 4 + 1], T2 = table[cfg2 * 4 + 2];
+    const double lhood12 = loglik(table[cfg1 * 4 + 3], std::exp(table[cfg1 * 4 + 0]), T2);
+    const double lhood21 = loglik(table[cfg2 * 4 + 3], std::exp(table[cfg2 * 4 + 0]), T1);
+    const double ex = (lhood12 - lhood1) + (lhood21 - lhood2);
+    const double prob = ex >= 0.0 ? 1.0 : std::exp(ex);
+    if ((double)uniforms[p] < prob) {
+      ++swapped;
+      src_out[p] = cfg2;
+      cfg_prev = cfg1; lh_prev = lhood12; T_prev = T1;
+    } else {
+      src_out[p] = cfg1;
+      cfg_prev = cfg2; lh_prev = lhood2; T_prev = T2;
+    }
+  }
+  src_out[n_rungs - 1] = cfg_prev;
+  if (n_swapped) *n_swapped = swapped;
+  return BAE_OK;
+}
+
 // All moves of an exchange round that stay on this GPU, in one gather + one scatter pass of the device's own swap
 // phases: position p receives the configuration of local chain src[p] (src[p] == p: keeps its own, or will be
 // overwritten by bae_exchange_unpack with a configuration from another rank). Like bae_exchange_finish, every

@@ -85,6 +85,22 @@ def sweep(table, n_elems, uniforms):
     return src, swapped
 
 
+def sweep_native(table, n_elems, uniforms):
+    """`sweep` through the library's host function `bae_host_sweep` (same arithmetic in C; None if the library is missing)."""
+    try:
+        import ctypes as C
+        from . import _native as N
+        lib = N.load()
+    except Exception:
+        return None
+    tab = np.ascontiguousarray(table, dtype=np.float64)
+    u = np.ascontiguousarray(uniforms, dtype=np.float32)
+    src = np.zeros(tab.shape[0], np.int32)
+    nsw = C.c_int(0)
+    N.check(lib.bae_host_sweep(tab.ctypes.data, int(tab.shape[0]), float(n_elems), u.ctypes.data, src.ctypes.data, C.byref(nsw)))
+    return [int(x) for x in src], int(nsw.value)
+
+
 class ShardedLadder:
     """Exchange rounds for a ladder sharded over `world_size` ranks. `transport` supplies the chain state:
 
@@ -102,6 +118,7 @@ class ShardedLadder:
         self.dist, self.rank, self.world = dist, rank, world_size
         self.E, self.R, self.L = n_ensembles, n_rungs, n_rungs // world_size
         self.n_elems, self.seed, self.t = n_elems, seed, transport
+        self.native_sweep = hasattr(transport, "apply_local")   # device transports use the library's host sweep
         self.round = 0
         self.num_swap = 0
         self.total_swap_proposals = 0
@@ -140,8 +157,10 @@ class ShardedLadder:
         perms = []
         uni = swap_uniforms(self.seed, list(range(self.E)), self.round, self.R - 1)
         for e in range(self.E):
-            u = [float(x) for x in uni[e]]
-            src, nsw = sweep(tab[e], self.n_elems, u)
+            res = sweep_native(tab[e], self.n_elems, uni[e]) if self.native_sweep else None
+            if res is None:
+                res = sweep(tab[e], self.n_elems, [float(x) for x in uni[e]])
+            src, nsw = res
             perms.append(src)
             self.num_swap += nsw
             self.total_swap_proposals += self.R - 1

@@ -243,6 +243,9 @@ def run_gpu(args):
         s = DeviceSampler(dims4, train, test, cpg, 1, SAMPLES, temps, swap_interval=SWAP_INTERVAL,
                           seed=0xBAE5EED, device=local, chain_id_base=rank * cpg, gemm_path=args.gemm_path)
         ladder = ShardedLadder(dist, rank, world, n_ens, N_RUNGS * world, train.size, 0xBAE5EED, DeviceTransport(s, local))
+        # NCCL opens peer connections lazily; a configuration can travel to any rank, so open all pairs before timing
+        a2a = torch.zeros(world * 4, device="cuda")
+        dist.all_to_all_single(torch.empty_like(a2a), a2a)
     else:
         temps = np.tile(bo.temperature_ladder(N_RUNGS, 2), n_ens)
         s = DeviceSampler(dims4, train, test, cpg, N_RUNGS, SAMPLES, temps, swap_interval=SWAP_INTERVAL,

@@ -139,6 +139,7 @@ int bae_exchange_pack(bae_handle* h, int chain, float* dev_w /*w_size*/, double*
 int bae_exchange_unpack(bae_handle* h, int chain, const float* dev_w, const double* host_scalars2 /*eta,last_sse*/);
 /* Marks `w` as a detached copy for every chain, as MAIN:602 does after each exchange round. */
 int bae_exchange_local(bae_handle* h, const int* src_chain /*[n_chains]*/);   /* every same-GPU move of a round + detach (MAIN:602), one gather/scatter pass */
+int bae_host_sweep(const double* table_nrungs_x4, int n_rungs, double n_elems, const float* uniforms, int* src_out, int* n_swapped);   /* HOST function: the sequential swap sweep of one ensemble (MAIN:962-1011, 1059-1065) */
 int bae_exchange_finish(bae_handle* h);
 
 /* Debug probe: raw copy of a per-chain device array ("H1","H2","Z","Y","H4","H5","DOUT","D5","D4","DY","D2","D1",

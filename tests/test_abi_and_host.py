@@ -148,3 +148,23 @@ def test_gelman_rubin_matches_direct_formulas():
     assert np.all(np.abs(r["simple"] - 1) < 0.05) and np.all(np.abs(r["advanced"] - 1) < 0.08)
     shifted = data + np.arange(5)[:, None, None] * 3.0        # chains that disagree -> R-hat >> 1
     assert np.all(gelman_rubin(shifted)["simple"] > 3)
+
+
+def test_host_sweep_matches_python_restatement():
+    """`bae_host_sweep` (C, used by the ladder-sharded exchange on GPU boxes) == `distributed.sweep` (Python, used by the
+    gloo test) on random tables: same permutation and swap count (MAIN:962-1011, 1059-1065)."""
+    from bayesianautoencoders_b200.distributed import sweep, sweep_native, swap_uniforms
+    rng = np.random.default_rng(11)
+    for R in (2, 8, 64):
+        for trial in range(5):
+            tab = np.zeros((R, 4))
+            tab[:, 0] = rng.normal(-2.0, 0.3, R)                       # eta
+            tab[:, 2] = 2.0 ** (np.arange(R) / max(1, R - 1))          # adapttemp
+            tab[:, 3] = rng.uniform(8.0e4, 8.5e4, R)                   # SSE of w
+            n = 1.0e6
+            tab[:, 1] = [(-(n * 0.5) * np.log(2 * np.pi * np.exp(e)) - 0.5 * np.exp(e) * s) / t for e, t, s in tab[:, [0, 2, 3]]]
+            u = swap_uniforms(123 + trial, [trial], 0, R - 1)[0]
+            res = sweep_native(tab, n, u)
+            assert res is not None
+            ref = sweep(tab, n, [float(x) for x in u])
+            assert res[0] == list(ref[0]) and res[1] == ref[1]
