@@ -12,6 +12,7 @@
 
 namespace bae {
 int max_coop_blocks_per_sm(int use_tc);
+int max_coop_grid_tc();
 cudaError_t launch_program(const DevState* dS, int use_tc, int grid, int ph_begin, int ph_end, int n_rep, int c_begin,
                            int c_end, int force_swap, cudaStream_t st);
 cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, cudaStream_t st);
@@ -132,7 +133,7 @@ static int tc_max_bn() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("BAE_TC_MAXBN");
-    v = e ? std::max(32, std::min(240, atoi(e) / 16 * 16)) : 240;
+    v = e ? std::max(32, std::min(256, atoi(e) / 16 * 16)) : 256;
   }
   return v;
 }
@@ -144,13 +145,15 @@ static GemmDesc make_gemm(const DevState& s, int M, int N, int K, int b_nmajor =
   g.biasCol = -1;
   g.ksplit = 1;
   if (s.tc) {
-    // tcgen05 tiles: 128 x BN, BN <= 240 (a multiple of 16) chosen so the N tiles are balanced. An N-major B
-    // operand is loaded in 32-column chunks, so its tile in shared memory may be wider than the MMA's N.
-    const int maxbn = b_nmajor ? std::min(tc_max_bn(), 224) : tc_max_bn();   // 7 chunks x 2 KB fit the 15 KB B slot
-    g.tm = (M + 127) / 128;
+    // tcgen05 CTA-pair tiles: 256 x BN, BN <= 256 (a multiple of 16) chosen so the N tiles are balanced. Each CTA of a
+    // pair holds BN/2 columns of B; an N-major B operand is loaded in 32-column chunks, so the half tile in shared
+    // memory may be wider than BN/2.
+    const int maxbn = tc_max_bn();
+    g.tm = (M + 255) / 256;
     g.tn = (N + maxbn - 1) / maxbn;
     g.tcBN = round_up((N + g.tn - 1) / g.tn, 16);
-    g.tcBBytes = b_nmajor ? round_up(g.tcBN, 32) / 32 * 2048 : g.tcBN * 64;   // chunks of [16 k][32 n] : rows of 64 B
+    const int half = g.tcBN / 2;
+    g.tcBBytes = b_nmajor ? round_up(half, 32) / 32 * 2048 : half * 64;   // chunks of [16 k][32 n] : rows of 64 B
     g.tcMain = 1;
     return g;
   }
@@ -244,16 +247,17 @@ static void build_program(bae_handle* h) {
         rc = g.aMode == 0 ? tmap_kmajor(&tm, ptrs[i], g.K, g.M, g.lda, nchA, g.sA, 128)
                           : tmap_mnmajor(&tm, ptrs[i], g.M, g.K, g.lda, nchA, g.sA, 4);
       } else {
-        rc = g.bMode == 0 ? tmap_kmajor(&tm, ptrs[i], g.K, g.N, g.ldb, nchB, g.sB, g.tcBN)
-                          : tmap_mnmajor(&tm, ptrs[i], g.N, g.K, g.ldb, nchB, g.sB, g.tcBN / 32);
+        rc = g.bMode == 0 ? tmap_kmajor(&tm, ptrs[i], g.K, g.N, g.ldb, nchB, g.sB, g.tcBN / 2)
+                          : tmap_mnmajor(&tm, ptrs[i], g.N, g.K, g.ldb, nchB, g.sB, 0);
       }
       if (rc != 0 && h->tmap_error.empty())
         h->tmap_error = "cuTensorMapEncodeTiled failed (CUresult " + std::to_string(rc) + ") for GEMM operand " + std::to_string(i);
       g.tmIdx[i] = (int)h->tmaps_host.size();
       h->tmaps_host.push_back(tm);
     }
+    // instruction descriptor of the pair's MMA (cta_group::2): M = 256, N = tcBN
     g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)g.aMode << 15) | ((unsigned)g.bMode << 16) |
-              ((unsigned)(g.tcBN >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+              ((unsigned)(g.tcBN >> 3) << 17) | ((unsigned)(256 >> 4) << 24);
   };
   int ng = 0;
   // ---- forward descriptors for (train, first pass), (train, second pass), (test)
@@ -460,10 +464,11 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   CU(dalloc(h, &s.DOUT, CA * nm * s.ld0)); CU(dalloc(h, &s.D5, CA * nm * s.ld1)); CU(dalloc(h, &s.D4, CA * nm * s.ld2));
   CU(dalloc(h, &s.DY, CA * nm * s.ld3)); CU(dalloc(h, &s.D2, CA * nm * s.ld2)); CU(dalloc(h, &s.D1, CA * nm * s.ld1));
   {
+    const int per_tile = s.tc ? 2 : 1;   // tcgen05 path: each CTA of a pair writes the partial of its 128 rows
     GemmDesc t = make_gemm(s, s.n_max, s.d0, s.d1);
-    s.loss_stride = t.tm * t.tn;
+    s.loss_stride = per_tile * t.tm * t.tn;
     GemmDesc t2 = make_gemm(s, std::min(s.n_train, s.n_test), s.d0, s.d1);
-    s.loss_stride = std::max(s.loss_stride, t2.tm * t2.tn);
+    s.loss_stride = std::max(s.loss_stride, per_tile * t2.tm * t2.tn);
   }
   if (s.tc) {
     // ones column (index d) of every activation that is the B operand of a weight-gradient GEMM
@@ -510,6 +515,10 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   const int bps = max_coop_blocks_per_sm(s.tc);
   if (bps < 1) return fail(BAE_ERR_CUDA, "step kernel cannot be made resident (occupancy 0)");
   h->grid = prop.multiProcessorCount * bps;
+  if (s.tc) {   // CTA pairs (cluster dimension 2): as many pairs as can be co-resident
+    h->grid = max_coop_grid_tc();
+    if (h->grid < 2) return fail(BAE_ERR_CUDA, "the tcgen05 step kernel (CTA pairs) cannot be made resident");
+  }
   CU(cudaStreamSynchronize(h->stream));
   *out = h;
   return BAE_OK;

@@ -787,7 +787,7 @@ constexpr int kAdamSub = 2048;                       // floats per staged sub-ch
 constexpr int kAdamArrays = 7;                       // theta, grad x 4 copies, m, v
 constexpr int kAdamStages = 3;
 constexpr int kAdamStageBytes = kAdamArrays * kAdamSub * 4;   // 56 KB
-static_assert(kAdamStages * kAdamStageBytes <= 2 * tc::kStages * tc::kStageBytes, "Adam staging fits the GEMM tile area");
+static_assert(kAdamStages * kAdamStageBytes <= tc::Smem::kTail, "Adam staging fits the GEMM tile ring + epilogue staging area");
 static_assert(kAdamChunk % kAdamSub == 0, "sub-chunks tile a work item");
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t bar_s) {
@@ -1517,6 +1517,19 @@ __global__ void bae_unpack_kernel(const DevState* __restrict__ S, const float* p
 // ---- launch wrappers used by bae_api.cu ----------------------------------------------------------
 namespace bae {
 
+// The tcgen05 kernels run as CTA pairs: cluster dimension 2, cooperative for the persistent kernel.
+static cudaError_t launch_tc(const void* fn, int grid, void** args, bool cooperative, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc::kThreadsTc); cfg.dynamicSmemBytes = tc::kSmemBytes; cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = cooperative ? 2 : 1;
+  return cudaLaunchKernelExC(&cfg, fn, args);
+}
+
 int max_coop_blocks_per_sm(int use_tc) {
   int nb = 0;
   if (use_tc) {
@@ -1529,20 +1542,35 @@ int max_coop_blocks_per_sm(int use_tc) {
   return nb;
 }
 
+// CTAs of the persistent tcgen05 kernel: 2 x the number of co-resident CTA pairs.
+int max_coop_grid_tc() {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2); cfg.blockDim = dim3(tc::kThreadsTc); cfg.dynamicSmemBytes = tc::kSmemBytes;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeCooperative;
+  at[1].val.cooperative = 1;
+  cfg.attrs = at; cfg.numAttrs = 2;
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, bae_program_kernel_tc, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return 2 * nclusters;
+}
+
 cudaError_t launch_program(const DevState* dS, int use_tc, int grid, int ph_begin, int ph_end, int n_rep, int c_begin,
                            int c_end, int force_swap, cudaStream_t st) {
   void* args[] = {(void*)&dS, (void*)&ph_begin, (void*)&ph_end, (void*)&n_rep, (void*)&c_begin, (void*)&c_end,
                   (void*)&force_swap};
-  if (use_tc)
-    return cudaLaunchCooperativeKernel((void*)bae_program_kernel_tc, dim3(grid), dim3(tc::kThreadsTc), args, tc::kSmemBytes, st);
+  if (use_tc) return launch_tc((const void*)bae_program_kernel_tc, grid, args, true, st);
   return cudaLaunchCooperativeKernel((void*)bae_program_kernel, dim3(grid), dim3(kThreads), args, 0, st);
 }
 
 cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, cudaStream_t st) {
-  if (use_tc)
-    bae_phase_kernel_tc<<<grid, tc::kThreadsTc, tc::kSmemBytes, st>>>(dS, pi, c_begin, c_end);
-  else
-    bae_phase_kernel<<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end);
+  if (use_tc) {
+    void* args[] = {(void*)&dS, (void*)&pi, (void*)&c_begin, (void*)&c_end};
+    return launch_tc((const void*)bae_phase_kernel_tc, grid, args, false, st);
+  }
+  bae_phase_kernel<<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end);
   return cudaGetLastError();
 }
 

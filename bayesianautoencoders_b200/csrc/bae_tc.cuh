@@ -7,15 +7,25 @@
 // compute lo = x - trunc_tf32(x) (exact in FP32) into a second shared-memory tile. Three kind::tf32 MMAs per
 // 8-wide K step then recover ~FP32 products with FP32 accumulation in TMEM.
 //
+// CTA PAIRS (tcgen05 cta_group::2, the kernel is launched with a cluster dimension of 2): a pair computes a 256 x BN tile.
+// CTA r of the pair loads and converts rows [128 r, 128 r + 128) of A and columns [BN/2 r, BN/2 r + BN/2) of B into ITS OWN
+// shared memory; the leader (rank 0) issues tcgen05.mma.cta_group::2 (M = 256), which reads both CTAs' shared memory and
+// writes each CTA's 128 accumulator rows into that CTA's TMEM; every CTA drains and post-processes its own rows. Per CTA
+// and K block this loads and converts 16 KB instead of 23.5 KB for the same tensor-pipe time: the hi/lo conversion
+// (shared-memory latency bound, tests/cuda/tc_microbench.cu) is what paces the tile loop.
+//
 // 512-thread CTA, one per SM, four warpgroups with their own register budgets (setmaxnreg):
 //   warp 0      TMA producer: raw tiles (16 floats of K per stage) into a 5-stage ring
-//   warp 1      MMA issuer (one elected lane, tcgen05.mma.cta_group::1.kind::tf32)
-//   warps 2-3, 12-15   hi/lo converters, two groups of three warps that take alternate K blocks, so the
-//                      wait -> LDS -> STS -> proxy fence -> arrive latency of one block overlaps the next
+//   warp 1      MMA issuer (leader CTA only; warp-uniform loop, one elected lane issues)
+//   warps 2-3, 12-15   hi/lo converters, three groups of two warps that take K blocks round-robin, so the
+//                      wait -> LDS -> STS -> proxy fence -> arrive latency of one block overlaps the next ones
 //   warps 4-11  epilogue: drain both accumulators into registers (tcgen05.ld), hand TMEM back to the MMA
 //               issuer at once, then run the fused epilogue (bias / sigmoid / loss / sigmoid' / gradient
 //               routing) from registers while the next tile's MMAs run. Values are transposed through
 //               shared memory so every global load and store is a coalesced 128-byte row segment.
+// Barriers live in every CTA at the same offsets. `full` (TMA landed) is local; `conv` (lo tiles written) and `tmem_empty`
+// (accumulators drained) are used in the leader's copy and collect arrivals from both CTAs (remote arrives through mapa);
+// `empty` (stage free) and `tmem_full` (accumulators complete) are signalled in both CTAs by multicast tcgen05.commit.
 // The tensor core adds into its FP32 accumulator with truncation, a bias that grows with the number of
 // accumulating MMAs: the two small cross terms therefore go to their own accumulator, and long contractions
 // (weight gradients, K = rows) are split over work items whose partial gradients are summed in FP32 by the
@@ -29,14 +39,14 @@ namespace bae {
 namespace tc {
 
 constexpr int kThreadsTc = 512;
-constexpr int kStages = 4;                     // pipeline stages; a stage = raw tile pair (TMA) + lo tile pair (converters)
+constexpr int kStages = 5;                     // pipeline stages; a stage = raw tile pair (TMA) + lo tile pair (converters)
 constexpr int kBM = 128;
 constexpr int kBK = 16;                        // floats of K per stage (64-byte rows: SWIZZLE_64B for K-major tiles)
-constexpr int kMaxBN = 240;
+constexpr int kMaxBN = 256;                    // pair tile width; each CTA holds BN/2 columns of B; 2 accumulators x 256 TMEM columns
 constexpr int kATileBytes = kBM * kBK * 4;     // 8 KB
-constexpr int kBTileBytes = kMaxBN * kBK * 4;  // 15 KB
+constexpr int kBTileBytes = (kMaxBN / 2) * kBK * 4;  // 8 KB: this CTA's half of the B tile
 constexpr int kMnChunkBytes = kBK * 128;       // MN-major chunk: [16 K-rows][32 floats]
-constexpr int kStageBytes = kATileBytes + kBTileBytes;          // one raw stage (A, B) or one lo stage = 23 KB
+constexpr int kStageBytes = kATileBytes + kBTileBytes;          // one raw stage (A, B half) or one lo stage = 16 KB
 constexpr int kEpiPitch = 36;                  // floats; 144-byte rows keep float4 accesses conflict-free
 constexpr int kEpiWarps = 8;
 constexpr int kConvGroups = 3;                 // converter groups; K block k is converted by group k % 3
@@ -44,7 +54,7 @@ constexpr int kConvGroupWarps = 2;             // 64 threads: every tile pair is
 constexpr int kConvGroupThreads = kConvGroupWarps * 32;
 constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch * 4;
 constexpr int kSmemBytes = 2 * kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kEpiBytes;
-// tile-pair layout: [A 8 KB][B 15 KB]; kStages raw pairs followed by kStages lo pairs
+// tile-pair layout: [A 8 KB][B half 8 KB]; kStages raw pairs followed by kStages lo pairs
 constexpr int kTmemCols = 512;                 // two accumulators of BN <= 256 columns each, single-buffered
 constexpr int kRegsLean = 48;                  // producer / MMA / converter warpgroups
 constexpr int kRegsEpi = 208;                  // epilogue warpgroups (also run the non-GEMM phases)
@@ -60,18 +70,19 @@ struct Ring {
 // base plus a compile-time offset (the persistent kernel keeps this struct live across all phases, and nothing there
 // may spill: with the carve-out at its maximum there is no L1 behind local memory).
 struct Smem {
-  uint8_t* tiles;        // 1024-byte aligned, 2 * kStages * kStageBytes, followed by barriers and epilogue staging
-  static constexpr int kTail = 2 * kStages * kStageBytes;
+  uint8_t* tiles;        // 1024-byte aligned: tile ring, then the epilogue staging tiles, then barriers and scratch
+  static constexpr int kEpiOff = 2 * kStages * kStageBytes;   // the Adam phases stage through [0, kEpiOff + kEpiBytes)
+  static constexpr int kTail = kEpiOff + kEpiBytes;
+  __device__ __forceinline__ float* epi_stage() const { return reinterpret_cast<float*>(tiles + kEpiOff); }           // [8][32][kEpiPitch]
   __device__ __forceinline__ uint64_t* full() const { return reinterpret_cast<uint64_t*>(tiles + kTail); }            // [kStages] TMA bytes landed
-  __device__ __forceinline__ uint64_t* conv() const { return full() + kStages; }        // [kStages] lo pair written
+  __device__ __forceinline__ uint64_t* conv() const { return full() + kStages; }        // [kStages] lo pair written (leader: both CTAs)
   __device__ __forceinline__ uint64_t* empty() const { return conv() + kStages; }       // [kStages] MMAs of the stage completed
   __device__ __forceinline__ uint64_t* tmem_full() const { return empty() + kStages; }  // [2]
-  __device__ __forceinline__ uint64_t* tmem_empty() const { return tmem_full() + 2; }   // [2]
+  __device__ __forceinline__ uint64_t* tmem_empty() const { return tmem_full() + 2; }   // [2] (leader: both CTAs)
   __device__ __forceinline__ uint32_t* tmem_base() const { return reinterpret_cast<uint32_t*>(tmem_empty() + 2); }   // TMEM base address
   __device__ __forceinline__ double* red() const { return reinterpret_cast<double*>(tiles + kTail + 256); }           // [16] reduction scratch
-  __device__ __forceinline__ float* epi_stage() const { return reinterpret_cast<float*>(tiles + kTail + 512); }       // [8][32][kEpiPitch]
 };
-static_assert((3 * kStages + 4) * 8 + 4 <= 256, "barrier area");
+static_assert((3 * kStages + 4) * 8 + 4 <= 160, "barrier area (three spare mbarriers for the Adam staging follow at +160)");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -107,6 +118,35 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---- CTA-pair (cluster of 2) helpers
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the LEADER's copy of a shared-memory object (same offset in every CTA of the pair)
+__device__ __forceinline__ uint32_t leader_addr(const void* p) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(0u));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_leader(const void* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+}
+// wait that acquires at cluster scope: the other CTA's shared-memory / tensor-memory accesses are ordered before it
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAITC_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra WAITC_DONE;\n\t"
+      "bra WAITC_LOOP;\n\t"
+      "WAITC_DONE:\n\t}"
+      ::"r"(a), "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -122,11 +162,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, ui
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -136,12 +176,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// arrives on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -230,19 +272,22 @@ __device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem) {
   uintptr_t base = (reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023;
   sm.tiles = reinterpret_cast<uint8_t*>(base);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full()[i], 1); mbar_init(&sm.conv()[i], kConvGroupWarps); mbar_init(&sm.empty()[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full()[i], 1); mbar_init(&sm.tmem_empty()[i], kEpiWarps); }
+    // `conv` and `tmem_empty` collect arrivals from both CTAs of the pair (only the leader's copies are waited on)
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full()[i], 1); mbar_init(&sm.conv()[i], 2 * kConvGroupWarps); mbar_init(&sm.empty()[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full()[i], 1); mbar_init(&sm.tmem_empty()[i], 2 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x / 32 == 2) tmem_alloc(sm.tmem_base(), kTmemCols);
   fence_before_sync();
   __syncthreads();
+  cluster_sync_all();   // the peer's barriers are initialised before anything can arrive on them
   fence_after_sync();
 }
 
 __device__ __forceinline__ void teardown(Smem& sm) {
   fence_before_sync();
   __syncthreads();
+  cluster_sync_all();   // both CTAs are done with the pair's tensor memory and with each other's shared memory
   if (threadIdx.x / 32 == 2) tmem_dealloc(*sm.tmem_base(), kTmemCols);
 }
 
@@ -297,6 +342,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
   const int total = phase_items(S, ph, c_begin, c_end);
   const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(S->tmaps);
   long long* dbg = (blockIdx.x == 0) ? S->dbg : nullptr;
+  const uint32_t rank = cluster_rank();
   // NOTE: every descriptor field used inside a K loop is copied into a local first. The loops are full of
   // asm volatile statements with memory clobbers, after which the compiler would re-load fields of *it.g from
   // global memory (an L2 round trip each) on every K block.
@@ -305,11 +351,12 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     // ================= TMA producer (warp-uniform loop, one elected lane issues) =================
     {
       int ntr = 0;
-      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs
         Item it;
         if (!decode_item(S, ph, c_begin, item, it)) continue;
         const GemmDesc& g = *it.g;
-        const int m0 = it.tile_m * kBM, n0 = it.tile_n * g.tcBN;
+        // this CTA's share of the pair's 256 x BN tile: 128 rows of A, BN/2 columns of B
+        const int m0 = it.tile_m * (2 * kBM) + (int)rank * kBM, n0 = it.tile_n * g.tcBN + (int)rank * (g.tcBN >> 1);
         const int ca = g.sA ? it.chain : 0, cb = g.sB ? it.chain : 0;
         const int dbgf = S->dbg_flags;
         const uint32_t bytes = ((dbgf & 64) ? 0u : (uint32_t)kATileBytes) + ((dbgf & 32) ? 0u : (uint32_t)g.tcBBytes);
@@ -347,16 +394,16 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (warp-uniform loop, one elected lane issues) =================
-    {
+    // ================= MMA issuer (leader CTA of the pair; warp-uniform loop, one elected lane issues) =================
+    if (rank == 0) {
       int ntr = 0;
       const int dbgf = S->dbg_flags;
       const uint32_t tmem = *sm.tmem_base();
-      for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs
         Item it;
         if (!decode_item(S, ph, c_begin, item, it)) continue;
         const GemmDesc& g = *it.g;
-        mbar_wait(&sm.tmem_empty()[0], ring.acc_phase ^ 1);   // the epilogue warps have drained the previous tile
+        mbar_wait_cluster(&sm.tmem_empty()[0], ring.acc_phase ^ 1);   // the epilogue warps of BOTH CTAs have drained the previous tile
         fence_after_sync();
         const uint32_t d_main = tmem, d_cross = tmem + (uint32_t)g.tcBN;
         const bool amn = g.aMode != 0, bmn = g.bMode != 0;
@@ -367,7 +414,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const uint64_t dA = make_desc(smem_u32(sm.tiles), amn), dB = make_desc(smem_u32(sm.tiles) + kATileBytes, bmn);
         for (int kb = 0; kb < nkb; ++kb) {
           // `conv` is signalled by converter warps that had themselves waited for the TMA bytes (`full`)
-          mbar_wait(&sm.conv()[ring.stage], ring.phase);
+          mbar_wait_cluster(&sm.conv()[ring.stage], ring.phase);   // both CTAs' raw and lo tiles of the stage are ready
           fence_after_sync();
           if (elect_one()) {
             trace(dbg, 1, ntr, kb);
@@ -407,22 +454,23 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     const uint32_t tiles_s = smem_u32(sm.tiles) + gt * 16;
     const bool skip = (S->dbg_flags & 1) != 0;
     uint32_t kbc = ring.kbc;
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs
       Item it;
       if (!decode_item(S, ph, c_begin, item, it)) continue;
-      const int nper = (kATileBytes + it.g->tcBBytes) / (16 * kConvGroupThreads);   // float4 per thread: 8 + BN/16
       const int nkb = it.nkb;
       for (int kb = 0; kb < nkb; ++kb) {
         if ((int)kbc == grp) {
           // Parity waits cannot tell phases two apart: a group that runs ahead of the producer would see the `full`
-          // phase of K block k - 4 as the one of k + 4. Waiting for the stage's previous MMAs first pins the phase.
+          // phase of K block k - 5 as the one of k + 5. Waiting for the stage's previous MMAs first pins the phase.
           mbar_wait(&sm.empty()[ring.stage], ring.phase ^ 1);
           mbar_wait(&sm.full()[ring.stage], ring.phase);
           const uint32_t src = tiles_s + ring.stage * kStageBytes;
           const uint32_t dst = src + kStages * kStageBytes;
-          int i = 0;
           if (!skip) {
-            for (; i + 8 <= nper; i += 8) {
+            // the whole 16 KB tile pair, 16 float4 per thread in two batches of 8 (bytes past a narrow B half are
+            // converted too: nobody reads them)
+#pragma unroll
+            for (int i = 0; i < kStageBytes / (16 * kConvGroupThreads); i += 8) {
               float4 v[8];
 #pragma unroll
               for (int u = 0; u < 8; ++u) v[u] = lds128(src + (i + u) * (16 * kConvGroupThreads));
@@ -435,16 +483,10 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
 #pragma unroll
               for (int u = 0; u < 8; ++u) sts128(dst + (i + u) * (16 * kConvGroupThreads), v[u]);
             }
-            for (; i < nper; ++i) {
-              float4 v = lds128(src + i * (16 * kConvGroupThreads));
-              float h;
-              split_tf32(v.x, h, v.x); split_tf32(v.y, h, v.y); split_tf32(v.z, h, v.z); split_tf32(v.w, h, v.w);
-              sts128(dst + i * (16 * kConvGroupThreads), v);
-            }
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> tensor-core (async proxy) reads
+          asm volatile("fence.proxy.async;" ::: "memory");   // generic smem writes -> tensor-core (async proxy) reads, issued by the leader CTA
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.conv()[ring.stage]);
+          if (lane == 0) mbar_arrive_leader(&sm.conv()[ring.stage]);
         }
         if (++kbc == (uint32_t)kConvGroups) kbc = 0;
         if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
@@ -470,8 +512,9 @@ __device__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int 
   const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;  // coalesced view: 4 rows x 128 B per instruction
   long long* dbg = (blockIdx.x == 0) ? S->dbg : nullptr;
   const int dbgf = S->dbg_flags;
+  const uint32_t rank = cluster_rank();
   int ntr = 0;
-  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+  for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs
     Item it;
     if (!decode_item(S, ph, c_begin, item, it)) continue;
     const GemmDesc& g = *it.g;
@@ -510,13 +553,13 @@ __device__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int 
     }
     fence_before_sync();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.tmem_empty()[0]);
+    if (lane == 0) mbar_arrive_leader(&sm.tmem_empty()[0]);   // the leader's MMA issuer waits for both CTAs' epilogue warps
     ring.acc_phase ^= 1;
     if (et == 0) trace(dbg, 3, ntr, 1);
 
     // locals: see the note in gemm_phase_front
     const int chain = it.chain;
-    const int m0 = it.tile_m * kBM;
+    const int m0 = it.tile_m * (2 * kBM) + (int)rank * kBM;   // this CTA's 128 rows of the pair's tile
     const size_t split_off = (size_t)it.split * S->C_alloc * S->Pp;   // gradient copy of this K split (EPI_GRADW only)
     float* C = g.C ? g.C + (size_t)chain * g.sC + split_off : nullptr;
     const float* bias = g.bias ? g.bias + (size_t)chain * g.sBias : nullptr;
@@ -608,7 +651,7 @@ __device__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int 
       if (lane == 0) { sm.red()[ew * 2] = s0; sm.red()[ew * 2 + 1] = s1; }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (et == 0) {
-        double* p = g.part + ((size_t)chain * g.partStride + (size_t)it.tile_m * g.tn + it.tile_n) * 2;
+        double* p = g.part + ((size_t)chain * g.partStride + (size_t)(it.tile_m * 2 + (int)rank) * g.tn + it.tile_n) * 2;
         double a0 = 0.0, a1 = 0.0;
         for (int w = 0; w < kEpiWarps; ++w) { a0 += sm.red()[w * 2]; a1 += sm.red()[w * 2 + 1]; }
         p[0] = a0;
