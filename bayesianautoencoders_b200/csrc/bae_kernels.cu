@@ -804,7 +804,7 @@ __device__ void run_adam_tc(const DevState* S, int which, int c_begin, int c_end
   const int ncopy = min(S->max_ksplit, 4);
   constexpr int kSubs = kAdamChunk / kAdamSub;
   const uint32_t stage_s = tc::smem_u32(tsm.tiles);
-  uint64_t* bars = tsm.full() + 3 * tc::kStages + 8;       // three spare mbarriers behind the GEMM ones
+  uint64_t* bars = tsm.spare_bars();                       // three spare mbarriers behind the GEMM ones
   const uint32_t bar_s = tc::smem_u32(bars);
   if (TID == 0) {
     for (int i = 0; i < kAdamStages; ++i) tc::mbar_init(&bars[i], 1);

@@ -39,7 +39,8 @@ namespace bae {
 namespace tc {
 
 constexpr int kThreadsTc = 512;
-constexpr int kStages = 5;                     // pipeline stages; a stage = raw tile pair (TMA) + lo tile pair (converters)
+constexpr int kStages = 7;                     // raw tile pairs (TMA ring): deep, the loads come from HBM (~2000 cycles under load)
+constexpr int kLoStages = 4;                   // lo tile pairs (converter ring): three groups converting + one being read
 constexpr int kBM = 128;
 constexpr int kBK = 16;                        // floats of K per stage (64-byte rows: SWIZZLE_64B for K-major tiles)
 constexpr int kMaxBN = 256;                    // pair tile width; each CTA holds BN/2 columns of B; 2 accumulators x 256 TMEM columns
@@ -53,36 +54,44 @@ constexpr int kConvGroups = 3;                 // converter groups; K block k is
 constexpr int kConvGroupWarps = 2;             // 64 threads: every tile pair is a multiple of 64 float4 (no predicates)
 constexpr int kConvGroupThreads = kConvGroupWarps * 32;
 constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch * 4;
-constexpr int kSmemBytes = 2 * kStages * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kEpiBytes;
-// tile-pair layout: [A 8 KB][B half 8 KB]; kStages raw pairs followed by kStages lo pairs
+constexpr int kSmemBytes = (kStages + kLoStages) * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kEpiBytes;
+static_assert(kSmemBytes + 4640 <= 232448, "dynamic + static shared memory of the tcgen05 kernels");
+// tile-pair layout: [A 8 KB][B half 8 KB]; kStages raw pairs followed by kLoStages lo pairs
 constexpr int kTmemCols = 512;                 // two accumulators of BN <= 256 columns each, single-buffered
 constexpr int kRegsLean = 48;                  // producer / MMA / converter warpgroups
 constexpr int kRegsEpi = 208;                  // epilogue warpgroups (also run the non-GEMM phases)
 static_assert(kRegsLean * 256 + kRegsEpi * 256 <= 65536, "register file");
 
 struct Ring {
-  uint32_t stage = 0, phase = 0;     // pipeline stage and its parity (producer / converters / MMA each keep a copy)
+  uint32_t stage = 0, phase = 0;     // raw-tile ring (producer / converters / MMA)
+  uint32_t lo = 0, lo_phase = 0;     // lo-tile ring (converters / MMA)
   uint32_t acc_phase = 0;            // TMEM accumulator hand-off parity (MMA / epilogue), one tile in flight
   uint32_t kbc = 0;                  // running K-block count of this CTA modulo kConvGroups
+  __device__ __forceinline__ void advance() {
+    if (++stage == kStages) { stage = 0; phase ^= 1; }
+    if (++lo == kLoStages) { lo = 0; lo_phase ^= 1; }
+  }
 };
 
 // Carve-up of the dynamic shared memory. Only the base pointer is kept in a register; every other address is the
 // base plus a compile-time offset (the persistent kernel keeps this struct live across all phases, and nothing there
 // may spill: with the carve-out at its maximum there is no L1 behind local memory).
 struct Smem {
-  uint8_t* tiles;        // 1024-byte aligned: tile ring, then the epilogue staging tiles, then barriers and scratch
-  static constexpr int kEpiOff = 2 * kStages * kStageBytes;   // the Adam phases stage through [0, kEpiOff + kEpiBytes)
+  uint8_t* tiles;        // 1024-byte aligned: tile rings, then the epilogue staging tiles, then barriers and scratch
+  static constexpr int kEpiOff = (kStages + kLoStages) * kStageBytes;   // the Adam phases stage through [0, kEpiOff + kEpiBytes)
   static constexpr int kTail = kEpiOff + kEpiBytes;
   __device__ __forceinline__ float* epi_stage() const { return reinterpret_cast<float*>(tiles + kEpiOff); }           // [8][32][kEpiPitch]
   __device__ __forceinline__ uint64_t* full() const { return reinterpret_cast<uint64_t*>(tiles + kTail); }            // [kStages] TMA bytes landed
-  __device__ __forceinline__ uint64_t* conv() const { return full() + kStages; }        // [kStages] lo pair written (leader: both CTAs)
-  __device__ __forceinline__ uint64_t* empty() const { return conv() + kStages; }       // [kStages] MMAs of the stage completed
-  __device__ __forceinline__ uint64_t* tmem_full() const { return empty() + kStages; }  // [2]
+  __device__ __forceinline__ uint64_t* empty() const { return full() + kStages; }       // [kStages] MMAs that read the raw stage completed
+  __device__ __forceinline__ uint64_t* conv() const { return empty() + kStages; }       // [kLoStages] lo pair written (leader: both CTAs)
+  __device__ __forceinline__ uint64_t* lo_empty() const { return conv() + kLoStages; }  // [kLoStages] MMAs that read the lo stage completed
+  __device__ __forceinline__ uint64_t* tmem_full() const { return lo_empty() + kLoStages; }  // [2]
   __device__ __forceinline__ uint64_t* tmem_empty() const { return tmem_full() + 2; }   // [2] (leader: both CTAs)
-  __device__ __forceinline__ uint32_t* tmem_base() const { return reinterpret_cast<uint32_t*>(tmem_empty() + 2); }   // TMEM base address
+  __device__ __forceinline__ uint64_t* spare_bars() const { return tmem_empty() + 2; }  // [3] Adam staging
+  __device__ __forceinline__ uint32_t* tmem_base() const { return reinterpret_cast<uint32_t*>(spare_bars() + 3); }   // TMEM base address
   __device__ __forceinline__ double* red() const { return reinterpret_cast<double*>(tiles + kTail + 256); }           // [16] reduction scratch
 };
-static_assert((3 * kStages + 4) * 8 + 4 <= 160, "barrier area (three spare mbarriers for the Adam staging follow at +160)");
+static_assert((2 * kStages + 2 * kLoStages + 4 + 3) * 8 + 4 <= 256, "barrier area");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -132,6 +141,12 @@ __device__ __forceinline__ uint32_t leader_addr(const void* p) {
 }
 __device__ __forceinline__ void mbar_arrive_leader(const void* bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
+}
+// Signal only: a release at cluster scope costs ~1500 cycles per arrival in this kernel. The converters use this one: what
+// they publish (the lo tile) stays in their own shared memory and is read by their own SM's tensor core, and the proxy
+// fence before the arrival has already ordered the writes.
+__device__ __forceinline__ void mbar_arrive_leader_relaxed(const void* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(leader_addr(bar)) : "memory");
 }
 // wait that acquires at cluster scope: the other CTA's shared-memory / tensor-memory accesses are ordered before it
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
@@ -273,7 +288,8 @@ __device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem) {
   sm.tiles = reinterpret_cast<uint8_t*>(base);
   if (threadIdx.x == 0) {
     // `conv` and `tmem_empty` collect arrivals from both CTAs of the pair (only the leader's copies are waited on)
-    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full()[i], 1); mbar_init(&sm.conv()[i], 2 * kConvGroupWarps); mbar_init(&sm.empty()[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full()[i], 1); mbar_init(&sm.empty()[i], 1); }
+    for (int i = 0; i < kLoStages; ++i) { mbar_init(&sm.conv()[i], 2 * kConvGroupWarps); mbar_init(&sm.lo_empty()[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full()[i], 1); mbar_init(&sm.tmem_empty()[i], 2 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -389,7 +405,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             }
           }
           __syncwarp();
-          if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
+          ring.advance();
         }
       }
     }
@@ -414,11 +430,11 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const uint64_t dA = make_desc(smem_u32(sm.tiles), amn), dB = make_desc(smem_u32(sm.tiles) + kATileBytes, bmn);
         for (int kb = 0; kb < nkb; ++kb) {
           // `conv` is signalled by converter warps that had themselves waited for the TMA bytes (`full`)
-          mbar_wait_cluster(&sm.conv()[ring.stage], ring.phase);   // both CTAs' raw and lo tiles of the stage are ready
+          mbar_wait(&sm.conv()[ring.lo], ring.lo_phase);   // both CTAs' raw and lo tiles of the K block are ready
           fence_after_sync();
           if (elect_one()) {
             trace(dbg, 1, ntr, kb);
-            const uint32_t so = ring.stage * (uint32_t)(kStageBytes >> 4), lo = so + kStages * (uint32_t)(kStageBytes >> 4);
+            const uint32_t so = ring.stage * (uint32_t)(kStageBytes >> 4), lo = (kStages + ring.lo) * (uint32_t)(kStageBytes >> 4);
             const uint64_t ah = dA + so, al = dA + lo, bh = dB + so, bl = dB + lo;
             const bool two = (krem0 - kb * kBK) > 8;   // second 8-wide K step present (not beyond K)
             const uint32_t acc0 = kb ? 1u : 0u;
@@ -432,14 +448,15 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
                 umma_tf32(d_cross, ah + astep, bl + bstep, idesc, 1u);
               }
             }
-            umma_commit(&sm.empty()[ring.stage]);   // frees the stage (raw and lo pairs) when these MMAs have read it
+            umma_commit(&sm.empty()[ring.stage]);    // frees the raw stage (in both CTAs) when these MMAs have read it
+            umma_commit(&sm.lo_empty()[ring.lo]);    // ... and the lo stage
             if (kb == nkb - 1) {
               trace(dbg, 1, ntr, 1000);
               umma_commit(&sm.tmem_full()[0]);      // accumulators complete -> epilogue
             }
           }
           __syncwarp();
-          if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
+          ring.advance();
         }
         ring.acc_phase ^= 1;
       }
@@ -453,6 +470,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     const int gt = ((warp & 1) << 5) + lane;   // 0..63 inside the group
     const uint32_t tiles_s = smem_u32(sm.tiles) + gt * 16;
     const bool skip = (S->dbg_flags & 1) != 0;
+    int ntr = (grp == 0) ? 0 : (grp == 1 ? 170 : 340);
     uint32_t kbc = ring.kbc;
     for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs
       Item it;
@@ -460,12 +478,16 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
       const int nkb = it.nkb;
       for (int kb = 0; kb < nkb; ++kb) {
         if ((int)kbc == grp) {
-          // Parity waits cannot tell phases two apart: a group that runs ahead of the producer would see the `full`
-          // phase of K block k - 5 as the one of k + 5. Waiting for the stage's previous MMAs first pins the phase.
-          mbar_wait(&sm.empty()[ring.stage], ring.phase ^ 1);
+          // The lo slot first (the MMAs of K block k - 4 are done): it also pins the phase of `full`. Parity waits cannot
+          // tell phases two apart, and a raw stage is served by all groups in turn; the MMAs of block k - 4 complete after
+          // those of k - 7, which consumed this raw stage's previous contents.
+          if (gt == 0) trace(dbg, 2, ntr, 7000 + kb);
+          mbar_wait(&sm.lo_empty()[ring.lo], ring.lo_phase ^ 1);
+          if (gt == 0) trace(dbg, 2, ntr, 8000 + kb);
           mbar_wait(&sm.full()[ring.stage], ring.phase);
+          if (gt == 0) trace(dbg, 2, ntr, kb);
           const uint32_t src = tiles_s + ring.stage * kStageBytes;
-          const uint32_t dst = src + kStages * kStageBytes;
+          const uint32_t dst = tiles_s + (kStages + ring.lo) * kStageBytes;
           if (!skip) {
             // the whole 16 KB tile pair, 16 float4 per thread in two batches of 8 (bytes past a narrow B half are
             // converted too: nobody reads them)
@@ -484,12 +506,17 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
               for (int u = 0; u < 8; ++u) sts128(dst + (i + u) * (16 * kConvGroupThreads), v[u]);
             }
           }
-          asm volatile("fence.proxy.async;" ::: "memory");   // generic smem writes -> tensor-core (async proxy) reads, issued by the leader CTA
+          if (gt == 0) trace(dbg, 2, ntr, 2000 + kb);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> tensor-core (async proxy) reads of THIS CTA's shared memory
           __syncwarp();
-          if (lane == 0) mbar_arrive_leader(&sm.conv()[ring.stage]);
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&sm.conv()[ring.lo]);
+            else mbar_arrive_leader_relaxed(&sm.conv()[ring.lo]);
+          }
+          if (gt == 0) trace(dbg, 2, ntr, 3000 + kb);
         }
         if (++kbc == (uint32_t)kConvGroups) kbc = 0;
-        if (++ring.stage == kStages) { ring.stage = 0; ring.phase ^= 1; }
+        ring.advance();
       }
     }
     ring.kbc = kbc;

@@ -15,6 +15,10 @@ N.check(s.lib.bae_debug_trace(s._h, buf.ctypes.data, 1))
 s.step(1); s.synchronize()
 N.check(s.lib.bae_debug_trace(s._h, buf.ctypes.data, 0))
 t0 = None
+ev = buf[2 * 1024:3 * 1024].reshape(-1, 2)
+for g in range(3):
+    e = ev[g * 170:(g + 1) * 170]; e = e[e[:, 1] != 0]
+    print("conv group", g, [(int(a), int(b - buf[1])) for a, b in e[:40]])
 for role, name in enumerate(["producer", "mma"]):
     ev = buf[role * 1024:(role + 1) * 1024].reshape(-1, 2)
     ev = ev[ev[:, 1] != 0]
