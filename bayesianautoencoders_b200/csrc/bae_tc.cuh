@@ -278,6 +278,14 @@ __device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// Global 16-byte load that stays where it is written (volatile asm): the epilogue issues its aux loads in two groups of
+// four; left to the compiler they were all hoisted above the staging stores and then spilled (no L1 behind local memory).
+__device__ __forceinline__ float4 ldg128_pinned(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   lo = x - hi;
@@ -609,14 +617,18 @@ __device__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int 
       if (c0 >= ncols || (dbgf & 16)) break;
       const int cc = n0 + c0 + sub_c;            // first of this thread's 4 output columns
       const bool cv = cc < n_end;
-      float4 t[8];
-      if (aux) {   // sigmoid outputs (EPI_DSIG) or data (EPI_LOSS), 4 rows x 128 B per instruction
-        const float* ap = aux + (size_t)(r0 + sub_r) * ldaux + cc;
+      // aux tile (sigmoid outputs for EPI_DSIG, data for EPI_LOSS), 4 rows x 128 B per instruction, in two groups of four
+      // pinned loads: eight float4 on top of the 128 accumulator registers do not fit the 208-register budget
+      float4 t[4];
+      const float* ap = aux ? aux + (size_t)(r0 + sub_r) * ldaux + cc : nullptr;
+      auto load_aux = [&](int half) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          t[i] = (cv && r0 + i * 4 + sub_r < gM) ? __ldg(reinterpret_cast<const float4*>(ap + (size_t)(i * 4) * ldaux))
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+        for (int i = 0; i < 4; ++i) {
+          const int ii = half * 4 + i;
+          t[i] = (cv && r0 + ii * 4 + sub_r < gM) ? ldg128_pinned(ap + (size_t)(ii * 4) * ldaux) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      if (aux) load_aux(0);
       float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
       if (bias && cv) b4 = __ldg(reinterpret_cast<const float4*>(&bias[cc]));
 #pragma unroll
@@ -631,6 +643,7 @@ __device__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int 
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
+        if (i == 4 && aux) load_aux(1);
         const int rr = r0 + i * 4 + sub_r;
         float4 o = lds128(stg_s + ((i * 4 + sub_r) * kEpiPitch + sub_c) * 4);
         if (rr >= gM || !cv) continue;
@@ -639,10 +652,10 @@ __device__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int 
           o.x = __fdividef(1.0f, 1.0f + __expf(-o.x)); o.y = __fdividef(1.0f, 1.0f + __expf(-o.y));
           o.z = __fdividef(1.0f, 1.0f + __expf(-o.z)); o.w = __fdividef(1.0f, 1.0f + __expf(-o.w));
         } else if (epi == EPI_DSIG) {
-          o.x *= t[i].x * (1.0f - t[i].x); o.y *= t[i].y * (1.0f - t[i].y);
-          o.z *= t[i].z * (1.0f - t[i].z); o.w *= t[i].w * (1.0f - t[i].w);
+          o.x *= t[i & 3].x * (1.0f - t[i & 3].x); o.y *= t[i & 3].y * (1.0f - t[i & 3].y);
+          o.z *= t[i & 3].z * (1.0f - t[i & 3].z); o.w *= t[i & 3].w * (1.0f - t[i & 3].w);
         } else if (epi == EPI_LOSS) {
-          float d[4] = {o.x - t[i].x, o.y - t[i].y, o.z - t[i].z, o.w - t[i].w};
+          float d[4] = {o.x - t[i & 3].x, o.y - t[i & 3].y, o.z - t[i & 3].z, o.w - t[i & 3].w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             if (cc + e < n_end) { l_sse = fmaf(d[e], d[e], l_sse); l_sd += d[e]; }
