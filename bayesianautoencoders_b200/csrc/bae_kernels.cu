@@ -802,6 +802,14 @@ __device__ void run_adam_tc(const DevState* S, int which, int c_begin, int c_end
   const float step_w = S->step_w;
   const size_t gstride = (size_t)S->C_alloc * Pp;   // distance between the K-split copies of the gradient
   const int ncopy = min(S->max_ksplit, 4);
+  // every pointer and per-chain array base in a local: this phase has no L1, each S-> access is an L2 round trip
+  float* const g_theta = S->theta; float* const g_m = S->m; float* const g_v = S->v; float* const g_wcur = S->wcur;
+  const float* const g_grad = S->grad;
+  const int* const a_lang = S->ch.is_lang; const int* const a_alias = S->ch.alias; const int* const a_step = S->ch.step;
+  const float* const a_ss = (which == 1) ? S->ch.ss1 : S->ch.ss2;
+  const float* const a_sq = (which == 1) ? S->ch.sq1 : S->ch.sq2;
+  const int chain_id_base = S->chain_id_base;
+  double* const g_part = S->adam_part;
   constexpr int kSubs = kAdamChunk / kAdamSub;
   const uint32_t stage_s = tc::smem_u32(tsm.tiles);
   uint64_t* bars = tsm.spare_bars();                       // three spare mbarriers behind the GEMM ones
@@ -818,40 +826,41 @@ __device__ void run_adam_tc(const DevState* S, int which, int c_begin, int c_end
   auto issue = [&](int u) {   // one thread: the bulk copies of unit u
     const int item = unit_item(u), sub = u % kSubs;
     const int chain = c_begin + item / nit, it = item % nit;
-    const bool lang = S->ch.is_lang[chain] != 0;
+    const bool lang = a_lang[chain] != 0;
     const uint32_t st = stage_s + (u % kAdamStages) * kAdamStageBytes, bar = bar_s + (u % kAdamStages) * 8;
     const size_t off = (size_t)chain * Pp + (size_t)it * kAdamChunk + (size_t)sub * kAdamSub;
     const bool gmv = (which == 2) ? lang : lang;   // random-walk chains only need theta
     const int narr = gmv ? (3 + ncopy) : 1;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(narr * kAdamSub * 4)) : "memory");
-    bulk_g2s(st, S->theta + off, kAdamSub * 4, bar);
+    bulk_g2s(st, g_theta + off, kAdamSub * 4, bar);
     if (gmv) {
-      bulk_g2s(st + 1 * kAdamSub * 4, S->m + off, kAdamSub * 4, bar);
-      bulk_g2s(st + 2 * kAdamSub * 4, S->v + off, kAdamSub * 4, bar);
-      for (int k = 0; k < ncopy; ++k) bulk_g2s(st + (3 + k) * kAdamSub * 4, S->grad + off + k * gstride, kAdamSub * 4, bar);
+      bulk_g2s(st + 1 * kAdamSub * 4, g_m + off, kAdamSub * 4, bar);
+      bulk_g2s(st + 2 * kAdamSub * 4, g_v + off, kAdamSub * 4, bar);
+      for (int k = 0; k < ncopy; ++k) bulk_g2s(st + (3 + k) * kAdamSub * 4, g_grad + off + k * gstride, kAdamSub * 4, bar);
     }
   };
   if (TID == 0)
     for (int u = 0; u < min(units, kAdamStages); ++u) issue(u);
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  bool lang = false, alias = false;
+  int step = 0;
+  float ss = 0.f, sq = 1.f;
   for (int u = 0; u < units; ++u) {
     const int item = unit_item(u), sub = u % kSubs;
     const int chain = c_begin + item / nit, it = item % nit;
-    const bool lang = S->ch.is_lang[chain] != 0;
-    const bool alias = S->ch.alias[chain] != 0;
+    if (sub == 0) {   // per-item scalars: one round of loads per 4 staged sub-chunks
+      lang = a_lang[chain] != 0; alias = a_alias[chain] != 0; step = a_step[chain]; ss = a_ss[chain]; sq = a_sq[chain];
+    }
     const int stg = u % kAdamStages;
     tc::mbar_wait(&bars[stg], (uint32_t)((u / kAdamStages) & 1));
     const bool active = !(which == 2 && !lang);
     if (active) {
       const size_t base = (size_t)chain * Pp;
-      float* __restrict__ th = S->theta + base;
-      float* __restrict__ mm = S->m + base;
-      float* __restrict__ vv = S->v + base;
-      float* __restrict__ wc = S->wcur + base;
-      const int step = S->ch.step[chain];
-      const int cg_id = S->chain_id_base + chain;
-      const float ss = (which == 1) ? S->ch.ss1[chain] : S->ch.ss2[chain];
-      const float sq = (which == 1) ? S->ch.sq1[chain] : S->ch.sq2[chain];
+      float* __restrict__ th = g_theta + base;
+      float* __restrict__ mm = g_m + base;
+      float* __restrict__ vv = g_v + base;
+      float* __restrict__ wc = g_wcur + base;
+      const int cg_id = chain_id_base + chain;
       const uint32_t sb = stage_s + stg * kAdamStageBytes;
 #pragma unroll
       for (int e = 0; e < kAdamSub / (kThreads * 4); ++e) {
@@ -878,7 +887,7 @@ __device__ void run_adam_tc(const DevState* S, int which, int c_begin, int c_end
               g[0] += x.x; g[1] += x.y; g[2] += x.z; g[3] += x.w;
             }
           for (int k = 4; k < ks; ++k) {   // more than four K splits (very long data sets): the rest straight from HBM
-            const float4 x = *reinterpret_cast<const float4*>(S->grad + base + p + k * gstride);
+            const float4 x = *reinterpret_cast<const float4*>(g_grad + base + p + k * gstride);
             g[0] += x.x; g[1] += x.y; g[2] += x.z; g[3] += x.w;
           }
         }
@@ -939,7 +948,7 @@ __device__ void run_adam_tc(const DevState* S, int which, int c_begin, int c_end
     BLOCK_SYNC();
     if (TID == 0 && u + kAdamStages < units) issue(u + kAdamStages);
     if (sub == kSubs - 1) {
-      double* part = S->adam_part + ((size_t)chain * nit + it) * 3;
+      double* part = g_part + ((size_t)chain * nit + it) * 3;
       if (which == 1) {
         double s0 = block_sum_d((double)a0, red);
         double s1 = block_sum_d((double)a1, red);
