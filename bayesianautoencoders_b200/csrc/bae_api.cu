@@ -8,6 +8,9 @@
 #include <cuda.h>
 #include <cuda_profiler_api.h>
 
+#include <array>
+#include <map>
+
 #include "bae_common.cuh"
 
 namespace bae {
@@ -15,7 +18,11 @@ int max_coop_blocks_per_sm(int use_tc);
 int max_coop_grid_tc();
 cudaError_t launch_program(const DevState* dS, int use_tc, int grid, int ph_begin, int ph_end, int n_rep, int c_begin,
                            int c_end, int force_swap, cudaStream_t st);
-cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, cudaStream_t st);
+cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, int force_swap,
+                         cudaStream_t st);
+int aux_blocks_per_sm(int kind);
+cudaError_t launch_aux(const DevState* dS, int kind, int grid, int pi, int c_begin, int c_end, int force_swap,
+                       cudaStream_t st);
 cudaError_t launch_split(const float* src, float* hi, float* lo, size_t n, cudaStream_t st);
 cudaError_t launch_grad_reduce(const DevState* dS, int chain, cudaStream_t st);
 cudaError_t launch_debug_draws(const DevState* dS, int chain, int step, float* noise, double* scalars, cudaStream_t st);
@@ -72,7 +79,11 @@ struct bae_handle {
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
-  bool phase_launch = false;
+  bool phase_launch_env = false;
+  bool phase_launch = false;   // one launch per phase (default on the tcgen05 path) instead of the persistent kernel
+  bool use_graph = true;       // phase launches of a call are replayed from a CUDA graph
+  int grid_aux[16] = {};       // CTAs of bae_aux_kernel per phase kind (non-GEMM phases of the tcgen05 path)
+  std::map<std::array<int, 4>, cudaGraphExec_t> graphs;   // (p_begin, p_end, n_rep, force_swap) -> instantiated graph
 };
 
 template <typename T>
@@ -416,6 +427,8 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   h->cfg = *cfg;
   h->device = device;
   h->phase_launch = getenv("BAE_PHASE_LAUNCH") != nullptr && getenv("BAE_PHASE_LAUNCH")[0] == '1';
+  h->phase_launch_env = getenv("BAE_PHASE_LAUNCH") != nullptr;
+  h->use_graph = !(getenv("BAE_NO_GRAPH") != nullptr && getenv("BAE_NO_GRAPH")[0] == '1');
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
@@ -518,6 +531,14 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   if (s.tc) {   // CTA pairs (cluster dimension 2): as many pairs as can be co-resident
     h->grid = max_coop_grid_tc();
     if (h->grid < 2) return fail(BAE_ERR_CUDA, "the tcgen05 step kernel (CTA pairs) cannot be made resident");
+    for (int k = 0; k <= PH_SWAP_SCATTER; ++k) {
+      const int abs = aux_blocks_per_sm(k);
+      if (abs < 1) return fail(BAE_ERR_CUDA, "bae_aux_kernel cannot be made resident");
+      h->grid_aux[k] = prop.multiProcessorCount * abs;
+    }
+    // Measured (Madelon, 64 chains): BatchNorm / Adam phases run 1.5-1.8x faster as their own many-CTA launches than on the two
+    // epilogue warpgroups of the persistent kernel, and a launch costs no more than a grid barrier.
+    if (!h->phase_launch_env) h->phase_launch = true;
   }
   CU(cudaStreamSynchronize(h->stream));
   *out = h;
@@ -531,6 +552,7 @@ int bae_destroy(bae_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
   cudaStreamDestroy(h->stream);
   delete h;
   return BAE_OK;
@@ -610,9 +632,17 @@ static int get1(bae_handle* h, const T* dev_arr, int idx, T* v) {
   return BAE_OK;
 }
 
+// One phase as its own launch: GEMM phases (and everything on the FP32 path) through the phase kernel of the path, the
+// non-GEMM phases of the tcgen05 path through bae_aux_kernel.
+static cudaError_t launch_one(bae_handle* h, int p, int c_begin, int c_end, int force_swap) {
+  if (h->hs.tc && h->hs.phase[p].kind != PH_GEMM)
+    return launch_aux(h->dS, h->hs.phase[p].kind, h->grid_aux[h->hs.phase[p].kind], p, c_begin, c_end, force_swap, h->stream);
+  return launch_phase(h->dS, h->hs.tc, h->grid, p, c_begin, c_end, force_swap, h->stream);
+}
+
 static int run_phases_plain(bae_handle* h, int p_begin, int p_end, int c_begin, int c_end) {
   for (int p = p_begin; p < p_end; ++p) {
-    CU(launch_phase(h->dS, h->hs.tc, h->grid, p, c_begin, c_end, h->stream));
+    CU(launch_one(h, p, c_begin, c_end, 1));
     h->launches++;
   }
   return BAE_OK;
@@ -777,20 +807,37 @@ static int coop_launch(bae_handle* h, int p_begin, int p_end, int n_rep, int for
   CU(cudaSetDevice(h->device));
   CU(cudaEventRecord(h->ev0, h->stream));
   if (h->phase_launch) {
-    // profiling aid (BAE_PHASE_LAUNCH=1): one plain launch per phase, so ncu lists each phase separately.
-    // Exchange phases need the step counter test that the cooperative kernel does on the device.
-    for (int r = 0; r < n_rep; ++r) {
-      for (int p = p_begin; p < p_end; ++p) {
-        if (p >= P_SWAP && !force_swap) {
-          int st = 0;
-          CU(cudaMemcpyAsync(&st, h->hs.ch.step, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-          CU(cudaStreamSynchronize(h->stream));
-          if (st == 0 || st % h->hs.swap_interval != 0) continue;
+    // One launch per phase (the exchange phases test the step counter on the device, like the persistent kernel); the
+    // launches of a call are captured once into a CUDA graph and replayed.
+    const int n_launch = n_rep * (p_end - p_begin);
+    if (h->use_graph && n_launch <= 8192) {
+      const std::array<int, 4> key = {p_begin, p_end, n_rep, force_swap};
+      auto it = h->graphs.find(key);
+      if (it == h->graphs.end()) {
+        cudaGraph_t graph = nullptr;
+        CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        cudaError_t e = cudaSuccess;
+        for (int r = 0; r < n_rep && e == cudaSuccess; ++r)
+          for (int p = p_begin; p < p_end && e == cudaSuccess; ++p) e = launch_one(h, p, 0, h->hs.C, force_swap);
+        cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
+        if (e != cudaSuccess || e2 != cudaSuccess) {
+          if (graph) cudaGraphDestroy(graph);
+          return fail(BAE_ERR_CUDA, std::string("graph capture of the step program failed: ") +
+                                        cudaGetErrorString(e != cudaSuccess ? e : e2));
         }
-        CU(launch_phase(h->dS, h->hs.tc, h->grid, p, 0, h->hs.C, h->stream));
-        h->launches++;
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(BAE_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        it = h->graphs.emplace(key, exec).first;
       }
+      CU(cudaEventRecord(h->ev0, h->stream));
+      CU(cudaGraphLaunch(it->second, h->stream));
+    } else {
+      for (int r = 0; r < n_rep; ++r)
+        for (int p = p_begin; p < p_end; ++p) CU(launch_one(h, p, 0, h->hs.C, force_swap));
     }
+    h->launches += n_launch;
   } else {
     CU(launch_program(h->dS, h->hs.tc, h->grid, p_begin, p_end, n_rep, 0, h->hs.C, force_swap, h->stream));
     h->launches++;

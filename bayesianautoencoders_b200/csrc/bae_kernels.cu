@@ -1356,11 +1356,32 @@ bae_program_kernel(const DevState* __restrict__ S, int ph_begin, int ph_end, int
 
 // Plain launch of ONE phase (no grid barrier): used for per-phase profiling and the parity probe.
 __global__ void __launch_bounds__(kThreads, 2)
-bae_phase_kernel(const DevState* __restrict__ S, int pi, int c_begin, int c_end) {
+bae_phase_kernel(const DevState* __restrict__ S, int pi, int c_begin, int c_end, int force_swap) {
   __shared__ __align__(16) float smem[2 * BK * 128 * 2];
   __shared__ double red[16];
   load_seg_table(S);
-  run_phase<true>(S, pi, c_begin, c_end, 1, smem, red);
+  run_phase<true>(S, pi, c_begin, c_end, force_swap, smem, red);
+}
+
+// Non-GEMM phases of the tcgen05 path when every phase is its own launch (the default there): plain 256-thread CTAs,
+// several per SM and with an L1 behind them, instead of the two epilogue warpgroups of the 1-CTA-per-SM tile engine.
+// One kernel per phase family, so that each gets its own register allocation.
+enum AuxGroup : int { AUX_ADAM = 0, AUX_BN = 1, AUX_MISC = 2 };
+template <int kGroup>
+__global__ void __launch_bounds__(kThreads, kGroup == AUX_ADAM ? kAuxAdamCtas : kGroup == AUX_BN ? kAuxBnCtas : 2)
+bae_aux_kernel(const DevState* __restrict__ S, int pi, int c_begin, int c_end, int force_swap) {
+  __shared__ __align__(16) float smem[1024];   // BatchNorm column reductions (512 doubles)
+  __shared__ double red[16];
+  load_seg_table(S);
+  const PhaseDesc& ph = S->phase[pi];
+  if constexpr (kGroup == AUX_ADAM) {
+    run_adam(S, ph.kind == PH_ADAM1 ? 1 : 2, c_begin, c_end, red);
+  } else if constexpr (kGroup == AUX_BN) {
+    if (ph.kind == PH_BN_FWD) run_bn_fwd_wide(S, ph, c_begin, c_end, reinterpret_cast<double*>(smem));
+    else run_bn_bwd_wide(S, ph, c_begin, c_end, reinterpret_cast<double*>(smem));
+  } else {
+    run_phase<false>(S, pi, c_begin, c_end, force_swap, smem, red);
+  }
 }
 
 // ---- tensor-core variants: GEMM phases go through the tcgen05 tile engine (1 CTA of 512 threads per SM).
@@ -1423,7 +1444,7 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
 }
 
 __global__ void __launch_bounds__(tc::kThreadsTc, 1)
-bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_end) {
+bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_end, int force_swap) {
   extern __shared__ uint8_t dyn_smem[];
   __shared__ __align__(16) float smem_small[1024];
   __shared__ double red[16];
@@ -1434,7 +1455,7 @@ bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_e
   const int wg = threadIdx.x >> 7;
   if (wg == 1 || wg == 2) {
     tc::regs_inc<tc::kRegsEpi>();
-    run_phase_tc_back(S, pi, c_begin, c_end, 1, tsm, ring, smem_small, red);
+    run_phase_tc_back(S, pi, c_begin, c_end, force_swap, tsm, ring, smem_small, red);
   } else {
     tc::regs_dec<tc::kRegsLean>();
     run_phase_tc_front(S, pi, c_begin, c_end, tsm, ring);
@@ -1574,12 +1595,39 @@ cudaError_t launch_program(const DevState* dS, int use_tc, int grid, int ph_begi
   return cudaLaunchCooperativeKernel((void*)bae_program_kernel, dim3(grid), dim3(kThreads), args, 0, st);
 }
 
-cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, cudaStream_t st) {
+cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, int force_swap,
+                         cudaStream_t st) {
   if (use_tc) {
-    void* args[] = {(void*)&dS, (void*)&pi, (void*)&c_begin, (void*)&c_end};
+    void* args[] = {(void*)&dS, (void*)&pi, (void*)&c_begin, (void*)&c_end, (void*)&force_swap};
     return launch_tc((const void*)bae_phase_kernel_tc, grid, args, false, st);
   }
-  bae_phase_kernel<<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end);
+  bae_phase_kernel<<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end, force_swap);
+  return cudaGetLastError();
+}
+
+static int aux_group(int kind) {
+  return (kind == PH_ADAM1 || kind == PH_ADAM2) ? AUX_ADAM : (kind == PH_BN_FWD || kind == PH_BN_BWD) ? AUX_BN : AUX_MISC;
+}
+
+// CTAs per SM of the aux kernel that runs phases of `kind`
+int aux_blocks_per_sm(int kind) {
+  int nb = 0;
+  switch (aux_group(kind)) {
+    case AUX_ADAM: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_aux_kernel<AUX_ADAM>, kThreads, 0); break;
+    case AUX_BN: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_aux_kernel<AUX_BN>, kThreads, 0); break;
+    default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_aux_kernel<AUX_MISC>, kThreads, 0); break;
+  }
+  return nb;
+}
+
+// `kind` is the phase's kind (host copy of the program); the tcgen05 path has d3 >= kBnCols, i.e. the wide BatchNorm code
+cudaError_t launch_aux(const DevState* dS, int kind, int grid, int pi, int c_begin, int c_end, int force_swap,
+                       cudaStream_t st) {
+  switch (aux_group(kind)) {
+    case AUX_ADAM: bae_aux_kernel<AUX_ADAM><<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end, force_swap); break;
+    case AUX_BN: bae_aux_kernel<AUX_BN><<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end, force_swap); break;
+    default: bae_aux_kernel<AUX_MISC><<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end, force_swap); break;
+  }
   return cudaGetLastError();
 }
 

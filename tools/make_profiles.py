@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
 """Turns the ncu exports of a profiling session into the committed summaries under profiles/.
 
-    ncu -i gpurun_out/prof_program_r1.ncu-rep --page raw --csv > /tmp/raw_prog.csv
-    python tools/make_profiles.py gpurun_out/launches_r1_final.csv /tmp/raw_prog.csv [gpurun_out/phases_final.log]
+    ncu -i /tmp/prof_phases_r1.ncu-rep --page raw --csv > gpurun_out/prof_phases_r1_raw.csv      (on the GPU box)
+    python tools/make_profiles.py gpurun_out/launches_r1_final.csv gpurun_out/prof_phases_r1_raw.csv [gpurun_out/phases_final.log]
 """
 import csv
 import json
@@ -68,47 +68,62 @@ behind local memory (the Adam inputs are already streamed through shared memory 
 open('profiles/r1_v4_tc_phase_launches.md', 'w').write(md)
 
 r = list(csv.reader(open(raw_csv)))
-d = {c: (u, v) for c, u, v in zip(r[0], r[1], r[2])}
-keys = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'launch__registers_per_thread', 'launch__shared_mem_per_block_dynamic',
-        'launch__shared_mem_per_block_static', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
-        'lts__t_sector_hit_rate.pct', 'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__m_xbar2l1tex_read_bytes.sum',
-        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
-        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum', 'sass__inst_executed_local_loads',
-        'sass__inst_executed_local_stores', 'sm__cycles_elapsed.max']
-tab = "\n".join(f"| {k} | {d[k][0]} | {d[k][1]} |" for k in keys if k in d)
+hdr, units, prow = r[0], r[1], r[2:]
+assert len(prow) == 39, "expected the 39 per-phase launches of one iteration"
+UNIT = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1, 'ms': 1e3, 's': 1e6}
 
 
-def to_bytes(k):
-    u, v = d[k]
-    return float(v) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
+def colv(k, scale=False):
+    i = hdr.index(k)
+    return [float(x[i].replace(',', '')) * (UNIT[units[i]] if scale else 1) for x in prow]
 
 
-rd, wr, ms = to_bytes('dram__bytes_read.sum'), to_bytes('dram__bytes_write.sum'), float(d['gpu__time_duration.sum'][1])
-md2 = f"""# Round 1, engine v4 (CTA pairs) - `bae_program_kernel_tc` (persistent step kernel, tcgen05 3xTF32 path), one `ncu --set full` capture
+dur = colv('gpu__time_duration.sum', True)            # us
+rdv, wrv = colv('dram__bytes_read.sum', True), colv('dram__bytes_write.sum', True)
+tens = colv('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')
+dramp = colv('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')
+l2hit = colv('lts__t_sector_hit_rate.pct')
+lld, lst = colv('sass__inst_executed_local_loads'), colv('sass__inst_executed_local_stores')
+inst = colv('smsp__inst_executed.sum')
+regs = colv('launch__registers_per_thread')
+rd, wr, us = sum(rdv), sum(wrv), sum(dur)
+ptab = "\n".join(f"| {n} | {dur[i]:.1f} | {rdv[i] / 1e6:.1f} | {wrv[i] / 1e6:.1f} | {(rdv[i] + wrv[i]) / dur[i] / 1e3:.0f} | {dramp[i]:.1f} | {tens[i]:.1f} | "
+                 f"{l2hit[i]:.0f} | {inst[i] / 1e6:.2f} | {lld[i] + lst[i]:.0f} |" for i, n in enumerate(names))
+gi = [i for i, n in enumerate(names) if n.split(' ')[0].rstrip('b') in fl]
+gt = sum(dur[i] for i in gi)
+md2 = f"""# Round 1, engine v4 (CTA pairs) - the persistent step program, one `ncu --set full` capture over its 39 phases
 
-Command: `ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:bae_program_kernel_tc -c 1 python tools/profile_step.py --chains 8 --rounds 2 --steps-per-round 1 --profile-round 1`
-(Madelon shape, 8 chains, ONE iteration = one cooperative launch: 148 CTAs = 74 CTA pairs (cluster dimension 2) x 512 threads, 1 CTA/SM; the report itself stays in `gpurun_out/`.)
+`ncu --set full` cannot replay the production launch of `bae_program_kernel_tc` (cooperative + cluster dimension 2: the profiler reports
+LaunchFailed for it and the report holds zeros; `--metrics gpu__time_duration.sum` alone works, see `r1_v4_tc_phase_launches.md`). The full-set
+capture is therefore taken over the same program with every phase launched as its own `bae_phase_kernel_tc` (same device code, cluster launch
+without the cooperative attribute):
 
-Kernel duration {ms:.3f} ms under ncu. Algorithmic FLOPs of this launch: 8 chains x 27.18 GFLOP = 217 GFLOP -> {217 / ms:.0f} TFLOP/s at 8 chains
-(production runs 64 chains per GPU: 121 TFLOP/s, `bench.py`).
-DRAM traffic per launch: read {rd / 1e6:.0f} MB + write {wr / 1e6:.0f} MB = {(rd + wr) / 8 / 1e6:.0f} MB per chain-iteration. Algorithmic weight-state traffic is
+`BAE_PHASE_LAUNCH=1 ncu --set full --clock-control none --profile-from-start off -k regex:bae_phase_kernel_tc -c 39 python tools/profile_step.py --chains 8 --rounds 2 --steps-per-round 1 --profile-round 1`
+(Madelon shape, 8 chains, ONE iteration = 39 launches of 148 CTAs = 74 CTA pairs x 512 threads, 1 CTA/SM, {regs[0]:.0f} registers/thread at launch,
+redistributed by `setmaxnreg`; the 124 MB report stays on the GPU box, its raw page export is what this file is built from.)
+
+Sum of the 39 kernel durations {us / 1e3:.3f} ms under ncu (cold caches, serialised). Algorithmic FLOPs of one iteration: 8 chains x 27.18 GFLOP = 217 GFLOP
+-> {217 / (us / 1e3):.0f} TFLOP/s at 8 chains over the whole iteration, {sum(fl[names[i].split(' ')[0].rstrip('b')] for i in gi) * 8 / (gt * 1e-6) / 1e12:.0f} TFLOP/s over the GEMM phases (8 chains fill only
+a fraction of the 74 CTA pairs per phase; production runs 64 chains per GPU: 121 TFLOP/s whole-step, `bench.py`).
+DRAM traffic per iteration: read {rd / 1e6:.0f} MB + write {wr / 1e6:.0f} MB = {(rd + wr) / 8 / 1e6:.0f} MB per chain-iteration. Algorithmic weight-state traffic is
 22 x 4 B x 1.05 M = 93 MB per chain-iteration (SURVEY 8d); the rest is activations and deltas (41 MB per chain, written once and re-read by the backward
 pass and the weight-gradient GEMMs) plus the four K-split copies of the gradient (4 x 4.2 MB written by the dW GEMMs, read by each Adam phase).
-SASS evidence (`cuobjdump -sass libbae_b200.so`): UTCHMMA (tcgen05.mma kind::tf32), UTMALDG (TMA), UBLKCP (cp.async.bulk, Adam staging), LDTM (tcgen05.ld),
-UTCBAR (tcgen05.commit), USETMAXREG (setmaxnreg), SYNCS (mbarrier).
+At 8 chains most of the working set (8 x 130 MB) does not fit the 126 MB L2 between phases, as in production.
+SASS evidence (`cuobjdump -sass libbae_b200.so`): UTCHMMA (tcgen05.mma cta_group::2 kind::tf32), UTMALDG (TMA), UBLKCP (cp.async.bulk, Adam staging),
+LDTM (tcgen05.ld), UTCBAR (tcgen05.commit, multicast), USETMAXREG (setmaxnreg), SYNCS (mbarrier), UCGABAR (cluster barrier).
 
-| metric | unit | value |
-|---|---|---|
-{tab}
+| phase | us | DRAM read MB | DRAM write MB | DRAM GB/s | DRAM % of peak | tensor pipe active % | L2 hit % | warp inst (M) | local ld+st inst |
+|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|
+{ptab}
 
-Reading: tensor pipe active {d['sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'][1][:5]}% of the cycles over the WHOLE step (GEMM phases are ~70% of it, and each 3xTF32 K block needs 6 MMAs);
-DRAM {d['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'][1][:4]}% of peak - the step is bound by the operand pipeline of the tile loop (TMA -> hi/lo conversion -> MMA, see
-`r1_tc_microbench.md`) and, in the BatchNorm / Adam phases, by the 256 threads per SM that run them. Local-memory instructions
-({d['sass__inst_executed_local_loads'][1][:7]} loads) are register spills of the persistent kernel; they go to L2 (no L1 with a 227 KB carve-out) - the next thing to remove.
+Reading: the GEMM phases keep the tensor pipe {min(tens[i] for i in gi):.0f}-{max(tens[i] for i in gi):.0f}% active at 8 chains (each 3xTF32 K block is 6 MMAs; at 64 chains every CTA pair
+has 3-7 tiles per phase and the traced tile loop runs at the tensor-pipe pace, see DESIGN.md 4); the Adam phases move {(rdv[15] + wrv[15]) / 1e6:.0f} MB at {(rdv[15] + wrv[15]) / dur[15] / 1e3:.0f} GB/s
+stand-alone, {100 * (rdv[15] + wrv[15]) / dur[15] / 1e3 / 6549:.0f}% of the measured HBM peak (6549 GB/s) - they are bound by the Philox/Box-Muller + Adam arithmetic of 256 threads per SM,
+not by HBM. Local-memory instructions are zero in the per-phase kernels; the persistent kernel's allocation spills in the BatchNorm and Adam phases
+(`tools/build_check.sh` prints the histogram), which go to L2 (no L1 behind local memory with a 227 KB carve-out).
 """
 open('profiles/r1_v4_program_kernel_ncu_full.md', 'w').write(md2)
-json.dump({"shape": "madelon", "gemm_path": 2, "chains": 8, "iterations": 1, "dram_bytes_read": rd, "dram_bytes_write": wr, "kernel_ms_under_ncu": ms,
-           "source": "ncu --set full, bae_program_kernel_tc, 8 chains x 1 iteration (profiles/r1_v4_program_kernel_ncu_full.md)"},
+json.dump({"shape": "madelon", "gemm_path": 2, "chains": 8, "iterations": 1, "dram_bytes_read": rd, "dram_bytes_write": wr, "kernel_ms_under_ncu": us / 1e3,
+           "source": "ncu --set full over the 39 bae_phase_kernel_tc launches of one iteration, 8 chains (profiles/r1_v4_program_kernel_ncu_full.md)"},
           open('profiles/r1_program_kernel_traffic.json', 'w'), indent=1)
 print("profiles written")
