@@ -19,7 +19,7 @@ int max_coop_grid_tc();
 cudaError_t launch_program(const DevState* dS, int use_tc, int grid, int ph_begin, int ph_end, int n_rep, int c_begin,
                            int c_end, int force_swap, cudaStream_t st);
 cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, int force_swap,
-                         cudaStream_t st);
+                         int epi_a, int epi_b, cudaStream_t st);
 int aux_blocks_per_sm(int kind);
 cudaError_t launch_aux(const DevState* dS, int kind, int grid, int pi, int c_begin, int c_end, int force_swap,
                        cudaStream_t st);
@@ -508,6 +508,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   CU(dalloc(h, &h->stage_d, 64));
   if (getenv("BAE_TC_TRACE") && getenv("BAE_TC_TRACE")[0] == '1') CU(dalloc(h, &s.dbg, 4096));
   s.dbg_flags = getenv("BAE_TC_DBGFLAGS") ? atoi(getenv("BAE_TC_DBGFLAGS")) : 0;
+  s.dbg_phase = getenv("BAE_TC_TRACE_PHASE") ? atoi(getenv("BAE_TC_TRACE_PHASE")) : -1;
   {
     void* q = nullptr;
     CU(cudaMalloc(&q, sizeof(DevState)));
@@ -637,7 +638,10 @@ static int get1(bae_handle* h, const T* dev_arr, int idx, T* v) {
 static cudaError_t launch_one(bae_handle* h, int p, int c_begin, int c_end, int force_swap) {
   if (h->hs.tc && h->hs.phase[p].kind != PH_GEMM)
     return launch_aux(h->dS, h->hs.phase[p].kind, h->grid_aux[h->hs.phase[p].kind], p, c_begin, c_end, force_swap, h->stream);
-  return launch_phase(h->dS, h->hs.tc, h->grid, p, c_begin, c_end, force_swap, h->stream);
+  const PhaseDesc& ph = h->hs.phase[p];
+  const int ea = ph.kind == PH_GEMM ? h->hs.gemm[ph.g0].epi : -1;
+  const int eb = (ph.kind == PH_GEMM && ph.g1 >= 0) ? h->hs.gemm[ph.g1].epi : -1;
+  return launch_phase(h->dS, h->hs.tc, h->grid, p, c_begin, c_end, force_swap, ea, eb, h->stream);
 }
 
 static int run_phases_plain(bae_handle* h, int p_begin, int p_end, int c_begin, int c_end) {

@@ -140,6 +140,7 @@ struct DevState {
   int tc;             // 1: GEMM phases run on the tensor cores (3xTF32); row pitches reserve a ones column
   void* tmaps;        // CUtensorMap array in global memory (64-byte aligned)
   int dbg_flags;      // BAE_TC_DBGFLAGS: timing experiments only (results are wrong when set), see bae_tc.cuh
+  int dbg_phase;      // BAE_TC_TRACE_PHASE: trace only this phase index (-1: every GEMM phase, the last one stays)
   long long* dbg;     // optional timeline trace of CTA 0 (BAE_TC_TRACE=1): [role][event] clock64 stamps
   // ---- program
   int n_gemm, n_phase;

@@ -1387,11 +1387,12 @@ bae_aux_kernel(const DevState* __restrict__ S, int pi, int c_begin, int c_end, i
 // ---- tensor-core variants: GEMM phases go through the tcgen05 tile engine (1 CTA of 512 threads per SM).
 // Warpgroups 1 and 2 (threads 128..383, 192 registers each) run the GEMM epilogues and every non-GEMM phase;
 // warpgroups 0 and 3 (64 registers) hold the TMA producer, the MMA issuer and the hi/lo converters.
+template <int kEpiA, int kEpiB>
 __device__ __forceinline__ void run_phase_tc_back(const DevState* S, int pi, int c_begin, int c_end, int force_swap,
                                                   tc::Smem& tsm, tc::Ring& ring, float* smem_small, double* red) {
   const PhaseDesc& ph = S->phase[pi];
   if (ph.kind == PH_GEMM)
-    tc::gemm_phase_epilogue(S, ph, c_begin, c_end, tsm, ring);
+    tc::gemm_phase_epilogue<kEpiA, kEpiB>(S, ph, c_begin, c_end, tsm, ring);
   else if (ph.kind == PH_ADAM1 || ph.kind == PH_ADAM2)
     run_adam_tc(S, ph.kind == PH_ADAM1 ? 1 : 2, c_begin, c_end, red, tsm);
   else
@@ -1422,7 +1423,7 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
     tc::regs_inc<tc::kRegsEpi>();
     for (int rep = 0; rep < n_rep; ++rep) {
       for (int pi = ph_begin; pi < ph_end; ++pi) {
-        run_phase_tc_back(S, pi, c_begin, c_end, force_swap, tsm, ring, smem_small, red);
+        run_phase_tc_back<-1, -1>(S, pi, c_begin, c_end, force_swap, tsm, ring, smem_small, red);
         grid.sync();
         if (S->dbg && blockIdx.x == 0 && threadIdx.x == 128 && rep == 1) {   // debug: phase end times of the 2nd iteration
           long long t;
@@ -1443,19 +1444,18 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
   tc::teardown(tsm);
 }
 
+// One GEMM phase as its own launch (the production path on tcgen05), specialised by the epilogue kinds of its GEMMs.
+template <int kEpiA, int kEpiB>
 __global__ void __launch_bounds__(tc::kThreadsTc, 1)
 bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_end, int force_swap) {
   extern __shared__ uint8_t dyn_smem[];
-  __shared__ __align__(16) float smem_small[1024];
-  __shared__ double red[16];
   tc::Smem tsm;
   tc::Ring ring;
   tc::setup(tsm, dyn_smem);
-  load_seg_table(S);
   const int wg = threadIdx.x >> 7;
   if (wg == 1 || wg == 2) {
     tc::regs_inc<tc::kRegsEpi>();
-    run_phase_tc_back(S, pi, c_begin, c_end, force_swap, tsm, ring, smem_small, red);
+    tc::gemm_phase_epilogue<kEpiA, kEpiB>(S, S->phase[pi], c_begin, c_end, tsm, ring);
   } else {
     tc::regs_dec<tc::kRegsLean>();
     run_phase_tc_front(S, pi, c_begin, c_end, tsm, ring);
@@ -1564,7 +1564,12 @@ int max_coop_blocks_per_sm(int use_tc) {
   int nb = 0;
   if (use_tc) {
     cudaFuncSetAttribute(bae_program_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    cudaFuncSetAttribute(bae_phase_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_SIGMOID, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_BIAS, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_LOSS, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_GRADW, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_DSIG, EPI_GRADW>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_PLAIN, EPI_GRADW>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel_tc, tc::kThreadsTc, tc::kSmemBytes);
   } else {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel, kThreads, 0);
@@ -1595,11 +1600,28 @@ cudaError_t launch_program(const DevState* dS, int use_tc, int grid, int ph_begi
   return cudaLaunchCooperativeKernel((void*)bae_program_kernel, dim3(grid), dim3(kThreads), args, 0, st);
 }
 
+// epi_a / epi_b: epilogue kinds of the phase's GEMMs (host copy of the program; epi_b < 0: one GEMM)
 cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, int force_swap,
-                         cudaStream_t st) {
+                         int epi_a, int epi_b, cudaStream_t st) {
   if (use_tc) {
     void* args[] = {(void*)&dS, (void*)&pi, (void*)&c_begin, (void*)&c_end, (void*)&force_swap};
-    return launch_tc((const void*)bae_phase_kernel_tc, grid, args, false, st);
+    const void* fn = nullptr;
+    if (epi_b >= 0 && epi_b < epi_a) { const int t = epi_a; epi_a = epi_b; epi_b = t; }
+    if (epi_b < 0 || epi_b == epi_a) {
+      switch (epi_a) {
+        case EPI_SIGMOID: fn = (const void*)bae_phase_kernel_tc<EPI_SIGMOID, -1>; break;
+        case EPI_BIAS: fn = (const void*)bae_phase_kernel_tc<EPI_BIAS, -1>; break;
+        case EPI_LOSS: fn = (const void*)bae_phase_kernel_tc<EPI_LOSS, -1>; break;
+        case EPI_GRADW: fn = (const void*)bae_phase_kernel_tc<EPI_GRADW, -1>; break;
+        default: break;
+      }
+    } else if (epi_a == EPI_DSIG && epi_b == EPI_GRADW) {
+      fn = (const void*)bae_phase_kernel_tc<EPI_DSIG, EPI_GRADW>;
+    } else if (epi_a == EPI_PLAIN && epi_b == EPI_GRADW) {
+      fn = (const void*)bae_phase_kernel_tc<EPI_PLAIN, EPI_GRADW>;
+    }
+    if (!fn) return cudaErrorInvalidDeviceFunction;   // a GEMM-kind combination the step program does not contain
+    return launch_tc(fn, grid, args, false, st);
   }
   bae_phase_kernel<<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end, force_swap);
   return cudaGetLastError();

@@ -365,7 +365,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = phase_items(S, ph, c_begin, c_end);
   const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(S->tmaps);
-  long long* dbg = (blockIdx.x == 0) ? S->dbg : nullptr;
+  long long* dbg = (blockIdx.x == 0 && (S->dbg_phase < 0 || S->dbg_phase == (int)(&ph - S->phase))) ? S->dbg : nullptr;
   const uint32_t rank = cluster_rank();
   // NOTE: every descriptor field used inside a K loop is copied into a local first. The loops are full of
   // asm volatile statements with memory clobbers, after which the compiler would re-load fields of *it.g from
@@ -427,7 +427,9 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         Item it;
         if (!decode_item(S, ph, c_begin, item, it)) continue;
         const GemmDesc& g = *it.g;
-        mbar_wait_cluster(&sm.tmem_empty()[0], ring.acc_phase ^ 1);   // the epilogue warps of BOTH CTAs have drained the previous tile
+        // the epilogue warps of BOTH CTAs have drained the main accumulator of the previous tile (the cross-term
+        // accumulator follows: tmem_empty[0], waited for before the first cross-term MMA)
+        mbar_wait_cluster(&sm.tmem_empty()[1], ring.acc_phase ^ 1);
         fence_after_sync();
         const uint32_t d_main = tmem, d_cross = tmem + (uint32_t)g.tcBN;
         const bool amn = g.aMode != 0, bmn = g.bMode != 0;
@@ -448,6 +450,10 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             const uint32_t acc0 = kb ? 1u : 0u;
             umma_tf32(d_main, ah, bh, idesc, acc0);
             if (two) umma_tf32(d_main, ah + astep, bh + bstep, idesc, 1u);
+            if (kb == 0) {
+              mbar_wait_cluster(&sm.tmem_empty()[0], ring.acc_phase ^ 1);
+              fence_after_sync();
+            }
             if (!(dbgf & 8)) {
               umma_tf32(d_cross, al, bh, idesc, acc0);
               umma_tf32(d_cross, ah, bl, idesc, 1u);
@@ -535,169 +541,221 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
 // One GEMM phase, back half: the eight epilogue warps (warpgroups 1 and 2). Returns after every tile of
 // this CTA is stored.
 // ---------------------------------------------------------------------------------------------------
-__device__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, Smem& sm, Ring& ring) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+struct EpiCtx {
+  int q, eg, ew, et, lane, sub_r, sub_c;
+  uint32_t tmem, stg_s, rank;
+  long long* dbg;
+  int dbgf;
+};
+
+// One tile, specialised by the epilogue kinds of the phase: the body holds only their code around the 128 accumulator
+// registers (a body with all six kinds selected at run time spilled inside the store loop, an L2 round trip per spill).
+template <int kEpi, int kEpiB>
+__device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it, const EpiCtx& c, Smem& sm, Ring& ring, int& ntr) {
+  const GemmDesc& g = *it.g;
+  const int tcBN = g.tcBN;
+  const int n0 = it.tile_n * tcBN;
+  const int n_end = min(g.N, n0 + tcBN);   // this tile owns output columns [n0, n_end)
+  const int ncols = n_end - n0;
+  const int eg = c.eg, lane = c.lane, sub_r = c.sub_r, sub_c = c.sub_c;
+  const uint32_t tbase = c.tmem + ((uint32_t)(c.q * 32) << 16);
+  long long* dbg = c.dbg;
+  // kEpi < 0: kind selected at run time (persistent kernel, debug); one kind: every test on `epi` below folds away; two
+  // kinds (a backward phase: weight gradient | delta): ONE body that keeps only these two kinds' code - two inlined bodies
+  // made the compiler keep one of the accumulator arrays in local memory
+  const int epi = (kEpi < 0) ? g.epi : (kEpiB < 0 ? kEpi : (g.epi == kEpi ? kEpi : kEpiB));
+  const bool kHasBias = (epi == EPI_SIGMOID || epi == EPI_BIAS || epi == EPI_LOSS);
+  const bool kHasAux = (epi == EPI_DSIG || epi == EPI_LOSS);
+
+  // bias of this thread's four output columns in each of its four chunks: requested before the accumulators are
+  // waited for (an L2 round trip per chunk otherwise, in a chunk loop that is not unrolled)
+  float4 b4s[4];
+  if (kHasBias) {
+    const float* bias0 = g.bias + (size_t)it.chain * g.sBias;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cc = n0 + (eg + 2 * j) * 32 + sub_c;
+      b4s[j] = (cc < n_end) ? __ldg(reinterpret_cast<const float4*>(&bias0[cc])) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+
+  // ---- drain: both accumulators of this warp's chunks -> registers, then TMEM goes back to the MMA issuer.
+  mbar_wait(&sm.tmem_full()[0], ring.acc_phase);
+  if (c.et == 0) trace(dbg, 3, ntr, 0);
+  fence_after_sync();
+  uint32_t acc[4][32];
+  {
+    // all main-accumulator chunks are requested at once, then the cross-term chunks 16 columns at a time. The first
+    // wait covers every main chunk: the main accumulator goes back to the MMA issuer there (tmem_empty[1]), which can
+    // start the next tile's hi*hi products while the cross-term accumulator is still being drained.
+    uint32_t pa[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if ((eg + 2 * j) * 32 < ncols) tmem_ld32_issue(tbase + (uint32_t)((eg + 2 * j) * 32), acc[j]);
+    if (eg * 32 >= ncols) {   // a narrow last tile: this warp owns no chunk at all
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&sm.tmem_empty()[1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c0 = (eg + 2 * j) * 32;
+      if (c0 < ncols) {
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          tmem_ld16_issue(tbase + (uint32_t)(tcBN + c0 + hh * 16), pa);
+          tmem_wait_ld16(pa);
+          if (j == 0 && hh == 0) {
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&sm.tmem_empty()[1]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            acc[j][hh * 16 + i] = __float_as_uint(__uint_as_float(acc[j][hh * 16 + i]) + __uint_as_float(pa[i]));
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_leader(&sm.tmem_empty()[0]);   // the leader's MMA issuer waits for both CTAs' epilogue warps
+  ring.acc_phase ^= 1;
+  if (c.et == 0) trace(dbg, 3, ntr, 1);
+
+  // locals: see the note in gemm_phase_front
+  const int chain = it.chain;
+  const int m0 = it.tile_m * (2 * kBM) + (int)c.rank * kBM;   // this CTA's 128 rows of the pair's tile
+  const size_t split_off = (epi == EPI_GRADW) ? (size_t)it.split * S->C_alloc * S->Pp : 0;   // gradient copy of this K split
+  float* C = g.C + (size_t)chain * g.sC + split_off;
+  const float* aux = (kHasAux && g.aux) ? g.aux + (size_t)chain * g.sAux : nullptr;
+  const int gM = g.M, ldaux = g.ldaux, ldc = g.ldc;
+  const int biasCol = (epi == EPI_GRADW) ? g.biasCol : -1;
+  float* gbias = (epi == EPI_GRADW && g.gbias) ? g.gbias + (size_t)chain * g.sGb + split_off : nullptr;
+  const float scale = g.scale;
+  const int r0 = m0 + c.q * 32;
+  const uint32_t stg_s = c.stg_s;
+
+  // ---- fused epilogue from registers, one 32 x 32 chunk at a time. The chunk loop is NOT unrolled (unrolled, this
+  // section was 160 KB of straight-line code and stalled on instruction fetch) and nothing may spill. The chunk's
+  // accumulators go to the staging tile, and all epilogue math runs in the coalesced (transposed) domain where aux
+  // loads, bias and stores share one address pattern.
+  float l_sse = 0.f, l_sd = 0.f;
+  const int lim = (epi == EPI_GRADW && biasCol >= 0) ? min(n_end, biasCol) : n_end;
+#pragma unroll 1
+  for (int jj = 0; jj < 4; ++jj) {
+    const int c0 = (eg + 2 * jj) * 32;
+    if (c0 >= ncols || (c.dbgf & 16)) break;
+    const int cc = n0 + c0 + sub_c;            // first of this thread's 4 output columns
+    const bool cv = cc < n_end;
+    // aux tile (sigmoid outputs for EPI_DSIG, data for EPI_LOSS), 4 rows x 128 B per instruction, in two groups of four
+    float4 t[4];
+    const float* ap = kHasAux ? aux + (size_t)(r0 + sub_r) * ldaux + cc : nullptr;
+    auto load_aux = [&](int half) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ii = half * 4 + i;
+        t[i] = (cv && r0 + ii * 4 + sub_r < gM) ? ldg128_pinned(ap + (size_t)(ii * 4) * ldaux) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (kHasAux) load_aux(0);
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kHasBias) {
+      b4 = b4s[0];
+#pragma unroll
+      for (int j = 1; j < 4; ++j)
+        if (j == jj) b4 = b4s[j];
+    }
+    if (c.et == 0) trace(dbg, 3, ntr, 10 + jj);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j == jj) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4)
+          sts128(stg_s + (lane * kEpiPitch + j4 * 4) * 4,
+                 make_float4(__uint_as_float(acc[j][j4 * 4]), __uint_as_float(acc[j][j4 * 4 + 1]),
+                             __uint_as_float(acc[j][j4 * 4 + 2]), __uint_as_float(acc[j][j4 * 4 + 3])));
+      }
+    __syncwarp();
+    if (c.et == 0) trace(dbg, 3, ntr, 20 + jj);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (kHasAux && i == 4) load_aux(1);
+      const int rr = r0 + i * 4 + sub_r;
+      float4 o = lds128(stg_s + ((i * 4 + sub_r) * kEpiPitch + sub_c) * 4);
+      if (rr >= gM || !cv) continue;
+      if (kHasBias) { o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
+      if (epi == EPI_SIGMOID) {
+        o.x = __fdividef(1.0f, 1.0f + __expf(-o.x)); o.y = __fdividef(1.0f, 1.0f + __expf(-o.y));
+        o.z = __fdividef(1.0f, 1.0f + __expf(-o.z)); o.w = __fdividef(1.0f, 1.0f + __expf(-o.w));
+      } else if (epi == EPI_DSIG) {
+        o.x *= t[i & 3].x * (1.0f - t[i & 3].x); o.y *= t[i & 3].y * (1.0f - t[i & 3].y);
+        o.z *= t[i & 3].z * (1.0f - t[i & 3].z); o.w *= t[i & 3].w * (1.0f - t[i & 3].w);
+      } else if (epi == EPI_LOSS) {
+        float d[4] = {o.x - t[i & 3].x, o.y - t[i & 3].y, o.z - t[i & 3].z, o.w - t[i & 3].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (cc + e < n_end) { l_sse = fmaf(d[e], d[e], l_sse); l_sd += d[e]; }
+          d[e] *= scale;
+        }
+        o = make_float4(d[0], d[1], d[2], d[3]);
+      }
+      float* dst = &C[(size_t)rr * ldc + cc];
+      if (cc + 4 <= lim) {
+        *reinterpret_cast<float4*>(dst) = o;
+      } else {
+        const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (cc + e < lim) dst[e] = ov[e];
+          else if (epi == EPI_GRADW && cc + e == biasCol) gbias[rr] = ov[e];   // ones-column trick
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (c.et == 0) trace(dbg, 3, ntr, 2);
+  if (epi == EPI_LOSS) {
+    double s0 = (double)l_sse, s1 = (double)l_sd;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (lane == 0) { sm.red()[c.ew * 2] = s0; sm.red()[c.ew * 2 + 1] = s1; }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (c.et == 0) {
+      double* p = g.part + ((size_t)chain * g.partStride + (size_t)(it.tile_m * 2 + (int)c.rank) * g.tn + it.tile_n) * 2;
+      double a0 = 0.0, a1 = 0.0;
+      for (int w = 0; w < kEpiWarps; ++w) { a0 += sm.red()[w * 2]; a1 += sm.red()[w * 2 + 1]; }
+      p[0] = a0;
+      p[1] = a1;
+    }
+  }
+}
+
+// kEpiA / kEpiB: epilogue kinds of the phase's GEMMs (kEpiB < 0: one kind; kEpiA < 0: selected at run time)
+template <int kEpiA, int kEpiB>
+__device__ __forceinline__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, Smem& sm, Ring& ring) {
+  const int warp = threadIdx.x >> 5;
   const int total = phase_items(S, ph, c_begin, c_end);
-  const int q = warp & 3;               // TMEM lane quarter this warp may access
-  const int eg = (warp - 4) >> 2;       // 0/1: which alternating 32-column chunks this warp owns
-  const int ew = warp - 4;              // 0..7
-  const int et = threadIdx.x - 128;     // 0..255
-  const uint32_t tmem = *sm.tmem_base();
-  const uint32_t stg_s = smem_u32(sm.epi_stage() + ew * (32 * kEpiPitch));   // this warp's 32 x 32 staging tile (pitch 36 floats)
-  const int sub_r = lane >> 3, sub_c = (lane & 7) * 4;  // coalesced view: 4 rows x 128 B per instruction
-  long long* dbg = (blockIdx.x == 0) ? S->dbg : nullptr;
-  const int dbgf = S->dbg_flags;
-  const uint32_t rank = cluster_rank();
+  EpiCtx c;
+  c.lane = threadIdx.x & 31;
+  c.q = warp & 3;               // TMEM lane quarter this warp may access
+  c.eg = (warp - 4) >> 2;       // 0/1: which alternating 32-column chunks this warp owns
+  c.ew = warp - 4;              // 0..7
+  c.et = threadIdx.x - 128;     // 0..255
+  c.tmem = *sm.tmem_base();
+  c.stg_s = smem_u32(sm.epi_stage() + c.ew * (32 * kEpiPitch));   // this warp's 32 x 32 staging tile (pitch 36 floats)
+  c.sub_r = c.lane >> 3; c.sub_c = (c.lane & 7) * 4;  // coalesced view: 4 rows x 128 B per instruction
+  c.dbg = (blockIdx.x == 0 && (S->dbg_phase < 0 || S->dbg_phase == (int)(&ph - S->phase))) ? S->dbg : nullptr;
+  c.dbgf = S->dbg_flags;
+  c.rank = cluster_rank();
   int ntr = 0;
   for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs
     Item it;
     if (!decode_item(S, ph, c_begin, item, it)) continue;
-    const GemmDesc& g = *it.g;
-    const int tcBN = g.tcBN;
-    const int n0 = it.tile_n * tcBN;
-    const int n_end = min(g.N, n0 + tcBN);   // this tile owns output columns [n0, n_end)
-    const int ncols = n_end - n0;
-    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16);
-
-    // ---- drain: both accumulators of this warp's chunks -> registers, then TMEM goes back to the MMA issuer.
-    // Only the few scalars above are live here: the 128 accumulator registers leave no room for more.
-    mbar_wait(&sm.tmem_full()[0], ring.acc_phase);
-    if (et == 0) trace(dbg, 3, ntr, 0);
-    fence_after_sync();
-    uint32_t acc[4][32];
-    {
-      // all main-accumulator chunks are requested at once, then the cross-term chunks 16 columns at a time
-      uint32_t pa[16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if ((eg + 2 * j) * 32 < ncols) tmem_ld32_issue(tbase + (uint32_t)((eg + 2 * j) * 32), acc[j]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c0 = (eg + 2 * j) * 32;
-        if (c0 < ncols) {
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            tmem_ld16_issue(tbase + (uint32_t)(tcBN + c0 + hh * 16), pa);
-            tmem_wait_ld16(pa);
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-              acc[j][hh * 16 + i] = __float_as_uint(__uint_as_float(acc[j][hh * 16 + i]) + __uint_as_float(pa[i]));
-          }
-        }
-      }
-    }
-    fence_before_sync();
-    __syncwarp();
-    if (lane == 0) mbar_arrive_leader(&sm.tmem_empty()[0]);   // the leader's MMA issuer waits for both CTAs' epilogue warps
-    ring.acc_phase ^= 1;
-    if (et == 0) trace(dbg, 3, ntr, 1);
-
-    // locals: see the note in gemm_phase_front
-    const int chain = it.chain;
-    const int m0 = it.tile_m * (2 * kBM) + (int)rank * kBM;   // this CTA's 128 rows of the pair's tile
-    const size_t split_off = (size_t)it.split * S->C_alloc * S->Pp;   // gradient copy of this K split (EPI_GRADW only)
-    float* C = g.C ? g.C + (size_t)chain * g.sC + split_off : nullptr;
-    const float* bias = g.bias ? g.bias + (size_t)chain * g.sBias : nullptr;
-    const float* aux = g.aux ? g.aux + (size_t)chain * g.sAux : nullptr;
-    float* gbias = g.gbias ? g.gbias + (size_t)chain * g.sGb + split_off : nullptr;
-    const int gM = g.M, epi = g.epi, ldaux = g.ldaux, ldc = g.ldc, biasCol = g.biasCol;
-    const float scale = g.scale;
-    const int r0 = m0 + q * 32;
-
-    // ---- fused epilogue from registers, one 32 x 32 chunk at a time. The chunk loop is NOT unrolled (unrolled, this
-    // section was 160 KB of straight-line code and stalled on instruction fetch) and nothing may spill: with the
-    // shared-memory carve-out at its maximum there is no L1 left to catch local-memory traffic. The chunk's
-    // accumulators go to the staging tile with predicated stores, and all epilogue math runs in the coalesced
-    // (transposed) domain where aux loads, bias and stores share one address pattern.
-    float l_sse = 0.f, l_sd = 0.f;
-    const int lim = (epi == EPI_GRADW && biasCol >= 0) ? min(n_end, biasCol) : n_end;
-#pragma unroll 1
-    for (int jj = 0; jj < 4; ++jj) {
-      const int c0 = (eg + 2 * jj) * 32;
-      if (c0 >= ncols || (dbgf & 16)) break;
-      const int cc = n0 + c0 + sub_c;            // first of this thread's 4 output columns
-      const bool cv = cc < n_end;
-      // aux tile (sigmoid outputs for EPI_DSIG, data for EPI_LOSS), 4 rows x 128 B per instruction, in two groups of four
-      // pinned loads: eight float4 on top of the 128 accumulator registers do not fit the 208-register budget
-      float4 t[4];
-      const float* ap = aux ? aux + (size_t)(r0 + sub_r) * ldaux + cc : nullptr;
-      auto load_aux = [&](int half) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ii = half * 4 + i;
-          t[i] = (cv && r0 + ii * 4 + sub_r < gM) ? ldg128_pinned(ap + (size_t)(ii * 4) * ldaux) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      if (aux) load_aux(0);
-      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bias && cv) b4 = __ldg(reinterpret_cast<const float4*>(&bias[cc]));
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (j == jj) {
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4)
-            sts128(stg_s + (lane * kEpiPitch + j4 * 4) * 4,
-                   make_float4(__uint_as_float(acc[j][j4 * 4]), __uint_as_float(acc[j][j4 * 4 + 1]),
-                               __uint_as_float(acc[j][j4 * 4 + 2]), __uint_as_float(acc[j][j4 * 4 + 3])));
-        }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (i == 4 && aux) load_aux(1);
-        const int rr = r0 + i * 4 + sub_r;
-        float4 o = lds128(stg_s + ((i * 4 + sub_r) * kEpiPitch + sub_c) * 4);
-        if (rr >= gM || !cv) continue;
-        o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-        if (epi == EPI_SIGMOID) {
-          o.x = __fdividef(1.0f, 1.0f + __expf(-o.x)); o.y = __fdividef(1.0f, 1.0f + __expf(-o.y));
-          o.z = __fdividef(1.0f, 1.0f + __expf(-o.z)); o.w = __fdividef(1.0f, 1.0f + __expf(-o.w));
-        } else if (epi == EPI_DSIG) {
-          o.x *= t[i & 3].x * (1.0f - t[i & 3].x); o.y *= t[i & 3].y * (1.0f - t[i & 3].y);
-          o.z *= t[i & 3].z * (1.0f - t[i & 3].z); o.w *= t[i & 3].w * (1.0f - t[i & 3].w);
-        } else if (epi == EPI_LOSS) {
-          float d[4] = {o.x - t[i & 3].x, o.y - t[i & 3].y, o.z - t[i & 3].z, o.w - t[i & 3].w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (cc + e < n_end) { l_sse = fmaf(d[e], d[e], l_sse); l_sd += d[e]; }
-            d[e] *= scale;
-          }
-          o = make_float4(d[0], d[1], d[2], d[3]);
-        }
-        if (C) {
-          float* dst = &C[(size_t)rr * ldc + cc];
-          if (cc + 4 <= lim) {
-            *reinterpret_cast<float4*>(dst) = o;
-          } else {
-            const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (cc + e < lim) dst[e] = ov[e];
-              else if (epi == EPI_GRADW && cc + e == biasCol) gbias[rr] = ov[e];   // ones-column trick
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
-    if (et == 0) trace(dbg, 3, ntr, 2);
-    if (epi == EPI_LOSS) {
-      double s0 = (double)l_sse, s1 = (double)l_sd;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (lane == 0) { sm.red()[ew * 2] = s0; sm.red()[ew * 2 + 1] = s1; }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (et == 0) {
-        double* p = g.part + ((size_t)chain * g.partStride + (size_t)(it.tile_m * 2 + (int)rank) * g.tn + it.tile_n) * 2;
-        double a0 = 0.0, a1 = 0.0;
-        for (int w = 0; w < kEpiWarps; ++w) { a0 += sm.red()[w * 2]; a1 += sm.red()[w * 2 + 1]; }
-        p[0] = a0;
-        p[1] = a1;
-      }
-    }
+    epilogue_tile<kEpiA, kEpiB>(S, it, c, sm, ring, ntr);
   }
 }
 

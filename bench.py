@@ -62,7 +62,7 @@ def measured_peaks():
 
 
 def ncu_traffic(shape, cpg, gemm_path):
-    """DRAM bytes (read + write) of one launch of the persistent kernel from the committed `ncu --set full` capture
+    """DRAM bytes (read + write) of one launch of the step program from the committed `ncu --set full` capture
     (profiles/r1_program_kernel_traffic.json), scaled to this run's chains x iterations per launch; None if no capture fits."""
     p = os.path.join(ROOT, "profiles", "r1_program_kernel_traffic.json")
     try:
@@ -257,7 +257,7 @@ def run_gpu(args):
     def pt_round():
         """One bench step: 5 iterations of every resident chain + one exchange sweep."""
         if ladder is None:
-            s.run(SWAP_INTERVAL)          # exchange phases run inside the persistent kernel
+            s.run(SWAP_INTERVAL)          # exchange phases are part of the step program
         else:
             s.step(SWAP_INTERVAL)
             s.synchronize()
@@ -302,7 +302,7 @@ def run_gpu(args):
     chain_steps = world * cpg * args.steps * SWAP_INTERVAL
     value = chain_steps / (ms / 1000.0)
 
-    # per-launch duration of the dominant (persistent step) kernel, measured live with CUDA events
+    # per-launch duration of the step program (graph of per-phase kernels / persistent kernel), measured live with CUDA events
     per_launch = []
     for _ in range(min(3, args.steps)):
         pt_round()
@@ -377,8 +377,11 @@ def run_gpu(args):
             "exchange_ms_per_round": (1000.0 * float(np.median(exch_s)) if exch_s else None),
             "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": achieved_tf / peaks["bf16_sustained"], "traffic": ncu_traffic(shape, cpg, gemm_path),
-                         "kernel": ("bae_program_kernel_tc" if gemm_path == 2 else "bae_program_kernel") + " (persistent step kernel, "
-                                   "one cooperative launch = 5 iterations of all resident chains" + ("" if sharded else " + exchange sweep") + ")",
+                         "kernel": (("bae_phase_kernel_tc (tcgen05 GEMM phases, ~80% of the step) + bae_aux_kernel (BatchNorm / Adam): the step "
+                                     "program of 5 iterations of all resident chains" + ("" if sharded else " + exchange sweep") +
+                                     ", one CUDA-graph launch of its per-phase kernels") if gemm_path == 2 else
+                                    ("bae_program_kernel (persistent step kernel, one cooperative launch = 5 iterations of all resident chains" +
+                                     ("" if sharded else " + exchange sweep") + ")")),
                          "kernel_ms_per_launch": kernel_ms,
                          "algorithmic_gflop_per_launch": flops_per_launch / 1e9,
                          "peak_source": peaks["source"] + " bf16 dense sustained (MEASURED_PEAKS.json); kind::tf32 dense is 1/2 of it, a 3-way split 1/6",

@@ -8,7 +8,7 @@ from bayesianautoencoders_b200 import _native as N
 from bench import SHAPES, synth
 dims4, ntr, nte = SHAPES["madelon"]
 train, test = synth(dims4, ntr, nte)
-C = 16
+C = int(os.environ.get('TRACE_CHAINS', '16'))
 s = DeviceSampler(dims4, train, test, C, 8, 100, np.tile(2.0 ** (np.arange(8) / 7), C // 8))
 rng = np.random.default_rng(0)
 for j in range(C): s.init_chain(j, default_theta_init(dims4, rng), rng.standard_normal(s.w_size))
@@ -36,6 +36,19 @@ for role, name in enumerate(["producer", "mma", "convert", "epilogue"]):
             if len(t) > 8:
                 d = np.diff([b for _, b in t[6:]])
                 print(f"{name} tile {ti}: start {t[0][1]} end {t[-1][1]} blocks {len(t)} pace median {np.median(d):.0f} mean {d.mean():.0f}")
+                if ti == 1 and role == 1: print("   mma tile 1 deltas", np.diff([b for _, b in t]).tolist())
+                if ti == 1 and role == 0: print("   producer tile 1 deltas", np.diff([b for _, b in t]).tolist())
     else:
-        print(name, rel[:12])
+        print(name, rel[:40])
+        tiles, cur = [], None
+        for a, b in rel:
+            if a == 0:
+                cur = {0: b}; tiles.append(cur)
+            elif cur is not None:
+                cur[a] = b
+        for t in tiles[1:6]:
+            keys = sorted(t)
+            print('  tile:', ' '.join(f"{k}:+{t[k] - t[0]}" for k in keys))
+        full = [t[0] for t in tiles]
+        print('  tile period', np.diff(full)[:10])
 s.close()

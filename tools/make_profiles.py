@@ -9,18 +9,20 @@ import json
 import sys
 
 launch_csv, raw_csv = sys.argv[1], sys.argv[2]
-phases_log = sys.argv[3] if len(sys.argv) > 3 else None
+bench_ms = sys.argv[3] if len(sys.argv) > 3 else '61-62'
 rows = [r for r in csv.reader(open(launch_csv)) if len(r) > 5]
 h, data = rows[0], rows[1:]
 iv, ik = h.index('Metric Value'), h.index('Kernel Name')
 vals = [float(r[iv].replace(',', '')) / 1000 for r in data]   # ns -> us
 names = ['PRO', 'F1', 'F2', 'F3', 'BNF', 'F4', 'F5', 'F6', 'B6 (dW6|dH5)', 'B5', 'B4', 'BNB', 'B3', 'B2', 'B1', 'ADAM1', 'F1b', 'F2b', 'F3b',
          'BNFb', 'F4b', 'F5b', 'F6b', 'B6b', 'B5b', 'B4b', 'BNBb', 'B3b', 'B2b', 'B1b', 'ADAM2', 'T1', 'T2', 'T3', 'BNT', 'T4', 'T5', 'T6', 'EPI']
-with open('profiles/r1_v4_tc_phase_launches.csv', 'w') as f:
+PER_IT = 42   # 39 step phases + 3 exchange phases (which return at once unless the step counter says "swap round")
+names_it = names + ['SWAP_DECIDE', 'SWAP_GATHER', 'SWAP_SCATTER']
+assert len(vals) == 5 * PER_IT, f"expected {5 * PER_IT} launches (5 iterations x 42 phases), got {len(vals)}"
+with open('profiles/r1_v5_step_program_launches.csv', 'w') as f:
     f.write("launch,iteration,phase,kernel,duration_us\n")
     for i, (r, v) in enumerate(zip(data, vals)):
-        ph = names[i % 39] if i < 195 else ['SWAP_DECIDE', 'SWAP_GATHER', 'SWAP_SCATTER'][i - 195]
-        f.write(f"{i},{min(i // 39, 4)},{ph},{r[ik].split('(')[0]},{v:.3f}\n")
+        f.write(f"{i},{i // PER_IT},{names_it[i % PER_IT]},{r[ik].split('(')[0].replace('void ', '')},{v:.3f}\n")
 F = {'F1': 2 * 2000 * 450 * 500, 'F2': 2 * 2000 * 400 * 450, 'F3': 2 * 2000 * 300 * 400, 'F4': 2 * 2000 * 400 * 300, 'F5': 2 * 2000 * 450 * 400,
      'F6': 2 * 2000 * 500 * 450}
 fl = dict(F)
@@ -29,9 +31,11 @@ for k, v in F.items():
 fl.update({'B6': 2 * 2000 * 500 * 450 * 2, 'B5': 2 * 2000 * 450 * 400 * 2, 'B4': 2 * 2000 * 400 * 300 * 2, 'B3': 2 * 2000 * 300 * 400 * 2,
            'B2': 2 * 2000 * 400 * 450 * 2, 'B1': 2 * 2000 * 450 * 500})
 it0 = vals[:39]
+sw = vals[4 * PER_IT + 39:5 * PER_IT]
 tot = sum(it0)
 lines, g, b, a, gf = [], 0.0, 0.0, 0.0, 0.0
-for n, v in zip(names, it0):
+kern = [r[ik].split('(')[0].replace('void ', '') for r in data[:39]]
+for n, v, kn in zip(names, it0, kern):
     base = n.split(' ')[0].rstrip('b')
     tf = f"{fl[base] * 64 / (v * 1e-6) / 1e12:.0f}" if base in fl else ""
     if base in fl:
@@ -40,36 +44,35 @@ for n, v in zip(names, it0):
         b += v
     if base.startswith('ADAM'):
         a += v
-    lines.append(f"| {n} | {v:.1f} | {100 * v / tot:.1f}% | {tf} |")
+    lines.append(f"| {n} | `{kn}` | {v:.1f} | {100 * v / tot:.1f}% | {tf} |")
 inkernel = ""
 if phases_log:
     txt = open(phases_log).read()
     inkernel = "\nIn-kernel phase times of the same build (`tests/dev_phases.py`, `%globaltimer` after every grid barrier of the persistent kernel, us):\n\n```\n" + \
         "\n".join(l for l in txt.splitlines() if l.startswith(('launch ms', '{', 'sum us'))) + "\n```\n"
-md = f"""# Round 1, engine v4 (CTA pairs) - tcgen05 3xTF32 path, per-phase launch list (ncu gpu__time_duration.sum, --clock-control none)
+md = f"""# Round 1, step program v5 (per-phase kernels in a CUDA graph) - launch list (ncu gpu__time_duration.sum, --clock-control none)
 
-Command: `BAE_PHASE_LAUNCH=1 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv python tools/profile_step.py --chains 64 --rounds 2 --steps-per-round 5 --profile-round 1`
-(Madelon shape, 64 chains, the 2nd PT round: 5 iterations + 1 exchange sweep; every phase of the persistent step program launched as its
-own `bae_phase_kernel_tc` so that ncu can list them; production = ONE cooperative launch per round). Raw list: `r1_v4_tc_phase_launches.csv`.
-Per-launch times are cold-cache and serialised; compare SHARES. Sum per iteration: {', '.join(f'{sum(vals[i * 39:(i + 1) * 39]) / 1000:.2f}' for i in range(5))} ms;
-exchange sweep (decide / gather / scatter): {vals[195]:.0f} / {vals[196]:.0f} / {vals[197]:.0f} us.
+Command: `BAE_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv python tools/profile_step.py --chains 64 --rounds 2 --steps-per-round 5 --profile-round 1`
+(Madelon shape, 64 chains, the 2nd PT round = ONE `bae_run(5)` call: 5 iterations x 42 phase launches, the exchange sweep in the last three; these
+are the production kernels - `BAE_NO_GRAPH=1` only makes the library launch them directly instead of replaying the captured graph).
+Raw list: `r1_v5_step_program_launches.csv`. Per-launch times are cold-cache and serialised (and the SM clock is higher than in a back-to-back run, which
+sits at the power cap); compare SHARES. Sum per iteration: {', '.join(f'{sum(vals[i * PER_IT:(i + 1) * PER_IT]) / 1000:.2f}' for i in range(5))} ms
+(later iterations have fewer chains on a Langevin step); exchange sweep (decide / gather / scatter): {sw[0]:.0f} / {sw[1]:.0f} / {sw[2]:.0f} us.
 
-| phase | iteration 0 (us) | share | algorithmic TFLOP/s (64 chains) |
-|---|---:|---:|---:|
+| phase | kernel | iteration 0 (us) | share | algorithmic TFLOP/s (64 chains) |
+|---|---|---:|---:|---:|
 """ + "\n".join(lines) + f"""
 
-GEMM phases: {100 * g / tot:.1f}% of the iteration ({gf / (g * 1e-6) / 1e12:.0f} TFLOP/s algorithmic over the GEMM phases; the sustained-clock ceiling of a
-3-way TF32 split is 1381.9 / 6 = 230 TFLOP/s); BatchNorm {100 * b / tot:.1f}%; Adam + noise {100 * a / tot:.1f}%.
-{inkernel}
-The shares agree for the GEMM phases (same time inside the persistent kernel as stand-alone). The BatchNorm and Adam phases are slower inside the
-persistent kernel than as stand-alone launches: its register allocation spills in these phases and the 227 KB shared-memory carve-out leaves no L1
-behind local memory (the Adam inputs are already streamed through shared memory by the bulk-copy engine; without that they took 1.8 / 1.4 ms).
+GEMM phases (`bae_phase_kernel_tc<kindA, kindB>`): {100 * g / tot:.1f}% of the iteration ({gf / (g * 1e-6) / 1e12:.0f} TFLOP/s algorithmic over the GEMM phases; the
+sustained-clock ceiling of a 3-way TF32 split is 1381.9 / 6 = 230 TFLOP/s); BatchNorm (`bae_aux_kernel<1>`) {100 * b / tot:.1f}%; Adam + noise
+(`bae_aux_kernel<0>`) {100 * a / tot:.1f}%. `bench.py` measures the same program at {bench_ms} ms per round back to back (graph replay, SM clock at the
+power cap): the GEMM kernels' share of the step is the same in both views.
 """
-open('profiles/r1_v4_tc_phase_launches.md', 'w').write(md)
+open('profiles/r1_v5_step_program_launches.md', 'w').write(md)
 
 r = list(csv.reader(open(raw_csv)))
 hdr, units, prow = r[0], r[1], r[2:]
-assert len(prow) == 39, "expected the 39 per-phase launches of one iteration"
+assert len(prow) == PER_IT, "expected the 42 per-phase launches of one iteration"
 UNIT = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1, 'ms': 1e3, 's': 1e6}
 
 
@@ -88,42 +91,36 @@ inst = colv('smsp__inst_executed.sum')
 regs = colv('launch__registers_per_thread')
 rd, wr, us = sum(rdv), sum(wrv), sum(dur)
 ptab = "\n".join(f"| {n} | {dur[i]:.1f} | {rdv[i] / 1e6:.1f} | {wrv[i] / 1e6:.1f} | {(rdv[i] + wrv[i]) / dur[i] / 1e3:.0f} | {dramp[i]:.1f} | {tens[i]:.1f} | "
-                 f"{l2hit[i]:.0f} | {inst[i] / 1e6:.2f} | {lld[i] + lst[i]:.0f} |" for i, n in enumerate(names))
+                 f"{l2hit[i]:.0f} | {inst[i] / 1e6:.2f} | {lld[i] + lst[i]:.0f} |" for i, n in enumerate(names_it))
 gi = [i for i, n in enumerate(names) if n.split(' ')[0].rstrip('b') in fl]
 gt = sum(dur[i] for i in gi)
-md2 = f"""# Round 1, engine v4 (CTA pairs) - the persistent step program, one `ncu --set full` capture over its 39 phases
+md2 = f"""# Round 1, step program v5 - one `ncu --set full` capture over the 42 kernels of an iteration
 
-`ncu --set full` cannot replay the production launch of `bae_program_kernel_tc` (cooperative + cluster dimension 2: the profiler reports
-LaunchFailed for it and the report holds zeros; `--metrics gpu__time_duration.sum` alone works, see `r1_v4_tc_phase_launches.md`). The full-set
-capture is therefore taken over the same program with every phase launched as its own `bae_phase_kernel_tc` (same device code, cluster launch
-without the cooperative attribute):
+`BAE_NO_GRAPH=1 ncu --set full --clock-control none --profile-from-start off -k regex:bae_ -c 42 python tools/profile_step.py --chains 8 --rounds 2 --steps-per-round 1 --profile-round 1`
+(Madelon shape, 8 chains, ONE iteration of the production step program: GEMM phases = `bae_phase_kernel_tc<kindA, kindB>`, 148 CTAs = 74 CTA pairs x 512
+threads, 1 CTA/SM, {regs[1]:.0f} registers/thread at launch redistributed by `setmaxnreg`; BatchNorm / Adam / scalar phases = `bae_aux_kernel<family>`,
+256-thread CTAs. The report (>100 MB) stays on the GPU box; this file is built from its raw page export by `tools/make_profiles.py`.)
 
-`BAE_PHASE_LAUNCH=1 ncu --set full --clock-control none --profile-from-start off -k regex:bae_phase_kernel_tc -c 39 python tools/profile_step.py --chains 8 --rounds 2 --steps-per-round 1 --profile-round 1`
-(Madelon shape, 8 chains, ONE iteration = 39 launches of 148 CTAs = 74 CTA pairs x 512 threads, 1 CTA/SM, {regs[0]:.0f} registers/thread at launch,
-redistributed by `setmaxnreg`; the 124 MB report stays on the GPU box, its raw page export is what this file is built from.)
-
-Sum of the 39 kernel durations {us / 1e3:.3f} ms under ncu (cold caches, serialised). Algorithmic FLOPs of one iteration: 8 chains x 27.18 GFLOP = 217 GFLOP
+Sum of the 42 kernel durations {us / 1e3:.3f} ms under ncu (cold caches, serialised). Algorithmic FLOPs of one iteration: 8 chains x 27.18 GFLOP = 217 GFLOP
 -> {217 / (us / 1e3):.0f} TFLOP/s at 8 chains over the whole iteration, {sum(fl[names[i].split(' ')[0].rstrip('b')] for i in gi) * 8 / (gt * 1e-6) / 1e12:.0f} TFLOP/s over the GEMM phases (8 chains fill only
-a fraction of the 74 CTA pairs per phase; production runs 64 chains per GPU: 121 TFLOP/s whole-step, `bench.py`).
+a fraction of the 74 CTA pairs per phase; production runs 64 chains per GPU, `bench.py`).
 DRAM traffic per iteration: read {rd / 1e6:.0f} MB + write {wr / 1e6:.0f} MB = {(rd + wr) / 8 / 1e6:.0f} MB per chain-iteration. Algorithmic weight-state traffic is
 22 x 4 B x 1.05 M = 93 MB per chain-iteration (SURVEY 8d); the rest is activations and deltas (41 MB per chain, written once and re-read by the backward
 pass and the weight-gradient GEMMs) plus the four K-split copies of the gradient (4 x 4.2 MB written by the dW GEMMs, read by each Adam phase).
-At 8 chains most of the working set (8 x 130 MB) does not fit the 126 MB L2 between phases, as in production.
-SASS evidence (`cuobjdump -sass libbae_b200.so`): UTCHMMA (tcgen05.mma cta_group::2 kind::tf32), UTMALDG (TMA), UBLKCP (cp.async.bulk, Adam staging),
-LDTM (tcgen05.ld), UTCBAR (tcgen05.commit, multicast), USETMAXREG (setmaxnreg), SYNCS (mbarrier), UCGABAR (cluster barrier).
+SASS evidence (`cuobjdump -sass libbae_b200.so`): UTCHMMA (tcgen05.mma cta_group::2 kind::tf32), UTMALDG (TMA), LDTM (tcgen05.ld),
+UTCBAR (tcgen05.commit, multicast), USETMAXREG (setmaxnreg), SYNCS (mbarrier), UCGABAR (cluster barrier).
 
 | phase | us | DRAM read MB | DRAM write MB | DRAM GB/s | DRAM % of peak | tensor pipe active % | L2 hit % | warp inst (M) | local ld+st inst |
 |---|---:|---:|---:|---:|---:|---:|---:|---:|---:|
 {ptab}
 
 Reading: the GEMM phases keep the tensor pipe {min(tens[i] for i in gi):.0f}-{max(tens[i] for i in gi):.0f}% active at 8 chains (each 3xTF32 K block is 6 MMAs; at 64 chains every CTA pair
-has 3-7 tiles per phase and the traced tile loop runs at the tensor-pipe pace, see DESIGN.md 4); the Adam phases move {(rdv[15] + wrv[15]) / 1e6:.0f} MB at {(rdv[15] + wrv[15]) / dur[15] / 1e3:.0f} GB/s
-stand-alone, {100 * (rdv[15] + wrv[15]) / dur[15] / 1e3 / 6549:.0f}% of the measured HBM peak (6549 GB/s) - they are bound by the Philox/Box-Muller + Adam arithmetic of 256 threads per SM,
-not by HBM. Local-memory instructions are zero in the per-phase kernels; the persistent kernel's allocation spills in the BatchNorm and Adam phases
-(`tools/build_check.sh` prints the histogram), which go to L2 (no L1 behind local memory with a 227 KB carve-out).
+has 3-14 tiles per phase and the traced tile loop runs close to the tensor-pipe pace, see DESIGN.md 4); the Adam phases move {(rdv[15] + wrv[15]) / 1e6:.0f} MB at
+{(rdv[15] + wrv[15]) / dur[15] / 1e3:.0f} GB/s = {100 * (rdv[15] + wrv[15]) / dur[15] / 1e3 / 6549:.0f}% of the measured HBM peak (6549 GB/s) at 8 chains. Local-memory instructions of the GEMM kernels are the
+front half's (TMA producer / MMA issuer at 48 registers) per-tile set-up; the epilogue half is spill free since it is specialised per kind.
 """
-open('profiles/r1_v4_program_kernel_ncu_full.md', 'w').write(md2)
+open('profiles/r1_v5_step_program_ncu_full.md', 'w').write(md2)
 json.dump({"shape": "madelon", "gemm_path": 2, "chains": 8, "iterations": 1, "dram_bytes_read": rd, "dram_bytes_write": wr, "kernel_ms_under_ncu": us / 1e3,
-           "source": "ncu --set full over the 39 bae_phase_kernel_tc launches of one iteration, 8 chains (profiles/r1_v4_program_kernel_ncu_full.md)"},
+           "source": "ncu --set full over the 42 kernels of one iteration of the step program, 8 chains (profiles/r1_v5_step_program_ncu_full.md)"},
           open('profiles/r1_program_kernel_traffic.json', 'w'), indent=1)
 print("profiles written")
