@@ -427,9 +427,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         Item it;
         if (!decode_item(S, ph, c_begin, item, it)) continue;
         const GemmDesc& g = *it.g;
-        // the epilogue warps of BOTH CTAs have drained the main accumulator of the previous tile (the cross-term
-        // accumulator follows: tmem_empty[0], waited for before the first cross-term MMA)
-        mbar_wait_cluster(&sm.tmem_empty()[1], ring.acc_phase ^ 1);
+        mbar_wait_cluster(&sm.tmem_empty()[0], ring.acc_phase ^ 1);   // the epilogue warps of BOTH CTAs have drained the previous tile
         fence_after_sync();
         const uint32_t d_main = tmem, d_cross = tmem + (uint32_t)g.tcBN;
         const bool amn = g.aMode != 0, bmn = g.bMode != 0;
@@ -450,10 +448,6 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             const uint32_t acc0 = kb ? 1u : 0u;
             umma_tf32(d_main, ah, bh, idesc, acc0);
             if (two) umma_tf32(d_main, ah + astep, bh + bstep, idesc, 1u);
-            if (kb == 0) {
-              mbar_wait_cluster(&sm.tmem_empty()[0], ring.acc_phase ^ 1);
-              fence_after_sync();
-            }
             if (!(dbgf & 8)) {
               umma_tf32(d_cross, al, bh, idesc, acc0);
               umma_tf32(d_cross, ah, bl, idesc, 1u);
@@ -585,17 +579,13 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
   fence_after_sync();
   uint32_t acc[4][32];
   {
-    // all main-accumulator chunks are requested at once, then the cross-term chunks 16 columns at a time. The first
-    // wait covers every main chunk: the main accumulator goes back to the MMA issuer there (tmem_empty[1]), which can
-    // start the next tile's hi*hi products while the cross-term accumulator is still being drained.
+    // all main-accumulator chunks are requested at once, then the cross-term chunks 16 columns at a time.
+    // (Handing the main accumulator back first, so that the next tile's hi*hi products start during the cross-term drain,
+    // was measured: the gap between tiles shrank by 1.7 k cycles, the step did not get faster - not kept.)
     uint32_t pa[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if ((eg + 2 * j) * 32 < ncols) tmem_ld32_issue(tbase + (uint32_t)((eg + 2 * j) * 32), acc[j]);
-    if (eg * 32 >= ncols) {   // a narrow last tile: this warp owns no chunk at all
-      __syncwarp();
-      if (lane == 0) mbar_arrive_leader(&sm.tmem_empty()[1]);
-    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c0 = (eg + 2 * j) * 32;
@@ -604,11 +594,6 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
         for (int hh = 0; hh < 2; ++hh) {
           tmem_ld16_issue(tbase + (uint32_t)(tcBN + c0 + hh * 16), pa);
           tmem_wait_ld16(pa);
-          if (j == 0 && hh == 0) {
-            fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_leader(&sm.tmem_empty()[1]);
-          }
 #pragma unroll
           for (int i = 0; i < 16; ++i)
             acc[j][hh * 16 + i] = __float_as_uint(__uint_as_float(acc[j][hh * 16 + i]) + __uint_as_float(pa[i]));
