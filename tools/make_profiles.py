@@ -6,7 +6,14 @@
 """
 import csv
 import json
+import re
 import sys
+
+
+def kname(full):
+    """'void bae::bae_phase_kernel_tc<(int)0, (int)-1>(const ...)' -> 'bae_phase_kernel_tc<0, -1>'"""
+    n = full.replace('(int)', '').replace('void ', '').replace('bae::', '')
+    return re.split(r'\(', n)[0]
 
 launch_csv, raw_csv = sys.argv[1], sys.argv[2]
 bench_ms = sys.argv[3] if len(sys.argv) > 3 else '61-62'
@@ -22,7 +29,7 @@ assert len(vals) == 5 * PER_IT, f"expected {5 * PER_IT} launches (5 iterations x
 with open('profiles/r1_v5_step_program_launches.csv', 'w') as f:
     f.write("launch,iteration,phase,kernel,duration_us\n")
     for i, (r, v) in enumerate(zip(data, vals)):
-        f.write(f"{i},{i // PER_IT},{names_it[i % PER_IT]},{r[ik].split('(')[0].replace('void ', '')},{v:.3f}\n")
+        f.write(f"{i},{i // PER_IT},{names_it[i % PER_IT]},{kname(r[ik])},{v:.3f}\n")
 F = {'F1': 2 * 2000 * 450 * 500, 'F2': 2 * 2000 * 400 * 450, 'F3': 2 * 2000 * 300 * 400, 'F4': 2 * 2000 * 400 * 300, 'F5': 2 * 2000 * 450 * 400,
      'F6': 2 * 2000 * 500 * 450}
 fl = dict(F)
@@ -34,7 +41,7 @@ it0 = vals[:39]
 sw = vals[4 * PER_IT + 39:5 * PER_IT]
 tot = sum(it0)
 lines, g, b, a, gf = [], 0.0, 0.0, 0.0, 0.0
-kern = [r[ik].split('(')[0].replace('void ', '') for r in data[:39]]
+kern = [kname(r[ik]) for r in data[:39]]
 for n, v, kn in zip(names, it0, kern):
     base = n.split(' ')[0].rstrip('b')
     tf = f"{fl[base] * 64 / (v * 1e-6) / 1e12:.0f}" if base in fl else ""
@@ -45,11 +52,6 @@ for n, v, kn in zip(names, it0, kern):
     if base.startswith('ADAM'):
         a += v
     lines.append(f"| {n} | `{kn}` | {v:.1f} | {100 * v / tot:.1f}% | {tf} |")
-inkernel = ""
-if phases_log:
-    txt = open(phases_log).read()
-    inkernel = "\nIn-kernel phase times of the same build (`tests/dev_phases.py`, `%globaltimer` after every grid barrier of the persistent kernel, us):\n\n```\n" + \
-        "\n".join(l for l in txt.splitlines() if l.startswith(('launch ms', '{', 'sum us'))) + "\n```\n"
 md = f"""# Round 1, step program v5 (per-phase kernels in a CUDA graph) - launch list (ncu gpu__time_duration.sum, --clock-control none)
 
 Command: `BAE_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv python tools/profile_step.py --chains 64 --rounds 2 --steps-per-round 5 --profile-round 1`
