@@ -234,6 +234,20 @@ static int tmap_mnmajor(CUtensorMap* out, const float* ptr, int extent, int K, i
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// Output of a GEMM: element (row, col) of slice z at ptr[z*cs + row*ld + col]; the epilogue stores 32 x 32 boxes from a
+// 128-byte-swizzled staging tile. Rows >= `rows` and columns >= `cols` of a box are clipped by the copy engine.
+static int tmap_store(CUtensorMap* out, const float* ptr, int cols, int rows, int ld, int nslice, long long cs) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)std::max(1, nslice)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(cs > 0 ? cs : (long long)rows * ld) * 4};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 static void build_program(bae_handle* h) {
   DevState& s = h->hs;
   const long long P = s.Pp;
@@ -264,6 +278,18 @@ static void build_program(bae_handle* h) {
       if (rc != 0 && h->tmap_error.empty())
         h->tmap_error = "cuTensorMapEncodeTiled failed (CUresult " + std::to_string(rc) + ") for GEMM operand " + std::to_string(i);
       g.tmIdx[i] = (int)h->tmaps_host.size();
+      h->tmaps_host.push_back(tm);
+    }
+    {
+      CUtensorMap tm;
+      memset(&tm, 0, sizeof(tm));
+      const bool gw = g.epi == EPI_GRADW;
+      const int cols = (gw && g.biasCol >= 0) ? std::min(g.N, g.biasCol) : g.N;
+      const int nslice = g.sC ? (gw ? std::max(1, s.max_ksplit) : 1) * s.C_alloc : 1;
+      const int rc = tmap_store(&tm, g.C, cols, g.M, g.ldc, nslice, g.sC);
+      if (rc != 0 && h->tmap_error.empty())
+        h->tmap_error = "cuTensorMapEncodeTiled failed (CUresult " + std::to_string(rc) + ") for a GEMM output";
+      g.tmIdx[2] = (int)h->tmaps_host.size();
       h->tmaps_host.push_back(tm);
     }
     // instruction descriptor of the pair's MMA (cta_group::2): M = 256, N = tcBN

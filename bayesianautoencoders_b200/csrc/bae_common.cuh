@@ -62,7 +62,7 @@ struct GemmDesc {
   int tcBN;             // tile width (multiple of 16; multiple of 32 when B is N-major), <= 256
   int tcBBytes;         // bytes of one B tile (hi or lo) per K block
   int tcMain;           // TMEM accumulators the hi*hi term rotates over; (tcMain + 1) * tcBN <= 512 columns
-  int tmIdx[2];         // tensor maps: A, B
+  int tmIdx[3];         // tensor maps: A, B (loads), C (32 x 32 store boxes of the epilogue)
   unsigned idesc;       // tcgen05 instruction descriptor
   int biasCol;          // EPI_GRADW: output column that holds the bias gradient (ones column trick), or -1
 };

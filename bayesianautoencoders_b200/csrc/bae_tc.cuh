@@ -324,6 +324,15 @@ __device__ __forceinline__ void trace(long long* dbg, int role, int& n, int tag)
   }
 }
 
+// Store of one 32 x 32 box from a 128-byte-swizzled staging tile (shared -> global through the copy engine)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src_s, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tm), "r"(src_s), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Decode the work item of a GEMM phase (same arithmetic in every role).
 struct Item { const GemmDesc* g; int chain, tile_m, tile_n, split, kb0, nkb; };
 
@@ -611,9 +620,12 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
   const int chain = it.chain;
   const int m0 = it.tile_m * (2 * kBM) + (int)c.rank * kBM;   // this CTA's 128 rows of the pair's tile
   const size_t split_off = (epi == EPI_GRADW) ? (size_t)it.split * S->C_alloc * S->Pp : 0;   // gradient copy of this K split
-  float* C = g.C + (size_t)chain * g.sC + split_off;
+  float* C = g.C + (size_t)chain * g.sC + split_off;   // direct stores: only chunks that straddle the next tile's columns
+  const int ldc = g.ldc;
+  const CUtensorMap* mapC = reinterpret_cast<const CUtensorMap*>(S->tmaps) + g.tmIdx[2];
+  const int zC = g.sC ? chain + ((epi == EPI_GRADW) ? it.split * S->C_alloc : 0) : 0;   // slice of the output tensor map
   const float* aux = (kHasAux && g.aux) ? g.aux + (size_t)chain * g.sAux : nullptr;
-  const int gM = g.M, ldaux = g.ldaux, ldc = g.ldc;
+  const int gM = g.M, ldaux = g.ldaux;
   const int biasCol = (epi == EPI_GRADW) ? g.biasCol : -1;
   float* gbias = (epi == EPI_GRADW && g.gbias) ? g.gbias + (size_t)chain * g.sGb + split_off : nullptr;
   const float scale = g.scale;
@@ -625,7 +637,7 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
   // accumulators go to the staging tile, and all epilogue math runs in the coalesced (transposed) domain where aux
   // loads, bias and stores share one address pattern.
   float l_sse = 0.f, l_sd = 0.f;
-  const int lim = (epi == EPI_GRADW && biasCol >= 0) ? min(n_end, biasCol) : n_end;
+  const int lim = (epi == EPI_GRADW && biasCol >= 0) ? min(n_end, biasCol) : n_end;   // columns >= lim are not stored
 #pragma unroll 1
   for (int jj = 0; jj < 4; ++jj) {
     const int c0 = (eg + 2 * jj) * 32;
@@ -651,12 +663,20 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
         if (j == jj) b4 = b4s[j];
     }
     if (c.et == 0) trace(dbg, 3, ntr, 10 + jj);
+    // only chunks whose 32 columns are all stored go through the copy engine; the last, partial chunk of a tile (tile widths
+    // are multiples of 16; the tensor's edge; the bias-gradient column) takes the masked direct-store path. The copy engine
+    // does clip at the tensor's edge, but in 16-byte units: with a width of 450 it wrote columns 450 and 451 as well.
+    const bool box = n0 + c0 + 32 <= lim;
+    // the previous chunk's box store must have read the staging tile before it is rewritten
+    if (lane == 0) bulk_wait_read();
+    __syncwarp();
+    // dense 32 x 128 B tile, 16-byte units XOR-swizzled by the row (the layout the store's tensor map expects)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (j == jj) {
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4)
-          sts128(stg_s + (lane * kEpiPitch + j4 * 4) * 4,
+          sts128(stg_s + lane * 128 + ((j4 ^ (lane & 7)) << 4),
                  make_float4(__uint_as_float(acc[j][j4 * 4]), __uint_as_float(acc[j][j4 * 4 + 1]),
                              __uint_as_float(acc[j][j4 * 4 + 2]), __uint_as_float(acc[j][j4 * 4 + 3])));
       }
@@ -666,7 +686,8 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
     for (int i = 0; i < 8; ++i) {
       if (kHasAux && i == 4) load_aux(1);
       const int rr = r0 + i * 4 + sub_r;
-      float4 o = lds128(stg_s + ((i * 4 + sub_r) * kEpiPitch + sub_c) * 4);
+      const uint32_t sa = stg_s + (i * 4 + sub_r) * 128 + (((lane & 7) ^ ((i * 4 + sub_r) & 7)) << 4);
+      float4 o = lds128(sa);
       if (rr >= gM || !cv) continue;
       if (kHasBias) { o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w; }
       if (epi == EPI_SIGMOID) {
@@ -684,16 +705,30 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
         }
         o = make_float4(d[0], d[1], d[2], d[3]);
       }
-      float* dst = &C[(size_t)rr * ldc + cc];
-      if (cc + 4 <= lim) {
-        *reinterpret_cast<float4*>(dst) = o;
+      if (box) {
+        sts128(sa, o);   // back to where this thread read it from
       } else {
-        const float ov[4] = {o.x, o.y, o.z, o.w};
+        float* dst = &C[(size_t)rr * ldc + cc];
+        if (cc + 4 <= lim) {
+          *reinterpret_cast<float4*>(dst) = o;
+        } else {
+          const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          if (cc + e < lim) dst[e] = ov[e];
-          else if (epi == EPI_GRADW && cc + e == biasCol) gbias[rr] = ov[e];   // ones-column trick
+          for (int e = 0; e < 4; ++e) {
+            if (cc + e < lim) dst[e] = ov[e];
+            else if (epi == EPI_GRADW && cc + e == biasCol) gbias[rr] = ov[e];
+          }
         }
+      }
+    }
+    // ONE box store per chunk through the copy engine (rows >= M are clipped by it): global
+    // stores issued by the epilogue warps themselves slowed the converters' shared-memory stream down (traced: 2.6 k cycles per tile)
+    if (box) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(mapC, stg_s, n0 + c0, r0, zC);
+        bulk_commit();
       }
     }
     __syncwarp();
@@ -731,7 +766,7 @@ __device__ __forceinline__ void gemm_phase_epilogue(const DevState* S, const Pha
   c.ew = warp - 4;              // 0..7
   c.et = threadIdx.x - 128;     // 0..255
   c.tmem = *sm.tmem_base();
-  c.stg_s = smem_u32(sm.epi_stage() + c.ew * (32 * kEpiPitch));   // this warp's 32 x 32 staging tile (pitch 36 floats)
+  c.stg_s = smem_u32(sm.epi_stage()) + c.ew * 4096;   // this warp's 32 x 32 staging tile (dense, 1024-byte aligned, swizzled)
   c.sub_r = c.lane >> 3; c.sub_c = (c.lane & 7) * 4;  // coalesced view: 4 rows x 128 B per instruction
   c.dbg = (blockIdx.x == 0 && (S->dbg_phase < 0 || S->dbg_phase == (int)(&ph - S->phase))) ? S->dbg : nullptr;
   c.dbgf = S->dbg_flags;
@@ -742,6 +777,8 @@ __device__ __forceinline__ void gemm_phase_epilogue(const DevState* S, const Pha
     if (!decode_item(S, ph, c_begin, item, it)) continue;
     epilogue_tile<kEpiA, kEpiB>(S, it, c, sm, ring, ntr);
   }
+  if (c.lane == 0) bulk_wait_all();   // this warp's box stores are complete before the kernel (or the phase) ends
+  __syncwarp();
 }
 
 }  // namespace tc
