@@ -691,6 +691,7 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
     const int cg_id = S->chain_id_base + chain;
     const float ss = (which == 1) ? S->ch.ss1[chain] : S->ch.ss2[chain];
     const float sq = (which == 1) ? S->ch.sq1[chain] : S->ch.sq2[chain];
+    const float inv_sq = 1.0f / sq;   // one IEEE division per item; per element: a multiply and an approximate reciprocal
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll 2
     for (int u = 0; u < kAdamChunk / (kThreads * 4); ++u) {
@@ -717,8 +718,8 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
           for (int j = 0; j < 4; ++j) {
             m[j] = m[j] + (g[j] - m[j]) * (1.0f - kB1);
             v[j] = v[j] * kB2 + (1.0f - kB2) * g[j] * g[j];
-            float denom = sqrtf(v[j]) / sq + kAdamEps;
-            o[j] = t[j] - ss * (m[j] / denom);
+            float denom = fmaf(sqrtf(v[j]), inv_sq, kAdamEps);
+            o[j] = t[j] - ss * __fdividef(m[j], denom);
           }
           *reinterpret_cast<float4*>(&mm[p]) = make_float4(m[0], m[1], m[2], m[3]);
           *reinterpret_cast<float4*>(&vv[p]) = make_float4(v[0], v[1], v[2], v[3]);
@@ -755,8 +756,8 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
         for (int j = 0; j < 4; ++j) {
           m[j] = m[j] + (g[j] - m[j]) * (1.0f - kB1);
           v[j] = v[j] * kB2 + (1.0f - kB2) * g[j] * g[j];
-          float denom = sqrtf(v[j]) / sq + kAdamEps;
-          float wpg = t[j] - ss * (m[j] / denom);   // w_prop_gd
+          float denom = fmaf(sqrtf(v[j]), inv_sq, kAdamEps);
+          float wpg = t[j] - ss * __fdividef(m[j], denom);   // w_prop_gd
           if (!alias && j < nval) {
             float dl = w0[j] - wpg;
             a2 = fmaf(dl, dl, a2);
@@ -898,8 +899,8 @@ __device__ void run_adam_tc(const DevState* S, int which, int c_begin, int c_end
             for (int j = 0; j < 4; ++j) {
               m[j] = m[j] + (g[j] - m[j]) * (1.0f - kB1);
               v[j] = v[j] * kB2 + (1.0f - kB2) * g[j] * g[j];
-              float denom = sqrtf(v[j]) / sq + kAdamEps;
-              o[j] = t[j] - ss * (m[j] / denom);
+              float denom = fmaf(sqrtf(v[j]), 1.0f / sq, kAdamEps);   // same arithmetic as run_adam (the compiler hoists the division)
+              o[j] = t[j] - ss * __fdividef(m[j], denom);
             }
             *reinterpret_cast<float4*>(&mm[p]) = make_float4(m[0], m[1], m[2], m[3]);
             *reinterpret_cast<float4*>(&vv[p]) = make_float4(v[0], v[1], v[2], v[3]);
@@ -932,8 +933,8 @@ __device__ void run_adam_tc(const DevState* S, int which, int c_begin, int c_end
           for (int j = 0; j < 4; ++j) {
             m[j] = m[j] + (g[j] - m[j]) * (1.0f - kB1);
             v[j] = v[j] * kB2 + (1.0f - kB2) * g[j] * g[j];
-            float denom = sqrtf(v[j]) / sq + kAdamEps;
-            float wpg = t[j] - ss * (m[j] / denom);   // w_prop_gd
+            float denom = fmaf(sqrtf(v[j]), 1.0f / sq, kAdamEps);   // same arithmetic as run_adam (the compiler hoists the division)
+            float wpg = t[j] - ss * __fdividef(m[j], denom);   // w_prop_gd
             if (!alias && j < nval) {
               float dl = w0[j] - wpg;
               a2 = fmaf(dl, dl, a2);
