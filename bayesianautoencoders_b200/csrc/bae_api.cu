@@ -840,8 +840,9 @@ static int coop_launch(bae_handle* h, int p_begin, int p_end, int n_rep, int for
     // One launch per phase (the exchange phases test the step counter on the device, like the persistent kernel); the
     // launches of a call are captured once into a CUDA graph and replayed.
     const int n_launch = n_rep * (p_end - p_begin);
-    if (h->use_graph && n_launch <= 8192) {
-      const std::array<int, 4> key = {p_begin, p_end, n_rep, force_swap};
+    const std::array<int, 4> key = {p_begin, p_end, n_rep, force_swap};
+    // at most 32 distinct call shapes are kept as graphs (a caller that varies n_steps freely falls back to direct launches)
+    if (h->use_graph && n_launch <= 8192 && (h->graphs.count(key) || h->graphs.size() < 32)) {
       auto it = h->graphs.find(key);
       if (it == h->graphs.end()) {
         cudaGraph_t graph = nullptr;
