@@ -76,13 +76,13 @@ __device__ __forceinline__ void noise_quad(const DevState* S, int chain_global, 
 
 // Tensor table of the flat parameter vector in shared memory (filled once per kernel): the tcgen05 kernels run with the
 // shared-memory carve-out at its maximum, i.e. without an L1 to cache the table in global memory.
-struct SegLite { int pad_off, span, cols, ld, trainable, ksplit; };   // span = rows * ld
+struct SegLite { int pad_off, span, cols, ld, trainable, ksplit; float inv_ld; };   // span = rows * ld
 __shared__ SegLite sh_seg[kNumSegs];
 
 __device__ __forceinline__ void load_seg_table(const DevState* S) {
   for (int i = threadIdx.x; i < kNumSegs; i += blockDim.x) {
     const Seg& g = S->seg[i];
-    sh_seg[i] = SegLite{g.pad_off, g.rows * g.ld, g.cols, g.ld, g.trainable, S->seg_ksplit[i]};
+    sh_seg[i] = SegLite{g.pad_off, g.rows * g.ld, g.cols, g.ld, g.trainable, S->seg_ksplit[i], 1.0f / (float)g.ld};
   }
   __syncthreads();
 }
@@ -691,18 +691,23 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
     const int cg_id = S->chain_id_base + chain;
     const float ss = (which == 1) ? S->ch.ss1[chain] : S->ch.ss2[chain];
     const float sq = (which == 1) ? S->ch.sq1[chain] : S->ch.sq2[chain];
+    // most 8192-float items lie inside one tensor: look the tensor up once per item then
+    const int sg_first = find_seg(S, it * kAdamChunk), sg_last = find_seg(S, min(Pp, (it + 1) * kAdamChunk) - 4);
     const float inv_sq = 1.0f / sq;   // one IEEE division per item; per element: a multiply and an approximate reciprocal
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll 2
     for (int u = 0; u < kAdamChunk / (kThreads * 4); ++u) {
       const int p = it * kAdamChunk + (u * kThreads + TID) * 4;
       if (p >= Pp) continue;
-      const int sg = find_seg(S, p);
+      const int sg = (sg_first == sg_last) ? sg_first : find_seg(S, p);
       const SegLite sd = sh_seg[sg];
       if (!sd.trainable) continue;
       const int local = p - sd.pad_off;
       if (local >= sd.span) continue;   // alignment gap between tensors
-      const int col = local % sd.ld;
+      // local % ld without an integer division: local < 2^24, so the float quotient is off by at most one
+      int col = local - __float2int_rz(__int2float_rz(local) * sd.inv_ld) * sd.ld;
+      col += (col < 0) ? sd.ld : 0;
+      col -= (col >= sd.ld) ? sd.ld : 0;
       const int nval = min(4, sd.cols - col);
       if (nval <= 0) continue;
       float4 t4 = *reinterpret_cast<const float4*>(&th[p]);
