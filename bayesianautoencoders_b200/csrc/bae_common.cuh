@@ -84,7 +84,7 @@ constexpr int kMaxGemm = 40;
 constexpr int kMaxPhase = 64;
 constexpr int kAdamChunk = 8192;   // floats per Adam work item (256 threads x 8 float4)
 constexpr int kThreads = 256;
-constexpr int kAuxAdamCtas = 3;      // bae_aux_kernel<AUX_ADAM>: 256-thread CTAs per SM
+constexpr int kAuxAdamCtas = 4;      // bae_aux_kernel<AUX_ADAM>: 256-thread CTAs per SM
 constexpr int kAuxBnCtas = 2;        // bae_aux_kernel<AUX_BN>
 
 // Per-chain scalar state (structure of arrays, length C_alloc = C + 1; slot C is the eval scratch chain).
