@@ -144,8 +144,8 @@ class Model:
 class ptReplica:
     """Mirror of `ptReplica` (MAIN:265-823): one temperature's chain, resident on the device.
 
-    `run()` executes the chain's `samples` iterations in blocks of `swap_interval` steps (one persistent
-    kernel launch per block) and performs the reference's rendezvous through the supplied queue / events
+    `run()` executes the chain's `samples` iterations in blocks of `swap_interval` steps (one step-program
+    launch per block) and performs the reference's rendezvous through the supplied queue / events
     after every block (MAIN:594-603). `multiprocessing.Process` is not involved: the chain state lives in HBM.
     """
 
@@ -239,7 +239,7 @@ class ptReplica:
 
 class ParallelTempering:
     """Mirror of `ParallelTempering` (MAIN:827-1329). All `num_chains` replicas live on one GPU handle;
-    `run_chains()` is a sequence of persistent-kernel launches (5 iterations + exchange sweep each)."""
+    `run_chains()` is a sequence of step-program launches (5 iterations + exchange sweep each)."""
 
     def __init__(self, use_langevin_gradients, num_chains, maxtemp, NumSample, swap_interval, path, batch_size, bi,
                  step_size, *, dims4, traindata, testdata, lrate=0.01, burnin=0.5, seed=0xBAE5EED, device=0,

@@ -2,7 +2,7 @@
 
 One `DeviceSampler` drives the chains resident on one GPU. All arithmetic of the reference's
 `ptReplica.run` loop body (MAIN:432-592) and of `ParallelTempering.swap_procedure` (MAIN:962-1011)
-happens inside the library's persistent CUDA kernels; this class only moves host buffers in and out.
+happens inside the library's CUDA step program; this class only moves host buffers in and out.
 """
 from __future__ import annotations
 

@@ -108,8 +108,9 @@ int bae_get_state(bae_handle* h, int chain, float* theta, float* w, float* m, fl
 int bae_set_state(bae_handle* h, int chain, const float* theta, const float* w, const float* m, const float* v,
                   const bae_chain_scalars* s);
 
-/* n_steps iterations of MAIN:432-592 for every chain on the handle: ONE persistent cooperative kernel
- * launch (forward/backward, Adam drift, noise, likelihood, prior, reverse-proposal density, MH test). */
+/* n_steps iterations of MAIN:432-592 for every chain on the handle (forward/backward, Adam drift, noise, likelihood,
+ * prior, reverse-proposal density, MH test): ONE device-side step program per call, no host work inside it - a replayed
+ * CUDA graph of per-phase kernels on the tcgen05 path, one persistent cooperative kernel on the FP32 path. */
 int bae_step(bae_handle* h, int n_steps);
 /* One exchange round (MAIN:594-603 + 962-1011 + 1059-1065) for every ensemble resident on the handle. */
 int bae_swap_local(bae_handle* h);
