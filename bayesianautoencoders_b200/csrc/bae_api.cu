@@ -27,6 +27,7 @@ cudaError_t launch_split(const float* src, float* hi, float* lo, size_t n, cudaS
 cudaError_t launch_grad_reduce(const DevState* dS, int chain, cudaStream_t st);
 cudaError_t launch_debug_draws(const DevState* dS, int chain, int step, float* noise, double* scalars, cudaStream_t st);
 cudaError_t launch_debug_swap_u(const DevState* dS, int ens, int round, int pair, double* out, cudaStream_t st);
+cudaError_t launch_scalars(const DevState* dS, int chain, bae_chain_scalars* staged, int put, cudaStream_t st);
 cudaError_t launch_pack(const DevState* dS, const float* ref_vec, float* pad_vec, cudaStream_t st);
 cudaError_t launch_unpack(const DevState* dS, const float* pad_vec, float* ref_vec, cudaStream_t st);
 }  // namespace bae
@@ -76,6 +77,7 @@ struct bae_handle {
   float* stage_ref = nullptr;    // [w_size] device staging, reference order
   float* stage_noise = nullptr;  // [w_size]
   double* stage_d = nullptr;     // small device scratch for doubles
+  bae_chain_scalars* stage_sc = nullptr;   // device staging of one chain's scalars (bae_get_state / bae_set_state)
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -450,6 +452,11 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
                                        ", this library is built for sm_100a only");
   CU(cudaSetDevice(device));
   bae_handle* h = new bae_handle();
+  // every failure path below releases the handle, its stream / events and all device allocations made so far
+  struct Guard {
+    bae_handle* h;
+    ~Guard() { if (h) bae_destroy(h); }
+  } guard{h};
   h->cfg = *cfg;
   h->device = device;
   h->phase_launch = getenv("BAE_PHASE_LAUNCH") != nullptr && getenv("BAE_PHASE_LAUNCH")[0] == '1';
@@ -532,8 +539,16 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   CU(dalloc(h, &s.num_swap, 1)); CU(dalloc(h, &s.total_swap, 1));
   CU(dalloc(h, &h->stage_ref, (size_t)s.w_size + 8)); CU(dalloc(h, &h->stage_noise, (size_t)s.w_size + 8));
   CU(dalloc(h, &h->stage_d, 64));
+  CU(dalloc(h, &h->stage_sc, 1));
   if (getenv("BAE_TC_TRACE") && getenv("BAE_TC_TRACE")[0] == '1') CU(dalloc(h, &s.dbg, 4096));
   s.dbg_flags = getenv("BAE_TC_DBGFLAGS") ? atoi(getenv("BAE_TC_DBGFLAGS")) : 0;
+#ifndef BAE_TC_DEBUG
+  // the timing-experiment branches (results are wrong when one is set) are compiled only with -DBAE_TC_DEBUG
+  if (s.dbg_flags != 0)
+    return fail(BAE_ERR_INVALID, "BAE_TC_DBGFLAGS is set, but this library was built without -DBAE_TC_DEBUG: refusing to sample");
+#endif
+  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE"})
+    if (getenv(knob)) fprintf(stderr, "[bae_b200] note: tuning variable %s=%s is in effect for this handle\n", knob, getenv(knob));
   s.dbg_phase = getenv("BAE_TC_TRACE_PHASE") ? atoi(getenv("BAE_TC_TRACE_PHASE")) : -1;
   {
     void* q = nullptr;
@@ -568,6 +583,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     if (!h->phase_launch_env) h->phase_launch = true;
   }
   CU(cudaStreamSynchronize(h->stream));
+  guard.h = nullptr;
   *out = h;
   return BAE_OK;
 }
@@ -785,15 +801,11 @@ int bae_get_state(bae_handle* h, int chain, float* theta, float* w, float* m, fl
       w[s.seg[SEG_BN_NBT].ref_off] = wb[2 * s.d3];
     }
   }
-  if (sc) {
-    const ChainArrays& c = s.ch;
-    if ((rc = get1(h, c.eta, chain, &sc->eta))) return rc;
-    get1(h, c.lik, chain, &sc->likelihood); get1(h, c.prior_cur, chain, &sc->prior_current);
-    get1(h, c.last_sse, chain, &sc->last_sse_train); get1(h, c.mse_tr, chain, &sc->mse_train);
-    get1(h, c.prop_sse, chain, &sc->prop_sse_train);
-    get1(h, c.mse_te, chain, &sc->mse_test); get1(h, c.T, chain, &sc->temperature); get1(h, c.adapt, chain, &sc->adapttemp);
-    get1(h, c.adam_t, chain, &sc->adam_t); get1(h, c.alias, chain, &sc->w_is_alias); get1(h, c.init_count, chain, &sc->init_count);
-    get1(h, c.nacc, chain, &sc->num_accepted); get1(h, c.nlang, chain, &sc->langevin_count); get1(h, c.step, chain, &sc->step);
+  if (sc) {   // one staged struct, one checked copy
+    CU(launch_scalars(h->dS, chain, h->stage_sc, 0, h->stream));
+    h->launches++;
+    CU(cudaMemcpyAsync(sc, h->stage_sc, sizeof(bae_chain_scalars), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
   }
   return BAE_OK;
 }
@@ -820,14 +832,10 @@ int bae_set_state(bae_handle* h, int chain, const float* theta, const float* w, 
     CU(cudaStreamSynchronize(h->stream));
   }
   if (sc) {
-    const ChainArrays& c = s.ch;
-    if ((rc = put1(h, c.eta, chain, sc->eta))) return rc;
-    put1(h, c.lik, chain, sc->likelihood); put1(h, c.prior_cur, chain, sc->prior_current);
-    put1(h, c.last_sse, chain, sc->last_sse_train); put1(h, c.mse_tr, chain, sc->mse_train);
-    put1(h, c.prop_sse, chain, sc->prop_sse_train);
-    put1(h, c.mse_te, chain, sc->mse_test); put1(h, c.T, chain, sc->temperature); put1(h, c.adapt, chain, sc->adapttemp);
-    put1(h, c.adam_t, chain, sc->adam_t); put1(h, c.alias, chain, sc->w_is_alias); put1(h, c.init_count, chain, sc->init_count);
-    put1(h, c.nacc, chain, sc->num_accepted); put1(h, c.nlang, chain, sc->langevin_count); put1(h, c.step, chain, sc->step);
+    CU(cudaMemcpyAsync(h->stage_sc, sc, sizeof(bae_chain_scalars), cudaMemcpyHostToDevice, h->stream));
+    CU(launch_scalars(h->dS, chain, h->stage_sc, 1, h->stream));
+    h->launches++;
+    CU(cudaStreamSynchronize(h->stream));   // `sc` is caller-owned pageable memory
   }
   return BAE_OK;
 }
@@ -1077,7 +1085,7 @@ int bae_host_sweep(const double* table, int n_rungs, double n_elems, const float
     const double lhood12 = loglik(table[cfg1 * 4 + 3], std::exp(table[cfg1 * 4 + 0]), T2);
     const double lhood21 = loglik(table[cfg2 * 4 + 3], std::exp(table[cfg2 * 4 + 0]), T1);
     const double ex = (lhood12 - lhood1) + (lhood21 - lhood2);
-    const double prob = ex >= 0.0 ? 1.0 : std::exp(ex);
+    const double prob = std::fmin(1.0, std::exp(ex));   // MAIN:988 min(1, exp(.)); a NaN exponent gives 1, as there and on the device
     if ((double)uniforms[p] < prob) {
       ++swapped;
       src_out[p] = cfg2;

@@ -1525,6 +1525,24 @@ __global__ void bae_debug_swap_u_kernel(const DevState* __restrict__ S, int ense
   out[0] = swap_uniform(S, ensemble_global, round, pair);
 }
 
+// ---- per-chain scalars <-> one staged struct (checkpoint / parity injection: one copy instead of 15) ----------
+__global__ void bae_scalars_kernel(const DevState* __restrict__ S, int chain, bae_chain_scalars* st, int put) {
+  const ChainArrays& c = S->ch;
+  if (put) {
+    c.eta[chain] = st->eta; c.lik[chain] = st->likelihood; c.prior_cur[chain] = st->prior_current;
+    c.last_sse[chain] = st->last_sse_train; c.mse_tr[chain] = st->mse_train; c.mse_te[chain] = st->mse_test;
+    c.T[chain] = st->temperature; c.adapt[chain] = st->adapttemp; c.adam_t[chain] = st->adam_t;
+    c.alias[chain] = st->w_is_alias; c.init_count[chain] = st->init_count; c.nacc[chain] = st->num_accepted;
+    c.nlang[chain] = st->langevin_count; c.step[chain] = st->step; c.prop_sse[chain] = st->prop_sse_train;
+  } else {
+    st->eta = c.eta[chain]; st->likelihood = c.lik[chain]; st->prior_current = c.prior_cur[chain];
+    st->last_sse_train = c.last_sse[chain]; st->mse_train = c.mse_tr[chain]; st->mse_test = c.mse_te[chain];
+    st->temperature = c.T[chain]; st->adapttemp = c.adapt[chain]; st->adam_t = c.adam_t[chain];
+    st->w_is_alias = c.alias[chain]; st->init_count = c.init_count[chain]; st->num_accepted = c.nacc[chain];
+    st->langevin_count = c.nlang[chain]; st->step = c.step[chain]; st->prop_sse_train = c.prop_sse[chain];
+  }
+}
+
 // ---- reference-order <-> padded-order packing -----------------------------------------------------
 __global__ void bae_pack_kernel(const DevState* __restrict__ S, const float* ref_vec, float* pad_vec) {
   for (int sg = 0; sg < kNumSegs; ++sg) {
@@ -1676,6 +1694,11 @@ cudaError_t launch_debug_draws(const DevState* dS, int chain, int step, float* n
 
 cudaError_t launch_debug_swap_u(const DevState* dS, int ens, int round, int pair, double* out, cudaStream_t st) {
   bae_debug_swap_u_kernel<<<1, 1, 0, st>>>(dS, ens, round, pair, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scalars(const DevState* dS, int chain, bae_chain_scalars* staged, int put, cudaStream_t st) {
+  bae_scalars_kernel<<<1, 1, 0, st>>>(dS, chain, staged, put);
   return cudaGetLastError();
 }
 

@@ -35,6 +35,15 @@
 
 #include "bae_common.cuh"
 
+// Timing-experiment switches (skip the hi/lo conversion, the cross-term MMAs, the epilogue math, the A / B loads) exist
+// only in builds with -DBAE_TC_DEBUG (tools/tc_experiments.sh): results are wrong when one is set, so the shipped library
+// does not contain the branches and bae_create refuses BAE_TC_DBGFLAGS.
+#ifdef BAE_TC_DEBUG
+#define BAE_DBGF(S) ((S)->dbg_flags)
+#else
+#define BAE_DBGF(S) 0
+#endif
+
 namespace bae {
 namespace tc {
 
@@ -391,7 +400,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         // this CTA's share of the pair's 256 x BN tile: 128 rows of A, BN/2 columns of B
         const int m0 = it.tile_m * (2 * kBM) + (int)rank * kBM, n0 = it.tile_n * g.tcBN + (int)rank * (g.tcBN >> 1);
         const int ca = g.sA ? it.chain : 0, cb = g.sB ? it.chain : 0;
-        const int dbgf = S->dbg_flags;
+        const int dbgf = BAE_DBGF(S);
         const uint32_t bytes = ((dbgf & 64) ? 0u : (uint32_t)kATileBytes) + ((dbgf & 32) ? 0u : (uint32_t)g.tcBBytes);
         const int aMode = g.aMode, bMode = g.bMode, nchB = g.tcBBytes / kMnChunkBytes, nkb = it.nkb, kb0 = it.kb0;
         const CUtensorMap* mapA = &maps[g.tmIdx[0]];
@@ -430,7 +439,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     // ================= MMA issuer (leader CTA of the pair; warp-uniform loop, one elected lane issues) =================
     if (rank == 0) {
       int ntr = 0;
-      const int dbgf = S->dbg_flags;
+      const int dbgf = BAE_DBGF(S);
       const uint32_t tmem = *sm.tmem_base();
       for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs
         Item it;
@@ -486,7 +495,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     const int grp = (warp < 4) ? 0 : 1 + ((warp - 12) >> 1);
     const int gt = ((warp & 1) << 5) + lane;   // 0..63 inside the group
     const uint32_t tiles_s = smem_u32(sm.tiles) + gt * 16;
-    const bool skip = (S->dbg_flags & 1) != 0;
+    const bool skip = (BAE_DBGF(S) & 1) != 0;
     int ntr = (grp == 0) ? 0 : (grp == 1 ? 170 : 340);
     uint32_t kbc = ring.kbc;
     for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs
@@ -769,7 +778,7 @@ __device__ __forceinline__ void gemm_phase_epilogue(const DevState* S, const Pha
   c.stg_s = smem_u32(sm.epi_stage()) + c.ew * 4096;   // this warp's 32 x 32 staging tile (dense, 1024-byte aligned, swizzled)
   c.sub_r = c.lane >> 3; c.sub_c = (c.lane & 7) * 4;  // coalesced view: 4 rows x 128 B per instruction
   c.dbg = (blockIdx.x == 0 && (S->dbg_phase < 0 || S->dbg_phase == (int)(&ph - S->phase))) ? S->dbg : nullptr;
-  c.dbgf = S->dbg_flags;
+  c.dbgf = BAE_DBGF(S);
   c.rank = cluster_rank();
   int ntr = 0;
   for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs

@@ -73,7 +73,11 @@ def sweep(table, n_elems, uniforms):
         lhood12 = loglik(table[cfg1, 3], n_elems, math.exp(table[cfg1, 0]), T2)
         lhood21 = loglik(table[cfg2, 3], n_elems, math.exp(table[cfg2, 0]), T1)
         ex = (lhood12 - lhood1) + (lhood21 - lhood2)
-        prob = 1.0 if ex >= 0 else math.exp(ex)
+        try:
+            ee = math.exp(ex)
+        except OverflowError:
+            ee = math.inf
+        prob = ee if ee < 1.0 else 1.0     # MAIN:988 min(1, exp(.)): a NaN exponent gives 1, as there and on the device
         if uniforms[p] < prob:
             swapped += 1
             src[p] = cfg2

@@ -23,3 +23,76 @@ def oracle_rnd_from_device(sampler, chain, n_steps, first_step=0):
 def rel(a, b):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def run_device_and_oracle(dims4, train, test, temps, S, si, theta_inits, w0s, n_rungs, do_swaps, seed=21, hyper=None,
+                          oracle_hyper=None, **sampler_kw):
+    """Run the CUDA sampler (through the C-ABI) and the CPU oracle on identical weights, proposals and
+    uniforms: the device's own Philox draws are read back (`bae_debug_draws`) and fed to `bo.run_pt`.
+    Returns dict(dev, records, swap_log, counts, reps, final, gemm_path)."""
+    from bayesianautoencoders_b200 import DeviceSampler
+    n = len(temps)
+    s = DeviceSampler(dims4, train, test, n, n_rungs, S, np.asarray(temps, float), seed=seed, swap_interval=si,
+                      hyper=hyper, **sampler_kw)
+    for j in range(n):
+        s.init_chain(j, theta_inits[j], w0s[j])
+    init_states = [s.get_state(j, vectors=False) for j in range(n)]
+    rnd = []
+    for j in range(n):
+        d = oracle_rnd_from_device(s, j, S)
+        d["w0_randn"] = w0s[j]
+        rnd.append(d)
+    # the oracle consumes swap uniforms round-major, pair-minor (one ensemble in these tests)
+    swap_u = [s.debug_swap_uniform(0, r, p) for r in range(S // si) for p in range(n - 1)]
+    s.run(S)
+    s.synchronize()
+    dev = [s.traces(j, 0, S) for j in range(n)]
+    counts = s.swap_counts()
+    final = [s.get_state(j) for j in range(n)]
+    path = s.gemm_path()
+    s.close()
+    reps, records, swap_log = bo.run_pt(dims4, train, test, temps, S, si, theta_inits, rnd, swap_u=swap_u,
+                                        do_swaps=do_swaps, hyper=oracle_hyper)
+    return dict(dev=dev, records=records, swap_log=swap_log, counts=counts, reps=reps, final=final,
+                init_states=init_states, gemm_path=path)
+
+
+def trace_errors(dev, records):
+    """Per-quantity worst errors of the device traces against the oracle's records, per iteration index.
+    Relative errors are taken against the oracle value; `sum_value` against the scale of its terms."""
+    S = len(records[0])
+    out = dict(lik_prop=np.zeros(S), lik=np.zeros(S), prior=np.zeros(S), diff_prop=np.zeros(S), sum_value=np.zeros(S),
+               mse_train=np.zeros(S), mse_test=np.zeros(S), log_u=np.zeros(S))
+    decisions = []   # (chain, step, margin / scale, device accepted, oracle accepted)
+    branch_ok = True
+    for j in range(len(dev)):
+        for i, rec in enumerate(records[j]):
+            d = dev[j][i]
+            branch_ok &= bool(d["langevin"]) == rec.langevin
+            out["lik_prop"][i] = max(out["lik_prop"][i], abs(d["likelihood_proposal"] - rec.likelihood_proposal) / abs(rec.likelihood_proposal))
+            out["lik"][i] = max(out["lik"][i], abs(d["likelihood"] - rec.likelihood) / abs(rec.likelihood))
+            out["prior"][i] = max(out["prior"][i], abs(d["prior_proposal"] - rec.prior_prop) / abs(rec.prior_prop))
+            scale = abs(rec.likelihood_proposal) + abs(rec.likelihood) + abs(rec.prior_prop) + abs(rec.diff_prop) + 1.0
+            dscale = abs(rec.first) + abs(rec.second) + 1.0
+            out["diff_prop"][i] = max(out["diff_prop"][i], abs(d["diff_prop"] - rec.diff_prop) / dscale)
+            out["sum_value"][i] = max(out["sum_value"][i], abs(d["sum_value"] - rec.sum_value) / scale)
+            out["mse_train"][i] = max(out["mse_train"][i], abs(d["mse_train_proposal"] - rec.mse_train) / rec.mse_train)
+            out["mse_test"][i] = max(out["mse_test"][i], abs(d["mse_test_proposal"] - rec.mse_test) / rec.mse_test)
+            out["log_u"][i] = max(out["log_u"][i], abs(d["log_u"] - rec.log_u) / max(1.0, abs(rec.log_u)))
+            decisions.append((j, i, abs(rec.sum_value - rec.log_u) / scale, bool(d["accepted"]), bool(rec.accepted)))
+    return out, decisions, branch_ok
+
+
+def dump_report(name, report):
+    """Measured parity errors go to gpurun_out/ (merged back from the GPU box) so that tolerances in the tests
+    can be stated from measurements."""
+    import json
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, f"parity_{name}.json"), "w") as f:
+            json.dump(report, f, indent=1, default=lambda x: np.asarray(x).tolist())
+    except OSError:
+        pass

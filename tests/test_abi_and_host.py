@@ -168,3 +168,23 @@ def test_host_sweep_matches_python_restatement():
             assert res is not None
             ref = sweep(tab, n, [float(x) for x in u])
             assert res[0] == list(ref[0]) and res[1] == ref[1]
+
+
+def test_sweep_non_finite_likelihoods_follow_the_reference_min():
+    """MAIN:988 `min(1, exp(x))`: a NaN exponent gives probability 1 (Python's min keeps its first argument),
+    +inf overflows to 1, -inf gives 0. The C host sweep, the Python sweep and the device decision (fmin) agree."""
+    from bayesianautoencoders_b200.distributed import sweep, sweep_native
+    n = 400.0
+    base = np.array([[-1.0, -300.0, 1.0, 60.0], [-1.1, -280.0, 1.5, 70.0], [-0.9, -260.0, 2.0, 65.0]])
+    for bad in (np.nan, np.inf, -np.inf):
+        tab = base.copy()
+        tab[1, 1] = bad                       # stored likelihood of the middle rung
+        u = np.array([0.999, 0.999], np.float32)
+        ref = sweep(tab, n, [float(x) for x in u])
+        res = sweep_native(tab, n, u)
+        assert res is not None and res[0] == list(ref[0]) and res[1] == ref[1], (bad, res, ref)
+        with np.errstate(all="ignore"):
+            lh12 = (-(n / 2) * np.log(2 * np.pi * np.exp(tab[0, 0])) - 0.5 * np.exp(tab[0, 0]) * tab[0, 3]) / tab[1, 2]
+            lh21 = (-(n / 2) * np.log(2 * np.pi * np.exp(tab[1, 0])) - 0.5 * np.exp(tab[1, 0]) * tab[1, 3]) / tab[0, 2]
+            want_first = 0.999 < min(1, np.exp((lh12 - tab[0, 1]) + (lh21 - tab[1, 1])))
+        assert (ref[0][0] == 1) == bool(want_first), bad

@@ -1,0 +1,123 @@
+"""Step-level oracle parity ON THE BENCHMARKED PATH: the tcgen05 step program at the full Madelon shape
+(BASELINE.json configs[2]: 500-450-400-300, 2000 / 1800 rows) and the FP32 step kernel at the full Coil-2000
+shape (configs[1]), compared with the CPU oracle for every record of every iteration (MAIN:432-603), the
+exchange rounds (MAIN:962-1011) and the final theta / Adam state.
+
+Both sides see identical weights, proposals and uniforms (the device's Philox draws are fed to the oracle).
+Tolerances are stated per quantity below; the north star's 1e-5 relative bound on the log-likelihood holds on
+every iteration, the decisions are identical away from the threshold. Measured errors are written to
+gpurun_out/parity_*.json."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bae_oracle as bo
+from tests.parity_util import dump_report, rel, run_device_and_oracle, synth_data, trace_errors
+
+pytestmark = pytest.mark.gpu
+
+# Per-quantity tolerances (relative to the oracle value unless noted). FP32 device arithmetic against the float64
+# oracle; the trajectories of the two sides separate slowly (the Adam step divides by sqrt(v): entries with tiny
+# gradients amplify rounding differences), hence the bounds for iterations > 0 are looser than for iteration 0.
+TOL = {
+    "lik_step0": 1e-5,       # north star: per-step log-likelihood within 1e-5 relative
+    "lik": 1e-5,             # ... and on every later iteration
+    "mse": 2e-5,             # SSE / n of the proposal (train, test)
+    "prior": 1e-6,           # sum of squares of ~1e6 entries, FP64 partials of FP32 squares
+    "diff_prop": 2e-5,       # relative to |first| + |second| + 1 (MAIN:481-485)
+    "sum_value": 2e-5,       # relative to the sum of the magnitudes of its terms (MAIN:524)
+    "theta": 1e-5,           # final live model, norm-wise
+    "adam_m": 1e-4,          # final Adam moments, norm-wise (they integrate the gradient differences)
+    "adam_v": 1e-4,
+    "decision_margin": 2e-4  # accept decisions must agree when |sum_value - log u| exceeds this x scale
+}
+
+
+def _check(name, r, S, temps, tol=TOL):
+    errs, decisions, branch_ok = trace_errors(r["dev"], r["records"])
+    reps, final = r["reps"], r["final"]
+    n = len(temps)
+    th = [rel(final[j]["theta"], reps[j].theta) for j in range(n)]
+    mm = [rel(final[j]["m"], reps[j].m) for j in range(n)]
+    vv = [rel(final[j]["v"], reps[j].v) for j in range(n)]
+    n_rw = sum(1 for j in range(n) for rec in r["records"][j] if not rec.langevin)
+    n_acc = sum(1 for j in range(n) for rec in r["records"][j] if rec.accepted)
+    report = dict(case=name, gemm_path=r["gemm_path"], errors={k: v.tolist() for k, v in errs.items()},
+                  theta=th, m=mm, v=vv, swap_log=r["swap_log"], swap_counts=r["counts"], random_walk_steps=n_rw,
+                  accepted=n_acc, decisions=[(j, i, float(mg), a, b) for j, i, mg, a, b in decisions],
+                  eta=[(final[j]["eta"], reps[j].eta) for j in range(n)])
+    dump_report(name, report)
+    assert branch_ok
+    assert errs["lik_prop"][0] <= tol["lik_step0"], errs["lik_prop"]
+    assert errs["lik_prop"].max() <= tol["lik"], errs["lik_prop"]
+    assert errs["lik"].max() <= tol["lik"], errs["lik"]
+    assert max(errs["mse_train"].max(), errs["mse_test"].max()) <= tol["mse"], (errs["mse_train"], errs["mse_test"])
+    assert errs["prior"].max() <= tol["prior"], errs["prior"]
+    assert errs["diff_prop"].max() <= tol["diff_prop"], errs["diff_prop"]
+    assert errs["sum_value"].max() <= tol["sum_value"], errs["sum_value"]
+    assert errs["log_u"].max() <= 1e-6
+    checked = 0
+    for j, i, margin, a, b in decisions:
+        if margin > tol["decision_margin"]:
+            assert a == b, (j, i, margin)
+            checked += 1
+    assert checked >= 0.8 * len(decisions)
+    # exchange rounds: every proposal counted, the same pairs swapped (eta travels with the configuration)
+    assert r["counts"][1] == len(r["swap_log"])
+    assert r["counts"][0] == sum(1 for s in r["swap_log"] if s[2])
+    for j in range(n):
+        assert abs(final[j]["eta"] - reps[j].eta) < 1e-6
+        assert final[j]["adam_t"] == reps[j].t
+        assert final[j]["num_accepted"] == reps[j].num_accepted
+    assert max(th) <= tol["theta"], th
+    assert max(mm) <= tol["adam_m"], mm
+    assert max(vv) <= tol["adam_v"], vv
+    return report
+
+
+def _inputs(dims4, n, seed):
+    from bayesianautoencoders_b200 import default_theta_init
+    L = bo.Layout(dims4)
+    rng = np.random.default_rng(seed)
+    return [default_theta_init(dims4, rng) for _ in range(n)], [rng.standard_normal(L.w_size) for _ in range(n)]
+
+
+@pytest.mark.parametrize("phase_launch", ["1", "0"])
+def test_madelon_tcgen05_step_program_matches_oracle(phase_launch, monkeypatch):
+    """2 chains (one 2-rung ensemble) x 10 iterations: the tempered -> canonical switch at i == 5, two exchange
+    rounds, random-walk iterations at (chain 0, i = 2), (chain 0, i = 7) and (chain 1, i = 5: the first step after
+    an exchange, fp32 `w`). phase_launch 1 = the CUDA graph of per-phase kernels (production), 0 = the persistent
+    cooperative kernel."""
+    monkeypatch.setenv("BAE_PHASE_LAUNCH", phase_launch)
+    dims4, ntr, nte = (500, 450, 400, 300), 2000, 1800
+    train, test = synth_data(dims4, ntr, nte)
+    temps = [1.0, 2.0]
+    th0, w0 = _inputs(dims4, 2, 17)
+    r = run_device_and_oracle(dims4, train, test, temps, 10, 5, th0, w0, n_rungs=2, do_swaps=True, seed=6, gemm_path=2)
+    assert r["gemm_path"] == 2
+    rep = _check(f"madelon_tc_phase_launch{phase_launch}", r, 10, temps)
+    assert rep["random_walk_steps"] == 3
+
+
+def test_coil_full_size_step_kernel_matches_oracle():
+    """Coil-2000 shape at full size (4366 / 1456 rows) on the FP32 CUDA-core step kernel: 2 chains x 9 iterations,
+    exchange every 3 (switch at i == 4)."""
+    dims4, ntr, nte = (85, 70, 60, 50), 4366, 1456
+    train, test = synth_data(dims4, ntr, nte)
+    temps = [1.0, 2.0]
+    th0, w0 = _inputs(dims4, 2, 18)
+    r = run_device_and_oracle(dims4, train, test, temps, 9, 3, th0, w0, n_rungs=2, do_swaps=True, seed=6)
+    assert r["gemm_path"] == 1
+    _check("coil_fp32", r, 9, temps)
+
+
+def test_madelon_eight_rung_ensemble_swaps_match_oracle():
+    """One 8-rung Madelon ensemble (BASELINE configs[2]) over one exchange round: the sequential sweep with the
+    message-slot quirk (MAIN:999-1005) on the tcgen05 path."""
+    dims4, ntr, nte = (500, 450, 400, 300), 2000, 1800
+    train, test = synth_data(dims4, ntr, nte)
+    temps = list(bo.temperature_ladder(8, 2))
+    th0, w0 = _inputs(dims4, 8, 19)
+    r = run_device_and_oracle(dims4, train, test, temps, 6, 5, th0, w0, n_rungs=8, do_swaps=True, seed=31, gemm_path=2)
+    _check("madelon_tc_8rungs", r, 6, temps)
