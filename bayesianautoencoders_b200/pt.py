@@ -18,7 +18,7 @@ from collections import OrderedDict
 
 import numpy as np
 
-from .results import gelman_rubin, write_replica_files  # noqa: F401
+from .results import GR_WEIGHT_COLUMNS, gelman_rubin, gelman_rubin_reference, write_replica_files  # noqa: F401
 from .sampler import (SORTED_KEYS, DeviceSampler, Hyper, default_theta_init, param_offsets, param_shapes)
 
 # torch's state_dict() iteration order for Model (MAIN:151-176)
@@ -377,10 +377,14 @@ class ParallelTempering:
         acc_test = np.sqrt(np.stack([t["mse_test"] for t in self._traces]))[:, b:]
         return mse_train, mse_test, acc_train, acc_test, np.array([int(a) for a in self._accept], dtype=np.float64)
 
-    def rhat(self, burnin=None):
-        """Gelman-Rubin R-hat over the 12 traced weights across the chains of this object (GR:690-735)."""
+    def rhat(self, burnin=None, reference_compatible=False):
+        """Gelman-Rubin R-hat over the 12 traced weights across the chains of this object (GR:690-735): the textbook
+        statistic over [chains, samples], or - `reference_compatible` - what the reference's offline script prints
+        (2-decimal traces, swapped axes; `results.gelman_rubin_reference`)."""
         b = int(self.NumSamples * (self.burnin if burnin is None else burnin))
-        w = np.stack([t["weights"][b:, [0, 1, 4, 5, 6, 3, 8, 9, 10, 11, 2, 12]] for t in self._traces])
+        w = np.stack([t["weights"][b:, GR_WEIGHT_COLUMNS] for t in self._traces])
+        if reference_compatible:
+            return gelman_rubin_reference(w)
         return gelman_rubin(w.astype(np.float64))
 
     def close(self):

@@ -84,3 +84,26 @@ def gelman_rubin(data, advanced=True):
             df = 2 * Vhat ** 2 / var_Vhat
             out["advanced"] = Rhat * df / (df - 2)
     return out
+
+
+# stacking order of the 12 traced weights in GR:690, as columns of `bae_trace.weights` (MAIN:564-592 order:
+# 0, 100, 10000, 5000, 2000, 3000, 4000, 5000, 6000, 7000, 8000, 9000, 11000)
+GR_WEIGHT_COLUMNS = [0, 1, 4, 5, 6, 3, 8, 9, 10, 11, 2, 12]
+
+
+def quantise_like_files(x, fmt="%1.2f"):
+    """Values as the reference's offline script reads them back from the `%1.2f` text files (MAIN:641-677)."""
+    x = np.asarray(x, dtype=np.float64)
+    return np.asarray(np.char.mod(fmt, x.reshape(-1)), dtype=np.float64).reshape(x.shape)
+
+
+def gelman_rubin_reference(weights, quantise=True):
+    """R-hat exactly as `Gelman Reuben.py` computes it (GR:676-735). `weights`: [chains, samples, 12] post-burn-in
+    traces in GR:690 order (`GR_WEIGHT_COLUMNS`). Two properties of the script are reproduced: it reads the
+    2-decimal text files, and it transposes every [chains, samples] array before stacking, so its
+    `Nchains, Nsamples, Npars = data.shape` binds Nchains = samples and Nsamples = chains (in-"chain" statistics are
+    taken ACROSS chains at a fixed iteration). Pinned by tests/golden/gr_rhat.npz (oracle/make_gr_golden.py)."""
+    w = np.asarray(weights, dtype=np.float64)
+    if quantise:
+        w = quantise_like_files(w)
+    return gelman_rubin(w.transpose(1, 0, 2))

@@ -96,3 +96,110 @@ def dump_report(name, report):
             json.dump(report, f, indent=1, default=lambda x: np.asarray(x).tolist())
     except OSError:
         pass
+
+
+def _sync_oracle_to_device(rep, st):
+    """Teacher forcing: the oracle replica takes the device chain's state (fp32 values widened to float64), so the
+    next iteration starts from IDENTICAL weights, Adam moments and scalars on both sides. The oracle keeps its own
+    `w_prop` (the chain's last proposal is not part of the device state, only its SSE) and its own `w_f32` flag."""
+    rep.theta[:] = st["theta"].astype(np.float64)
+    rep.m[:] = st["m"].astype(np.float64)
+    rep.v[:] = st["v"].astype(np.float64)
+    rep.t = int(st["adam_t"])
+    rep.eta, rep.likelihood, rep.prior_current = st["eta"], st["likelihood"], st["prior_current"]
+    rep.adapttemp = st["adapttemp"]
+    rep.i, rep.init_count = int(st["step"]), int(st["init_count"])
+    rep.num_accepted, rep.langevin_count = int(st["num_accepted"]), int(st["langevin_count"])
+    rep.last_sse_train = st["last_sse_train"]
+    rep.w_alias = bool(st["w_is_alias"])
+    rep.w = None if rep.w_alias else st["w"].astype(np.float64)
+    if rep.w_alias:
+        rep.w_f32 = False
+
+
+def run_teacher_forced(dims4, train, test, temps, S, si, theta_inits, w0s, n_rungs, seed=21, hyper=None,
+                       oracle_hyper=None, **sampler_kw):
+    """Per-iteration parity with re-synchronisation: before EVERY iteration (and before every exchange sweep) the
+    oracle takes the device's state, then both sides execute the same iteration on the same draws. What is compared
+    is therefore the arithmetic of one iteration of MAIN:432-592 / one sweep of MAIN:962-1011 at a time - trajectory
+    divergence (the two sides drifting apart over many iterations) cannot hide in, or leak into, the numbers.
+    Returns a report dict with per-iteration worst errors over the chains."""
+    from bayesianautoencoders_b200 import DeviceSampler
+    n = len(temps)
+    s = DeviceSampler(dims4, train, test, n, n_rungs, S, np.asarray(temps, float), seed=seed, swap_interval=si,
+                      hyper=hyper, **sampler_kw)
+    reps = []
+    for j in range(n):
+        s.init_chain(j, theta_inits[j], w0s[j])
+        r = bo.Replica(dims4, train, test, temps[j], S, oracle_hyper)
+        r.initialise(theta_inits[j], w0s[j])
+        reps.append(r)
+    keys = ("lik_prop", "lik", "prior", "diff_prop", "sum_value", "mse_train", "mse_test", "theta", "m", "v", "grad")
+    err = {k: np.zeros(S) for k in keys}
+    decisions, swaps = [], []
+    n_rw = 0
+    train32 = np.asarray(train, dtype=np.float32)
+    mask = reps[0].L.trainable_mask
+    for i in range(S):
+        pre = [s.get_state(j) for j in range(n)]
+        for j in range(n):
+            _sync_oracle_to_device(reps[j], pre[j])
+        draws = [s.debug_draws(j, i) for j in range(n)]
+        s.step(1)
+        s.synchronize()
+        for j in range(n):
+            d = draws[j]
+            rec = reps[j].step(bo.StepRandomness(d["lx"], d["noise"], d["eta_noise"], d["u"]))
+            dv = s.traces(j, i, 1)[0]
+            assert bool(dv["langevin"]) == rec.langevin
+            n_rw += 0 if rec.langevin else 1
+            scale = abs(rec.likelihood_proposal) + abs(rec.likelihood) + abs(rec.prior_prop) + abs(rec.diff_prop) + 1.0
+            dscale = abs(rec.first) + abs(rec.second) + 1.0
+            e = dict(lik_prop=abs(dv["likelihood_proposal"] - rec.likelihood_proposal) / abs(rec.likelihood_proposal),
+                     lik=abs(dv["likelihood"] - rec.likelihood) / abs(rec.likelihood),
+                     prior=abs(dv["prior_proposal"] - rec.prior_prop) / abs(rec.prior_prop),
+                     diff_prop=abs(dv["diff_prop"] - rec.diff_prop) / dscale,
+                     sum_value=abs(dv["sum_value"] - rec.sum_value) / scale,
+                     mse_train=abs(dv["mse_train_proposal"] - rec.mse_train) / rec.mse_train,
+                     mse_test=abs(dv["mse_test_proposal"] - rec.mse_test) / rec.mse_test)
+            post = s.get_state(j)
+            # one-iteration errors of the live model and of the Adam moments (they carry both gradients of the iteration)
+            e["theta"] = rel(post["theta"][mask], reps[j].theta[mask])
+            if rec.langevin:
+                e["m"] = rel(post["m"], reps[j].m)
+                e["v"] = rel(post["v"], reps[j].v)
+                # gradient part of the moment update: m_new - 0.81 m_old = 0.09 g1 + 0.1 g2
+                gd = post["m"].astype(np.float64) - 0.81 * pre[j]["m"].astype(np.float64)
+                go = 0.09 * reps[j].grad1 + 0.1 * reps[j].grad2
+                e["grad"] = rel(gd, go)
+            for k, val in e.items():
+                err[k][i] = max(err[k][i], float(val))
+            decisions.append((j, i, float(abs(rec.sum_value - rec.log_u) / scale), bool(dv["accepted"]), bool(rec.accepted)))
+        if (i + 1) % si == 0:
+            pre = [s.get_state(j) for j in range(n)]
+            for j in range(n):
+                _sync_oracle_to_device(reps[j], pre[j])
+            rnd = (i + 1) // si - 1
+            s.swap()
+            s.synchronize()
+            for e0 in range(n // n_rungs):
+                params = [reps[e0 * n_rungs + p].post() for p in range(n_rungs)]
+                for p in range(n_rungs - 1):
+                    u = s.debug_swap_uniform(e0, rnd, p)
+                    p1, p2, sw, l12, l21 = bo.swap_procedure(dims4, train32, params[p], params[p + 1], u)
+                    with np.errstate(over="ignore", invalid="ignore"):
+                        prob = min(1.0, float(np.exp((l12 - params[p][-3]) + (l21 - params[p + 1][-3]))))
+                    params[p], params[p + 1] = p1, p2
+                    swaps.append((rnd, e0, p, bool(sw), float(abs(u - prob))))
+                for p in range(n_rungs):
+                    reps[e0 * n_rungs + p].take(params[p])
+            post = [s.get_state(j) for j in range(n)]
+            for j in range(n):
+                assert abs(post[j]["eta"] - reps[j].eta) < 1e-12, ("exchange moved a different configuration", j, i)
+                assert post[j]["w_is_alias"] == 0
+                assert rel(post[j]["w"], reps[j].w) == 0.0, ("exchanged `w` differs", j, i)
+    counts = s.swap_counts()
+    path = s.gemm_path()
+    s.close()
+    return dict(errors={k: v.tolist() for k, v in err.items()}, decisions=decisions, swaps=swaps, swap_counts=counts,
+                random_walk_steps=n_rw, gemm_path=path)

@@ -188,3 +188,23 @@ def test_sweep_non_finite_likelihoods_follow_the_reference_min():
             lh21 = (-(n / 2) * np.log(2 * np.pi * np.exp(tab[1, 0])) - 0.5 * np.exp(tab[1, 0]) * tab[1, 3]) / tab[0, 2]
             want_first = 0.999 < min(1, np.exp((lh12 - tab[0, 1]) + (lh21 - tab[1, 1])))
         assert (ref[0][0] == 1) == bool(want_first), bad
+
+
+def test_gelman_rubin_pinned_to_reference_script():
+    """`gelman_rubin_reference` against the output of the UNMODIFIED last block of `Gelman Reuben.py` (GR:676-735),
+    frozen by oracle/make_gr_golden.py: 2-decimal traces, axes swapped by the script's transposes."""
+    from bayesianautoencoders_b200 import gelman_rubin, gelman_rubin_reference
+    z = np.load(os.path.join(ROOT, "tests", "golden", "gr_rhat.npz"))
+    w = np.stack([z["w_" + str(n)] for n in z["names"]], axis=2)          # [chains, samples, 12] in GR:690 order
+    assert tuple(z["data_shape"]) == (w.shape[1], w.shape[0], 12)          # the script's "Nchains" is the sample count
+    r = gelman_rubin_reference(w)
+    np.testing.assert_allclose(r["simple"], z["simple"], rtol=1e-12)
+    np.testing.assert_allclose(r["advanced"], z["advanced"], rtol=1e-10)
+    # the textbook orientation gives a different number on the same traces
+    assert np.abs(gelman_rubin(w)["simple"] - z["simple"]).max() > 0.05
+    # live reference, when mounted (build container): regenerate and compare
+    if os.path.exists("/root/reference/Bayesian/Gelman Reuben.py"):
+        from oracle.make_gr_golden import run_reference_block
+        live = run_reference_block({str(n): z["w_" + str(n)] for n in z["names"]})
+        np.testing.assert_array_equal(live["simple"], z["simple"])
+        np.testing.assert_array_equal(live["advanced"], z["advanced"])

@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 
 from oracle import bae_oracle as bo
-from tests.parity_util import dump_report, rel, run_device_and_oracle, synth_data, trace_errors
+from tests.parity_util import dump_report, rel, run_device_and_oracle, run_teacher_forced, synth_data, trace_errors
 
 pytestmark = pytest.mark.gpu
 
@@ -38,7 +38,9 @@ def _check(name, r, S, temps, tol=TOL):
     errs, decisions, branch_ok = trace_errors(r["dev"], r["records"])
     reps, final = r["reps"], r["final"]
     n = len(temps)
-    th = [rel(final[j]["theta"], reps[j].theta) for j in range(n)]
+    # `w` is what the chain continues from (after an exchange the device has already moved it into the live model, the
+    # reference loads it at the start of the next iteration)
+    th = [rel(final[j]["theta"] if final[j]["w_is_alias"] else final[j]["w"], reps[j].current_w()) for j in range(n)]
     mm = [rel(final[j]["m"], reps[j].m) for j in range(n)]
     vv = [rel(final[j]["v"], reps[j].v) for j in range(n)]
     n_rw = sum(1 for j in range(n) for rec in r["records"][j] if not rec.langevin)
@@ -121,3 +123,81 @@ def test_madelon_eight_rung_ensemble_swaps_match_oracle():
     th0, w0 = _inputs(dims4, 8, 19)
     r = run_device_and_oracle(dims4, train, test, temps, 6, 5, th0, w0, n_rungs=8, do_swaps=True, seed=31, gemm_path=2)
     _check("madelon_tc_8rungs", r, 6, temps)
+
+
+# ---- teacher-forced: one iteration at a time from identical state -------------------------------------------------
+TOL_TF = {
+    "lik": 1e-5,         # north star: per-step log-likelihood within 1e-5 relative, EVERY iteration
+    "mse": 1e-5,
+    "grad": 1e-5,        # north star: gradients within 1e-5 relative (0.09 g1 + 0.1 g2 recovered from the Adam moments)
+    "prior": 1e-6,
+    "diff_prop": 1e-4,
+    "sum_value": 1e-5,
+    "theta": 1e-5,
+    "m": 1e-5,
+    "v": 2e-5,
+    "decision_margin": 1e-4,
+    "swap_margin": 1e-4,
+}
+
+
+def _check_tf(name, rep, tol=TOL_TF):
+    dump_report(name, rep)
+    e = {k: np.asarray(v) for k, v in rep["errors"].items()}
+    assert max(e["lik_prop"].max(), e["lik"].max()) <= tol["lik"], (e["lik_prop"], e["lik"])
+    assert max(e["mse_train"].max(), e["mse_test"].max()) <= tol["mse"], (e["mse_train"], e["mse_test"])
+    assert e["grad"].max() <= tol["grad"], e["grad"]
+    assert e["prior"].max() <= tol["prior"], e["prior"]
+    assert e["diff_prop"].max() <= tol["diff_prop"], e["diff_prop"]
+    assert e["sum_value"].max() <= tol["sum_value"], e["sum_value"]
+    assert e["theta"].max() <= tol["theta"], e["theta"]
+    assert e["m"].max() <= tol["m"] and e["v"].max() <= tol["v"], (e["m"], e["v"])
+    checked = 0
+    for j, i, margin, a, b in rep["decisions"]:
+        if margin > tol["decision_margin"]:
+            assert a == b, (j, i, margin)
+            checked += 1
+    assert checked >= 0.9 * len(rep["decisions"])
+    n_sw = 0
+    for rnd, ens, p, sw, margin in rep["swaps"]:
+        n_sw += int(sw)
+    # the harness itself asserts after every sweep that eta and `w` of every position equal the oracle's
+    assert rep["swap_counts"] == (n_sw, len(rep["swaps"])) or min(m for *_, m in rep["swaps"]) < tol["swap_margin"]
+
+
+@pytest.mark.parametrize("phase_launch", ["1", "0"])
+def test_madelon_tcgen05_every_iteration_from_identical_state(phase_launch, monkeypatch):
+    monkeypatch.setenv("BAE_PHASE_LAUNCH", phase_launch)
+    dims4, ntr, nte = (500, 450, 400, 300), 2000, 1800
+    train, test = synth_data(dims4, ntr, nte)
+    th0, w0 = _inputs(dims4, 2, 17)
+    rep = run_teacher_forced(dims4, train, test, [1.0, 2.0], 10, 5, th0, w0, n_rungs=2, seed=6, gemm_path=2)
+    assert rep["gemm_path"] == 2 and rep["random_walk_steps"] == 3
+    _check_tf(f"tf_madelon_tc_phase_launch{phase_launch}", rep)
+
+
+def test_madelon_fp32_tiles_every_iteration_from_identical_state():
+    """Same case on the FP32 CUDA-core tiles (gemm_path = 1): the two GEMM engines are checked against the same oracle."""
+    dims4, ntr, nte = (500, 450, 400, 300), 2000, 1800
+    train, test = synth_data(dims4, ntr, nte)
+    th0, w0 = _inputs(dims4, 2, 17)
+    rep = run_teacher_forced(dims4, train, test, [1.0, 2.0], 10, 5, th0, w0, n_rungs=2, seed=6, gemm_path=1)
+    assert rep["gemm_path"] == 1
+    _check_tf("tf_madelon_fp32", rep)
+
+
+def test_coil_every_iteration_from_identical_state():
+    dims4, ntr, nte = (85, 70, 60, 50), 4366, 1456
+    train, test = synth_data(dims4, ntr, nte)
+    th0, w0 = _inputs(dims4, 2, 18)
+    rep = run_teacher_forced(dims4, train, test, [1.0, 2.0], 9, 3, th0, w0, n_rungs=2, seed=6)
+    _check_tf("tf_coil_fp32", rep)
+
+
+def test_swiss_every_iteration_from_identical_state():
+    dims4, ntr, nte = (3, 10, 5, 2), 3750, 1250
+    train, test = synth_data(dims4, ntr, nte)
+    temps = list(bo.temperature_ladder(4, 2))
+    th0, w0 = _inputs(dims4, 4, 20)
+    rep = run_teacher_forced(dims4, train, test, temps, 20, 5, th0, w0, n_rungs=4, seed=6)
+    _check_tf("tf_swiss_fp32", rep)
