@@ -9,14 +9,15 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbae_b200.so")
+# BAE_B200_LIB selects another build of the same library (A/B experiments: tools/); the default is the in-tree build
+LIB_PATH = os.environ.get("BAE_B200_LIB") or os.path.join(_HERE, "lib", "libbae_b200.so")
 
 EXPORTS = [
     "bae_last_error", "bae_version", "bae_create", "bae_destroy", "bae_w_size", "bae_n_trainable",
     "bae_upload_data", "bae_set_ladder", "bae_init_chain", "bae_get_state", "bae_set_state", "bae_step",
     "bae_swap_local", "bae_run", "bae_synchronize", "bae_eval", "bae_debug_draws", "bae_debug_swap_uniform",
     "bae_read_traces", "bae_swap_counts", "bae_exchange_pack", "bae_exchange_unpack", "bae_exchange_finish",
-    "bae_launch_count", "bae_last_step_ms", "bae_gemm_path", "bae_stream", "bae_debug_buffer", "bae_debug_trace", "bae_debug_profiler", "bae_exchange_table", "bae_exchange_local", "bae_host_sweep",
+    "bae_launch_count", "bae_last_step_ms", "bae_gemm_path", "bae_stream", "bae_debug_buffer", "bae_debug_trace", "bae_debug_profiler", "bae_exchange_table", "bae_exchange_local", "bae_host_sweep", "bae_last_sweep",
 ]
 
 
@@ -88,6 +89,7 @@ def load():
     lib.bae_debug_swap_uniform.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, P(C.c_double)]
     lib.bae_read_traces.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.bae_swap_counts.argtypes = [C.c_void_p, P(C.c_int64), P(C.c_int64)]
+    lib.bae_last_sweep.argtypes = [C.c_void_p, C.c_void_p]
     lib.bae_exchange_table.argtypes = [C.c_void_p, C.c_void_p]
     lib.bae_exchange_local.argtypes = [C.c_void_p, C.c_void_p]
     lib.bae_host_sweep.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, P(C.c_int)]

@@ -1000,6 +1000,14 @@ int bae_swap_counts(bae_handle* h, int64_t* num_swap, int64_t* total) {
   return BAE_OK;
 }
 
+int bae_last_sweep(bae_handle* h, int32_t* src_out) {
+  if (!h || !src_out) return fail(BAE_ERR_INVALID, "null argument");
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(src_out, h->hs.swap_src, sizeof(int32_t) * h->hs.C, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+
 // (eta, stored likelihood, adapttemp, SSE of `w`) of every resident chain: the rows a rank contributes to the
 // all-gather of an exchange round (MAIN:594-597 posts these scalars next to the weights). out: [n_chains][4].
 int bae_exchange_table(bae_handle* h, double* out) {

@@ -295,9 +295,22 @@ __device__ __forceinline__ float4 ldg128_pinned(const float* p) {
   return v;
 }
 
+// hi = what the tensor core reads from the raw FP32 container (it ignores the low 13 mantissa bits: truncation);
+// lo = x - hi is exact in FP32 but has up to 24 significant bits, of which the tensor core would again keep only the top 11
+// by TRUNCATION: x would then be represented with a one-sided error of up to 2^-21 |x| (mean 2^-22), a systematic
+// shrink of every product that adds up over the layers. lo is therefore ROUNDED to the nearest TF32 value here (ties
+// away from zero; an integer add on the bit pattern): the representation error of x becomes two-sided, zero-mean.
+#ifndef BAE_LO_RN
+#define BAE_LO_RN 1
+#endif
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = x - hi;
+  const float l = x - hi;
+#if BAE_LO_RN
+  lo = __uint_as_float((__float_as_uint(l) + 0x1000u) & 0xFFFFE000u);
+#else
+  lo = l;
+#endif
 }
 
 __device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem) {

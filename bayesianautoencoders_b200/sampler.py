@@ -216,6 +216,12 @@ class DeviceSampler:
         N.check(self.lib.bae_swap_counts(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def last_sweep(self):
+        """src[p] = chain whose configuration ended at position p in the most recent exchange sweep."""
+        src = np.zeros(self.n_chains, np.int32)
+        N.check(self.lib.bae_last_sweep(self._h, src.ctypes.data))
+        return src
+
     # -- probes -------------------------------------------------------------------------------
     def eval(self, chain, which=0, w=None, grads=False, out=False):
         sse, mse = C.c_double(), C.c_double()

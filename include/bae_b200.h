@@ -132,6 +132,10 @@ int bae_debug_swap_uniform(bae_handle* h, int ensemble, int round, int pair, dou
 /* Trace ring: records of iterations [first_step, first_step+n) of one chain. */
 int bae_read_traces(bae_handle* h, int chain, int first_step, int n, bae_trace* out);
 int bae_swap_counts(bae_handle* h, int64_t* num_swap, int64_t* total_swap_proposals);
+/* Result of the most recent exchange sweep on this handle (MAIN:1059-1065): src[p] = local chain whose configuration
+ * ended at ladder position p (length n_chains). Pair (p, p+1) of an ensemble swapped iff src[p] == p + 1 (`swapped`,
+ * MAIN:995-1011). */
+int bae_last_sweep(bae_handle* h, int32_t* src_out);
 
 /* Multi-GPU ladder sharding (one process per GPU): export / import the exchange view of a chain
  * ([vec(w), eta, likelihood, adapttemp, last_sse], MAIN:595-596) as DEVICE buffers usable with NCCL. */
