@@ -17,7 +17,7 @@ EXPORTS = [
     "bae_upload_data", "bae_set_ladder", "bae_init_chain", "bae_get_state", "bae_set_state", "bae_step",
     "bae_swap_local", "bae_run", "bae_synchronize", "bae_eval", "bae_debug_draws", "bae_debug_swap_uniform",
     "bae_read_traces", "bae_swap_counts", "bae_exchange_pack", "bae_exchange_unpack", "bae_exchange_finish",
-    "bae_launch_count", "bae_last_step_ms", "bae_gemm_path", "bae_stream", "bae_debug_buffer", "bae_debug_trace", "bae_debug_profiler", "bae_exchange_table", "bae_exchange_local", "bae_host_sweep", "bae_last_sweep",
+    "bae_launch_count", "bae_last_step_ms", "bae_gemm_path", "bae_stream", "bae_debug_buffer", "bae_debug_trace", "bae_debug_profiler", "bae_exchange_table", "bae_exchange_local", "bae_host_sweep", "bae_last_sweep", "bae_forward_all",
 ]
 
 
@@ -32,7 +32,7 @@ class Config(C.Structure):
         ("pt_switch_step", C.c_int32), ("swap_interval", C.c_int32), ("use_langevin", C.c_int32),
         ("lr", C.c_float), ("step_w", C.c_float), ("step_eta", C.c_float), ("l_prob", C.c_float),
         ("sigma_squared", C.c_float), ("nu_1", C.c_float), ("nu_2", C.c_float),
-        ("seed", C.c_uint64), ("gemm_path", C.c_int32), ("reserved", C.c_int32),
+        ("seed", C.c_uint64), ("gemm_path", C.c_int32), ("drift_mode", C.c_int32),
     ]
 
 
@@ -90,6 +90,7 @@ def load():
     lib.bae_read_traces.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.bae_swap_counts.argtypes = [C.c_void_p, P(C.c_int64), P(C.c_int64)]
     lib.bae_last_sweep.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bae_forward_all.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bae_exchange_table.argtypes = [C.c_void_p, C.c_void_p]
     lib.bae_exchange_local.argtypes = [C.c_void_p, C.c_void_p]
     lib.bae_host_sweep.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p, P(C.c_int)]

@@ -28,6 +28,8 @@ cudaError_t launch_grad_reduce(const DevState* dS, int chain, cudaStream_t st);
 cudaError_t launch_debug_draws(const DevState* dS, int chain, int step, float* noise, double* scalars, cudaStream_t st);
 cudaError_t launch_debug_swap_u(const DevState* dS, int ens, int round, int pair, double* out, cudaStream_t st);
 cudaError_t launch_scalars(const DevState* dS, int chain, bae_chain_scalars* staged, int put, cudaStream_t st);
+cudaError_t launch_extract(const float* src, int ld, const float* X, int ldx, int rows, int d, float inv_scale, int mode,
+                           float* out, cudaStream_t st);
 cudaError_t launch_pack(const DevState* dS, const float* ref_vec, float* pad_vec, cudaStream_t st);
 cudaError_t launch_unpack(const DevState* dS, const float* pad_vec, float* ref_vec, cudaStream_t st);
 }  // namespace bae
@@ -78,6 +80,7 @@ struct bae_handle {
   float* stage_noise = nullptr;  // [w_size]
   double* stage_d = nullptr;     // small device scratch for doubles
   bae_chain_scalars* stage_sc = nullptr;   // device staging of one chain's scalars (bae_get_state / bae_set_state)
+  float* stage_rows = nullptr;             // [n_max][max(d0, d3)] dense staging of bae_forward_all (allocated on first use)
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -486,6 +489,8 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   s.C = cfg->n_chains; s.C_alloc = s.C + 1; s.n_rungs = cfg->n_rungs; s.chain_id_base = cfg->chain_id_base;
   s.samples = cfg->samples; s.pt_step = cfg->pt_switch_step; s.swap_interval = cfg->swap_interval;
   s.use_langevin = cfg->use_langevin;
+  if (cfg->drift_mode < 0 || cfg->drift_mode > 2) return fail(BAE_ERR_INVALID, "drift_mode must be 0 (Adam), 1 (Adam, SGD after pt) or 2 (MALA)");
+  s.drift_mode = cfg->drift_mode;
   s.lr = cfg->lr; s.step_w = cfg->step_w; s.step_eta = cfg->step_eta; s.l_prob = cfg->l_prob;
   s.sigma_sq = cfg->sigma_squared; s.nu1 = cfg->nu_1; s.nu2 = cfg->nu_2;
   s.seed_lo = (unsigned)(cfg->seed & 0xffffffffull); s.seed_hi = (unsigned)(cfg->seed >> 32);
@@ -534,6 +539,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   CU(dalloc(h, &c.nlang, CA)); CU(dalloc(h, &c.step, CA)); CU(dalloc(h, &c.is_lang, CA));
   CU(dalloc(h, &c.lx, CA)); CU(dalloc(h, &c.eta_noise, CA)); CU(dalloc(h, &c.u, CA));
   CU(dalloc(h, &c.ss1, CA)); CU(dalloc(h, &c.sq1, CA)); CU(dalloc(h, &c.ss2, CA)); CU(dalloc(h, &c.sq2, CA));
+  CU(dalloc(h, &c.plain, CA)); CU(dalloc(h, &c.drift_a, CA)); CU(dalloc(h, &c.drift_b, CA));
   CU(dalloc(h, &s.traces, (size_t)s.C * s.samples));
   CU(dalloc(h, &s.swap_src, CA)); CU(dalloc(h, &s.swap_flag, CA)); CU(dalloc(h, &s.swap_tmp, CA * 2));
   CU(dalloc(h, &s.num_swap, 1)); CU(dalloc(h, &s.total_swap, 1));
@@ -581,6 +587,8 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     // Measured (Madelon, 64 chains): BatchNorm / Adam phases run 1.5-1.8x faster as their own many-CTA launches than on the two
     // epilogue warpgroups of the persistent kernel, and a launch costs no more than a grid barrier.
     if (!h->phase_launch_env) h->phase_launch = true;
+    if (s.drift_mode != 0 && !h->phase_launch)
+      return fail(BAE_ERR_INVALID, "drift_mode 1 / 2 on the tcgen05 path needs the per-phase step program (unset BAE_PHASE_LAUNCH=0)");
   }
   CU(cudaStreamSynchronize(h->stream));
   guard.h = nullptr;
@@ -951,6 +959,51 @@ int bae_eval(bae_handle* h, int chain, int which, const float* w, double* sse, d
     if ((rc = run_phases_plain(h, P_BWD1, P_BWD1 + 7, E, E + 1))) return rc;
     if (s.max_ksplit > 1) CU(launch_grad_reduce(h->dS, E, h->stream));
     if ((rc = get_vec(h, s.grad + (size_t)E * s.Pp, grads))) return rc;
+  }
+  return BAE_OK;
+}
+
+int bae_forward_all(bae_handle* h, int which, float* features, float* recon, double* sse) {
+  if (!h) return fail(BAE_ERR_INVALID, "null handle");
+  if (!h->data_loaded) return fail(BAE_ERR_STATE, "upload data first");
+  if (which != 0 && which != 1) return fail(BAE_ERR_INVALID, "which must be 0 (train) or 1 (test)");
+  const DevState& s = h->hs;
+  CU(cudaSetDevice(h->device));
+  // the second-pass train forward phases / the test forward phases run for every chain (needLang = 0); they write
+  // activations, batch statistics and loss partials only
+  const int p0 = which == 0 ? P_FWD2 : P_FWDT, pass = which == 0 ? 1 : 2;
+  const int rows = which == 0 ? s.n_train : s.n_test;
+  const float* X = which == 0 ? s.Xtrain : s.Xtest;
+  for (int p = p0; p < p0 + 7; ++p) {
+    CU(launch_one(h, p, 0, s.C, 1));
+    h->launches++;
+  }
+  if (!h->stage_rows && (features || recon)) CU(dalloc(h, &h->stage_rows, (size_t)s.n_max * std::max(s.d0, s.d3)));
+  const float inv_scale = (float)(((double)rows * s.d0) / 2.0);
+  for (int c = 0; c < s.C; ++c) {
+    if (features) {
+      CU(launch_extract(s.Z + (size_t)c * s.n_max * s.ld3, s.ld3, nullptr, 0, rows, s.d3, 0.f, 0, h->stage_rows, h->stream));
+      h->launches++;
+      CU(cudaMemcpyAsync(features + (size_t)c * rows * s.d3, h->stage_rows, sizeof(float) * rows * s.d3, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));   // pageable destination; the staging buffer is reused
+    }
+    if (recon) {
+      CU(launch_extract(s.DOUT + (size_t)c * s.n_max * s.ld0, s.ld0, X, s.ld0, rows, s.d0, inv_scale, 1, h->stage_rows, h->stream));
+      h->launches++;
+      CU(cudaMemcpyAsync(recon + (size_t)c * rows * s.d0, h->stage_rows, sizeof(float) * rows * s.d0, cudaMemcpyDeviceToHost, h->stream));
+      CU(cudaStreamSynchronize(h->stream));
+    }
+  }
+  if (sse) {
+    std::vector<double> part((size_t)s.C * s.loss_stride * 2);
+    CU(cudaMemcpyAsync(part.data(), s.loss_part + (size_t)pass * s.C_alloc * s.loss_stride * 2, sizeof(double) * part.size(),
+                       cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < s.C; ++c) {
+      double a = 0;
+      for (int i = 0; i < s.loss_stride; ++i) a += part[((size_t)c * s.loss_stride + i) * 2];
+      sse[c] = a;
+    }
   }
   return BAE_OK;
 }

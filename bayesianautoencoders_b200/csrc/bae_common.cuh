@@ -95,6 +95,8 @@ struct ChainArrays {
   int* is_lang;
   double *lx, *eta_noise, *u;
   float *ss1, *sq1, *ss2, *sq2;  // Adam step_size and sqrt(bias_correction2) for the two drift calls
+  int* plain;                    // 1: this iteration's drift is w - drift_a * grad - drift_b * w (SGD after pt / MALA), no Adam state
+  float *drift_a, *drift_b;
 };
 
 struct DevState {
@@ -103,7 +105,7 @@ struct DevState {
   int ld0, ld1, ld2, ld3;
   int n_train, n_test, n_max;
   int C, C_alloc, n_rungs, chain_id_base;
-  int samples, pt_step, swap_interval, use_langevin;
+  int samples, pt_step, swap_interval, use_langevin, drift_mode;
   float lr, step_w, step_eta, l_prob, sigma_sq, nu1, nu2;
   unsigned seed_lo, seed_hi;
   int w_size, Pp, n_adam_items, nbuf;  // nbuf = 2*d3 + 1

@@ -691,6 +691,8 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
     const int cg_id = S->chain_id_base + chain;
     const float ss = (which == 1) ? S->ch.ss1[chain] : S->ch.ss2[chain];
     const float sq = (which == 1) ? S->ch.sq1[chain] : S->ch.sq2[chain];
+    const bool plain = S->ch.plain[chain] != 0;               // SGD after pt / MALA: no Adam state involved
+    const float da = S->ch.drift_a[chain], db = S->ch.drift_b[chain];
     // most 8192-float items lie inside one tensor: look the tensor up once per item then
     const int sg_first = find_seg(S, it * kAdamChunk), sg_last = find_seg(S, min(Pp, (it + 1) * kAdamChunk) - 4);
     const float inv_sq = 1.0f / sq;   // one IEEE division per item; per element: a multiply and an approximate reciprocal
@@ -714,7 +716,13 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
       float t[4] = {t4.x, t4.y, t4.z, t4.w};
       if (which == 1) {
         float o[4];
-        if (lang) {
+        if (lang && plain) {
+          const float4 g4 = load_grad4(gr, p, sd.ksplit, gstride);
+          const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = t[j] - da * g[j] - db * t[j];
+          if (!alias) *reinterpret_cast<float4*>(&wc[p]) = t4;
+        } else if (lang) {
           float4 g4 = load_grad4(gr, p, sd.ksplit, gstride);
           float4 m4 = *reinterpret_cast<const float4*>(&mm[p]);
           float4 v4 = *reinterpret_cast<const float4*>(&vv[p]);
@@ -747,6 +755,19 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
           }
         }
         *reinterpret_cast<float4*>(&th[p]) = make_float4(o[0], o[1], o[2], o[3]);
+      } else if (plain) {
+        if (alias) continue;    // w IS the live model: w - w_prop_gd is exactly 0 (MAIN:476 with MAIN:449/555)
+        const float4 g4 = load_grad4(gr, p, sd.ksplit, gstride);
+        const float4 w4 = *reinterpret_cast<const float4*>(&wc[p]);
+        const float g[4] = {g4.x, g4.y, g4.z, g4.w}, w0[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float wpg = t[j] - da * g[j] - db * t[j];   // w_prop_gd
+          if (j < nval) {
+            const float dl = w0[j] - wpg;
+            a2 = fmaf(dl, dl, a2);
+          }
+        }
       } else {
         float4 g4 = load_grad4(gr, p, sd.ksplit, gstride);
         float4 m4 = *reinterpret_cast<const float4*>(&mm[p]);
@@ -1009,7 +1030,22 @@ __device__ void run_prologue(const DevState* S, int c_begin, int c_end) {
     ch.u[chain] = u;
     const int lang = (S->use_langevin && lx < (double)S->l_prob) ? 1 : 0;       // MAIN:452
     ch.is_lang[chain] = lang;
-    if (lang) {
+    // drift of this iteration: Adam (the reference's setting), or a plain gradient step w - a * grad - b * w:
+    //   drift_mode 1 (experiment_type = 1, MAIN:454-470): i > pt -> fresh SGD(lr = 0.1): a = 0.1, b = 0
+    //   drift_mode 2 (MALA): a = (eps^2 / 2) * tau * n / (2 T), b = (eps^2 / 2) / sigma^2 with grad = d MSE / d w
+    int plain = 0;
+    float da = 0.f, db = 0.f;
+    if (S->drift_mode == 1 && i > S->pt_step) { plain = 1; da = 0.1f; }
+    if (S->drift_mode == 2) {
+      plain = 1;
+      const double h2 = 0.5 * (double)S->step_w * (double)S->step_w;
+      da = (float)(h2 * 0.5 * exp(ch.eta[chain]) * ((double)S->n_train * S->d0) / ch.adapt[chain]);
+      db = (float)(h2 / (double)S->sigma_sq);
+    }
+    ch.plain[chain] = plain;
+    ch.drift_a[chain] = da;
+    ch.drift_b[chain] = db;
+    if (lang && !plain) {
       const int t1 = ch.adam_t[chain] + 1, t2 = t1 + 1;
       ch.ss1[chain] = (float)((double)S->lr / (1.0 - pow((double)kB1, (double)t1)));
       ch.sq1[chain] = (float)sqrt(1.0 - pow((double)kB2, (double)t1));
@@ -1159,7 +1195,7 @@ __device__ void run_epilogue(const DevState* S, int c_begin, int c_end, double* 
       }
       if (lang) {
         ch.nlang[chain] += 1;
-        ch.adam_t[chain] += 2;
+        if (!ch.plain[chain]) ch.adam_t[chain] += 2;
       }
       ch.last_sse[chain] = sse_tr;
       ch.prop_sse[chain] = sse_tr;
@@ -1525,6 +1561,18 @@ __global__ void bae_debug_swap_u_kernel(const DevState* __restrict__ S, int ense
   out[0] = swap_uniform(S, ensemble_global, round, pair);
 }
 
+// ---- posterior-predictive extraction: dense [rows][d] copies of one chain's bottleneck features / reconstruction ----
+// mode 0: out = src (features: Z, pitch ld);  mode 1: out = src / scale + X (the loss epilogue stored (o - x) * scale)
+__global__ void bae_extract_kernel(const float* __restrict__ src, int ld, const float* __restrict__ X, int ldx, int rows, int d,
+                                   float inv_scale, int mode, float* __restrict__ out) {
+  const long long n = (long long)rows * d;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / d), c = (int)(e % d);
+    const float v = src[(size_t)r * ld + c];
+    out[e] = mode ? fmaf(v, inv_scale, X[(size_t)r * ldx + c]) : v;
+  }
+}
+
 // ---- per-chain scalars <-> one staged struct (checkpoint / parity injection: one copy instead of 15) ----------
 __global__ void bae_scalars_kernel(const DevState* __restrict__ S, int chain, bae_chain_scalars* st, int put) {
   const ChainArrays& c = S->ch;
@@ -1694,6 +1742,12 @@ cudaError_t launch_debug_draws(const DevState* dS, int chain, int step, float* n
 
 cudaError_t launch_debug_swap_u(const DevState* dS, int ens, int round, int pair, double* out, cudaStream_t st) {
   bae_debug_swap_u_kernel<<<1, 1, 0, st>>>(dS, ens, round, pair, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_extract(const float* src, int ld, const float* X, int ldx, int rows, int d, float inv_scale, int mode,
+                           float* out, cudaStream_t st) {
+  bae_extract_kernel<<<592, 256, 0, st>>>(src, ld, X, ldx, rows, d, inv_scale, mode, out);
   return cudaGetLastError();
 }
 

@@ -271,7 +271,11 @@ class ParallelTempering:
         self.sampler = None
 
     def default_beta_ladder(self, ndim, ntemps, Tmax):
-        """MAIN:867-920 (finite Tmax, given ntemps): betas = logspace(0, -log10(Tmax), ntemps)."""
+        """MAIN:867-920, every branch. Inverse temperatures `logspace(0, -log10(Tmax), ntemps)`; when `Tmax` is
+        None it is derived from `ntemps` and a per-dimension temperature step, when `ntemps` is None it is derived from
+        `Tmax`; `Tmax = inf` replaces the coldest inverse temperature by 0. As in the reference the step table is built
+        with `range(maxtemp)`, so `Tmax` must be an int (or None / inf raise TypeError there too) - the sampler itself
+        always calls it with (2, num_chains, maxtemp) (MAIN:924)."""
         if type(ndim) != int or ndim < 1:
             raise ValueError('Invalid number of dimensions specified.')
         if ntemps is None and Tmax is None:
@@ -280,7 +284,30 @@ class ParallelTempering:
             raise ValueError('``Tmax`` must be greater than 1.')
         if ntemps is not None and (type(ntemps) != int or ntemps < 1):
             raise ValueError('Invalid number of temperatures specified.')
-        return np.logspace(0, -np.log10(Tmax), ntemps)
+        # step table: Tmax * ntemps^(-k / (ntemps - 1)), k = 0 .. Tmax   (MAIN:878-885)
+        steps = [Tmax]
+        for _ in range(Tmax):
+            steps.append(steps[-1] * (ntemps ** (-1 / (ntemps - 1))))
+        steps = np.array(steps)
+        if ndim > steps.shape[0]:
+            tstep = 1.0 + 2.0 * np.sqrt(np.log(4.0)) / np.sqrt(ndim)      # large-dimension approximation (MAIN:887-890)
+        else:
+            tstep = steps[ndim - 1]
+        append_inf = Tmax == np.inf
+        if append_inf:
+            Tmax = None
+            ntemps = ntemps - 1
+        if ntemps is not None:
+            if Tmax is None:
+                Tmax = tstep ** (ntemps - 1)
+        else:
+            if Tmax is None:
+                raise ValueError('Must specify at least one of ``ntemps\'\' and finite ``Tmax``.')
+            ntemps = int(np.log(Tmax) / np.log(tstep) + 2)
+        betas = np.logspace(0, -np.log10(Tmax), ntemps)
+        if append_inf:
+            betas = np.concatenate((betas, [0]))
+        return betas
 
     def assign_temperatures(self):
         """MAIN:922-935."""

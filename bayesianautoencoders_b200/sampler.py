@@ -75,6 +75,7 @@ class Hyper:
     nu_2: float = 3.0
     use_langevin: bool = True
     pt_samples: float = 0.5   # MAIN:65
+    drift_mode: int = 0       # 0 Adam only (experiment_type 2, MAIN:72); 1 Adam then SGD after pt (experiment_type 1); 2 MALA
 
 
 TRACE_DTYPE = np.dtype([
@@ -109,6 +110,7 @@ class DeviceSampler:
         cfg.sigma_squared, cfg.nu_1, cfg.nu_2 = h.sigma_squared, h.nu_1, h.nu_2
         cfg.seed = int(seed)
         cfg.gemm_path = int(gemm_path)
+        cfg.drift_mode = int(h.drift_mode)
         self.cfg = cfg
         self.dims4 = tuple(int(x) for x in dims4)
         self.n_chains, self.n_rungs, self.samples = int(n_chains), int(n_rungs), int(samples)
@@ -215,6 +217,17 @@ class DeviceSampler:
         a, b = C.c_int64(), C.c_int64()
         N.check(self.lib.bae_swap_counts(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def forward_all(self, which=0, features=True, recon=True):
+        """Batched forward of the train (0) / test (1) matrix through every resident chain's live model:
+        dict(features [C, rows, d3] = `encode(x)`, recon [C, rows, d0] = `forward(x)`, sse [C]); MAIN:709-818."""
+        rows = self.cfg.n_train if which == 0 else self.cfg.n_test
+        f = np.zeros((self.n_chains, rows, self.dims4[3]), np.float32) if features else None
+        r = np.zeros((self.n_chains, rows, self.dims4[0]), np.float32) if recon else None
+        sse = np.zeros(self.n_chains, np.float64)
+        N.check(self.lib.bae_forward_all(self._h, int(which), f.ctypes.data if features else None,
+                                         r.ctypes.data if recon else None, sse.ctypes.data))
+        return dict(features=f, recon=r, sse=sse)
 
     def last_sweep(self):
         """src[p] = chain whose configuration ended at position p in the most recent exchange sweep."""

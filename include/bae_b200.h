@@ -55,7 +55,10 @@ typedef struct bae_config {
   float nu_2;             /* 3                                                    MAIN:398 */
   uint64_t seed;          /* Philox4x32-10 key */
   int32_t gemm_path;      /* 0 = auto, 1 = FP32 CUDA-core tiles only, 2 = tcgen05 3xTF32 where widths allow */
-  int32_t reserved;
+  int32_t drift_mode;     /* 0 = Adam drift in every Langevin iteration (experiment_type = 2, the reference's setting, MAIN:72)
+                           * 1 = experiment_type = 1: Adam while i <= pt, then a stateless SGD(lr = 0.1) step (MAIN:209-210, 454-470)
+                           * 2 = plain-gradient MALA on the tempered log-posterior (not in the reference):
+                           *     drift = (step_w^2 / 2) * grad[ loglik(w; tau = exp(eta)) / adapttemp + log prior(w) ] */
 } bae_config;
 
 /* Per-step record, one per (chain, iteration): what MAIN:520-592 stores into its trace arrays. */
@@ -122,6 +125,15 @@ int bae_synchronize(bae_handle* h);
  * grads != NULL) of `w` (w_size floats, or NULL for the chain's live model) on the train (which=0) or test
  * (which=1) matrix. Does not disturb the chain state. out: n x dims[0] or NULL. */
 int bae_eval(bae_handle* h, int chain, int which, const float* w, double* sse, double* mse, float* grads, float* out);
+
+/* Posterior-predictive pass, batched over every resident chain (MAIN:709-818 runs `cae.encode(X)` / `cae.forward(X)` on the
+ * final weights of one chain): forward of the training (which = 0) or test (which = 1) matrix through each chain's live
+ * model, BatchNorm in training mode on that batch as everywhere in the reference. Any output may be NULL.
+ *   features: [n_chains][rows][dims[3]]  encoder output `encode(x)`, i.e. the pre-BatchNorm bottleneck      MAIN:714, 787
+ *   recon:    [n_chains][rows][dims[0]]  reconstruction `forward(x)`                                       MAIN:752
+ *   sse:      [n_chains]                 sum of squared reconstruction errors
+ * Chain state (weights, BatchNorm buffers, Adam moments, scalars, traces) is not disturbed. */
+int bae_forward_all(bae_handle* h, int which, float* features, float* recon, double* sse);
 
 /* The draws iteration `step` of global chain id (chain_id_base + chain) consumes: noise = w_size fp32
  * normals * step_w in reference order (MAIN:260), scalars = {lx, eta_noise, u} (MAIN:447,500,526). */

@@ -265,6 +265,8 @@ class Hyper:
     nu_1: float = 0.0         # MAIN:397
     nu_2: float = 3.0         # MAIN:398
     use_langevin: bool = True
+    experiment_type: int = 2  # MAIN:72: 2 = Adam only; 1 = Adam while i <= pt, then `SGD(lr=0.1)` (MAIN:209-210, 454-470)
+    mala: bool = False        # NOT in the reference: plain-gradient drift on the tempered log-posterior
 
 
 @dataclass
@@ -351,9 +353,10 @@ class Replica:
         out, _ = forward(self.L, self.theta, data)
         return out
 
-    def langevin_gradient(self, x, w):
-        """MAIN:208-226 with optimizer_mode=1: load, forward (train-mode BN), MSE, backward, Adam.step;
-        returns a deep copy of the state_dict (BN buffers as updated by the forward)."""
+    def langevin_gradient(self, x, w, optimizer_mode=1):
+        """MAIN:208-226: load, forward (train-mode BN), MSE, backward, optimizer step; returns a deep copy of the
+        state_dict (BN buffers as updated by the forward). optimizer_mode=1: the persistent Adam (MAIN:178);
+        optimizer_mode=2: a fresh `torch.optim.SGD(lr=0.1)` (MAIN:209-210; no momentum, the Adam state is left alone)."""
         if w is not self.theta:
             self._load(w)
         _, cache = forward(self.L, self.theta, x)
@@ -362,7 +365,19 @@ class Replica:
             g = self.grad_hook(g)           # rounding noise on the analytically-zero encode.4.bias gradient
         self.last_grad = g
         self.last_cache = cache
-        self.t = adam_step(self.L, self.theta, g, self.m, self.v, self.t, self.h.lr)
+        msk = self.L.trainable_mask
+        if self.h.mala:
+            # extension, not in the reference: theta += (eps^2 / 2) grad[ loglik(theta; tau) / T + log prior(theta) ] with
+            # grad loglik = -tau/2 * grad SSE = -tau/2 * n * grad MSE and grad log prior = -theta / sigma^2
+            h2 = 0.5 * self.h.step_w ** 2
+            n = x.shape[0] * x.shape[1]
+            a = h2 * 0.5 * math.exp(self.eta) * n / self.adapttemp
+            b = h2 / self.h.sigma_squared
+            self.theta[msk] = self.theta[msk] - a * g[msk] - b * self.theta[msk]
+        elif optimizer_mode == 2:
+            self.theta[msk] = self.theta[msk] - 0.1 * g[msk]
+        else:
+            self.t = adam_step(self.L, self.theta, g, self.m, self.v, self.t, self.h.lr)
         return self.theta.copy()
 
     def addnoiseandcopy(self, w, noise, w_is_f32=False):
@@ -418,11 +433,12 @@ class Replica:
         prop_f32 = False
         langevin = bool(h.use_langevin and rnd.lx < h.l_prob)                            # MAIN:452
         if langevin:
+            mode = 2 if (i > self.pt and h.experiment_type == 1) else 1                  # MAIN:454
             w_cur = self.current_w()
-            w_gd = self.langevin_gradient(self.train, w_cur.copy())                      # MAIN:473
+            w_gd = self.langevin_gradient(self.train, w_cur.copy(), mode)                # MAIN:473 / 455
             self.grad1 = self.last_grad
             w_proposal = self.addnoiseandcopy(w_gd, rnd.noise)                           # MAIN:474
-            w_prop_gd = self.langevin_gradient(self.train, w_proposal.copy())            # MAIN:475
+            w_prop_gd = self.langevin_gradient(self.train, w_proposal.copy(), mode)      # MAIN:475 / 457
             self.grad2 = self.last_grad
             wc_delta = self.current_w() - w_prop_gd                                      # MAIN:476 (alias -> 0)
             wp_delta = w_proposal - w_gd                                                 # MAIN:477

@@ -25,6 +25,9 @@ CASES = {
     "swiss_1chain": dict(dims4=(3, 10, 5, 2), n_train=300, n_test=100, temps=[1.5], S=12, si=5, swaps=False, seed=11),
     "swiss_pt4": dict(dims4=(3, 10, 5, 2), n_train=256, n_test=64, temps=None, n_chains=4, S=20, si=5, swaps=True, seed=12),
     "mid_pt3": dict(dims4=(24, 20, 16, 12), n_train=96, n_test=40, temps=None, n_chains=3, S=10, si=5, swaps=True, seed=13),
+    # experiment_type = 1 (MAIN:72): Adam while i <= pt = 6, stateless SGD(lr = 0.1) afterwards (MAIN:454-470)
+    "mid_sgd2": dict(dims4=(24, 20, 16, 12), n_train=96, n_test=40, temps=None, n_chains=2, S=12, si=5, swaps=True, seed=14,
+                     experiment_type=1),
 }
 
 
@@ -60,11 +63,13 @@ def build_case(name, spec):
     n_rounds = spec["S"] // spec["si"]
     swap_u = list(np.random.default_rng([spec["seed"], 999]).random(n_rounds * max(n - 1, 1)))
     res = ref_driver.run_reference_pt(spec["dims4"], train, test, temps, spec["S"], spec["si"], rnd,
-                                      swap_u=swap_u, do_swaps=spec["swaps"], torch_seed=spec["seed"])
+                                      swap_u=swap_u, do_swaps=spec["swaps"], torch_seed=spec["seed"],
+                                      experiment_type=spec.get("experiment_type", 2))
     out = dict(dims4=np.array(spec["dims4"]), train=train, test=test, temps=np.array(temps, dtype=np.float64),
                S=spec["S"], swap_interval=spec["si"], do_swaps=spec["swaps"], swap_u=np.array(swap_u),
                swap_log=np.array(res["swap_log"], dtype=np.int64).reshape(-1, 3),
-               num_swap=res["num_swap"], total_swap_proposals=res["total_swap_proposals"])
+               num_swap=res["num_swap"], total_swap_proposals=res["total_swap_proposals"],
+               experiment_type=spec.get("experiment_type", 2))
     for j, c in enumerate(res["ctxs"]):
         s = c.saved
         out[f"c{j}_theta_init"] = c.theta_init
@@ -86,7 +91,10 @@ def build_case(name, spec):
 
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only = sys.argv[1:]
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         out = build_case(name, spec)
         path = os.path.join(GOLDEN_DIR, name + ".npz")
         np.savez_compressed(path, **out)

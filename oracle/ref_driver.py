@@ -153,7 +153,7 @@ class _MainCtx:
 
 
 def run_reference_pt(dims4, train, test, temperatures, samples_per_chain, swap_interval, rnd,
-                     swap_u=None, do_swaps=True, lrate=0.01, step_size=0.005, torch_seed=0):
+                     swap_u=None, do_swaps=True, lrate=0.01, step_size=0.005, torch_seed=0, experiment_type=2):
     """Run `len(temperatures)` reference replicas for `samples_per_chain` iterations each.
 
     rnd: list (one per replica) of dict(w0_randn, lx, noise, eta_noise, u).
@@ -162,6 +162,7 @@ def run_reference_pt(dims4, train, test, temperatures, samples_per_chain, swap_i
     """
     ref = ref_import.load_reference()
     ref_import.set_shape(ref, dims4, lrate=lrate, step_size=step_size)
+    ref.experiment_type = int(experiment_type)     # module global read inside ptReplica.run (MAIN:72, 454)
     L = Layout(dims4)
     n = len(temperatures)
     train = np.asarray(train, dtype=np.float64)
@@ -249,6 +250,7 @@ def run_reference_pt(dims4, train, test, temperatures, samples_per_chain, swap_i
         for p in patches:
             p.stop()
         _tls.ctx = None
+        ref.experiment_type = 2
     if errors:
         raise errors[0][1]
     return dict(ctxs=ctxs, swap_log=swap_log, num_swap=pt.num_swap, total_swap_proposals=pt.total_swap_proposals,

@@ -19,6 +19,7 @@ class GoldenCase:
         self.swap_u = list(z["swap_u"])
         self.swap_log = [(int(a), int(b), bool(c)) for a, b, c in z["swap_log"]]
         self.n = len(self.temps)
+        self.experiment_type = int(z["experiment_type"]) if "experiment_type" in z else 2
 
     def rnd(self, j):
         z = self.z

@@ -101,6 +101,26 @@ def test_ladder_matches_reference_formula():
             pt.default_beta_ladder(*bad)
     with pytest.raises(ValueError):
         pt.default_beta_ladder(2, None, None)
+    # every branch of MAIN:867-920 behaves like the reference, its dead ones included (values probed from the reference)
+    np.testing.assert_allclose(pt.default_beta_ladder(3, 4, 4)[:3], [1.0, 0.6299605249474366, 0.3968502629920499], rtol=1e-14)
+    np.testing.assert_allclose(pt.default_beta_ladder(5, 8, 3)[-1], 1.0 / 3.0, rtol=1e-14)
+    with pytest.raises(TypeError):
+        pt.default_beta_ladder(2, None, 3)          # `ntemps ** ...` with ntemps None: the reference raises here as well
+    with pytest.raises(ZeroDivisionError):
+        pt.default_beta_ladder(2, 1, 2)
+    if os.path.exists("/root/reference/Bayesian/bayes_autoenc_langevincheck.py"):
+        from oracle import ref_import
+        ref = ref_import.load_reference()
+        rp = ref.ParallelTempering.__new__(ref.ParallelTempering)
+        for args in [(2, 8, 2), (2, 64, 2), (1, 8, 3), (5, 8, 3), (3, 4, 4), (40, 8, 2)]:
+            np.testing.assert_array_equal(rp.default_beta_ladder(*args), pt.default_beta_ladder(*args))
+    # linear ladder (geometric = False, MAIN:930-934)
+    pt2 = ParallelTempering(True, 4, 2, 400, 5, None, 10, 0.5, 0.005, dims4=(3, 10, 5, 2),
+                            traindata=np.zeros((4, 3)), testdata=np.zeros((4, 3)))
+    pt2.geometric = False
+    pt2.assign_temperatures()
+    np.testing.assert_allclose(pt2.temperatures, [1.0, 1.5, 2.0, 2.5])
+    np.testing.assert_allclose(pt2.temperatures, bo.temperature_ladder(4, 2, geometric=False))
 
 
 def test_replica_files_names_and_formats(tmp_path):

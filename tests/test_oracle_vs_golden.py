@@ -7,7 +7,7 @@ import pytest
 from oracle import bae_oracle as bo
 from tests.golden_util import GoldenCase
 
-CASES = ["swiss_1chain", "swiss_pt4", "mid_pt3"]
+CASES = ["swiss_1chain", "swiss_pt4", "mid_pt3", "mid_sgd2"]
 
 
 @pytest.mark.parametrize("inject_b3_noise", [True, False])
@@ -43,7 +43,8 @@ def test_replica_traces_match_reference(name, inject_b3_noise):
 
     reps, records, swap_log = bo.run_pt(g.dims4, g.train, g.test, g.temps, g.S, g.swap_interval,
                                         [g.theta_init(j) for j in range(g.n)], [g.rnd(j) for j in range(g.n)],
-                                        swap_u=g.swap_u, do_swaps=g.do_swaps, on_step=on_step, grad_hooks=hooks)
+                                        swap_u=g.swap_u, do_swaps=g.do_swaps, on_step=on_step, grad_hooks=hooks,
+                                        hyper=bo.Hyper(experiment_type=g.experiment_type))
     assert swap_log == g.swap_log
     for j in range(g.n):
         rec = records[j]
