@@ -17,7 +17,8 @@ EXPORTS = [
     "bae_upload_data", "bae_set_ladder", "bae_init_chain", "bae_get_state", "bae_set_state", "bae_step",
     "bae_swap_local", "bae_run", "bae_synchronize", "bae_eval", "bae_debug_draws", "bae_debug_swap_uniform",
     "bae_read_traces", "bae_swap_counts", "bae_exchange_pack", "bae_exchange_unpack", "bae_exchange_finish",
-    "bae_launch_count", "bae_last_step_ms", "bae_gemm_path", "bae_stream", "bae_debug_buffer", "bae_debug_trace", "bae_debug_profiler", "bae_exchange_table", "bae_exchange_local", "bae_host_sweep", "bae_last_sweep", "bae_forward_all",
+    "bae_launch_count", "bae_last_step_ms", "bae_gemm_path", "bae_stream", "bae_debug_buffer", "bae_debug_trace", "bae_debug_profiler", "bae_exchange_table", "bae_exchange_local", "bae_host_sweep", "bae_last_sweep", "bae_forward_all", "bae_shard_config", "bae_swap_exchange", "bae_plan_exchange",
+    "bae_exchange_vectors_sent",
 ]
 
 
@@ -90,6 +91,11 @@ def load():
     lib.bae_read_traces.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     lib.bae_swap_counts.argtypes = [C.c_void_p, P(C.c_int64), P(C.c_int64)]
     lib.bae_last_sweep.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bae_shard_config.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.bae_swap_exchange.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bae_plan_exchange.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.bae_exchange_vectors_sent.argtypes = [C.c_void_p]
+    lib.bae_exchange_vectors_sent.restype = C.c_int64
     lib.bae_forward_all.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bae_exchange_table.argtypes = [C.c_void_p, C.c_void_p]
     lib.bae_exchange_local.argtypes = [C.c_void_p, C.c_void_p]

@@ -7,6 +7,7 @@
 
 #include <cuda.h>
 #include <cuda_profiler_api.h>
+#include <dlfcn.h>
 
 #include <array>
 #include <map>
@@ -28,6 +29,10 @@ cudaError_t launch_grad_reduce(const DevState* dS, int chain, cudaStream_t st);
 cudaError_t launch_debug_draws(const DevState* dS, int chain, int step, float* noise, double* scalars, cudaStream_t st);
 cudaError_t launch_debug_swap_u(const DevState* dS, int ens, int round, int pair, double* out, cudaStream_t st);
 cudaError_t launch_scalars(const DevState* dS, int chain, bae_chain_scalars* staged, int put, cudaStream_t st);
+cudaError_t launch_xtable(const DevState* dS, cudaStream_t st);
+cudaError_t launch_xsweep(const DevState* dS, cudaStream_t st);
+cudaError_t launch_xgather(const DevState* dS, int grid, cudaStream_t st);
+cudaError_t launch_xscatter(const DevState* dS, int grid, cudaStream_t st);
 cudaError_t launch_extract(const float* src, int ld, const float* X, int ldx, int rows, int d, float inv_scale, int mode,
                            float* out, cudaStream_t st);
 cudaError_t launch_pack(const DevState* dS, const float* ref_vec, float* pad_vec, cudaStream_t st);
@@ -81,6 +86,10 @@ struct bae_handle {
   double* stage_d = nullptr;     // small device scratch for doubles
   bae_chain_scalars* stage_sc = nullptr;   // device staging of one chain's scalars (bae_get_state / bae_set_state)
   float* stage_rows = nullptr;             // [n_max][max(d0, d3)] dense staging of bae_forward_all (allocated on first use)
+  int32_t* xsrc_host = nullptr;            // pinned [E][R]: the permutation of the last sharded exchange round
+  std::vector<int32_t> xops;
+  int64_t vectors_sent = 0;
+  int n_sms = 148;
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -540,6 +549,15 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   CU(dalloc(h, &c.lx, CA)); CU(dalloc(h, &c.eta_noise, CA)); CU(dalloc(h, &c.u, CA));
   CU(dalloc(h, &c.ss1, CA)); CU(dalloc(h, &c.sq1, CA)); CU(dalloc(h, &c.ss2, CA)); CU(dalloc(h, &c.sq2, CA));
   CU(dalloc(h, &c.plain, CA)); CU(dalloc(h, &c.drift_a, CA)); CU(dalloc(h, &c.drift_b, CA));
+  CU(dalloc(h, &c.gid, CA));
+  {
+    std::vector<int> gid(CA);
+    for (size_t i = 0; i < CA; ++i) gid[i] = cfg->chain_id_base + (int)i;
+    CU(cudaMemcpyAsync(c.gid, gid.data(), sizeof(int) * CA, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+  }
+  s.shard_rank = 0; s.shard_world = 1;
+  h->n_sms = prop.multiProcessorCount;
   CU(dalloc(h, &s.traces, (size_t)s.C * s.samples));
   CU(dalloc(h, &s.swap_src, CA)); CU(dalloc(h, &s.swap_flag, CA)); CU(dalloc(h, &s.swap_tmp, CA * 2));
   CU(dalloc(h, &s.num_swap, 1)); CU(dalloc(h, &s.total_swap, 1));
@@ -601,6 +619,7 @@ int bae_destroy(bae_handle* h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->xsrc_host) cudaFreeHost(h->xsrc_host);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
@@ -908,6 +927,8 @@ int bae_swap_local(bae_handle* h) {
 int bae_run(bae_handle* h, int n_steps) {
   if (!h || n_steps < 0) return fail(BAE_ERR_INVALID, "bad argument");
   if (n_steps == 0) return BAE_OK;
+  if (h->hs.shard_world > 1)
+    return fail(BAE_ERR_STATE, "this handle holds a block of a sharded ladder: use bae_step + bae_swap_exchange");
   return coop_launch(h, P_PRO, P_END, n_steps, 0);
 }
 
@@ -1050,6 +1071,144 @@ int bae_swap_counts(bae_handle* h, int64_t* num_swap, int64_t* total) {
   CU(cudaStreamSynchronize(h->stream));
   *num_swap = a;
   *total = b;
+  return BAE_OK;
+}
+
+// ---- ladder sharded over ranks ------------------------------------------------------------------------------------
+namespace {
+struct Nccl {
+  int (*all_gather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*group_start)() = nullptr;
+  int (*group_end)() = nullptr;
+  const char* (*error_string)(int) = nullptr;
+  int (*comm_count)(void*, int*) = nullptr;
+  int (*comm_user_rank)(void*, int*) = nullptr;
+  bool ok = false;
+};
+constexpr int kNcclFloat = 7, kNcclDouble = 8;   // ncclFloat32 / ncclFloat64 of nccl.h
+
+Nccl* nccl_api() {
+  static Nccl api;
+  static bool tried = false;
+  if (tried) return &api;
+  tried = true;
+  // the caller created its communicator with the libnccl.so.2 already loaded into this process: bind to that one
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return &api;
+  api.all_gather = reinterpret_cast<decltype(api.all_gather)>(dlsym(lib, "ncclAllGather"));
+  api.send = reinterpret_cast<decltype(api.send)>(dlsym(lib, "ncclSend"));
+  api.recv = reinterpret_cast<decltype(api.recv)>(dlsym(lib, "ncclRecv"));
+  api.group_start = reinterpret_cast<decltype(api.group_start)>(dlsym(lib, "ncclGroupStart"));
+  api.group_end = reinterpret_cast<decltype(api.group_end)>(dlsym(lib, "ncclGroupEnd"));
+  api.error_string = reinterpret_cast<decltype(api.error_string)>(dlsym(lib, "ncclGetErrorString"));
+  api.comm_count = reinterpret_cast<decltype(api.comm_count)>(dlsym(lib, "ncclCommCount"));
+  api.comm_user_rank = reinterpret_cast<decltype(api.comm_user_rank)>(dlsym(lib, "ncclCommUserRank"));
+  api.ok = api.all_gather && api.send && api.recv && api.group_start && api.group_end && api.comm_count && api.comm_user_rank;
+  return &api;
+}
+}  // namespace
+#define NC(x)                                                                                                     \
+  do {                                                                                                            \
+    int r_ = (x);                                                                                                 \
+    if (r_ != 0) return fail(BAE_ERR_CUDA, std::string(#x) + ": NCCL error " + (nc->error_string ? nc->error_string(r_) : "?")); \
+  } while (0)
+
+int bae_shard_config(bae_handle* h, int rank, int world) {
+  if (!h) return fail(BAE_ERR_INVALID, "null handle");
+  if (world < 1 || rank < 0 || rank >= world) return fail(BAE_ERR_INVALID, "bad rank / world");
+  DevState& s = h->hs;
+  const int L = s.n_rungs, R = L * world, E = s.C / L;
+  if (s.chain_id_base % R != 0) return fail(BAE_ERR_INVALID, "chain_id_base must be a multiple of the ladder length n_rungs * world");
+  CU(cudaSetDevice(h->device));
+  s.shard_rank = rank; s.shard_world = world;
+  std::vector<int> gid(s.C_alloc);
+  for (int e = 0; e < E; ++e)
+    for (int l = 0; l < L; ++l) gid[e * L + l] = s.chain_id_base + e * R + rank * L + l;   // the ladder position keys the streams
+  gid[s.C] = s.chain_id_base + E * R + rank;
+  CU(cudaMemcpyAsync(s.ch.gid, gid.data(), sizeof(int) * s.C_alloc, cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  if (!s.xt_local) {
+    CU(dalloc(h, &s.xt_local, (size_t)s.C * 5));
+    CU(dalloc(h, &s.xt_all, (size_t)world * s.C * 5));
+    CU(dalloc(h, &s.xsrc, (size_t)E * R));
+    CU(cudaMallocHost(reinterpret_cast<void**>(&h->xsrc_host), sizeof(int32_t) * E * R));
+  }
+  int rc = upload_state(h);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+
+int bae_plan_exchange(const int32_t* src, int E, int R, int world, int rank, int32_t* out, int max_ops) {
+  if (!src || !out || E < 1 || R < 1 || world < 1 || R % world != 0 || rank < 0 || rank >= world)
+    return fail(BAE_ERR_INVALID, "bad argument");
+  const int L = R / world;
+  int n = 0;
+  // both sides walk (ensemble, destination rung) in ascending order: the k-th message from rank a to rank b is the same
+  // configuration on both, which is all NCCL's point-to-point matching needs
+  for (int e = 0; e < E; ++e)
+    for (int p = 0; p < R; ++p) {
+      const int sr = src[(size_t)e * R + p];
+      if (sr < 0 || sr >= R) return fail(BAE_ERR_INVALID, "permutation entry out of range");
+      const int po = p / L, so = sr / L;
+      if (po == so) continue;
+      if (so != rank && po != rank) continue;
+      if (n >= max_ops) return fail(BAE_ERR_INVALID, "operation buffer too small");
+      out[4 * n + 0] = so == rank ? 0 : 1;
+      out[4 * n + 1] = so == rank ? po : so;
+      out[4 * n + 2] = e;
+      out[4 * n + 3] = so == rank ? sr : p;
+      ++n;
+    }
+  return n;
+}
+
+int64_t bae_exchange_vectors_sent(const bae_handle* h) { return h ? h->vectors_sent : 0; }
+
+int bae_swap_exchange(bae_handle* h, void* comm) {
+  if (!h || !comm) return fail(BAE_ERR_INVALID, "null argument");
+  DevState& s = h->hs;
+  if (s.shard_world < 2 || !s.xt_local) return fail(BAE_ERR_STATE, "call bae_shard_config(rank, world >= 2) first");
+  Nccl* nc = nccl_api();
+  if (!nc->ok) return fail(BAE_ERR_CUDA, "libnccl.so.2 is not loadable in this process");
+  int cnt = 0, urank = -1;
+  NC(nc->comm_count(comm, &cnt));
+  NC(nc->comm_user_rank(comm, &urank));
+  if (cnt != s.shard_world || urank != s.shard_rank) return fail(BAE_ERR_INVALID, "communicator does not match bae_shard_config(rank, world)");
+  CU(cudaSetDevice(h->device));
+  const int L = s.n_rungs, R = L * s.shard_world, E = s.C / L, rank = s.shard_rank;
+  cudaStream_t st = h->stream;
+  CU(launch_xtable(h->dS, st));
+  NC(nc->all_gather(s.xt_local, s.xt_all, (size_t)s.C * 5, kNcclDouble, comm, st));
+  CU(launch_xsweep(h->dS, st));
+  CU(cudaMemcpyAsync(h->xsrc_host, s.xsrc, sizeof(int32_t) * E * R, cudaMemcpyDeviceToHost, st));
+  CU(launch_xgather(h->dS, 2 * h->n_sms, st));     // same-GPU moves overlap the host's planning below
+  h->launches += 3;
+  CU(cudaStreamSynchronize(st));                   // the one host synchronisation of the round: the permutation
+  h->xops.resize((size_t)4 * 2 * E * R);
+  const int nops = bae_plan_exchange(h->xsrc_host, E, R, s.shard_world, rank, h->xops.data(), 2 * E * R);
+  if (nops < 0) return nops;
+  if (nops > 0) {
+    NC(nc->group_start());
+    for (int k = 0; k < nops; ++k) {
+      const int kind = h->xops[4 * k], peer = h->xops[4 * k + 1], e = h->xops[4 * k + 2], rung = h->xops[4 * k + 3];
+      const size_t c = (size_t)e * L + (rung - rank * L);
+      if (kind == 0) {
+        NC(nc->send(s.theta + c * s.Pp, (size_t)s.Pp, kNcclFloat, peer, comm, st));
+        NC(nc->send(s.wb + c * s.nbuf, (size_t)s.nbuf, kNcclFloat, peer, comm, st));
+        h->vectors_sent++;
+      } else {
+        NC(nc->recv(s.wcur + c * s.Pp, (size_t)s.Pp, kNcclFloat, peer, comm, st));
+        NC(nc->recv(s.wb_tmp + c * s.nbuf, (size_t)s.nbuf, kNcclFloat, peer, comm, st));
+      }
+    }
+    NC(nc->group_end());
+  }
+  CU(launch_xscatter(h->dS, 2 * h->n_sms, st));
+  h->launches++;
   return BAE_OK;
 }
 

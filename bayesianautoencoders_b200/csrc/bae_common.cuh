@@ -91,6 +91,7 @@ constexpr int kAuxBnCtas = 2;        // bae_aux_kernel<AUX_BN>
 struct ChainArrays {
   double *eta, *lik, *prior_cur, *last_sse, *prop_sse, *mse_tr, *mse_te, *T, *adapt;
   int *adam_t, *alias, *init_count, *nacc, *nlang, *step;
+  int* gid;   // global chain id (keys the Philox streams): chain_id_base + chain, or the ladder position of a sharded run
   // per-step scratch
   int* is_lang;
   double *lx, *eta_noise, *u;
@@ -138,6 +139,11 @@ struct DevState {
   double* swap_tmp;  // [C][2] eta, last_sse scratch
   long long *num_swap, *total_swap;
   int swap_round;
+  // ---- ladder sharded over ranks (bae_shard_config / bae_swap_exchange); world == 1: not sharded
+  int shard_rank, shard_world;
+  double* xt_local;   // [C][5]         (eta, stored likelihood, adapttemp, SSE of w, alias flag) of the resident chains
+  double* xt_all;     // [world][C][5]  all-gathered
+  int* xsrc;          // [E][R]         global rung whose configuration ends at rung p (identical on every rank)
   // ---- tcgen05 path
   int tc;             // 1: GEMM phases run on the tensor cores (3xTF32); row pitches reserve a ones column
   void* tmaps;        // CUtensorMap array in global memory (64-byte aligned)

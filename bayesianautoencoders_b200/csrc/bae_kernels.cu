@@ -688,7 +688,7 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
     float* __restrict__ wc = S->wcur + base;
     const float* __restrict__ gr = S->grad + base;
     const int step = S->ch.step[chain];
-    const int cg_id = S->chain_id_base + chain;
+    const int cg_id = S->ch.gid[chain];
     const float ss = (which == 1) ? S->ch.ss1[chain] : S->ch.ss2[chain];
     const float sq = (which == 1) ? S->ch.sq1[chain] : S->ch.sq2[chain];
     const bool plain = S->ch.plain[chain] != 0;               // SGD after pt / MALA: no Adam state involved
@@ -835,7 +835,7 @@ __device__ void run_adam_tc(const DevState* S, int which, int c_begin, int c_end
   const int* const a_lang = S->ch.is_lang; const int* const a_alias = S->ch.alias; const int* const a_step = S->ch.step;
   const float* const a_ss = (which == 1) ? S->ch.ss1 : S->ch.ss2;
   const float* const a_sq = (which == 1) ? S->ch.sq1 : S->ch.sq2;
-  const int chain_id_base = S->chain_id_base;
+  const int* const a_gid = S->ch.gid;
   double* const g_part = S->adam_part;
   constexpr int kSubs = kAdamChunk / kAdamSub;
   const uint32_t stage_s = tc::smem_u32(tsm.tiles);
@@ -887,7 +887,7 @@ __device__ void run_adam_tc(const DevState* S, int which, int c_begin, int c_end
       float* __restrict__ mm = g_m + base;
       float* __restrict__ vv = g_v + base;
       float* __restrict__ wc = g_wcur + base;
-      const int cg_id = chain_id_base + chain;
+      const int cg_id = a_gid[chain];
       const uint32_t sb = stage_s + stg * kAdamStageBytes;
 #pragma unroll
       for (int e = 0; e < kAdamSub / (kThreads * 4); ++e) {
@@ -1024,7 +1024,7 @@ __device__ void run_prologue(const DevState* S, int c_begin, int c_end) {
       ch.init_count[chain] = 1;
     }
     double lx, en, u;
-    step_scalars(S, S->chain_id_base + chain, i, lx, en, u);
+    step_scalars(S, ch.gid[chain], i, lx, en, u);
     ch.lx[chain] = lx;
     ch.eta_noise[chain] = en;
     ch.u[chain] = u;
@@ -1066,7 +1066,7 @@ __device__ void run_epilogue(const DevState* S, int c_begin, int c_end, double* 
     const bool lang = ch.is_lang[chain] != 0;
     const bool alias = ch.alias[chain] != 0;
     const int step = ch.step[chain];
-    const int cg_id = S->chain_id_base + chain;
+    const int cg_id = ch.gid[chain];
     float* th = S->theta + (size_t)chain * S->Pp;
     float* wb = S->wb + (size_t)chain * S->nbuf;   // rm[d3], rv[d3], nbt
     float* rm = th + S->seg[SEG_BN_RM].pad_off;
@@ -1346,6 +1346,135 @@ __device__ void run_swap_scatter(const DevState* S) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Exchange round of a ladder SHARDED over ranks (one process per GPU; bae_swap_exchange): every rank holds rungs
+// [rank L, rank L + L) of each of its E ensembles (local chain = e L + l), R = L x world rungs per ladder.
+//   xtable  : (eta, stored likelihood, adapttemp, SSE of w, alias) of the resident chains -> xt_local, all-gathered by NCCL
+//   xsweep  : the same sequential sweep as run_swap_decide on the all-gathered table; every rank computes the identical
+//             permutation (same doubles, same Philox uniforms), so no second collective is needed for agreement
+//   xgather : same-GPU moves into the wcur staging slabs + the posted BatchNorm buffers of every position
+//   (NCCL)  : configurations whose destination is on another rank: theta slab -> the receiver's wcur slab, wb -> wb_tmp
+//   xscatter: staged configurations into the live models, eta / SSE from the table, `w` becomes a detached dict (MAIN:602)
+// ------------------------------------------------------------------------------------------------
+constexpr int kXtCols = 5;
+
+__device__ __forceinline__ double xt_at(const DevState* S, int L, int e, int rung, int k) {
+  return S->xt_all[((size_t)(rung / L) * S->C + (size_t)e * L + (rung % L)) * kXtCols + k];
+}
+
+__global__ void bae_xtable_kernel(const DevState* __restrict__ S) {
+  const ChainArrays& ch = S->ch;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < S->C; c += gridDim.x * blockDim.x) {
+    double* t = S->xt_local + (size_t)c * kXtCols;
+    t[0] = ch.eta[c]; t[1] = ch.lik[c]; t[2] = ch.adapt[c]; t[3] = ch.last_sse[c]; t[4] = (double)ch.alias[c];
+  }
+}
+
+__global__ void bae_xsweep_kernel(const DevState* __restrict__ S) {
+  const int L = S->n_rungs, R = L * S->shard_world, E = S->C / L;
+  const double ntr = (double)S->n_train * S->d0;
+  const int ens_base = S->chain_id_base / R;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    int* src = S->xsrc + (size_t)e * R;
+    double lh_prev = xt_at(S, L, e, 0, 1), T_prev = xt_at(S, L, e, 0, 2);
+    int cfg_prev = 0;
+    const int round = S->ch.step[e * L] / S->swap_interval - 1;
+    long long nsw = 0;
+    for (int p = 0; p + 1 < R; ++p) {
+      const int cfg1 = cfg_prev, cfg2 = p + 1;
+      const double lhood1 = lh_prev, T1 = T_prev;
+      const double lhood2 = xt_at(S, L, e, cfg2, 1), T2 = xt_at(S, L, e, cfg2, 2);
+      const double lhood12 = loglik_d(xt_at(S, L, e, cfg1, 3), ntr, exp(xt_at(S, L, e, cfg1, 0)), T2);   // MAIN:980
+      const double lhood21 = loglik_d(xt_at(S, L, e, cfg2, 3), ntr, exp(xt_at(S, L, e, cfg2, 0)), T1);   // MAIN:982
+      const double ex = (lhood12 - lhood1) + (lhood21 - lhood2);
+      const double prob = fmin(1.0, exp(ex));                                                            // MAIN:988
+      const double u = swap_uniform(S, ens_base + e, round, p);
+      if (u < prob) {
+        ++nsw;
+        src[p] = cfg2; cfg_prev = cfg1; lh_prev = lhood12; T_prev = T1;
+      } else {
+        src[p] = cfg1; cfg_prev = cfg2; lh_prev = lhood2; T_prev = T2;
+      }
+    }
+    src[R - 1] = cfg_prev;
+    atomicAdd((unsigned long long*)S->total_swap, (unsigned long long)(R - 1));
+    atomicAdd((unsigned long long*)S->num_swap, (unsigned long long)nsw);
+  }
+}
+
+// posted BatchNorm buffers of local chain `c` (rm[d3], rv[d3], nbt): the detached copy, or the live model's (MAIN:595)
+__device__ __forceinline__ float posted_buffer(const DevState* S, int c, int i) {
+  if (S->ch.alias[c] == 0) return S->wb[(size_t)c * S->nbuf + i];
+  const float* th = S->theta + (size_t)c * S->Pp;
+  if (i < S->d3) return th[S->seg[SEG_BN_RM].pad_off + i];
+  if (i < 2 * S->d3) return th[S->seg[SEG_BN_RV].pad_off + i - S->d3];
+  return th[S->seg[SEG_BN_NBT].pad_off];
+}
+
+__global__ void __launch_bounds__(kThreads) bae_xgather_kernel(const DevState* __restrict__ S) {
+  const int L = S->n_rungs, R = L * S->shard_world, rank = S->shard_rank;
+  const int nit = S->Pp / kAdamChunk;
+  const int total = nit * S->C;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int p = item / nit, it = item % nit;
+    const int e = p / L, rung = rank * L + p % L;
+    const int sr = S->xsrc[(size_t)e * R + rung];
+    if (sr / L != rank) continue;                 // arrives over NCCL
+    const int src = e * L + sr % L;
+    if (it == 0)
+      for (int i = threadIdx.x; i < S->nbuf; i += kThreads) S->wb_tmp[(size_t)p * S->nbuf + i] = posted_buffer(S, src, i);
+    if (src == p) continue;
+    const float4* s4 = reinterpret_cast<const float4*>(S->theta + (size_t)src * S->Pp + (size_t)it * kAdamChunk);
+    float4* d4 = reinterpret_cast<float4*>(S->wcur + (size_t)p * S->Pp + (size_t)it * kAdamChunk);
+    for (int i = threadIdx.x; i < kAdamChunk / 4; i += kThreads) d4[i] = s4[i];
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) bae_xscatter_kernel(const DevState* __restrict__ S) {
+  const int L = S->n_rungs, R = L * S->shard_world, rank = S->shard_rank;
+  const int nit = S->Pp / kAdamChunk;
+  const int total = nit * S->C;
+  __shared__ int seg_off[kNumSegs], seg_train[kNumSegs];
+  for (int i = threadIdx.x; i < kNumSegs; i += kThreads) { seg_off[i] = S->seg[i].pad_off; seg_train[i] = S->seg[i].trainable; }
+  __syncthreads();
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int p = item / nit, it = item % nit;
+    const int e = p / L, rung = rank * L + p % L;
+    const int sr = S->xsrc[(size_t)e * R + rung];
+    const bool remote = sr / L != rank;
+    const float* stage = S->wcur + (size_t)p * S->Pp;
+    if (it == 0) {
+      // buffers of the received dict: a sender whose `w` was the live model posted them inside the theta slab
+      const bool from_slab = remote && xt_at(S, L, e, sr, 4) != 0.0;
+      for (int i = threadIdx.x; i < S->nbuf; i += kThreads) {
+        float v;
+        if (from_slab)
+          v = i < S->d3 ? stage[S->seg[SEG_BN_RM].pad_off + i]
+                        : (i < 2 * S->d3 ? stage[S->seg[SEG_BN_RV].pad_off + i - S->d3] : stage[S->seg[SEG_BN_NBT].pad_off]);
+        else
+          v = S->wb_tmp[(size_t)p * S->nbuf + i];
+        S->wb[(size_t)p * S->nbuf + i] = v;
+      }
+      if (threadIdx.x == 0) {
+        S->ch.eta[p] = xt_at(S, L, e, sr, 0);          // MAIN:603
+        S->ch.last_sse[p] = xt_at(S, L, e, sr, 3);
+        S->ch.alias[p] = 0;                            // MAIN:602: w = dictfromlist(...) is a detached dict
+      }
+    }
+    if (sr == rung) continue;
+    // only trainable entries move into the live model; its BatchNorm buffers are reloaded from `w` next step
+    float* dbase = S->theta + (size_t)p * S->Pp;
+    for (int i = threadIdx.x; i < kAdamChunk / 4; i += kThreads) {
+      const int pidx = it * kAdamChunk + i * 4;
+      int sg = 0;
+#pragma unroll
+      for (int k = 1; k < kNumSegs; ++k) sg += (pidx >= seg_off[k]) ? 1 : 0;
+      if (!seg_train[sg]) continue;
+      *reinterpret_cast<float4*>(dbase + pidx) = *reinterpret_cast<const float4*>(stage + pidx);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // The persistent program kernel
 // ------------------------------------------------------------------------------------------------
 template <bool kSimtGemm>
@@ -1535,7 +1664,7 @@ __global__ void bae_split_kernel(const float* __restrict__ src, float* hi, float
 // Writes the proposal noise of (chain, step) in REFERENCE order, plus the three step scalars.
 __global__ void bae_debug_draws_kernel(const DevState* __restrict__ S, int chain, int step, float* noise,
                                        double* scalars) {
-  const int cg_id = S->chain_id_base + chain;
+  const int cg_id = S->ch.gid[chain];
   for (int sg = 0; sg < kNumSegs; ++sg) {
     const Seg& sd = S->seg[sg];
     const int n = sd.rows * sd.cols;
@@ -1750,6 +1879,11 @@ cudaError_t launch_extract(const float* src, int ld, const float* X, int ldx, in
   bae_extract_kernel<<<592, 256, 0, st>>>(src, ld, X, ldx, rows, d, inv_scale, mode, out);
   return cudaGetLastError();
 }
+
+cudaError_t launch_xtable(const DevState* dS, cudaStream_t st) { bae_xtable_kernel<<<8, 256, 0, st>>>(dS); return cudaGetLastError(); }
+cudaError_t launch_xsweep(const DevState* dS, cudaStream_t st) { bae_xsweep_kernel<<<4, 64, 0, st>>>(dS); return cudaGetLastError(); }
+cudaError_t launch_xgather(const DevState* dS, int grid, cudaStream_t st) { bae_xgather_kernel<<<grid, kThreads, 0, st>>>(dS); return cudaGetLastError(); }
+cudaError_t launch_xscatter(const DevState* dS, int grid, cudaStream_t st) { bae_xscatter_kernel<<<grid, kThreads, 0, st>>>(dS); return cudaGetLastError(); }
 
 cudaError_t launch_scalars(const DevState* dS, int chain, bae_chain_scalars* staged, int put, cudaStream_t st) {
   bae_scalars_kernel<<<1, 1, 0, st>>>(dS, chain, staged, put);

@@ -105,6 +105,60 @@ def sweep_native(table, n_elems, uniforms):
     return [int(x) for x in src], int(nsw.value)
 
 
+def plan_exchange(src, world, rank):
+    """The transfers `rank` posts for the permutation `src` [E, R] (library host function `bae_plan_exchange`):
+    list of (kind 'send' / 'recv', peer, ensemble, rung)."""
+    import ctypes as C
+    from . import _native as N
+    lib = N.load()
+    src = np.ascontiguousarray(src, dtype=np.int32)
+    E, R = src.shape
+    out = np.zeros((2 * E * R, 4), np.int32)
+    n = lib.bae_plan_exchange(src.ctypes.data, E, R, int(world), int(rank), out.ctypes.data, 2 * E * R)
+    if n < 0:
+        N.check(n)
+    return [("send" if k == 0 else "recv", int(peer), int(e), int(r)) for k, peer, e, r in out[:n]]
+
+
+class NcclComm:
+    """An ncclComm_t over the ranks of a torch.distributed job, created with the libnccl.so.2 that torch has loaded
+    (the unique id travels through torch.distributed). The library never creates communicators itself:
+    this object is what a caller passes to `DeviceSampler.swap_exchange` / `bae_swap_exchange`."""
+
+    def __init__(self, dist, rank, world, device):
+        import ctypes as C
+        import torch
+
+        class UniqueId(C.Structure):
+            _fields_ = [("internal", C.c_byte * 128)]
+
+        self._lib = C.CDLL("libnccl.so.2")
+        self._lib.ncclGetErrorString.restype = C.c_char_p
+        uid = UniqueId()
+        if rank == 0:
+            self._check(self._lib.ncclGetUniqueId(C.byref(uid)))
+        backend = dist.get_backend()
+        t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=(torch.device("cuda", device) if backend == "nccl" else "cpu"))
+        dist.broadcast(t, 0)
+        C.memmove(C.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+        torch.cuda.set_device(device)
+        comm = C.c_void_p()
+        self._lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+        self._check(self._lib.ncclCommInitRank(C.byref(comm), int(world), uid, int(rank)))
+        self.handle = comm
+        self.rank, self.world = rank, world
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"NCCL error {rc}: {self._lib.ncclGetErrorString(rc).decode()}")
+
+    def close(self):
+        if self.handle:
+            self._lib.ncclCommDestroy.argtypes = [__import__("ctypes").c_void_p]
+            self._lib.ncclCommDestroy(self.handle)
+            self.handle = None
+
+
 class ShardedLadder:
     """Exchange rounds for a ladder sharded over `world_size` ranks. `transport` supplies the chain state:
 

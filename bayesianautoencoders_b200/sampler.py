@@ -229,6 +229,20 @@ class DeviceSampler:
                                          r.ctypes.data if recon else None, sse.ctypes.data))
         return dict(features=f, recon=r, sse=sse)
 
+    # -- ladder sharded over GPUs (one process per GPU) ---------------------------------------------------
+    def shard(self, rank, world):
+        """Declare this handle's chains (E ensembles x n_rungs local rungs) to be rank `rank`'s block of ladders of
+        n_rungs * world rungs (`bae_shard_config`); create every rank's sampler with the SAME chain_id_base."""
+        N.check(self.lib.bae_shard_config(self._h, int(rank), int(world)))
+        self.shard_rank, self.shard_world = int(rank), int(world)
+
+    def swap_exchange(self, nccl_comm):
+        """One exchange round across the ranks (`bae_swap_exchange`); `nccl_comm`: distributed.NcclComm or a raw ncclComm_t."""
+        N.check(self.lib.bae_swap_exchange(self._h, getattr(nccl_comm, "handle", nccl_comm)))
+
+    def vectors_sent(self):
+        return int(self.lib.bae_exchange_vectors_sent(self._h))
+
     def last_sweep(self):
         """src[p] = chain whose configuration ended at position p in the most recent exchange sweep."""
         src = np.zeros(self.n_chains, np.int32)

@@ -149,7 +149,29 @@ int bae_swap_counts(bae_handle* h, int64_t* num_swap, int64_t* total_swap_propos
  * MAIN:995-1011). */
 int bae_last_sweep(bae_handle* h, int32_t* src_out);
 
-/* Multi-GPU ladder sharding (one process per GPU): export / import the exchange view of a chain
+/* ---- Ladder sharded over GPUs, one process per GPU (BASELINE.json configs[3]) -------------------------
+ * A handle created with n_chains = E * L, n_rungs = L and the SAME chain_id_base on every rank holds rungs
+ * [rank * L, rank * L + L) of each of E ladders of R = L * world rungs. bae_shard_config declares that (it re-keys the
+ * Philox streams to the ladder positions, so a sharded run draws exactly what a one-GPU run of the same ladders draws);
+ * afterwards bae_run is refused: advance with bae_step(swap_interval), then call bae_swap_exchange on every rank.
+ *
+ * bae_swap_exchange = one exchange round (MAIN:594-603, 962-1011, 1059-1065), stream-ordered on the handle's stream:
+ *   ncclAllGather of 40 B per chain (eta, stored likelihood, adapttemp, SSE of w, alias flag); the sequential sweep as a
+ *   device kernel on every rank (identical permutation everywhere: same doubles, same Philox uniforms); ONE small
+ *   device-to-host copy of the permutation (the only host synchronisation); grouped ncclSend / ncclRecv of the weight
+ *   vectors whose destination is on another rank, straight from the theta slabs into the receiver's staging slabs (no
+ *   packing); one gather and one scatter kernel for everything else. `nccl_comm` is an ncclComm_t created by the caller
+ *   over exactly `world` ranks (never created here); NCCL is resolved from the already-loaded libnccl.so.2 at run time. */
+int bae_shard_config(bae_handle* h, int rank, int world);
+int bae_swap_exchange(bae_handle* h, void* nccl_comm);
+/* HOST function: the transfers rank `rank` must post for the permutation `src` ([E][R]: rung whose configuration ends at
+ * rung p): out_ops[4 * k] = (kind 0 send / 1 recv, peer rank, ensemble, rung = source rung of a send / destination rung of a
+ * receive), in the order both sides issue them. Returns the number of operations (<= max_ops) or a negative bae_status. */
+int bae_plan_exchange(const int32_t* src, int n_ensembles, int n_rungs_total, int world, int rank, int32_t* out_ops, int max_ops);
+int64_t bae_exchange_vectors_sent(const bae_handle* h);   /* weight vectors this rank has sent over NCCL so far */
+
+/* (older, host-driven variant of the same exchange, kept for callers that move the vectors themselves)
+ * Multi-GPU ladder sharding (one process per GPU): export / import the exchange view of a chain
  * ([vec(w), eta, likelihood, adapttemp, last_sse], MAIN:595-596) as DEVICE buffers usable with NCCL. */
 int bae_exchange_table(bae_handle* h, double* out_nchains_x4);   /* eta, likelihood, adapttemp, SSE of w for every chain (MAIN:594-597) */
 int bae_exchange_pack(bae_handle* h, int chain, float* dev_w /*w_size*/, double* host_scalars4);

@@ -228,3 +228,37 @@ def test_gelman_rubin_pinned_to_reference_script():
         live = run_reference_block({str(n): z["w_" + str(n)] for n in z["names"]})
         np.testing.assert_array_equal(live["simple"], z["simple"])
         np.testing.assert_array_equal(live["advanced"], z["advanced"])
+
+
+def test_plan_exchange_matches_permutation_semantics():
+    """`bae_plan_exchange` (host side of bae_swap_exchange): for random sweep results, every configuration that changes
+    GPU appears exactly once as a send on its owner and once as a receive on its destination's owner, and the k-th
+    message from rank a to rank b is the same (ensemble, configuration) on both sides (NCCL point-to-point matching)."""
+    from bayesianautoencoders_b200.distributed import plan_exchange, sweep
+    rng = np.random.default_rng(3)
+    for world, L, E in ((2, 8, 3), (4, 2, 5), (8, 8, 8), (8, 1, 2)):
+        R = world * L
+        src = np.zeros((E, R), np.int32)
+        for e in range(E):
+            # a permutation the sequential sweep can produce: carried configuration + downward shifts
+            cfg_prev = 0
+            for p in range(R - 1):
+                if rng.random() < 0.6:
+                    src[e, p] = p + 1
+                else:
+                    src[e, p] = cfg_prev
+                    cfg_prev = p + 1
+            src[e, R - 1] = cfg_prev
+            assert sorted(src[e]) == list(range(R))
+        plans = [plan_exchange(src, world, r) for r in range(world)]
+        crossing = [(e, int(src[e, p]), p) for e in range(E) for p in range(R) if src[e, p] // L != p // L]
+        sends = [(r, peer, e, rung) for r in range(world) for kind, peer, e, rung in plans[r] if kind == "send"]
+        recvs = [(r, peer, e, rung) for r in range(world) for kind, peer, e, rung in plans[r] if kind == "recv"]
+        assert len(sends) == len(recvs) == len(crossing)
+        for a in range(world):
+            for b in range(world):
+                if a == b:
+                    continue
+                s_ab = [(e, rung) for r, peer, e, rung in sends if r == a and peer == b]          # (ensemble, source rung)
+                r_ab = [(e, int(src[e, rung])) for r, peer, e, rung in recvs if r == b and peer == a]  # destination -> its source
+                assert s_ab == r_ab, (world, a, b)
