@@ -61,6 +61,20 @@ def measured_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
 
 
+def tf32_peak():
+    """kind::tf32 dense peak measured on a B200 of this pool (tools/measure_tf32_peak.py -> profiles/r2_tf32_peak.json):
+    cuBLAS TF32 8192^3 sustained / burst, and the raw tcgen05.mma.cta_group::2.kind::tf32 issue rate of all SM pairs."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_tf32_peak.json")) as f:
+            d = json.load(f)
+        issue = d.get("tcgen05_issue_rate", [{}])[0]
+        return dict(sustained=d["cublas_tf32_8192"]["sustained_tflops"], burst=d["cublas_tf32_8192"]["burst_tflops"],
+                    sustained_sm_mhz=d["cublas_tf32_8192"]["clocks_under_load"].get("sm_mhz"),
+                    issue_rate=issue.get("tflops"), issue_rate_sm_mhz=issue.get("sm_mhz"))
+    except Exception:
+        return None
+
+
 def ncu_traffic(shape, cpg, gemm_path):
     """DRAM bytes (read + write) of one launch of the step program from the committed `ncu --set full` capture
     (profiles/r1_program_kernel_traffic.json), scaled to this run's chains x iterations per launch; None if no capture fits."""
@@ -211,11 +225,126 @@ def workload_name(shape, cpg, world=1, sharded=False):
 # ---------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------
+class PtJob:
+    """`n_ens` ensembles of `rungs_total` rungs on `world` GPUs: whole ladders per GPU (world == 1 or ladder == 'local'), or
+    every ladder cut into contiguous blocks of rungs_total / world rungs per GPU (the exchange crosses NVLink via NCCL)."""
+
+    def __init__(self, shape, n_ens, rungs_total, world, rank, local, sharded, comm, gemm_path, samples=SAMPLES, seed=0xBAE5EED):
+        from bayesianautoencoders_b200 import DeviceSampler, default_theta_init
+        from oracle import bae_oracle as bo   # ladder helper + layout size only
+        self.shape, self.world, self.rank, self.sharded, self.comm = shape, world, rank, sharded, comm
+        dims4, n_train, n_test = SHAPES[shape]
+        self.dims4, self.n_train, self.n_test = dims4, n_train, n_test
+        self.train, self.test = synth(dims4, n_train, n_test)
+        L = bo.Layout(dims4)
+        if sharded:
+            self.L = rungs_total // world
+            t_all = bo.temperature_ladder(rungs_total, 2)
+            temps = np.tile(t_all[rank * self.L:(rank + 1) * self.L], n_ens)
+            self.s = DeviceSampler(dims4, self.train, self.test, n_ens * self.L, self.L, samples, temps, swap_interval=SWAP_INTERVAL,
+                                   seed=seed, device=local, chain_id_base=0, gemm_path=gemm_path)
+            self.s.shard(rank, world)
+        else:
+            self.L = rungs_total
+            temps = np.tile(bo.temperature_ladder(rungs_total, 2), n_ens)
+            self.s = DeviceSampler(dims4, self.train, self.test, n_ens * rungs_total, rungs_total, samples, temps,
+                                   swap_interval=SWAP_INTERVAL, seed=seed, device=local, chain_id_base=rank * n_ens * rungs_total,
+                                   gemm_path=gemm_path)
+        self.chains = n_ens * self.L
+        rng = np.random.default_rng(100 + rank)
+        for j in range(self.chains):
+            self.s.init_chain(j, default_theta_init(dims4, rng), rng.standard_normal(L.w_size))
+        self.s.synchronize()
+        self.iters_done = 0
+
+    def pt_round(self):
+        """One bench step: 5 iterations of every resident chain + one exchange sweep; stream-ordered, returns at once."""
+        if self.sharded:
+            self.s.step(SWAP_INTERVAL)
+            self.s.swap_exchange(self.comm)     # all-gather of 40 B/chain + device sweep + boundary-crossing weight vectors
+        else:
+            self.s.run(SWAP_INTERVAL)           # exchange phases are part of the step program
+        self.iters_done += SWAP_INTERVAL
+
+    def close(self):
+        self.s.close()
+
+
+def timed_rounds(job, steps, warmup, barrier, dist, world):
+    """W untimed + K timed rounds, CUDA events on the library's stream, max over ranks. Returns ms for the K rounds."""
+    import torch
+    stream = torch.cuda.ExternalStream(job.s.lib.bae_stream(job.s._h))
+    for _ in range(warmup):
+        job.pt_round()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(steps):
+        job.pt_round()
+    ev1.record(stream)
+    job.s.synchronize()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def roofline_block(job, kernel_ms, n_launch_rounds, sharded):
+    """Algorithmic FLOPs of the launches just timed (Langevin / random-walk iterations counted from the traces) over the
+    measured launch duration, against the measured peaks."""
+    f_l, f_r = flops_per_step(job.dims4, job.n_train, job.n_test)
+    n_l = n_r = 0
+    first = job.iters_done - SWAP_INTERVAL * n_launch_rounds
+    for j in range(job.chains):
+        tr = job.s.traces(j, first, SWAP_INTERVAL * n_launch_rounds)
+        n_l += int(tr["langevin"].sum())
+        n_r += int((1 - tr["langevin"]).sum())
+    flops_per_launch = (n_l * f_l + n_r * f_r) / n_launch_rounds
+    achieved_tf = flops_per_launch / (kernel_ms / 1000.0) / 1e12
+    peaks = measured_peaks()
+    gemm_path = job.s.gemm_path()
+    if gemm_path == 2:
+        kind = "tcgen05 kind::tf32, 3-way split (3xTF32), FP32 accumulate in TMEM"
+        tf = tf32_peak()
+        out = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+               "frac": achieved_tf / peaks["bf16_sustained"],
+               "traffic": ncu_traffic(job.shape, job.chains, gemm_path),
+               "kernel": ("bae_phase_kernel_tc (tcgen05 GEMM phases) + bae_aux_kernel (BatchNorm / Adam): the step program of 5 "
+                          "iterations of all resident chains" + ("" if sharded else " + exchange sweep") +
+                          ", one CUDA-graph launch of its per-phase kernels"),
+               "peak_source": peaks["source"] + " bf16 dense sustained (MEASURED_PEAKS.json)", "mma_kind": kind}
+        if tf:
+            # the MMA kind actually issued, measured on this pool (profiles/r2_tf32_peak.json): cuBLAS TF32 sustained; every
+            # algorithmic FLOP costs three kind::tf32 MMA FLOPs (hi*hi, hi*lo, lo*hi), so the attainable algorithmic rate is 1/3
+            out.update({"peak_tf32_measured": tf["sustained"], "peak_tf32_burst": tf["burst"],
+                        "peak_tf32_sm_mhz": tf["sustained_sm_mhz"], "frac_of_tf32": achieved_tf / tf["sustained"],
+                        "frac_of_3xtf32_ceiling": 3.0 * achieved_tf / tf["sustained"],
+                        "tcgen05_issue_rate_tflops": tf["issue_rate"], "tcgen05_issue_rate_sm_mhz": tf["issue_rate_sm_mhz"],
+                        "mma_tflops_issued": 3.0 * achieved_tf})
+    else:
+        kind = "fp32 CUDA-core tiles (FFMA)"
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                mhz = float(json.load(f).get("sm_max_mhz", 1965.0))
+        except Exception:
+            mhz = 1965.0
+        peak = 148 * 128 * 2 * mhz * 1e6 / 1e12
+        out = {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tf / peak, "traffic": None,
+               "kernel": ("bae_program_kernel (persistent FP32 step kernel, one cooperative launch = 5 iterations of all resident "
+                          "chains" + ("" if sharded else " + exchange sweep") + ")"),
+               "peak_source": f"derived: 148 SMs x 128 FP32 lanes x 2 FLOP x {mhz:.0f} MHz (max SM clock, MEASURED_PEAKS.json); "
+                              "narrow layers are latency / SFU bound, see DESIGN.md", "mma_kind": kind}
+    out.update({"kernel_ms_per_launch": kernel_ms, "algorithmic_gflop_per_launch": flops_per_launch / 1e9})
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    from bayesianautoencoders_b200 import DeviceSampler, default_theta_init
-    from oracle import bae_oracle as bo   # cpu_baseline leg + ladder helper only
+    from bayesianautoencoders_b200.distributed import NcclComm
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -223,108 +352,65 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no CPU fallback")
     torch.cuda.set_device(local)
+    comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    shape = args.shape
-    dims4, n_train, n_test = SHAPES[shape]
-    train, test = synth(dims4, n_train, n_test)
-    cpg = args.chains_per_gpu
-    L = bo.Layout(dims4)
-    sharded = world > 1 and args.ladder == "sharded"
-    n_ens = cpg // N_RUNGS
-    if sharded:
-        # BASELINE.json configs[3]: every ensemble's ladder has 8 x world rungs (64 at 8 GPUs) and is cut into contiguous
-        # blocks of 8 rungs per GPU; the exchange sweep crosses GPU boundaries (scalar all-gather + weight vectors over NCCL)
-        from bayesianautoencoders_b200.distributed import DeviceTransport, ShardedLadder
-        t_all = bo.temperature_ladder(N_RUNGS * world, 2)
-        temps = np.tile(t_all[rank * N_RUNGS:(rank + 1) * N_RUNGS], n_ens)
-        s = DeviceSampler(dims4, train, test, cpg, 1, SAMPLES, temps, swap_interval=SWAP_INTERVAL,
-                          seed=0xBAE5EED, device=local, chain_id_base=rank * cpg, gemm_path=args.gemm_path)
-        ladder = ShardedLadder(dist, rank, world, n_ens, N_RUNGS * world, train.size, 0xBAE5EED, DeviceTransport(s, local))
-        # NCCL opens peer connections lazily; a configuration can travel to any rank, so open all pairs before timing
-        a2a = torch.zeros(world * 4, device="cuda")
-        dist.all_to_all_single(torch.empty_like(a2a), a2a)
-    else:
-        temps = np.tile(bo.temperature_ladder(N_RUNGS, 2), n_ens)
-        s = DeviceSampler(dims4, train, test, cpg, N_RUNGS, SAMPLES, temps, swap_interval=SWAP_INTERVAL,
-                          seed=0xBAE5EED, device=local, chain_id_base=rank * cpg, gemm_path=args.gemm_path)
-        ladder = None
-
-    exch_s = []
-
-    def pt_round():
-        """One bench step: 5 iterations of every resident chain + one exchange sweep."""
-        if ladder is None:
-            s.run(SWAP_INTERVAL)          # exchange phases are part of the step program
-        else:
-            s.step(SWAP_INTERVAL)
-            s.synchronize()
-            t_x = time.perf_counter()
-            ladder.exchange()             # NCCL: 32 B/chain all-gather + boundary-crossing weight vectors
-            exch_s.append(time.perf_counter() - t_x)
-    rng = np.random.default_rng(100 + rank)
-    for j in range(cpg):
-        s.init_chain(j, default_theta_init(dims4, rng), rng.standard_normal(L.w_size))
-    s.synchronize()
-    stream = torch.cuda.ExternalStream(s.lib.bae_stream(s._h), device=torch.device("cuda", local))
+        comm = NcclComm(dist, rank, world, local)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        pt_round()
-    barrier()
-    exch_s.clear()
+    shape = args.shape
+    cpg = args.chains_per_gpu
+    sharded = world > 1 and args.ladder == "sharded"
+    n_ens = cpg // N_RUNGS
+    # BASELINE.json configs[3]: every ensemble's ladder has 8 x world rungs (64 at 8 GPUs), cut into blocks of 8 rungs per GPU
+    job = PtJob(shape, n_ens, N_RUNGS * (world if sharded else 1), world, rank, local, sharded, comm, args.gemm_path)
+    s = job.s
+    dims4, n_train, n_test = job.dims4, job.n_train, job.n_test
+    if sharded:
+        for _ in range(2):     # opens the NCCL point-to-point connections of the pairs that exchange (lazy in NCCL)
+            job.pt_round()
     clocks = ClockSampler(local)
+    l0 = None
+    for _ in range(args.warmup):
+        job.pt_round()
+    barrier()
     if rank == 0:
         clocks.start()
     l0 = s.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    ev0.record(stream)
-    for _ in range(args.steps):
-        pt_round()
-    ev1.record(stream)
-    s.synchronize()
-    barrier()
+    ms = timed_rounds(job, args.steps, 0, barrier, dist, world)
     launches = s.launch_count() - l0
-    ms = ev0.elapsed_time(ev1)
     clk = clocks.stop() if rank == 0 else {}
-    if world > 1:
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    iters_done = (args.warmup + args.steps) * SWAP_INTERVAL
-    chain_steps = world * cpg * args.steps * SWAP_INTERVAL
-    value = chain_steps / (ms / 1000.0)
+    value = world * cpg * args.steps * SWAP_INTERVAL / (ms / 1000.0)
 
-    # per-launch duration of the step program (graph of per-phase kernels / persistent kernel), measured live with CUDA events
-    per_launch = []
+    # per-launch duration of the step program (graph of per-phase kernels / persistent kernel) and of the exchange, CUDA events
+    stream = torch.cuda.ExternalStream(s.lib.bae_stream(s._h))
+    per_launch, exch_ms = [], []
     for _ in range(min(3, args.steps)):
-        pt_round()
-        per_launch.append(s.last_ms())
-        iters_done += SWAP_INTERVAL
+        if sharded:
+            s.step(SWAP_INTERVAL)
+            step_ms = s.last_ms()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(stream)
+            s.swap_exchange(comm)
+            eb.record(stream)
+            s.synchronize()
+            exch_ms.append(ea.elapsed_time(eb))
+            job.iters_done += SWAP_INTERVAL
+        else:
+            job.pt_round()
+            step_ms = s.last_ms()
+        per_launch.append(step_ms)
     kernel_ms = float(np.mean(per_launch))
-    # algorithmic FLOPs of the launches just timed: count the Langevin / random-walk iterations from the traces
-    f_l, f_r = flops_per_step(dims4, n_train, n_test)
-    n_l = n_r = 0
-    first = iters_done - SWAP_INTERVAL * len(per_launch)
-    for j in range(cpg):
-        tr = s.traces(j, first, SWAP_INTERVAL * len(per_launch))
-        n_l += int(tr["langevin"].sum())
-        n_r += int((1 - tr["langevin"]).sum())
-    flops_per_launch = (n_l * f_l + n_r * f_r) / len(per_launch)
-    achieved_tf = flops_per_launch / (kernel_ms / 1000.0) / 1e12
-    peaks = measured_peaks()
-    gemm_path = s.gemm_path()
+    roof = roofline_block(job, kernel_ms, len(per_launch), sharded)
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region
-    pin_train = torch.from_numpy(train).pin_memory()
-    pin_test = torch.from_numpy(test).pin_memory()
+    pin_train = torch.from_numpy(job.train).pin_memory()
+    pin_test = torch.from_numpy(job.test).pin_memory()
     h2d = pin_train.numel() * 4 + pin_test.numel() * 4
     d2h = 0
     e2e_steps = max(1, min(args.steps, 10))
@@ -332,12 +418,11 @@ def run_gpu(args):
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         s.upload_data(pin_train.numpy(), pin_test.numpy())
-        pt_round()
+        job.pt_round()
         d2h = 0
-        for j in range(cpg):
-            tr = s.traces(j, iters_done, SWAP_INTERVAL)   # device -> host read of the step's results
+        for j in range(job.chains):
+            tr = s.traces(j, job.iters_done - SWAP_INTERVAL, SWAP_INTERVAL)   # device -> host read of the step's results
             d2h += tr.nbytes
-        iters_done += SWAP_INTERVAL
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -345,9 +430,34 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_value = world * cpg * e2e_steps * SWAP_INTERVAL / e2e_s
-    assert iters_done <= SAMPLES
+    assert job.iters_done <= SAMPLES
+    vectors_sent = s.vectors_sent() if sharded else 0
+    job.close()
 
-    line = None
+    # ---- the other BASELINE.json shapes, 8 replicas in all (the reference's own configurations), on the same N GPUs: one
+    # 8-rung ladder, cut over the GPUs when N > 1 (strong scaling of a latency-bound job: reported, not the scaling claim)
+    extra = []
+    if not args.no_extra:
+        for xshape in ("swiss", "coil", "madelon"):
+            xjob = PtJob(xshape, 1, N_RUNGS, world, rank, local, world > 1, comm, 0, samples=4000)
+            xsteps = 40 if xshape != "madelon" else 10
+            if world > 1:
+                for _ in range(2):
+                    xjob.pt_round()
+            xms = timed_rounds(xjob, xsteps, 3, barrier, dist, world)
+            xk = []
+            if world == 1:
+                for _ in range(3):
+                    xjob.pt_round()
+                    xk.append(xjob.s.last_ms())
+            xroof = roofline_block(xjob, float(np.mean(xk)), 3, False) if xk else None
+            extra.append({"workload": f"{xshape} shape, 8 replicas = one 8-rung ladder" + (f" cut over {world} GPUs" if world > 1 else "") +
+                                      f" (BASELINE.json configs[{['swiss', 'coil', 'madelon'].index(xshape)}])",
+                          "metric": METRIC, "value": N_RUNGS * xsteps * SWAP_INTERVAL / (xms / 1000.0), "unit": UNIT, "n_gpus": world,
+                          "ms_per_step": xms / xsteps, "steps": xsteps, "scaling": "strong",
+                          "gemm_path": xjob.s.gemm_path(), "roofline": xroof})
+            xjob.close()
+
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -355,7 +465,6 @@ def run_gpu(args):
             cpu = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port",
                    "sample": f"{N_RUNGS} replica processes x {args.ref_iters} iterations, float64 numpy oracle, "
                              f"{info['threads_per_proc']} BLAS threads each ({info['loop_s']:.1f} s)"}
-        kind = {1: "fp32 CUDA-core tiles (FFMA)", 2: "tcgen05 kind::tf32, 3-way split (3xTF32), FP32 accumulate in TMEM"}.get(gemm_path, "?")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -363,33 +472,26 @@ def run_gpu(args):
             "config": {"workload": workload_name(shape, cpg, world, sharded), "shape": shape, "dims": list(dims4), "n_train": n_train,
                        "n_test": n_test, "chains_per_gpu": cpg, "n_rungs": N_RUNGS * (world if sharded else 1), "swap_interval": SWAP_INTERVAL,
                        "parallelism": (f"{world} GPUs x {cpg} chains: {n_ens} ensembles, each ladder of {N_RUNGS * world} rungs cut into "
-                                       f"{N_RUNGS}-rung blocks per GPU; per round one 32 B/chain all-gather + the weight vectors of "
-                                       f"configurations that cross a GPU boundary over NCCL ({ladder.vectors_sent} vectors sent by rank 0)"
+                                       f"{N_RUNGS}-rung blocks per GPU; per round one 40 B/chain ncclAllGather, the sweep as a device kernel on "
+                                       f"every rank, and ncclSend/ncclRecv of the weight vectors that cross a GPU boundary straight between the "
+                                       f"theta slabs ({vectors_sent} vectors sent by rank 0)"
                                        if sharded else
                                        f"{world} GPU(s) x {cpg} chains, whole ensembles per GPU (no data-path collective)"),
                        "l2_policy": "working set per step (chain state + activations) exceeds the 126 MB L2 many times over; no flush needed",
-                       "gemm_path": kind},
+                       "gemm_path": roof["mma_kind"]},
             "clocks": {"sm_mhz": clk.get("sm_mhz"), "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": clk.get("reasons", []),
                        "samples": clk.get("samples", 0)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps},
             "gpu_launches": int(launches),
-            "exchange_ms_per_round": (1000.0 * float(np.median(exch_s)) if exch_s else None),
-            "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved_tf / peaks["bf16_sustained"], "traffic": ncu_traffic(shape, cpg, gemm_path),
-                         "kernel": (("bae_phase_kernel_tc (tcgen05 GEMM phases, ~80% of the step) + bae_aux_kernel (BatchNorm / Adam): the step "
-                                     "program of 5 iterations of all resident chains" + ("" if sharded else " + exchange sweep") +
-                                     ", one CUDA-graph launch of its per-phase kernels") if gemm_path == 2 else
-                                    ("bae_program_kernel (persistent step kernel, one cooperative launch = 5 iterations of all resident chains" +
-                                     ("" if sharded else " + exchange sweep") + ")")),
-                         "kernel_ms_per_launch": kernel_ms,
-                         "algorithmic_gflop_per_launch": flops_per_launch / 1e9,
-                         "peak_source": peaks["source"] + " bf16 dense sustained (MEASURED_PEAKS.json); kind::tf32 dense is 1/2 of it, a 3-way split 1/6",
-                         "mma_kind": kind},
+            "exchange_ms_per_round": (float(np.median(exch_ms)) if exch_ms else None),
+            "roofline": roof,
             "cpu_baseline": cpu,
+            "extra_configs": extra,
         }
         print(json.dumps(line), flush=True)
-    s.close()
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -406,6 +508,7 @@ def main():
     ap.add_argument("--gemm-path", type=int, default=0)
     ap.add_argument("--ref-iters", type=int, default=2, help="iterations per replica process in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the Swiss / Coil / Madelon 8-replica lines (extra_configs)")
     ap.add_argument("--ladder", default="sharded", choices=["sharded", "local"],
                     help="N > 1: 'sharded' cuts every ladder across the GPUs (NCCL exchange), 'local' keeps whole ensembles per GPU")
     args = ap.parse_args()
