@@ -9,6 +9,7 @@
 #include <cuda_profiler_api.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <array>
 #include <map>
 
@@ -197,7 +198,7 @@ static int grad_ksplit(const DevState& s, int grid_hint, const GemmDesc& g, int 
     // at the length of a forward layer's (<= ~640 rows, 40 K blocks); extra splits also balance the phase
     const char* e = getenv("BAE_TC_KSPLIT_ROWS");
     const int per = e ? std::max(64, atoi(e)) : 640;
-    return std::max(1, std::min(16, (rows + per - 1) / per));
+    return std::max(1, (rows + per - 1) / per);   // segments run back to back on one CTA pair and accumulate into one copy
   }
   const int tiles = g.tm * g.tn * s.C;
   const int nk = (rows + 15) / 16;
@@ -370,9 +371,11 @@ static void build_program(bae_handle* h) {
     {
       const int ks = grad_ksplit(s, h->grid_hint, g, N);
       g.ksplit = ks;
-      s.seg_ksplit[bl[l].wseg] = ks;
-      if (bl[l].bseg >= 0) s.seg_ksplit[bl[l].bseg] = ks;
-      s.max_ksplit = std::max(s.max_ksplit, ks);
+      if (!tcm) {   // FP32 path: one gradient copy per segment, summed by the Adam phase
+        s.seg_ksplit[bl[l].wseg] = ks;
+        if (bl[l].bseg >= 0) s.seg_ksplit[bl[l].bseg] = ks;
+        s.max_ksplit = std::max(s.max_ksplit, ks);
+      }
     }
     if (ones) g.biasCol = bl[l].din;
     g.needLang = 1;
@@ -399,6 +402,7 @@ static void build_program(bae_handle* h) {
   auto set = [&](int pi, int kind, int g0, int g1, int arg, int rows, int need) {
     PhaseDesc& p = s.phase[pi];
     p.kind = kind; p.g0 = g0; p.g1 = g1; p.arg = arg; p.argRows = rows; p.needLang = need;
+    p.sched_off = -1; p.sched_max = 0;
   };
   set(P_PRO, PH_PROLOGUE, -1, -1, 0, 0, 0);
   const int fstart[3] = {P_FWD1, P_FWD2, P_FWDT};
@@ -432,6 +436,56 @@ static void build_program(bae_handle* h) {
   set(P_SWAP + 1, PH_SWAP_GATHER, -1, -1, 0, 0, 0);
   set(P_SWAP + 2, PH_SWAP_SCATTER, -1, -1, 0, 0, 0);
   s.n_phase = P_END;
+}
+
+// Longest-first (LPT) schedules of the GEMM phases of the tcgen05 path for launches over `nch` chains on `npairs` CTA
+// pairs: a weight-gradient tile (all K segments, ~4 x 40 K blocks at Madelon) is several times longer than the other tiles of
+// its phase, and round-robin dealing would leave the pairs up to one such tile apart. Cost model: K blocks + 6 per segment
+// (accumulator drain and hand-off). Every pair walks its own list; the lists of a phase hold each item exactly once.
+static int build_schedule(bae_handle* h, int nch, int npairs) {
+  DevState& s = h->hs;
+  std::vector<int> all;
+  for (int p = 0; p < s.n_phase; ++p) {
+    PhaseDesc& ph = s.phase[p];
+    ph.sched_off = -1; ph.sched_max = 0;
+    if (ph.kind != PH_GEMM) continue;
+    std::vector<std::pair<int, int>> items;   // (cost, item index)
+    const GemmDesc& ga = s.gemm[ph.g0];
+    const int ta = ga.tm * ga.tn, tb = ph.g1 >= 0 ? s.gemm[ph.g1].tm * s.gemm[ph.g1].tn : 0;
+    for (int c = 0; c < nch; ++c)
+      for (int t = 0; t < ta + tb; ++t) {
+        const GemmDesc& g = t < ta ? ga : s.gemm[ph.g1];
+        items.emplace_back((g.K + 15) / 16 + 6 * g.ksplit, c * (ta + tb) + t);
+      }
+    std::stable_sort(items.begin(), items.end(), [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first > b.first; });
+    std::vector<long long> load(npairs, 0);
+    std::vector<std::vector<int>> lists(npairs);
+    for (const auto& it : items) {
+      int best = 0;
+      for (int q = 1; q < npairs; ++q)
+        if (load[q] < load[best]) best = q;
+      load[best] += it.first;
+      lists[best].push_back(it.second);
+    }
+    size_t mx = 0;
+    for (auto& l : lists) mx = std::max(mx, l.size());
+    ph.sched_off = (int)all.size();
+    ph.sched_max = (int)mx;
+    for (auto& l : lists) {
+      // items of one chain next to each other (operands shared in L2), longest first inside the list as dealt
+      for (size_t k = 0; k < mx; ++k) all.push_back(k < l.size() ? l[k] : -1);
+    }
+  }
+  if (all.empty()) return BAE_OK;
+  void* q = nullptr;
+  CU(cudaMalloc(&q, all.size() * sizeof(int)));
+  h->allocs.push_back(q);
+  CU(cudaMemcpyAsync(q, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  s.sched = reinterpret_cast<int*>(q);
+  s.sched_chains = nch;
+  s.sched_pairs = npairs;
+  return BAE_OK;
 }
 
 static int upload_state(bae_handle* h) {
@@ -511,7 +565,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   s.max_ksplit = 1;
   {
     const int dd[7] = {s.d0, s.d1, s.d2, s.d3, s.d2, s.d1, s.d0};
-    for (int l = 0; l < 6; ++l)
+    for (int l = 0; l < 6 && !s.tc; ++l)
       s.max_ksplit = std::max(s.max_ksplit, grad_ksplit(s, h->grid_hint, make_gemm(s, dd[l + 1], dd[l], s.n_train, 1), s.n_train));
   }
   CU(dalloc(h, &s.grad, (size_t)s.max_ksplit * CA * P));   // K-split copies of the gradient (copy 0 is the result)
@@ -571,7 +625,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   if (s.dbg_flags != 0)
     return fail(BAE_ERR_INVALID, "BAE_TC_DBGFLAGS is set, but this library was built without -DBAE_TC_DEBUG: refusing to sample");
 #endif
-  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE"})
+  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED"})
     if (getenv(knob)) fprintf(stderr, "[bae_b200] note: tuning variable %s=%s is in effect for this handle\n", knob, getenv(knob));
   s.dbg_phase = getenv("BAE_TC_TRACE_PHASE") ? atoi(getenv("BAE_TC_TRACE_PHASE")) : -1;
   {
@@ -589,8 +643,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     CU(cudaMemcpyAsync(q, h->tmaps_host.data(), h->tmaps_host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, h->stream));
     s.tmaps = q;
   }
-  int rc = upload_state(h);
-  if (rc) return rc;
+  int rc;
   const int bps = max_coop_blocks_per_sm(s.tc);
   if (bps < 1) return fail(BAE_ERR_CUDA, "step kernel cannot be made resident (occupancy 0)");
   h->grid = prop.multiProcessorCount * bps;
@@ -607,7 +660,10 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     if (!h->phase_launch_env) h->phase_launch = true;
     if (s.drift_mode != 0 && !h->phase_launch)
       return fail(BAE_ERR_INVALID, "drift_mode 1 / 2 on the tcgen05 path needs the per-phase step program (unset BAE_PHASE_LAUNCH=0)");
+    if (!(getenv("BAE_TC_NO_SCHED") && getenv("BAE_TC_NO_SCHED")[0] == '1'))
+      if ((rc = build_schedule(h, s.C, h->grid / 2))) return rc;
   }
+  if ((rc = upload_state(h))) return rc;
   CU(cudaStreamSynchronize(h->stream));
   guard.h = nullptr;
   *out = h;

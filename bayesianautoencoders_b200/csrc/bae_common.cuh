@@ -56,8 +56,10 @@ struct GemmDesc {
   int needLang;  // 1: only chains whose current step is a Langevin step
   int tm, tn;    // tiles along M and N
   int big;       // 1: 128x128 tiles, 0: 64x64 tiles
-  int ksplit;    // FP32 path, weight-gradient GEMMs: K (= rows) split over this many work items; split s writes
-                 // gradient copy s (stride = C_alloc * Pp floats), summed in fixed order by the Adam phase
+  int ksplit;    // weight-gradient GEMMs: the contraction K (= data rows) is cut into this many segments.
+                 // FP32 path: one work item per segment, segment s writes gradient copy s (stride = C_alloc * Pp floats),
+                 //            summed in fixed order by the Adam phase.
+                 // tcgen05 path: the segments of a tile run back to back on one CTA pair and accumulate into ONE copy.
   // ---- tcgen05 path (3xTF32 with the hi/lo split done in shared memory)
   int tcBN;             // tile width (multiple of 16; multiple of 32 when B is N-major), <= 256
   int tcBBytes;         // bytes of one B tile (hi or lo) per K block
@@ -78,6 +80,7 @@ struct PhaseDesc {
   int arg;      // BN: stats slot (0 first train pass, 1 second train pass, 2 test); rows via argRows
   int argRows;  // BN: number of data rows
   int needLang;
+  int sched_off, sched_max;   // tcgen05 path: this phase's item schedule inside DevState::sched ([pair][sched_max], -1 padded), or -1
 };
 
 constexpr int kMaxGemm = 40;
@@ -147,6 +150,8 @@ struct DevState {
   // ---- tcgen05 path
   int tc;             // 1: GEMM phases run on the tensor cores (3xTF32); row pitches reserve a ones column
   void* tmaps;        // CUtensorMap array in global memory (64-byte aligned)
+  int* sched;         // longest-first item schedules of the GEMM phases (PhaseDesc::sched_off), built for `sched_chains` chains
+  int sched_chains, sched_pairs;   // ... per launch and `sched_pairs` CTA pairs
   int dbg_flags;      // BAE_TC_DBGFLAGS: timing experiments only (results are wrong when set), see bae_tc.cuh
   int dbg_phase;      // BAE_TC_TRACE_PHASE: trace only this phase index (-1: every GEMM phase, the last one stays)
   long long* dbg;     // optional timeline trace of CTA 0 (BAE_TC_TRACE=1): [role][event] clock64 stamps

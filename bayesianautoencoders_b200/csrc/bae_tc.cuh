@@ -351,18 +351,35 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(tm), "r"(src_s), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// Same box, ADDED to global memory (FP32 add performed at the L2; one box per instruction, elements do not interact)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, uint32_t src_s, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tm), "r"(src_s), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// Decode the work item of a GEMM phase (same arithmetic in every role).
-struct Item { const GemmDesc* g; int chain, tile_m, tile_n, split, kb0, nkb; };
+// Work items of a GEMM phase (same arithmetic in every role): one item = one output tile of one chain. The K SEGMENTS of
+// a weight-gradient tile (GemmDesc::ksplit: the contraction over the data rows, cut so that no TMEM accumulation chain is
+// longer than ~640 rows) are processed back to back by the SAME CTA pair: segment 0 stores the tile, every later segment
+// adds into it (TMA reduce-add in L2 / read-modify-write by the thread that wrote the element), in segment order - one
+// gradient copy in HBM, summed in a fixed order.
+struct Item { const GemmDesc* g; int chain, tile_m, tile_n, split, kb0, nkb, nsplit; };
 
 __device__ __forceinline__ int items_per_chain(const DevState* S, const PhaseDesc& ph, int& ta) {
   const GemmDesc& ga = S->gemm[ph.g0];
-  ta = ga.tm * ga.tn * ga.ksplit;
-  const int tb = (ph.g1 >= 0) ? S->gemm[ph.g1].tm * S->gemm[ph.g1].tn * S->gemm[ph.g1].ksplit : 0;
+  ta = ga.tm * ga.tn;
+  const int tb = (ph.g1 >= 0) ? S->gemm[ph.g1].tm * S->gemm[ph.g1].tn : 0;
   return ta + tb;
+}
+
+__device__ __forceinline__ void set_split(Item& it, int sp) {
+  const GemmDesc& g = *it.g;
+  const int nkb_all = (g.K + kBK - 1) / kBK;
+  it.split = sp;
+  it.kb0 = (int)(((long long)nkb_all * sp) / g.ksplit);
+  it.nkb = (int)(((long long)nkb_all * (sp + 1)) / g.ksplit) - it.kb0;
 }
 
 __device__ __forceinline__ bool decode_item(const DevState* S, const PhaseDesc& ph, int c_begin, int item, Item& it) {
@@ -373,13 +390,10 @@ __device__ __forceinline__ bool decode_item(const DevState* S, const PhaseDesc& 
   it.g = (t < ta) ? &S->gemm[ph.g0] : &S->gemm[ph.g1];
   if (t >= ta) t -= ta;
   const GemmDesc& g = *it.g;
-  it.split = t % g.ksplit;
-  t /= g.ksplit;
   it.tile_m = t / g.tn;
   it.tile_n = t % g.tn;
-  const int nkb_all = (g.K + kBK - 1) / kBK;
-  it.kb0 = (int)(((long long)nkb_all * it.split) / g.ksplit);
-  it.nkb = (int)(((long long)nkb_all * (it.split + 1)) / g.ksplit) - it.kb0;
+  it.nsplit = g.ksplit;
+  set_split(it, 0);
   return !(g.needLang && !S->ch.is_lang[it.chain]);
 }
 
@@ -388,13 +402,33 @@ __device__ __forceinline__ int phase_items(const DevState* S, const PhaseDesc& p
   return items_per_chain(S, ph, ta) * (c_end - c_begin);
 }
 
+// Which items this CTA pair processes, in order: the host-computed longest-first schedule of the phase (bae_api.cu:
+// build_schedule; weight-gradient tiles are ~4x longer than the other tiles of a backward phase) when the launch covers
+// the chain count the schedule was built for, round-robin otherwise (parity probe, a short last chain group).
+struct Sched { const int* list; int cnt, pair, npairs, total; };
+__device__ __forceinline__ Sched make_sched(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end) {
+  Sched sc;
+  sc.pair = (int)(blockIdx.x >> 1);
+  sc.npairs = (int)(gridDim.x >> 1);
+  sc.total = phase_items(S, ph, c_begin, c_end);
+  const bool tab = S->sched != nullptr && ph.sched_off >= 0 && (c_end - c_begin) == S->sched_chains && sc.npairs == S->sched_pairs;
+  sc.list = tab ? S->sched + ph.sched_off + (size_t)sc.pair * ph.sched_max : nullptr;
+  sc.cnt = tab ? ph.sched_max : 0;
+  return sc;
+}
+__device__ __forceinline__ int sched_next(const Sched& sc, int k) {
+  if (sc.list) return k < sc.cnt ? sc.list[k] : -1;     // lists are padded with -1
+  const int item = sc.pair + k * sc.npairs;
+  return item < sc.total ? item : -1;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // One GEMM phase on the tensor cores, front half: TMA producer, MMA issuer and the hi/lo converters
 // (warpgroups 0 and 3). Returns when this CTA's last MMA has been issued / last lo tile written.
 // ---------------------------------------------------------------------------------------------------
 __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, Smem& sm, Ring& ring) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total = phase_items(S, ph, c_begin, c_end);
+  const Sched sched = make_sched(S, ph, c_begin, c_end);
   const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(S->tmaps);
   long long* dbg = (blockIdx.x == 0 && (S->dbg_phase < 0 || S->dbg_phase == (int)(&ph - S->phase))) ? S->dbg : nullptr;
   const uint32_t rank = cluster_rank();
@@ -406,10 +440,14 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     // ================= TMA producer (warp-uniform loop, one elected lane issues) =================
     {
       int ntr = 0;
-      for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs
+      for (int ki = 0;; ++ki) {   // items go to CTA pairs
+        const int item = sched_next(sched, ki);
+        if (item < 0) break;
         Item it;
         if (!decode_item(S, ph, c_begin, item, it)) continue;
         const GemmDesc& g = *it.g;
+        for (int sp = 0; sp < it.nsplit; ++sp) {
+        set_split(it, sp);
         // this CTA's share of the pair's 256 x BN tile: 128 rows of A, BN/2 columns of B
         const int m0 = it.tile_m * (2 * kBM) + (int)rank * kBM, n0 = it.tile_n * g.tcBN + (int)rank * (g.tcBN >> 1);
         const int ca = g.sA ? it.chain : 0, cb = g.sB ? it.chain : 0;
@@ -446,6 +484,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
           __syncwarp();
           ring.advance();
         }
+        }
       }
     }
   } else if (warp == 1) {
@@ -454,10 +493,14 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
       int ntr = 0;
       const int dbgf = BAE_DBGF(S);
       const uint32_t tmem = *sm.tmem_base();
-      for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs
+      for (int ki = 0;; ++ki) {   // items go to CTA pairs
+        const int item = sched_next(sched, ki);
+        if (item < 0) break;
         Item it;
         if (!decode_item(S, ph, c_begin, item, it)) continue;
         const GemmDesc& g = *it.g;
+        for (int sp = 0; sp < it.nsplit; ++sp) {
+        set_split(it, sp);
         mbar_wait_cluster(&sm.tmem_empty()[0], ring.acc_phase ^ 1);   // the epilogue warps of BOTH CTAs have drained the previous tile
         fence_after_sync();
         const uint32_t d_main = tmem, d_cross = tmem + (uint32_t)g.tcBN;
@@ -498,6 +541,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
           ring.advance();
         }
         ring.acc_phase ^= 1;
+        }
       }
     }
   } else {
@@ -511,10 +555,12 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     const bool skip = (BAE_DBGF(S) & 1) != 0;
     int ntr = (grp == 0) ? 0 : (grp == 1 ? 170 : 340);
     uint32_t kbc = ring.kbc;
-    for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs
+    for (int ki = 0;; ++ki) {   // items go to CTA pairs
+      const int item = sched_next(sched, ki);
+      if (item < 0) break;
       Item it;
       if (!decode_item(S, ph, c_begin, item, it)) continue;
-      const int nkb = it.nkb;
+      const int nkb = (it.g->K + kBK - 1) / kBK;   // all K segments of the tile, back to back
       for (int kb = 0; kb < nkb; ++kb) {
         if ((int)kbc == grp) {
           // The lo slot first (the MMAs of K block k - 4 are done): it also pins the phase of `full`. Parity waits cannot
@@ -641,15 +687,16 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
   // locals: see the note in gemm_phase_front
   const int chain = it.chain;
   const int m0 = it.tile_m * (2 * kBM) + (int)c.rank * kBM;   // this CTA's 128 rows of the pair's tile
-  const size_t split_off = (epi == EPI_GRADW) ? (size_t)it.split * S->C_alloc * S->Pp : 0;   // gradient copy of this K split
-  float* C = g.C + (size_t)chain * g.sC + split_off;   // direct stores: only chunks that straddle the next tile's columns
+  // K segments after the first ADD into what this CTA pair stored for the previous ones (same warp, same lane per element)
+  const bool accum = (epi == EPI_GRADW) && it.split > 0;
+  float* C = g.C + (size_t)chain * g.sC;   // direct stores: only chunks that straddle the next tile's columns
   const int ldc = g.ldc;
   const CUtensorMap* mapC = reinterpret_cast<const CUtensorMap*>(S->tmaps) + g.tmIdx[2];
-  const int zC = g.sC ? chain + ((epi == EPI_GRADW) ? it.split * S->C_alloc : 0) : 0;   // slice of the output tensor map
+  const int zC = g.sC ? chain : 0;   // slice of the output tensor map
   const float* aux = (kHasAux && g.aux) ? g.aux + (size_t)chain * g.sAux : nullptr;
   const int gM = g.M, ldaux = g.ldaux;
   const int biasCol = (epi == EPI_GRADW) ? g.biasCol : -1;
-  float* gbias = (epi == EPI_GRADW && g.gbias) ? g.gbias + (size_t)chain * g.sGb + split_off : nullptr;
+  float* gbias = (epi == EPI_GRADW && g.gbias) ? g.gbias + (size_t)chain * g.sGb : nullptr;
   const float scale = g.scale;
   const int r0 = m0 + c.q * 32;
   const uint32_t stg_s = c.stg_s;
@@ -660,6 +707,12 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
   // loads, bias and stores share one address pattern.
   float l_sse = 0.f, l_sd = 0.f;
   const int lim = (epi == EPI_GRADW && biasCol >= 0) ? min(n_end, biasCol) : n_end;   // columns >= lim are not stored
+  if (accum) {
+    // the previous segment's box stores of this warp are COMPLETE (not just read) before anything is added to them; they
+    // were issued a whole main loop ago, so this does not wait in practice
+    if (lane == 0) bulk_wait_all();
+    __syncwarp();
+  }
 #pragma unroll 1
   for (int jj = 0; jj < 4; ++jj) {
     const int c0 = (eg + 2 * jj) * 32;
@@ -732,13 +785,17 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
       } else {
         float* dst = &C[(size_t)rr * ldc + cc];
         if (cc + 4 <= lim) {
+          if (accum) {
+            const float4 p4 = *reinterpret_cast<const float4*>(dst);
+            o.x += p4.x; o.y += p4.y; o.z += p4.z; o.w += p4.w;
+          }
           *reinterpret_cast<float4*>(dst) = o;
         } else {
           const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            if (cc + e < lim) dst[e] = ov[e];
-            else if (epi == EPI_GRADW && cc + e == biasCol) gbias[rr] = ov[e];
+            if (cc + e < lim) dst[e] = accum ? dst[e] + ov[e] : ov[e];
+            else if (epi == EPI_GRADW && cc + e == biasCol) gbias[rr] = accum ? gbias[rr] + ov[e] : ov[e];
           }
         }
       }
@@ -749,7 +806,8 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
-        tma_store_3d(mapC, stg_s, n0 + c0, r0, zC);
+        if (accum) tma_reduce_add_3d(mapC, stg_s, n0 + c0, r0, zC);
+        else tma_store_3d(mapC, stg_s, n0 + c0, r0, zC);
         bulk_commit();
       }
     }
@@ -780,7 +838,7 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
 template <int kEpiA, int kEpiB>
 __device__ __forceinline__ void gemm_phase_epilogue(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, Smem& sm, Ring& ring) {
   const int warp = threadIdx.x >> 5;
-  const int total = phase_items(S, ph, c_begin, c_end);
+  const Sched sched = make_sched(S, ph, c_begin, c_end);
   EpiCtx c;
   c.lane = threadIdx.x & 31;
   c.q = warp & 3;               // TMEM lane quarter this warp may access
@@ -794,10 +852,15 @@ __device__ __forceinline__ void gemm_phase_epilogue(const DevState* S, const Pha
   c.dbgf = BAE_DBGF(S);
   c.rank = cluster_rank();
   int ntr = 0;
-  for (int item = (int)(blockIdx.x >> 1); item < total; item += (int)(gridDim.x >> 1)) {   // items go to CTA pairs
+  for (int ki = 0;; ++ki) {   // items go to CTA pairs
+    const int item = sched_next(sched, ki);
+    if (item < 0) break;
     Item it;
     if (!decode_item(S, ph, c_begin, item, it)) continue;
-    epilogue_tile<kEpiA, kEpiB>(S, it, c, sm, ring, ntr);
+    for (int sp = 0; sp < it.nsplit; ++sp) {
+      set_split(it, sp);
+      epilogue_tile<kEpiA, kEpiB>(S, it, c, sm, ring, ntr);
+    }
   }
   if (c.lane == 0) bulk_wait_all();   // this warp's box stores are complete before the kernel (or the phase) ends
   __syncwarp();
