@@ -34,6 +34,7 @@ class Config(C.Structure):
         ("lr", C.c_float), ("step_w", C.c_float), ("step_eta", C.c_float), ("l_prob", C.c_float),
         ("sigma_squared", C.c_float), ("nu_1", C.c_float), ("nu_2", C.c_float),
         ("seed", C.c_uint64), ("gemm_path", C.c_int32), ("drift_mode", C.c_int32),
+        ("act_group", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

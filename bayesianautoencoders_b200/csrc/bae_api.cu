@@ -99,6 +99,7 @@ struct bae_handle {
   bool use_graph = true;       // phase launches of a call are replayed from a CUDA graph
   int grid_aux[16] = {};       // CTAs of bae_aux_kernel per phase kind (non-GEMM phases of the tcgen05 path)
   std::map<std::array<int, 4>, cudaGraphExec_t> graphs;   // (p_begin, p_end, n_rep, force_swap) -> instantiated graph
+  std::map<std::array<int, 4>, int> graph_launches;       // kernel nodes of each graph
 };
 
 template <typename T>
@@ -277,7 +278,7 @@ static void build_program(bae_handle* h) {
   // registers the two tensor maps (A, B) of a GEMM
   auto add_maps = [&](GemmDesc& g) {
     if (!tcm) return;
-    const int nchA = g.sA ? s.C_alloc : 1, nchB = g.sB ? s.C_alloc : 1;
+    const int nchA = g.sA ? (g.aAct ? s.G : s.C_alloc) : 1, nchB = g.sB ? (g.bAct ? s.G : s.C_alloc) : 1;
     const float* ptrs[2] = {g.A, g.B};
     for (int i = 0; i < 2; ++i) {
       CUtensorMap tm;
@@ -300,7 +301,7 @@ static void build_program(bae_handle* h) {
       memset(&tm, 0, sizeof(tm));
       const bool gw = g.epi == EPI_GRADW;
       const int cols = (gw && g.biasCol >= 0) ? std::min(g.N, g.biasCol) : g.N;
-      const int nslice = g.sC ? (gw ? std::max(1, s.max_ksplit) : 1) * s.C_alloc : 1;
+      const int nslice = g.sC ? (g.cAct ? s.G : (gw ? std::max(1, s.max_ksplit) : 1) * s.C_alloc) : 1;
       const int rc = tmap_store(&tm, g.C, cols, g.M, g.ldc, nslice, g.sC);
       if (rc != 0 && h->tmap_error.empty())
         h->tmap_error = "cuTensorMapEncodeTiled failed (CUresult " + std::to_string(rc) + ") for a GEMM output";
@@ -333,6 +334,7 @@ static void build_program(bae_handle* h) {
       g.A = ls[l].A; g.sA = ls[l].sA; g.lda = ls[l].lda; g.aMode = 0;
       g.B = W(ls[l].wseg); g.sB = P; g.ldb = s.seg[ls[l].wseg].ld; g.bMode = 0;
       g.C = ls[l].C; g.sC = ls[l].sC; g.ldc = ls[l].ldc;
+      g.aAct = ls[l].sA != 0; g.cAct = 1;      // activations: slot of the resident chain group
       g.epi = ls[l].epi;
       g.bias = Wraw(ls[l].bseg); g.sBias = P;
       g.needLang = need;
@@ -366,6 +368,7 @@ static void build_program(bae_handle* h) {
     g.A = bl[l].dOut; g.sA = bl[l].sD; g.lda = bl[l].ldd; g.aMode = 1;
     g.B = bl[l].Ain; g.sB = bl[l].sAin; g.ldb = bl[l].ldain; g.bMode = 1;
     g.C = G(bl[l].wseg); g.sC = P; g.ldc = s.seg[bl[l].wseg].ld;
+    g.aAct = 1; g.bAct = bl[l].sAin != 0;
     g.epi = EPI_GRADW;
     if (bl[l].bseg >= 0) { g.gbias = G(bl[l].bseg); g.sGb = P; }
     {
@@ -389,8 +392,9 @@ static void build_program(bae_handle* h) {
       x.A = bl[l].dOut; x.sA = bl[l].sD; x.lda = bl[l].ldd; x.aMode = 0;
       x.B = W(bl[l].wseg); x.sB = P; x.ldb = s.seg[bl[l].wseg].ld; x.bMode = 1;
       x.C = bl[l].dIn; x.sC = bl[l].sDin; x.ldc = bl[l].lddin;
+      x.aAct = 1; x.cAct = 1;
       x.epi = bl[l].epi_x;
-      if (bl[l].Hin) { x.aux = bl[l].Hin; x.sAux = bl[l].sDin; x.ldaux = bl[l].lddin; }
+      if (bl[l].Hin) { x.aux = bl[l].Hin; x.sAux = bl[l].sDin; x.ldaux = bl[l].lddin; x.auxAct = 1; }
       x.needLang = 1;
       add_maps(x);
       bx_idx[l] = ng;
@@ -573,10 +577,25 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   CU(dalloc(h, &s.bn_mu, 3 * CA * s.ld3)); CU(dalloc(h, &s.bn_var, 3 * CA * s.ld3)); CU(dalloc(h, &s.bn_inv, CA * s.ld3));
   CU(dalloc(h, &s.Xtrain, (size_t)s.n_train * s.ld0)); CU(dalloc(h, &s.Xtest, (size_t)s.n_test * s.ld0));
   const size_t nm = s.n_max;
-  CU(dalloc(h, &s.H1, CA * nm * s.ld1)); CU(dalloc(h, &s.H2, CA * nm * s.ld2)); CU(dalloc(h, &s.Z, CA * nm * s.ld3));
-  CU(dalloc(h, &s.Y, CA * nm * s.ld3)); CU(dalloc(h, &s.H4, CA * nm * s.ld2)); CU(dalloc(h, &s.H5, CA * nm * s.ld1));
-  CU(dalloc(h, &s.DOUT, CA * nm * s.ld0)); CU(dalloc(h, &s.D5, CA * nm * s.ld1)); CU(dalloc(h, &s.D4, CA * nm * s.ld2));
-  CU(dalloc(h, &s.DY, CA * nm * s.ld3)); CU(dalloc(h, &s.D2, CA * nm * s.ld2)); CU(dalloc(h, &s.D1, CA * nm * s.ld1));
+  {
+    // chain groups: activation / delta buffers exist for G chains at a time (G = C unless they do not fit)
+    const size_t per_chain = nm * (size_t)(s.ld0 + 4 * s.ld1 + 4 * s.ld2 + 3 * s.ld3) * sizeof(float);   // H1 H2 Z Y H4 H5 + DOUT D5 D4 DY D2 D1
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    int G = s.C;
+    if (cfg->act_group > 0) {
+      G = std::min(s.C, cfg->act_group);
+    } else {
+      const size_t budget = (size_t)(0.70 * (double)free_b);
+      if ((size_t)s.C * per_chain > budget) G = (int)std::max<size_t>(1, budget / per_chain);
+    }
+    s.G = std::max(1, std::min(G, s.C));
+  }
+  const size_t CA_act = s.G;   // the parity probe's scratch chain runs alone and uses slot 0
+  CU(dalloc(h, &s.H1, CA_act * nm * s.ld1)); CU(dalloc(h, &s.H2, CA_act * nm * s.ld2)); CU(dalloc(h, &s.Z, CA_act * nm * s.ld3));
+  CU(dalloc(h, &s.Y, CA_act * nm * s.ld3)); CU(dalloc(h, &s.H4, CA_act * nm * s.ld2)); CU(dalloc(h, &s.H5, CA_act * nm * s.ld1));
+  CU(dalloc(h, &s.DOUT, CA_act * nm * s.ld0)); CU(dalloc(h, &s.D5, CA_act * nm * s.ld1)); CU(dalloc(h, &s.D4, CA_act * nm * s.ld2));
+  CU(dalloc(h, &s.DY, CA_act * nm * s.ld3)); CU(dalloc(h, &s.D2, CA_act * nm * s.ld2)); CU(dalloc(h, &s.D1, CA_act * nm * s.ld1));
   {
     const int per_tile = s.tc ? 2 : 1;   // tcgen05 path: each CTA of a pair writes the partial of its 128 rows
     GemmDesc t = make_gemm(s, s.n_max, s.d0, s.d1);
@@ -586,11 +605,11 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   }
   if (s.tc) {
     // ones column (index d) of every activation that is the B operand of a weight-gradient GEMM
-    std::vector<float> ones(CA * nm, 1.0f);
+    std::vector<float> ones(CA_act * nm, 1.0f);
     struct OC { float* p; int ld, d; };
     const OC oc[5] = {{s.H1, s.ld1, s.d1}, {s.H2, s.ld2, s.d2}, {s.Y, s.ld3, s.d3}, {s.H4, s.ld2, s.d2}, {s.H5, s.ld1, s.d1}};
     for (const OC& o : oc)
-      CU(cudaMemcpy2DAsync(o.p + o.d, (size_t)o.ld * 4, ones.data(), 4, 4, CA * nm, cudaMemcpyHostToDevice, h->stream));
+      CU(cudaMemcpy2DAsync(o.p + o.d, (size_t)o.ld * 4, ones.data(), 4, 4, CA_act * nm, cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));
   }
   CU(dalloc(h, &s.loss_part, 3 * CA * (size_t)s.loss_stride * 2));
@@ -661,7 +680,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     if (s.drift_mode != 0 && !h->phase_launch)
       return fail(BAE_ERR_INVALID, "drift_mode 1 / 2 on the tcgen05 path needs the per-phase step program (unset BAE_PHASE_LAUNCH=0)");
     if (!(getenv("BAE_TC_NO_SCHED") && getenv("BAE_TC_NO_SCHED")[0] == '1'))
-      if ((rc = build_schedule(h, s.C, h->grid / 2))) return rc;
+      if ((rc = build_schedule(h, s.G, h->grid / 2))) return rc;
   }
   if ((rc = upload_state(h))) return rc;
   CU(cudaStreamSynchronize(h->stream));
@@ -923,46 +942,80 @@ int bae_set_state(bae_handle* h, int chain, const float* theta, const float* w, 
   return BAE_OK;
 }
 
+// Issues the per-phase launches of `n_rep` iterations of phases [p_begin, p_end): the step phases (prologue .. epilogue)
+// chain group after chain group (the activation buffers hold G chains), the exchange phases once over all chains.
+static cudaError_t emit_phases(bae_handle* h, int p_begin, int p_end, int n_rep, int force_swap, int* n_launch) {
+  const int C = h->hs.C, G = h->hs.G;
+  const int ps_end = std::min(p_end, (int)P_SWAP);
+  cudaError_t e = cudaSuccess;
+  int n = 0;
+  for (int r = 0; r < n_rep && e == cudaSuccess; ++r) {
+    if (p_begin < ps_end)
+      for (int cb = 0; cb < C && e == cudaSuccess; cb += G)
+        for (int p = p_begin; p < ps_end && e == cudaSuccess; ++p, ++n) e = launch_one(h, p, cb, std::min(cb + G, C), force_swap);
+    for (int p = std::max(p_begin, (int)P_SWAP); p < p_end && e == cudaSuccess; ++p, ++n) e = launch_one(h, p, 0, C, force_swap);
+  }
+  if (n_launch) *n_launch = n;
+  return e;
+}
+
 static int coop_launch(bae_handle* h, int p_begin, int p_end, int n_rep, int force_swap) {
   if (!h->data_loaded) return fail(BAE_ERR_STATE, "upload data first");
   CU(cudaSetDevice(h->device));
   CU(cudaEventRecord(h->ev0, h->stream));
+  const int C = h->hs.C, G = h->hs.G;
   if (h->phase_launch) {
     // One launch per phase (the exchange phases test the step counter on the device, like the persistent kernel); the
     // launches of a call are captured once into a CUDA graph and replayed.
-    const int n_launch = n_rep * (p_end - p_begin);
+    const int groups = (C + G - 1) / G;
+    const int n_est = n_rep * (p_end - p_begin) * groups;
+    int n_launch = 0;
     const std::array<int, 4> key = {p_begin, p_end, n_rep, force_swap};
     // at most 32 distinct call shapes are kept as graphs (a caller that varies n_steps freely falls back to direct launches)
-    if (h->use_graph && n_launch <= 8192 && (h->graphs.count(key) || h->graphs.size() < 32)) {
+    if (h->use_graph && n_est <= 8192 && (h->graphs.count(key) || h->graphs.size() < 32)) {
       auto it = h->graphs.find(key);
       if (it == h->graphs.end()) {
         cudaGraph_t graph = nullptr;
         CU(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-        cudaError_t e = cudaSuccess;
-        for (int r = 0; r < n_rep && e == cudaSuccess; ++r)
-          for (int p = p_begin; p < p_end && e == cudaSuccess; ++p) e = launch_one(h, p, 0, h->hs.C, force_swap);
-        cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
+        const cudaError_t e = emit_phases(h, p_begin, p_end, n_rep, force_swap, &n_launch);
+        const cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
         if (e != cudaSuccess || e2 != cudaSuccess) {
           if (graph) cudaGraphDestroy(graph);
           return fail(BAE_ERR_CUDA, std::string("graph capture of the step program failed: ") +
                                         cudaGetErrorString(e != cudaSuccess ? e : e2));
         }
         cudaGraphExec_t exec = nullptr;
-        e = cudaGraphInstantiate(&exec, graph, 0);
+        const cudaError_t e3 = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
-        if (e != cudaSuccess) return fail(BAE_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        if (e3 != cudaSuccess) return fail(BAE_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e3));
         it = h->graphs.emplace(key, exec).first;
+        h->graph_launches[key] = n_launch;
       }
+      n_launch = h->graph_launches[key];
       CU(cudaEventRecord(h->ev0, h->stream));
       CU(cudaGraphLaunch(it->second, h->stream));
     } else {
-      for (int r = 0; r < n_rep; ++r)
-        for (int p = p_begin; p < p_end; ++p) CU(launch_one(h, p, 0, h->hs.C, force_swap));
+      CU(emit_phases(h, p_begin, p_end, n_rep, force_swap, &n_launch));
     }
     h->launches += n_launch;
-  } else {
-    CU(launch_program(h->dS, h->hs.tc, h->grid, p_begin, p_end, n_rep, 0, h->hs.C, force_swap, h->stream));
+  } else if (G >= C) {
+    CU(launch_program(h->dS, h->hs.tc, h->grid, p_begin, p_end, n_rep, 0, C, force_swap, h->stream));
     h->launches++;
+  } else {
+    // persistent kernel with chain groups: the step phases of an iteration group after group, then the exchange phases
+    const int ps_end = std::min(p_end, (int)P_SWAP);
+    const bool swap_inside = p_end > P_SWAP;
+    for (int r = 0; r < (swap_inside ? n_rep : 1); ++r) {
+      if (p_begin < ps_end)
+        for (int cb = 0; cb < C; cb += G) {
+          CU(launch_program(h->dS, h->hs.tc, h->grid, p_begin, ps_end, swap_inside ? 1 : n_rep, cb, std::min(cb + G, C), force_swap, h->stream));
+          h->launches++;
+        }
+      if (swap_inside) {
+        CU(launch_program(h->dS, h->hs.tc, h->grid, std::max(p_begin, (int)P_SWAP), p_end, 1, 0, C, force_swap, h->stream));
+        h->launches++;
+      }
+    }
   }
   CU(cudaEventRecord(h->ev1, h->stream));
   h->timed = true;
@@ -1021,7 +1074,7 @@ int bae_eval(bae_handle* h, int chain, int which, const float* w, double* sse, d
   if (out) {
     // the loss epilogue stores (out - X) * scale; undo it on the host
     std::vector<float> d((size_t)rows * s.ld0), x((size_t)rows * s.ld0);
-    CU(cudaMemcpyAsync(d.data(), s.DOUT + (size_t)E * s.n_max * s.ld0, sizeof(float) * d.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(d.data(), s.DOUT, sizeof(float) * d.size(), cudaMemcpyDeviceToHost, h->stream));   // the probe ran alone: slot 0
     CU(cudaMemcpyAsync(x.data(), which == 0 ? s.Xtrain : s.Xtest, sizeof(float) * x.size(), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
 
@@ -1051,24 +1104,28 @@ int bae_forward_all(bae_handle* h, int which, float* features, float* recon, dou
   const int p0 = which == 0 ? P_FWD2 : P_FWDT, pass = which == 0 ? 1 : 2;
   const int rows = which == 0 ? s.n_train : s.n_test;
   const float* X = which == 0 ? s.Xtrain : s.Xtest;
-  for (int p = p0; p < p0 + 7; ++p) {
-    CU(launch_one(h, p, 0, s.C, 1));
-    h->launches++;
-  }
   if (!h->stage_rows && (features || recon)) CU(dalloc(h, &h->stage_rows, (size_t)s.n_max * std::max(s.d0, s.d3)));
   const float inv_scale = (float)(((double)rows * s.d0) / 2.0);
-  for (int c = 0; c < s.C; ++c) {
-    if (features) {
-      CU(launch_extract(s.Z + (size_t)c * s.n_max * s.ld3, s.ld3, nullptr, 0, rows, s.d3, 0.f, 0, h->stage_rows, h->stream));
+  for (int cb = 0; cb < s.C; cb += s.G) {       // chain group after chain group (the activation buffers hold G chains)
+    const int ce = std::min(cb + s.G, s.C);
+    for (int p = p0; p < p0 + 7; ++p) {
+      CU(launch_one(h, p, cb, ce, 1));
       h->launches++;
-      CU(cudaMemcpyAsync(features + (size_t)c * rows * s.d3, h->stage_rows, sizeof(float) * rows * s.d3, cudaMemcpyDeviceToHost, h->stream));
-      CU(cudaStreamSynchronize(h->stream));   // pageable destination; the staging buffer is reused
     }
-    if (recon) {
-      CU(launch_extract(s.DOUT + (size_t)c * s.n_max * s.ld0, s.ld0, X, s.ld0, rows, s.d0, inv_scale, 1, h->stage_rows, h->stream));
-      h->launches++;
-      CU(cudaMemcpyAsync(recon + (size_t)c * rows * s.d0, h->stage_rows, sizeof(float) * rows * s.d0, cudaMemcpyDeviceToHost, h->stream));
-      CU(cudaStreamSynchronize(h->stream));
+    for (int c = cb; c < ce; ++c) {
+      const size_t slot = (size_t)(c - cb);
+      if (features) {
+        CU(launch_extract(s.Z + slot * s.n_max * s.ld3, s.ld3, nullptr, 0, rows, s.d3, 0.f, 0, h->stage_rows, h->stream));
+        h->launches++;
+        CU(cudaMemcpyAsync(features + (size_t)c * rows * s.d3, h->stage_rows, sizeof(float) * rows * s.d3, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));   // pageable destination; the staging buffer is reused
+      }
+      if (recon) {
+        CU(launch_extract(s.DOUT + slot * s.n_max * s.ld0, s.ld0, X, s.ld0, rows, s.d0, inv_scale, 1, h->stage_rows, h->stream));
+        h->launches++;
+        CU(cudaMemcpyAsync(recon + (size_t)c * rows * s.d0, h->stage_rows, sizeof(float) * rows * s.d0, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+      }
     }
   }
   if (sse) {
@@ -1433,7 +1490,9 @@ int bae_debug_buffer(bae_handle* h, const char* name, int chain, float* out, int
     if (!src) return fail(BAE_ERR_INVALID, "no such part");
     const size_t per = (size_t)s.n_max * e.ld;
     if ((size_t)n_floats > per) return fail(BAE_ERR_INVALID, "too many floats");
-    CU(cudaMemcpyAsync(out, src + (size_t)chain * per, sizeof(float) * n_floats, cudaMemcpyDeviceToHost, h->stream));
+    // activation buffers hold the last chain group that ran; the parity probe's scratch chain (chain == n_chains) ran alone
+    const size_t slot = chain == s.C ? 0 : (size_t)(chain % s.G);
+    CU(cudaMemcpyAsync(out, src + slot * per, sizeof(float) * n_floats, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     if (ld) *ld = e.ld;
     return BAE_OK;

@@ -54,6 +54,8 @@ struct GemmDesc {
   double* part; int partStride;  // [chain][partStride][2] loss partials (sum d^2, sum d)
   float scale;
   int needLang;  // 1: only chains whose current step is a Langevin step
+  int aAct, bAct, cAct, auxAct;   // operand is an activation / delta buffer: indexed by the chain's slot in the resident GROUP
+                                  // (chain - c_begin of the launch), not by the chain (DevState::G)
   int tm, tn;    // tiles along M and N
   int big;       // 1: 128x128 tiles, 0: 64x64 tiles
   int ksplit;    // weight-gradient GEMMs: the contraction K (= data rows) is cut into this many segments.
@@ -109,6 +111,7 @@ struct DevState {
   int ld0, ld1, ld2, ld3;
   int n_train, n_test, n_max;
   int C, C_alloc, n_rungs, chain_id_base;
+  int G;              // chains whose activation buffers are resident at a time (chain groups; G == C: all of them)
   int samples, pt_step, swap_interval, use_langevin, drift_mode;
   float lr, step_w, step_eta, l_prob, sigma_sq, nu1, nu2;
   unsigned seed_lo, seed_hi;

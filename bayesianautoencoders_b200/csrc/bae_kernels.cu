@@ -143,7 +143,7 @@ __device__ __forceinline__ void tile_store(float* __restrict__ sm /*[BK][BT]*/, 
 }
 
 template <int BM, int BN>
-__device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int tile_m, int tile_n, int split, float* smem,
+__device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int slot, int tile_m, int tile_n, int split, float* smem,
                           double* red) {
   constexpr int TM = BM / 16, TN = BN / 16;  // 8x8 (128) or 4x4 (64) per thread
   constexpr int GM = TM / 4, GN = TN / 4;
@@ -152,8 +152,8 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
   const int lda = g.lda, ldb = g.ldb, aMode = g.aMode, bMode = g.bMode, gM = g.M, gN = g.N, gK = g.K, ksplit = g.ksplit;
   float* As = smem;                 // [2][BK][BM]
   float* Bs = smem + 2 * BK * BM;   // [2][BK][BN]
-  const float* A = g.A + (size_t)chain * g.sA;
-  const float* B = g.B + (size_t)chain * g.sB;
+  const float* A = g.A + (size_t)(g.aAct ? slot : chain) * g.sA;   // activations live in the chain's slot of the resident group
+  const float* B = g.B + (size_t)(g.bAct ? slot : chain) * g.sB;
   const int m0 = tile_m * BM, n0 = tile_n * BN;
   const int tx = TID & 15, ty = TID >> 4;
   float acc[TM][TN];
@@ -216,9 +216,9 @@ __device__ void gemm_item(const DevState* S, const GemmDesc& g, int chain, int t
 
   // ---- epilogue
   const size_t split_off = (size_t)split * S->C_alloc * S->Pp;   // gradient copy of this K split (0 when ksplit == 1)
-  float* C = g.C ? g.C + (size_t)chain * g.sC + split_off : nullptr;
+  float* C = g.C ? g.C + (size_t)(g.cAct ? slot : chain) * g.sC + split_off : nullptr;
   const float* bias = g.bias ? g.bias + (size_t)chain * g.sBias : nullptr;
-  const float* aux = g.aux ? g.aux + (size_t)chain * g.sAux : nullptr;
+  const float* aux = g.aux ? g.aux + (size_t)(g.auxAct ? slot : chain) * g.sAux : nullptr;
   float l_sse = 0.f, l_sd = 0.f;
 #pragma unroll
   for (int gi = 0; gi < GM; ++gi) {
@@ -313,9 +313,9 @@ __device__ void run_gemm_phase(const DevState* S, const PhaseDesc& ph, int c_beg
     t /= g.ksplit;
     const int tile_m = t / g.tn, tile_n = t % g.tn;
     if (g.big)
-      gemm_item<128, 128>(S, g, chain, tile_m, tile_n, split, smem, red);
+      gemm_item<128, 128>(S, g, chain, chain - c_begin, tile_m, tile_n, split, smem, red);
     else
-      gemm_item<64, 64>(S, g, chain, tile_m, tile_n, split, smem, red);
+      gemm_item<64, 64>(S, g, chain, chain - c_begin, tile_m, tile_n, split, smem, red);
   }
 }
 
@@ -364,8 +364,8 @@ __device__ void run_bn_fwd_wide(const DevState* S, const PhaseDesc& ph, int c_be
     if (need && !S->ch.is_lang[chain]) continue;
     const int c0 = (item % nblk) * kBnCols + c4 * 4;
     const bool cv = c0 < d3;   // a float4 may reach past d3 (pad / ones column: read, never written)
-    const float* __restrict__ Z = S->Z + (size_t)chain * slab + c0;
-    float* __restrict__ Y = S->Y + (size_t)chain * slab + c0;
+    const float* __restrict__ Z = S->Z + (size_t)(chain - c_begin) * slab + c0;
+    float* __restrict__ Y = S->Y + (size_t)(chain - c_begin) * slab + c0;
     double a[4] = {0.0, 0.0, 0.0, 0.0};
     if (cv)
       for (int base = rl; base < N; base += kBnLanes * kBnUnroll) {
@@ -454,8 +454,8 @@ __device__ void run_bn_bwd_wide(const DevState* S, const PhaseDesc& ph, int c_be
     if (need && !S->ch.is_lang[chain]) continue;
     const int c0 = (item % nblk) * kBnCols + c4 * 4;
     const bool cv = c0 < d3;
-    const float* __restrict__ Z = S->Z + (size_t)chain * slab + c0;
-    float* DY = S->DY + (size_t)chain * slab + c0;
+    const float* __restrict__ Z = S->Z + (size_t)(chain - c_begin) * slab + c0;
+    float* DY = S->DY + (size_t)(chain - c_begin) * slab + c0;
     float mean[4] = {0.f, 0.f, 0.f, 0.f}, inv[4] = {0.f, 0.f, 0.f, 0.f}, gam[4] = {0.f, 0.f, 0.f, 0.f};
     if (cv) {
 #pragma unroll
@@ -558,8 +558,8 @@ __device__ void run_bn_fwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
     if (ph.needLang && !S->ch.is_lang[chain]) continue;
     const int c = (item % nblk) * cpb + cl;
     const bool cv = c < d3;
-    const float* Z = S->Z + (size_t)chain * S->n_max * ld3;
-    float* Y = S->Y + (size_t)chain * S->n_max * ld3;
+    const float* Z = S->Z + (size_t)(chain - c_begin) * S->n_max * ld3;
+    float* Y = S->Y + (size_t)(chain - c_begin) * S->n_max * ld3;
     double s = 0.0;
     if (cv)
       for (int r = rl; r < N; r += rln) s += (double)Z[(size_t)r * ld3 + c];
@@ -612,8 +612,8 @@ __device__ void run_bn_bwd(const DevState* S, const PhaseDesc& ph, int c_begin, 
     if (ph.needLang && !S->ch.is_lang[chain]) continue;
     const int c = (item % nblk) * cpb + cl;
     const bool cv = c < d3;
-    const float* Z = S->Z + (size_t)chain * S->n_max * ld3;
-    float* DY = S->DY + (size_t)chain * S->n_max * ld3;
+    const float* Z = S->Z + (size_t)(chain - c_begin) * S->n_max * ld3;
+    float* DY = S->DY + (size_t)(chain - c_begin) * S->n_max * ld3;
     float mean = 0.f, inv = 0.f, gam = 0.f;
     if (cv) {
       mean = S->bn_mu[((size_t)slot * S->C_alloc + chain) * ld3 + c];

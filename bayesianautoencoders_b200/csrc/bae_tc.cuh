@@ -450,7 +450,8 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         set_split(it, sp);
         // this CTA's share of the pair's 256 x BN tile: 128 rows of A, BN/2 columns of B
         const int m0 = it.tile_m * (2 * kBM) + (int)rank * kBM, n0 = it.tile_n * g.tcBN + (int)rank * (g.tcBN >> 1);
-        const int ca = g.sA ? it.chain : 0, cb = g.sB ? it.chain : 0;
+        // chain coordinate of the tensor maps: activations / deltas are indexed by the slot in the resident chain group
+        const int ca = g.sA ? (g.aAct ? it.chain - c_begin : it.chain) : 0, cb = g.sB ? (g.bAct ? it.chain - c_begin : it.chain) : 0;
         const int dbgf = BAE_DBGF(S);
         const uint32_t bytes = ((dbgf & 64) ? 0u : (uint32_t)kATileBytes) + ((dbgf & 32) ? 0u : (uint32_t)g.tcBBytes);
         const int aMode = g.aMode, bMode = g.bMode, nchB = g.tcBBytes / kMnChunkBytes, nkb = it.nkb, kb0 = it.kb0;
@@ -622,7 +623,7 @@ struct EpiCtx {
 // One tile, specialised by the epilogue kinds of the phase: the body holds only their code around the 128 accumulator
 // registers (a body with all six kinds selected at run time spilled inside the store loop, an L2 round trip per spill).
 template <int kEpi, int kEpiB>
-__device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it, const EpiCtx& c, Smem& sm, Ring& ring, int& ntr) {
+__device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it, const EpiCtx& c, Smem& sm, Ring& ring, int& ntr, int c_begin) {
   const GemmDesc& g = *it.g;
   const int tcBN = g.tcBN;
   const int n0 = it.tile_n * tcBN;
@@ -689,11 +690,12 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
   const int m0 = it.tile_m * (2 * kBM) + (int)c.rank * kBM;   // this CTA's 128 rows of the pair's tile
   // K segments after the first ADD into what this CTA pair stored for the previous ones (same warp, same lane per element)
   const bool accum = (epi == EPI_GRADW) && it.split > 0;
-  float* C = g.C + (size_t)chain * g.sC;   // direct stores: only chunks that straddle the next tile's columns
+  const int slot = chain - c_begin;        // the chain's slot in the resident group (activation / delta buffers)
+  float* C = g.C + (size_t)(g.cAct ? slot : chain) * g.sC;   // direct stores: only chunks that straddle the next tile's columns
   const int ldc = g.ldc;
   const CUtensorMap* mapC = reinterpret_cast<const CUtensorMap*>(S->tmaps) + g.tmIdx[2];
-  const int zC = g.sC ? chain : 0;   // slice of the output tensor map
-  const float* aux = (kHasAux && g.aux) ? g.aux + (size_t)chain * g.sAux : nullptr;
+  const int zC = g.sC ? (g.cAct ? slot : chain) : 0;   // slice of the output tensor map
+  const float* aux = (kHasAux && g.aux) ? g.aux + (size_t)(g.auxAct ? slot : chain) * g.sAux : nullptr;
   const int gM = g.M, ldaux = g.ldaux;
   const int biasCol = (epi == EPI_GRADW) ? g.biasCol : -1;
   float* gbias = (epi == EPI_GRADW && g.gbias) ? g.gbias + (size_t)chain * g.sGb : nullptr;
@@ -859,7 +861,7 @@ __device__ __forceinline__ void gemm_phase_epilogue(const DevState* S, const Pha
     if (!decode_item(S, ph, c_begin, item, it)) continue;
     for (int sp = 0; sp < it.nsplit; ++sp) {
       set_split(it, sp);
-      epilogue_tile<kEpiA, kEpiB>(S, it, c, sm, ring, ntr);
+      epilogue_tile<kEpiA, kEpiB>(S, it, c, sm, ring, ntr, c_begin);
     }
   }
   if (c.lane == 0) bulk_wait_all();   // this warp's box stores are complete before the kernel (or the phase) ends

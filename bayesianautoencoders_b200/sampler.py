@@ -89,7 +89,7 @@ assert TRACE_DTYPE.itemsize == C.sizeof(N.Trace), (TRACE_DTYPE.itemsize, C.sizeo
 
 class DeviceSampler:
     def __init__(self, dims4, train, test, n_chains, n_rungs, samples, temperatures, swap_interval=5,
-                 seed=0xBAE5EED, device=0, chain_id_base=0, hyper: Hyper = None, gemm_path=0):
+                 seed=0xBAE5EED, device=0, chain_id_base=0, hyper: Hyper = None, gemm_path=0, act_group=0):
         self.lib = N.load()
         self.hyper = hyper or Hyper()
         h = self.hyper
@@ -111,6 +111,7 @@ class DeviceSampler:
         cfg.seed = int(seed)
         cfg.gemm_path = int(gemm_path)
         cfg.drift_mode = int(h.drift_mode)
+        cfg.act_group = int(act_group)
         self.cfg = cfg
         self.dims4 = tuple(int(x) for x in dims4)
         self.n_chains, self.n_rungs, self.samples = int(n_chains), int(n_rungs), int(samples)

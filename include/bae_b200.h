@@ -59,6 +59,10 @@ typedef struct bae_config {
                            * 1 = experiment_type = 1: Adam while i <= pt, then a stateless SGD(lr = 0.1) step (MAIN:209-210, 454-470)
                            * 2 = plain-gradient MALA on the tempered log-posterior (not in the reference):
                            *     drift = (step_w^2 / 2) * grad[ loglik(w; tau = exp(eta)) / adapttemp + log prior(w) ] */
+  int32_t act_group;      /* chains whose activation / delta buffers are resident at a time (BASELINE.json configs[4]: 100k rows x
+                           * 2048 features = 7.7 GB of activations per chain). 0 = automatic: all chains if they fit in 70% of the
+                           * free device memory, else as many as fit. The step program then runs group after group. */
+  int32_t reserved;
 } bae_config;
 
 /* Per-step record, one per (chain, iteration): what MAIN:520-592 stores into its trace arrays. */

@@ -35,7 +35,7 @@ def test_struct_layouts_match_header():
     from bayesianautoencoders_b200 import _native as N
     assert C.sizeof(N.Trace) == 152            # 11 doubles + 13 floats + 3 ints
     assert C.sizeof(N.ChainScalars) == 96      # 8 doubles + 6 ints + 1 double
-    assert C.sizeof(N.Config) == 96
+    assert C.sizeof(N.Config) == 104
     assert N.Config.seed.offset % 8 == 0
 
 

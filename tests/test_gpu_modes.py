@@ -89,3 +89,27 @@ def test_posterior_predictive_batch_matches_oracle(shape):
     # the handle's chain state is untouched by the pass: same weights -> same answer twice
     assert np.array_equal(pp.encode(), feats)
     pp.close()
+
+
+@pytest.mark.parametrize("shape", ["mid_fp32", "wide_tc"])
+def test_chain_groups_are_bit_identical(shape):
+    """Chain-group scheduling of the activation buffers (`act_group`; BASELINE.json configs[4] needs it: 7.7 GB of
+    activations per chain): the step program run group after group gives the traces of the all-resident run, bit for bit."""
+    from bayesianautoencoders_b200 import DeviceSampler, default_theta_init
+    dims4, ntr, nte, n, gp, grp = {"mid_fp32": ((24, 20, 16, 12), 96, 40, 3, 0, 2), "wide_tc": ((160, 144, 136, 128), 384, 256, 4, 2, 3)}[shape]
+    train, test = synth_data(dims4, ntr, nte)
+    L = bo.Layout(dims4)
+    temps = bo.temperature_ladder(n, 2)
+    runs = []
+    for act_group in (0, grp, 1):
+        s = DeviceSampler(dims4, train, test, n, n, 10, temps, swap_interval=5, seed=9, gemm_path=gp, act_group=act_group)
+        rng = np.random.default_rng(2)
+        for j in range(n):
+            s.init_chain(j, default_theta_init(dims4, rng), rng.standard_normal(L.w_size))
+        s.run(10)
+        s.synchronize()
+        fa = s.forward_all(1)
+        runs.append(([s.traces(j, 0, 10).tobytes() for j in range(n)], [s.get_state(j)["theta"].tobytes() for j in range(n)],
+                     fa["features"].tobytes(), fa["recon"].tobytes(), s.swap_counts()))
+        s.close()
+    assert runs[0] == runs[1] == runs[2]

@@ -1,0 +1,73 @@
+"""BASELINE.json configs[4]: synthetic 2048-feature autoencoder (hidden widths 1792-1536-1280: the Madelon ratios in
+multiples of 256), 100 000 rows - the scaling-stress shape of the tensor-core path.
+
+* parity on a row-subsampled case (1024 rows; the float64 oracle needs seconds there, hours at 100k rows): forward /
+  backward through the parity probe and one teacher-forced iteration;
+* at the full 100 000 rows: size-independent properties - determinism, the chain sits at its last proposal, chain groups
+  (activations of one chain resident at a time) - with weight-gradient contractions of 157 K segments per tile."""
+import numpy as np
+import pytest
+
+from oracle import bae_oracle as bo
+from tests.parity_util import rel, run_teacher_forced, synth_data
+
+pytestmark = pytest.mark.gpu
+DIMS4 = (2048, 1792, 1536, 1280)
+
+
+def test_stress_widths_forward_backward_and_one_iteration_match_oracle():
+    from bayesianautoencoders_b200 import DeviceSampler, default_theta_init
+    ntr, nte = 1024, 256
+    train, test = synth_data(DIMS4, ntr, nte)
+    L = bo.Layout(DIMS4)
+    assert L.n_trainable == 16_797_952 - 0 or L.n_trainable > 16_000_000
+    s = DeviceSampler(DIMS4, train, test, 1, 1, 4, [1.0], gemm_path=2)
+    assert s.gemm_path() == 2
+    rng = np.random.default_rng(3)
+    w = (rng.standard_normal(L.w_size) * 0.05).astype(np.float32)      # |W x| ~ 1: unsaturated sigmoids
+    w[L.nbt_index] = 2.0
+    r = s.eval(0, 0, w=w, grads=True)
+    th = w.astype(np.float64)
+    out, cache = bo.forward(L, th, train.astype(np.float64), update_buffers=False)
+    g = bo.backward(L, th, cache)
+    sse = float(np.sum((out - train) ** 2))
+    assert abs(r["sse"] - sse) <= 1e-5 * sse
+    assert rel(r["grads"], g) <= 3e-5, rel(r["grads"], g)             # tensor-core tolerance, see test_gpu_step_parity.TOL_MADELON_TC
+    s.close()
+    th0 = [default_theta_init(DIMS4, rng)]
+    w0 = [rng.standard_normal(L.w_size)]
+    rep, _ = run_teacher_forced(DIMS4, train, test, [1.3], 4, 5, th0, w0, n_rungs=1, seed=11, n_run=2, gemm_path=2)
+    e = {k: np.asarray(v) for k, v in rep["errors"].items()}
+    assert max(e["lik_prop"].max(), e["lik"].max()) <= 1e-5, (e["lik_prop"], e["lik"])
+    assert max(e["mse_train"].max(), e["mse_test"].max()) <= 1e-5
+    assert e["grad"].max() <= 3e-5, e["grad"]
+    assert e["sum_value"].max() <= 3e-5, e["sum_value"]
+    for j, i, margin, a, b in rep["decisions"]:
+        assert a == b or margin < 1e-4
+
+
+def test_stress_shape_full_rows_properties():
+    from bayesianautoencoders_b200 import DeviceSampler, default_theta_init
+    ntr, nte = 100_000, 256
+    train, test = synth_data(DIMS4, ntr, nte)
+    L = bo.Layout(DIMS4)
+    temps = np.array([1.0, 2.0])
+    runs = []
+    for rep in range(2):
+        s = DeviceSampler(DIMS4, train, test, 2, 2, 4, temps, swap_interval=2, seed=5, gemm_path=2, act_group=1)
+        rng = np.random.default_rng(1)
+        for j in range(2):
+            s.init_chain(j, default_theta_init(DIMS4, rng), rng.standard_normal(L.w_size) * 0.05)
+        s.run(2)
+        s.synchronize()
+        tr = [s.traces(j, 0, 2) for j in range(2)]
+        runs.append([t.tobytes() for t in tr])
+        if rep == 0:
+            st = s.get_state(0)
+            r = s.eval(0, 0, w=st["theta"] if st["w_is_alias"] else st["w"])
+            assert abs(r["sse"] - st["last_sse_train"]) <= 1e-6 * r["sse"]     # the chain sits at its last proposal
+            for t in tr:
+                assert np.all(np.isfinite(t["sum_value"])) and np.all(np.isfinite(t["likelihood_proposal"]))
+                assert np.all(t["mse_train_proposal"] > 0)
+        s.close()
+    assert runs[0] == runs[1]
