@@ -28,6 +28,9 @@ SHAPES = {
     "madelon": ((500, 450, 400, 300), 2000, 1800),
     "coil": ((85, 70, 60, 50), 4366, 1456),
     "swiss": ((3, 10, 5, 2), 3750, 1250),
+    # BASELINE.json configs[4]: synthetic 2048-feature, 100k-row autoencoder; hidden widths = the Madelon ratios in multiples of
+    # 256; BASELINE names no test set: a token 256-row test matrix keeps the step program unchanged
+    "stress2048": ((2048, 1792, 1536, 1280), 100000, 256),
 }
 METRIC = "pt_langevin_chain_steps_per_sec"
 UNIT = "chain-steps/s"
@@ -438,21 +441,25 @@ def run_gpu(args):
     # 8-rung ladder, cut over the GPUs when N > 1 (strong scaling of a latency-bound job: reported, not the scaling claim)
     extra = []
     if not args.no_extra:
-        for xshape in ("swiss", "coil", "madelon"):
-            xjob = PtJob(xshape, 1, N_RUNGS, world, rank, local, world > 1, comm, 0, samples=4000)
-            xsteps = 40 if xshape != "madelon" else 10
+        for xshape in ("swiss", "coil", "madelon", "stress2048"):
+            if xshape == "stress2048" and args.no_stress:
+                continue
+            xjob = PtJob(xshape, 1, N_RUNGS, world, rank, local, world > 1, comm, 0, samples=4000 if xshape != "stress2048" else 64)
+            xsteps = {"swiss": 40, "coil": 40, "madelon": 10, "stress2048": 2}[xshape]
             if world > 1:
                 for _ in range(2):
                     xjob.pt_round()
-            xms = timed_rounds(xjob, xsteps, 3, barrier, dist, world)
+            xms = timed_rounds(xjob, xsteps, 3 if xshape != "stress2048" else 1, barrier, dist, world)
             xk = []
+            nk = 3 if xshape != "stress2048" else 1
             if world == 1:
-                for _ in range(3):
+                for _ in range(nk):
                     xjob.pt_round()
                     xk.append(xjob.s.last_ms())
-            xroof = roofline_block(xjob, float(np.mean(xk)), 3, False) if xk else None
+            xroof = roofline_block(xjob, float(np.mean(xk)), nk, False) if xk else None
             extra.append({"workload": f"{xshape} shape, 8 replicas = one 8-rung ladder" + (f" cut over {world} GPUs" if world > 1 else "") +
-                                      f" (BASELINE.json configs[{['swiss', 'coil', 'madelon'].index(xshape)}])",
+                                      f" (BASELINE.json configs[{ {'swiss': 0, 'coil': 1, 'madelon': 2, 'stress2048': 4}[xshape] }]" +
+                                      (": 2048-1792-1536-1280, 100 000 rows, 8 of the 1024 replicas" if xshape == "stress2048" else "") + ")",
                           "metric": METRIC, "value": N_RUNGS * xsteps * SWAP_INTERVAL / (xms / 1000.0), "unit": UNIT, "n_gpus": world,
                           "ms_per_step": xms / xsteps, "steps": xsteps, "scaling": "strong",
                           "gemm_path": xjob.s.gemm_path(), "roofline": xroof})
@@ -509,6 +516,7 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=2, help="iterations per replica process in the CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the Swiss / Coil / Madelon 8-replica lines (extra_configs)")
+    ap.add_argument("--no-stress", action="store_true", help="skip the 2048-feature / 100k-row line of extra_configs (about 25 s)")
     ap.add_argument("--ladder", default="sharded", choices=["sharded", "local"],
                     help="N > 1: 'sharded' cuts every ladder across the GPUs (NCCL exchange), 'local' keeps whole ensembles per GPU")
     args = ap.parse_args()
