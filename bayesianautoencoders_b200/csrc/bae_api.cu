@@ -30,6 +30,8 @@ cudaError_t launch_grad_reduce(const DevState* dS, int chain, cudaStream_t st);
 cudaError_t launch_debug_draws(const DevState* dS, int chain, int step, float* noise, double* scalars, cudaStream_t st);
 cudaError_t launch_debug_swap_u(const DevState* dS, int ens, int round, int pair, double* out, cudaStream_t st);
 cudaError_t launch_scalars(const DevState* dS, int chain, bae_chain_scalars* staged, int put, cudaStream_t st);
+bool narrow_supported(const int dims[4], int n_train, int n_test, int p_used);
+cudaError_t launch_narrow(const DevState* dS, int n_chains, int cluster, int n_iter, int p_used, cudaStream_t st);
 cudaError_t launch_xtable(const DevState* dS, cudaStream_t st);
 cudaError_t launch_xsweep(const DevState* dS, cudaStream_t st);
 cudaError_t launch_xgather(const DevState* dS, int grid, cudaStream_t st);
@@ -91,6 +93,10 @@ struct bae_handle {
   std::vector<int32_t> xops;
   int64_t vectors_sent = 0;
   int n_sms = 148;
+  // narrow-width step kernel (bae_narrow.cu): one thread-block cluster per chain
+  bool narrow = false;
+  int narrow_cluster = 1, p_used = 0;
+  long long host_step = 0;   // iterations executed since the chains were initialised (all chains advance together)
   int64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
@@ -631,6 +637,14 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   }
   s.shard_rank = 0; s.shard_world = 1;
   h->n_sms = prop.multiProcessorCount;
+  {
+    const Seg& last = s.seg[kNumSegs - 1];
+    h->p_used = last.pad_off + round_up(last.rows * last.ld, 32);
+    const bool off = getenv("BAE_NO_NARROW") && getenv("BAE_NO_NARROW")[0] == '1';
+    h->narrow = !off && !s.tc && cfg->gemm_path != 1 && s.drift_mode == 0 && narrow_supported(cfg->dims, cfg->n_train, cfg->n_test, h->p_used);
+    // few chains: more CTAs per chain (the rows of the data set are cut over the cluster); many chains: one CTA each
+    h->narrow_cluster = s.C <= 16 ? 8 : (s.C <= 32 ? 4 : (s.C <= 64 ? 2 : 1));
+  }
   CU(dalloc(h, &s.traces, (size_t)s.C * s.samples));
   CU(dalloc(h, &s.swap_src, CA)); CU(dalloc(h, &s.swap_flag, CA)); CU(dalloc(h, &s.swap_tmp, CA * 2));
   CU(dalloc(h, &s.num_swap, 1)); CU(dalloc(h, &s.total_swap, 1));
@@ -644,7 +658,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   if (s.dbg_flags != 0)
     return fail(BAE_ERR_INVALID, "BAE_TC_DBGFLAGS is set, but this library was built without -DBAE_TC_DEBUG: refusing to sample");
 #endif
-  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED"})
+  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW"})
     if (getenv(knob)) fprintf(stderr, "[bae_b200] note: tuning variable %s=%s is in effect for this handle\n", knob, getenv(knob));
   s.dbg_phase = getenv("BAE_TC_TRACE_PHASE") ? atoi(getenv("BAE_TC_TRACE_PHASE")) : -1;
   {
@@ -706,6 +720,7 @@ int bae_destroy(bae_handle* h) {
 int bae_w_size(const bae_handle* h) { return h ? h->hs.w_size : BAE_ERR_INVALID; }
 int bae_n_trainable(const bae_handle* h) { return h ? h->hs.w_size - h->hs.nbuf : BAE_ERR_INVALID; }
 int bae_gemm_path(const bae_handle* h) { return h ? (h->hs.tc ? 2 : 1) : BAE_ERR_INVALID; }
+int bae_step_kernel(const bae_handle* h) { return h ? (h->narrow ? 3 : (h->hs.tc ? 2 : 1)) : BAE_ERR_INVALID; }
 void* bae_stream(bae_handle* h) { return h ? (void*)h->stream : nullptr; }
 int64_t bae_launch_count(const bae_handle* h) { return h ? h->launches : 0; }
 
@@ -874,7 +889,7 @@ int bae_init_chain(bae_handle* h, int chain, const float* theta_init, const doub
   memset(&sc, 0, sizeof(sc));
   sc.eta = eta; sc.likelihood = lik; sc.prior_current = prior; sc.last_sse_train = sse; sc.prop_sse_train = sse;
   sc.temperature = T; sc.adapttemp = T; sc.w_is_alias = 1;
-  return bae_set_state(h, chain, nullptr, nullptr, nullptr, nullptr, &sc);
+  return bae_set_state(h, chain, nullptr, nullptr, nullptr, nullptr, &sc);   // (sets the host's iteration mirror to 0)
 }
 
 int bae_get_state(bae_handle* h, int chain, float* theta, float* w, float* m, float* v, bae_chain_scalars* sc) {
@@ -934,6 +949,7 @@ int bae_set_state(bae_handle* h, int chain, const float* theta, const float* w, 
     CU(cudaStreamSynchronize(h->stream));
   }
   if (sc) {
+    h->host_step = sc->step;   // all chains of a handle advance together (bae_step / bae_run)
     CU(cudaMemcpyAsync(h->stage_sc, sc, sizeof(bae_chain_scalars), cudaMemcpyHostToDevice, h->stream));
     CU(launch_scalars(h->dS, chain, h->stage_sc, 1, h->stream));
     h->launches++;
@@ -964,6 +980,28 @@ static int coop_launch(bae_handle* h, int p_begin, int p_end, int n_rep, int for
   CU(cudaSetDevice(h->device));
   CU(cudaEventRecord(h->ev0, h->stream));
   const int C = h->hs.C, G = h->hs.G;
+  if (h->narrow && p_begin == P_PRO && p_end > P_EPI) {
+    // narrow-width shapes: the iterations between two exchange rounds are ONE launch of the cluster kernel; the exchange
+    // sweep (gated on the device's step counter like everywhere) is the generic swap phase program
+    const bool with_swap = p_end > P_SWAP;
+    const int si = h->hs.swap_interval;
+    int left = n_rep;
+    while (left > 0) {
+      const int k = with_swap ? (int)std::min<long long>(left, si - h->host_step % si) : left;
+      CU(launch_narrow(h->dS, C, h->narrow_cluster, k, h->p_used, h->stream));
+      h->launches++;
+      h->host_step += k;
+      left -= k;
+      if (with_swap && h->host_step % si == 0) {
+        CU(launch_program(h->dS, 0, h->grid, P_SWAP, P_END, 1, 0, C, force_swap, h->stream));
+        h->launches++;
+      }
+    }
+    CU(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    return BAE_OK;
+  }
+  if (p_begin == P_PRO && p_end > P_EPI) h->host_step += n_rep;
   if (h->phase_launch) {
     // One launch per phase (the exchange phases test the step counter on the device, like the persistent kernel); the
     // launches of a call are captured once into a CUDA graph and replayed.

@@ -208,6 +208,10 @@ class DeviceSampler:
     def gemm_path(self):
         return int(self.lib.bae_gemm_path(self._h))
 
+    def step_kernel(self):
+        """1 = persistent FP32 tile kernel, 2 = tcgen05 phase program, 3 = narrow-width cluster kernel."""
+        return int(self.lib.bae_step_kernel(self._h))
+
     def traces(self, chain, first=0, n=None):
         n = self.samples - first if n is None else n
         out = np.zeros(n, dtype=TRACE_DTYPE)
