@@ -32,6 +32,7 @@ cudaError_t launch_debug_swap_u(const DevState* dS, int ens, int round, int pair
 cudaError_t launch_scalars(const DevState* dS, int chain, bae_chain_scalars* staged, int put, cudaStream_t st);
 bool narrow_supported(const int dims[4], int n_train, int n_test, int p_used);
 cudaError_t launch_narrow(const DevState* dS, int n_chains, int cluster, int n_iter, int p_used, cudaStream_t st);
+cudaError_t launch_swap_cta(const DevState* dS, int force_swap, cudaStream_t st);
 cudaError_t launch_xtable(const DevState* dS, cudaStream_t st);
 cudaError_t launch_xsweep(const DevState* dS, cudaStream_t st);
 cudaError_t launch_xgather(const DevState* dS, int grid, cudaStream_t st);
@@ -644,6 +645,10 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     h->narrow = !off && !s.tc && cfg->gemm_path != 1 && s.drift_mode == 0 && narrow_supported(cfg->dims, cfg->n_train, cfg->n_test, h->p_used);
     // few chains: more CTAs per chain (the rows of the data set are cut over the cluster); many chains: one CTA each
     h->narrow_cluster = s.C <= 16 ? 8 : (s.C <= 32 ? 4 : (s.C <= 64 ? 2 : 1));
+    if (const char* e = getenv("BAE_NARROW_CLUSTER")) {
+      const int v = atoi(e);
+      if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) h->narrow_cluster = v;
+    }
   }
   CU(dalloc(h, &s.traces, (size_t)s.C * s.samples));
   CU(dalloc(h, &s.swap_src, CA)); CU(dalloc(h, &s.swap_flag, CA)); CU(dalloc(h, &s.swap_tmp, CA * 2));
@@ -658,7 +663,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   if (s.dbg_flags != 0)
     return fail(BAE_ERR_INVALID, "BAE_TC_DBGFLAGS is set, but this library was built without -DBAE_TC_DEBUG: refusing to sample");
 #endif
-  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW"})
+  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW", "BAE_NARROW_CLUSTER"})
     if (getenv(knob)) fprintf(stderr, "[bae_b200] note: tuning variable %s=%s is in effect for this handle\n", knob, getenv(knob));
   s.dbg_phase = getenv("BAE_TC_TRACE_PHASE") ? atoi(getenv("BAE_TC_TRACE_PHASE")) : -1;
   {
@@ -993,7 +998,8 @@ static int coop_launch(bae_handle* h, int p_begin, int p_end, int n_rep, int for
       h->host_step += k;
       left -= k;
       if (with_swap && h->host_step % si == 0) {
-        CU(launch_program(h->dS, 0, h->grid, P_SWAP, P_END, 1, 0, C, force_swap, h->stream));
+        if (C <= 16) CU(launch_swap_cta(h->dS, force_swap, h->stream));   // the three exchange phases in one CTA
+        else CU(launch_program(h->dS, 0, h->grid, P_SWAP, P_END, 1, 0, C, force_swap, h->stream));
         h->launches++;
       }
     }

@@ -1534,6 +1534,23 @@ bae_phase_kernel(const DevState* __restrict__ S, int pi, int c_begin, int c_end,
   run_phase<true>(S, pi, c_begin, c_end, force_swap, smem, red);
 }
 
+// The three exchange phases in ONE CTA (few chains, small parameter vectors: the narrow-width step kernel's companion) -
+// no cooperative launch, no grid barriers.
+__global__ void __launch_bounds__(kThreads, 1) bae_swap_cta_kernel(const DevState* __restrict__ S, int force_swap) {
+  load_seg_table(S);
+  if (!force_swap) {
+    const int st = S->ch.step[0];
+    if (st == 0 || (st % S->swap_interval) != 0) return;
+  }
+  run_swap_decide(S);
+  __threadfence_block();
+  __syncthreads();
+  run_swap_gather(S);
+  __threadfence_block();
+  __syncthreads();
+  run_swap_scatter(S);
+}
+
 // Non-GEMM phases of the tcgen05 path when every phase is its own launch (the default there): plain 256-thread CTAs,
 // several per SM and with an L1 behind them, instead of the two epilogue warpgroups of the 1-CTA-per-SM tile engine.
 // One kernel per phase family, so that each gets its own register allocation.
@@ -1851,6 +1868,11 @@ cudaError_t launch_aux(const DevState* dS, int kind, int grid, int pi, int c_beg
     case AUX_BN: bae_aux_kernel<AUX_BN><<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end, force_swap); break;
     default: bae_aux_kernel<AUX_MISC><<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end, force_swap); break;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_swap_cta(const DevState* dS, int force_swap, cudaStream_t st) {
+  bae_swap_cta_kernel<<<1, kThreads, 0, st>>>(dS, force_swap);
   return cudaGetLastError();
 }
 

@@ -10,10 +10,11 @@
 //   `n_iter` iterations per launch (the exchange sweep between launches is the generic swap phase program)
 //
 // One forward / backward over this CTA's rows (a drift call, MAIN:208-226):
-//   pass A  x -> h1 -> h2 -> z per row, z kept in shared memory; sum z, then sum (z - mean)^2 (two-pass batch statistics
-//           in FP64)                                                                        [2 cluster reductions]
+//   pass A  x -> h1 -> h2 -> z per row, z kept in shared memory; sum z and sum z^2 in FP64 (batch statistics)
+//                                                                                           [1 cluster reduction]
 //   pass B  z -> BatchNorm -> h4 -> h5 -> out, loss, deltas back to dy, in chunks of 256 rows: per-row values are staged
-//           in shared memory and every decoder parameter is a dot product over the staged rows (one thread per parameter);
+//           in shared memory and the decoder parameters are dot products over the staged rows (a thread = one delta column
+//           x four activation columns x 64 rows: one scalar and one 16-byte shared-memory load per four FMAs);
 //           sum dy, sum dy * zhat (BatchNorm backward and the gamma / beta gradients), SSE   [1 cluster reduction]
 //   pass C  dz from the BatchNorm backward formula, deltas back to layer 1 (h1, h2 recomputed from x), encoder parameters
 //           as dot products; the per-CTA partial gradient of all parameters                 [1 cluster reduction]
@@ -37,7 +38,8 @@ constexpr float kBnEps = 1e-5f, kBnMom = 0.1f, kB1 = 0.9f, kB2 = 0.999f, kAdamEp
 
 __host__ __device__ constexpr int r4(int x) { return (x + 3) / 4 * 4; }
 
-__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + expf(-x)); }
+// same form as the tensor-core epilogue (bae_tc.cuh): two MUFU operations
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
 struct SegN { int pad_off, span, cols, ld, trainable; };
 
@@ -52,9 +54,14 @@ struct ChainSm {
 template <int D0, int D1, int D2, int D3>
 struct Smem {
   static constexpr int NB = 2 * D3 + 1;
-  static constexpr int SW = 2 * D0 + 2 * D1 + 2 * D2 + 2 * D3 + 2;   // staged floats per row (max of the two passes) + ones column, even
+  // staged floats per row: three delta blocks and three [activation | 1] blocks, each padded to a multiple of 4 floats
+  static constexpr int SWB = r4(D0) + r4(D1) + r4(D2) + r4(D1 + 1) + r4(D2 + 1) + r4(D3 + 1);
+  static constexpr int SWC = r4(D3) + r4(D2) + r4(D1) + r4(D2) + r4(D1 + 1) + r4(D0 + 1);
+  static constexpr int SW0 = SWB > SWC ? SWB : SWC;
+  static constexpr int SW = (SW0 % 32 == 20) ? SW0 : SW0 + ((20 - SW0 % 32 + 32) % 32);   // pitch = 20 mod 32 floats: 16-byte row stores of a warp hit distinct banks
   float th[kMaxP], m[kMaxP], v[kMaxP], wc[kMaxP], grad[kMaxP];
   float gpart[2][kMaxP];   // this CTA's partial gradient, double-buffered; the peers read it through DSMEM
+  float dotq[4][kMaxP];    // dot-product partials of the four 64-row groups of the staged chunks
   double dpart[2][8];      // this CTA's partial FP64 sums, double-buffered
   double dsum[8];          // cluster totals
   double red[64];          // block reduction scratch
@@ -64,7 +71,7 @@ struct Smem {
   ChainSm c;
   float zs[kMaxRows * D3];
   float dys[kMaxRows * D3];
-  float stage[kT * SW];
+  alignas(16) float stage[kT * SW];
 };
 
 // ---- reductions ------------------------------------------------------------------------------------------------
@@ -161,49 +168,68 @@ __device__ __forceinline__ int find_seg(const SM& sm, int p) {
 }
 
 // =====================================================================================================================
+// 16-byte stores of one block of a staged row: the N values, a 1.0 when the block carries the ones column (bias gradients),
+// zeros up to the next multiple of 4
+template <int N, bool ONE>
+__device__ __forceinline__ void store_block(float* __restrict__ st, const float (&v)[N]) {
+  constexpr int W = r4(N + (ONE ? 1 : 0));
+  float t[W];
+#pragma unroll
+  for (int i = 0; i < W; ++i) t[i] = i < N ? v[i] : ((ONE && i == N) ? 1.0f : 0.0f);
+#pragma unroll
+  for (int i = 0; i < W; i += 4) *reinterpret_cast<float4*>(st + i) = make_float4(t[i], t[i + 1], t[i + 2], t[i + 3]);
+}
+
 template <int D0, int D1, int D2, int D3>
 struct Net {
   using SM = Smem<D0, D1, D2, D3>;
   static constexpr int SW = SM::SW;
-  // staged columns, pass B (decoder): dout | h5 | d5 | h4 | d4 | y | 1      pass C (encoder): dz | h2 | d2 | h1 | d1 | x | 1
-  static constexpr int B_DOUT = 0, B_H5 = D0, B_D5 = D0 + D1, B_H4 = D0 + 2 * D1, B_D4 = D0 + 2 * D1 + D2, B_Y = D0 + 2 * D1 + 2 * D2,
-                       B_ONE = D0 + 2 * D1 + 2 * D2 + D3;
-  static constexpr int C_DZ = 0, C_H2 = D3, C_D2 = D3 + D2, C_H1 = D3 + 2 * D2, C_D1 = D3 + 2 * D2 + D1, C_X = D3 + 2 * D2 + 2 * D1,
-                       C_ONE = D3 + 2 * D2 + 2 * D1 + D0;
-  static constexpr int ND = D0 * D1 + D0 + D1 * D2 + D1 + D2 * D3 + D2;   // decoder entries produced by dot products (gamma / beta come from the sums)
-  static constexpr int NE = D3 * D2 + D2 * D1 + D2 + D1 * D0 + D1;         // encoder entries (encode.4.bias has an exactly zero gradient)
-  static_assert(ND <= kT && NE <= kT, "one thread per parameter in the dot phases");
-  static_assert(B_ONE < SW && C_ONE < SW, "stage width");
+  // staged row of pass B (decoder): dout | d5 | d4 | [h5 1] | [h4 1] | [y 1]      pass C (encoder): dz | d2 | d1 | h2 | [h1 1] | [x 1]
+  static constexpr int B_DOUT = 0, B_D5 = r4(D0), B_D4 = B_D5 + r4(D1), B_H5 = B_D4 + r4(D2), B_H4 = B_H5 + r4(D1 + 1), B_Y = B_H4 + r4(D2 + 1);
+  static constexpr int C_DZ = 0, C_D2 = r4(D3), C_D1 = C_D2 + r4(D2), C_H2 = C_D1 + r4(D1), C_H1 = C_H2 + r4(D2), C_X = C_H1 + r4(D1 + 1);
+  __host__ __device__ static constexpr int q4(int n) { return (n + 3) / 4; }
+  // A dot GROUP = one delta column (a) times one 4-float block of an [activation | 1] block (b): four gradient entries of one
+  // weight row (the ones column yields the bias gradient). A thread takes one group over the 64 rows of one row group.
+  static constexpr int GD0 = D0 * q4(D1 + 1), GD1 = D1 * q4(D2 + 1), GD2 = D2 * q4(D3 + 1), GD = GD0 + GD1 + GD2;   // W6|b6, W5|b5, W4|b4
+  static constexpr int GE0 = D3 * q4(D2), GE1 = D2 * q4(D1 + 1), GE2 = D1 * q4(D0 + 1), GE = GE0 + GE1 + GE2;       // W3, W2|b2, W1|b1
+  static_assert(GD <= 64 && GE <= 64, "64 groups x 4 row groups = 256 threads");
+  static_assert(SM::SWB <= SW && SM::SWC <= SW && SW % 4 == 0, "stage width");
 
-  // which staged columns parameter `p` of the decoder / encoder list multiplies, and where its gradient goes (padded offset)
-  struct Dot { int a, b, dst; };
-  __device__ static Dot dec_dot(const SM& sm, int p) {
-    Dot d{0, 0, -1};
-    if (p < D0 * D1) { d = {B_DOUT + p / D1, B_H5 + p % D1, sm.seg[SEG_D5_W].pad_off + (p / D1) * r4(D1) + p % D1}; return d; }
-    p -= D0 * D1;
-    if (p < D0) { d = {B_DOUT + p, B_ONE, sm.seg[SEG_D5_B].pad_off + p}; return d; }
-    p -= D0;
-    if (p < D1 * D2) { d = {B_D5 + p / D2, B_H4 + p % D2, sm.seg[SEG_D3_W].pad_off + (p / D2) * r4(D2) + p % D2}; return d; }
-    p -= D1 * D2;
-    if (p < D1) { d = {B_D5 + p, B_ONE, sm.seg[SEG_D3_B].pad_off + p}; return d; }
-    p -= D1;
-    if (p < D2 * D3) { d = {B_D4 + p / D3, B_Y + p % D3, sm.seg[SEG_D1_W].pad_off + (p / D3) * r4(D3) + p % D3}; return d; }
-    p -= D2 * D3;
-    if (p < D2) { d = {B_D4 + p, B_ONE, sm.seg[SEG_D1_B].pad_off + p}; return d; }
+  struct Dot { int a, b, dst[4]; };
+  __device__ static void fill(Dot& d, int g, int nb, int NI, int acol0, int bcol0, int w_off, int b_off) {
+    const int o = g / nb, jb = g % nb;
+    d.a = acol0 + o;
+    d.b = bcol0 + jb * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = jb * 4 + j;
+      d.dst[j] = i < NI ? w_off + o * r4(NI) + i : ((i == NI && b_off >= 0) ? b_off + o : -1);
+    }
+  }
+  __device__ static Dot dec_dot(const SM& sm, int g) {
+    Dot d{0, 0, {-1, -1, -1, -1}};
+    if (g < GD0) fill(d, g, q4(D1 + 1), D1, B_DOUT, B_H5, sm.seg[SEG_D5_W].pad_off, sm.seg[SEG_D5_B].pad_off);
+    else if (g < GD0 + GD1) fill(d, g - GD0, q4(D2 + 1), D2, B_D5, B_H4, sm.seg[SEG_D3_W].pad_off, sm.seg[SEG_D3_B].pad_off);
+    else if (g < GD) fill(d, g - GD0 - GD1, q4(D3 + 1), D3, B_D4, B_Y, sm.seg[SEG_D1_W].pad_off, sm.seg[SEG_D1_B].pad_off);
     return d;
   }
-  __device__ static Dot enc_dot(const SM& sm, int p) {
-    Dot d{0, 0, -1};
-    if (p < D3 * D2) { d = {C_DZ + p / D2, C_H2 + p % D2, sm.seg[SEG_E4_W].pad_off + (p / D2) * r4(D2) + p % D2}; return d; }
-    p -= D3 * D2;
-    if (p < D2 * D1) { d = {C_D2 + p / D1, C_H1 + p % D1, sm.seg[SEG_E2_W].pad_off + (p / D1) * r4(D1) + p % D1}; return d; }
-    p -= D2 * D1;
-    if (p < D2) { d = {C_D2 + p, C_ONE, sm.seg[SEG_E2_B].pad_off + p}; return d; }
-    p -= D2;
-    if (p < D1 * D0) { d = {C_D1 + p / D0, C_X + p % D0, sm.seg[SEG_E0_W].pad_off + (p / D0) * r4(D0) + p % D0}; return d; }
-    p -= D1 * D0;
-    if (p < D1) { d = {C_D1 + p, C_ONE, sm.seg[SEG_E0_B].pad_off + p}; return d; }
+  __device__ static Dot enc_dot(const SM& sm, int g) {
+    Dot d{0, 0, {-1, -1, -1, -1}};
+    if (g < GE0) fill(d, g, q4(D2), D2, C_DZ, C_H2, sm.seg[SEG_E4_W].pad_off, -1);   // encode.4.bias: gradient exactly 0 (BatchNorm removes it)
+    else if (g < GE0 + GE1) fill(d, g - GE0, q4(D1 + 1), D1, C_D2, C_H1, sm.seg[SEG_E2_W].pad_off, sm.seg[SEG_E2_B].pad_off);
+    else if (g < GE) fill(d, g - GE0 - GE1, q4(D0 + 1), D0, C_D1, C_X, sm.seg[SEG_E0_W].pad_off, sm.seg[SEG_E0_B].pad_off);
     return d;
+  }
+  // 64 staged rows of this thread's row group: acc[j] += a * b[j]
+  __device__ static __forceinline__ void dot64(const float* __restrict__ stage, const Dot& d, float (&acc)[4]) {
+    const float* a = stage + (threadIdx.x >> 6) * 64 * SW + d.a;
+    const float* b = stage + (threadIdx.x >> 6) * 64 * SW + d.b;
+#pragma unroll 8
+    for (int k = 0; k < 64; ++k) {
+      const float av = a[k * SW];
+      const float4 bv = *reinterpret_cast<const float4*>(b + k * SW);
+      acc[0] = fmaf(av, bv.x, acc[0]); acc[1] = fmaf(av, bv.y, acc[1]); acc[2] = fmaf(av, bv.z, acc[2]); acc[3] = fmaf(av, bv.w, acc[3]);
+    }
   }
 
   __device__ static void encoder(const SM& sm, const float (&x)[D0], float (&h1)[D1], float (&h2)[D2], float (&z)[D3]) {
@@ -213,58 +239,52 @@ struct Net {
   }
 
   // Forward (and backward when `back`) of the rows [r0, r1) of X [n_rows x D0] (pitch ldx) at the weights in sm.th.
-  // Leaves: batch statistics in sm.mu / sm.var [slot] and sm.inv; cluster totals sm.dsum[0] = SSE (and, with `back`, the
-  // full gradient in sm.grad). `buf_d` / `buf_g` are the double-buffer indices of the cluster reductions.
+  // Leaves: batch statistics in sm.mu / sm.var [slot] and sm.inv; cluster total sm.dsum[0] = SSE; with `back` the full
+  // gradient in sm.grad. `buf_d` / `buf_g` are the double-buffer indices of the cluster reductions.
   __device__ static void pass(cg::cluster_group& cl, SM& sm, const float* __restrict__ X, int ldx, int n_rows, int r0, int r1, int slot,
                               bool back, int& buf_d, int& buf_g) {
     const int tid = threadIdx.x;
     const int nr = r1 - r0;
-    // ---- pass A: z of every row, batch statistics (two passes, FP64 accumulators, as run_bn_fwd)
+    // ---- pass A: z of every row; batch statistics from sum z and sum z^2 in FP64
     {
-      double sz[D3];
+      double sz[2 * D3];
 #pragma unroll
-      for (int c = 0; c < D3; ++c) sz[c] = 0.0;
+      for (int c = 0; c < 2 * D3; ++c) sz[c] = 0.0;
       for (int r = tid; r < nr; r += kT) {
         float x[D0], h1[D1], h2[D2], z[D3];
 #pragma unroll
         for (int i = 0; i < D0; ++i) x[i] = __ldg(&X[(size_t)(r0 + r) * ldx + i]);
         encoder(sm, x, h1, h2, z);
 #pragma unroll
-        for (int c = 0; c < D3; ++c) { sm.zs[r * D3 + c] = z[c]; sz[c] += (double)z[c]; }
-      }
-      block_sum<D3>(sz, sm.red);
-      cluster_sum(cl, sm, sz, D3, buf_d);
-      float mean[D3];
-#pragma unroll
-      for (int c = 0; c < D3; ++c) mean[c] = (float)(sm.dsum[c] / n_rows);
-      double sq[D3];
-#pragma unroll
-      for (int c = 0; c < D3; ++c) sq[c] = 0.0;
-      for (int r = tid; r < nr; r += kT)
-#pragma unroll
         for (int c = 0; c < D3; ++c) {
-          const float dz = sm.zs[r * D3 + c] - mean[c];
-          sq[c] += (double)dz * (double)dz;
+          sm.zs[r * D3 + c] = z[c];
+          sz[c] += (double)z[c];
+          sz[D3 + c] += (double)z[c] * (double)z[c];
         }
-      block_sum<D3>(sq, sm.red);
-      cluster_sum(cl, sm, sq, D3, buf_d);
+      }
+      block_sum<2 * D3>(sz, sm.red);
+      cluster_sum(cl, sm, sz, 2 * D3, buf_d);
       if (tid < D3) {
-        const float var = (float)(sm.dsum[tid] / n_rows);
-        sm.mu[slot][tid] = mean[tid];
+        const double mean = sm.dsum[tid] / n_rows;
+        const float var = (float)fmax(sm.dsum[D3 + tid] / n_rows - mean * mean, 0.0);   // biased batch variance
+        sm.mu[slot][tid] = (float)mean;
         sm.var[slot][tid] = var;
         sm.inv[tid] = 1.0f / sqrtf(var + kBnEps);
       }
+      if (back)
+        for (int i = tid; i < 4 * kMaxP; i += kT) (&sm.dotq[0][0])[i] = 0.f;
       __syncthreads();
     }
     const float* gam = sm.th + sm.seg[SEG_BN_W].pad_off;
     const float* bet = sm.th + sm.seg[SEG_BN_BIAS].pad_off;
     const float scale = 2.0f / ((float)n_rows * (float)D0);   // d MSELoss / d out (mean over all N*d0 elements, MAIN:150,223)
-    // ---- pass B: decoder forward, loss, decoder backward; decoder gradients as dot products over staged rows
+    const int q = tid >> 6, g = tid & 63;
+    // ---- pass B: decoder forward, loss, decoder backward; decoder gradients as dot products over the staged rows
     double acc3[1 + 2 * D3];   // SSE, sum dy[c], sum dy[c] * zhat[c]
 #pragma unroll
     for (int k = 0; k < 1 + 2 * D3; ++k) acc3[k] = 0.0;
-    float accD = 0.f;
-    const Dot dd = dec_dot(sm, tid);
+    float accD[4] = {0.f, 0.f, 0.f, 0.f};
+    const Dot dd = dec_dot(sm, g);
     for (int c0 = 0; c0 < nr; c0 += kT) {
       const int r = c0 + tid;
       float* st = sm.stage + tid * SW;
@@ -304,28 +324,20 @@ struct Net {
             acc3[1 + c] += (double)dy[c];
             acc3[1 + D3 + c] += (double)dy[c] * (double)zhat[c];
           }
-#pragma unroll
-          for (int i = 0; i < D0; ++i) st[B_DOUT + i] = dout[i];
-#pragma unroll
-          for (int i = 0; i < D1; ++i) { st[B_H5 + i] = h5[i]; st[B_D5 + i] = d5[i]; }
-#pragma unroll
-          for (int i = 0; i < D2; ++i) { st[B_H4 + i] = h4[i]; st[B_D4 + i] = d4[i]; }
-#pragma unroll
-          for (int i = 0; i < D3; ++i) st[B_Y + i] = y[i];
-          st[B_ONE] = 1.0f;
+          store_block<D0, false>(st + B_DOUT, dout);
+          store_block<D1, false>(st + B_D5, d5);
+          store_block<D2, false>(st + B_D4, d4);
+          store_block<D1, true>(st + B_H5, h5);
+          store_block<D2, true>(st + B_H4, h4);
+          store_block<D3, true>(st + B_Y, y);
         }
       } else if (back) {
 #pragma unroll
-        for (int i = 0; i <= B_ONE; ++i) st[i] = 0.f;
+        for (int i = 0; i < SM::SWB; i += 4) *reinterpret_cast<float4*>(st + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       if (back) {
         __syncthreads();
-        if (tid < ND) {
-          const float* a = sm.stage + dd.a;
-          const float* b = sm.stage + dd.b;
-#pragma unroll 8
-          for (int k = 0; k < kT; ++k) accD = fmaf(a[k * SW], b[k * SW], accD);
-        }
+        if (g < GD) dot64(sm.stage, dd, accD);
         __syncthreads();
       }
     }
@@ -342,8 +354,8 @@ struct Net {
     const float g_beta = tid < D3 ? (float)sm.dsum[1 + tid] : 0.f;          // d beta  = sum dy
     const float g_gamma = tid < D3 ? (float)sm.dsum[1 + D3 + tid] : 0.f;    // d gamma = sum dy * zhat
     // ---- pass C: BatchNorm backward, encoder backward (h1, h2 recomputed from x), encoder gradients as dot products
-    float accE = 0.f;
-    const Dot de = enc_dot(sm, tid);
+    float accE[4] = {0.f, 0.f, 0.f, 0.f};
+    const Dot de = enc_dot(sm, g);
     for (int c0 = 0; c0 < nr; c0 += kT) {
       const int r = c0 + tid;
       float* st = sm.stage + tid * SW;
@@ -363,34 +375,29 @@ struct Net {
         dense_t<D2, D1>(sm.th + sm.seg[SEG_E2_W].pad_off, d2, d1);
 #pragma unroll
         for (int i = 0; i < D1; ++i) d1[i] *= h1[i] * (1.0f - h1[i]);
-#pragma unroll
-        for (int i = 0; i < D3; ++i) st[C_DZ + i] = dz[i];
-#pragma unroll
-        for (int i = 0; i < D2; ++i) { st[C_H2 + i] = h2[i]; st[C_D2 + i] = d2[i]; }
-#pragma unroll
-        for (int i = 0; i < D1; ++i) { st[C_H1 + i] = h1[i]; st[C_D1 + i] = d1[i]; }
-#pragma unroll
-        for (int i = 0; i < D0; ++i) st[C_X + i] = x[i];
-        st[C_ONE] = 1.0f;
+        store_block<D3, false>(st + C_DZ, dz);
+        store_block<D2, false>(st + C_D2, d2);
+        store_block<D1, false>(st + C_D1, d1);
+        store_block<D2, false>(st + C_H2, h2);
+        store_block<D1, true>(st + C_H1, h1);
+        store_block<D0, true>(st + C_X, x);
       } else {
 #pragma unroll
-        for (int i = 0; i <= C_ONE; ++i) st[i] = 0.f;
+        for (int i = 0; i < SM::SWC; i += 4) *reinterpret_cast<float4*>(st + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       __syncthreads();
-      if (tid < NE) {
-        const float* a = sm.stage + de.a;
-        const float* b = sm.stage + de.b;
-#pragma unroll 8
-        for (int k = 0; k < kT; ++k) accE = fmaf(a[k * SW], b[k * SW], accE);
-      }
+      if (g < GE) dot64(sm.stage, de, accE);
       __syncthreads();
     }
-    // ---- the partial gradient of this CTA -> cluster total in sm.grad (rank order, identical in every CTA)
-    float* gp = sm.gpart[buf_g];
-    for (int i = tid; i < kMaxP; i += kT) gp[i] = 0.f;
+    // ---- partial gradient of this CTA: the four row groups in fixed order, then the cluster total in rank order
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (g < GD && dd.dst[j] >= 0) sm.dotq[q][dd.dst[j]] = accD[j];
+      if (g < GE && de.dst[j] >= 0) sm.dotq[q][de.dst[j]] = accE[j];
+    }
     __syncthreads();
-    if (tid < ND) gp[dd.dst] = accD;
-    if (tid < NE) gp[de.dst] = accE;
+    float* gp = sm.gpart[buf_g];
+    for (int i = tid; i < kMaxP; i += kT) gp[i] = ((sm.dotq[0][i] + sm.dotq[1][i]) + sm.dotq[2][i]) + sm.dotq[3][i];
     cl.sync();
     {
       const unsigned nrk = cl.num_blocks();
@@ -549,13 +556,14 @@ __global__ void __launch_bounds__(kT, 1) bae_narrow_kernel(const DevState* __res
       c.eta_noise = (double)n0 * (double)S->step_eta;
       c.u = (double)u01(r.w);
       c.is_lang = (S->use_langevin && c.lx < (double)S->l_prob) ? 1 : 0;
-      if (c.is_lang) {
-        const int t1 = c.adam_t + 1, t2 = t1 + 1;
-        c.ss1 = (float)((double)S->lr / (1.0 - pow((double)kB1, (double)t1)));
-        c.sq1 = (float)sqrt(1.0 - pow((double)kB2, (double)t1));
-        c.ss2 = (float)((double)S->lr / (1.0 - pow((double)kB1, (double)t2)));
-        c.sq2 = (float)sqrt(1.0 - pow((double)kB2, (double)t2));
-      }
+    }
+    // Adam bias corrections of the two drift calls: four double-precision pow() evaluations, one thread each (they only
+    // depend on adam_t, which the previous iteration left in shared memory)
+    if (tid >= 32 && tid < 36) {
+      ChainSm& c = sm.c;
+      const int k = tid - 32, t = c.adam_t + 1 + (k >> 1);
+      if ((k & 1) == 0) (k == 0 ? c.ss1 : c.ss2) = (float)((double)S->lr / (1.0 - pow((double)kB1, (double)t)));
+      else (k == 1 ? c.sq1 : c.sq2) = (float)sqrt(1.0 - pow((double)kB2, (double)t));
     }
     __syncthreads();
     const bool lang = sm.c.is_lang != 0;
@@ -713,6 +721,8 @@ cudaError_t launch_narrow(const DevState* dS, int n_chains, int cluster, int n_i
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);   // clusters of 16 CTAs
     if (e != cudaSuccess) return e;
     attr_set = true;
   }

@@ -335,9 +335,12 @@ def roofline_block(job, kernel_ms, n_launch_rounds, sharded):
         except Exception:
             mhz = 1965.0
         peak = 148 * 128 * 2 * mhz * 1e6 / 1e12
+        narrow = job.s.step_kernel() == 3
         out = {"bound": "fp32", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s", "frac": achieved_tf / peak, "traffic": None,
-               "kernel": ("bae_program_kernel (persistent FP32 step kernel, one cooperative launch = 5 iterations of all resident "
-                          "chains" + ("" if sharded else " + exchange sweep") + ")"),
+               "kernel": (("bae_narrow_kernel (one thread-block cluster per chain, rows in registers, DSMEM reductions; one launch = 5 "
+                           "iterations of all resident chains) + the exchange sweep kernel") if narrow else
+                          ("bae_program_kernel (persistent FP32 step kernel, one cooperative launch = 5 iterations of all resident "
+                           "chains" + ("" if sharded else " + exchange sweep") + ")")),
                "peak_source": f"derived: 148 SMs x 128 FP32 lanes x 2 FLOP x {mhz:.0f} MHz (max SM clock, MEASURED_PEAKS.json); "
                               "narrow layers are latency / SFU bound, see DESIGN.md", "mma_kind": kind}
     out.update({"kernel_ms_per_launch": kernel_ms, "algorithmic_gflop_per_launch": flops_per_launch / 1e9})

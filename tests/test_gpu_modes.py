@@ -113,3 +113,47 @@ def test_chain_groups_are_bit_identical(shape):
                      fa["features"].tobytes(), fa["recon"].tobytes(), s.swap_counts()))
         s.close()
     assert runs[0] == runs[1] == runs[2]
+
+
+def test_narrow_kernel_is_used_and_agrees_with_the_generic_step_kernel(monkeypatch):
+    """Swiss Roll widths run the cluster kernel of csrc/bae_narrow.cu (step_kernel 3). Same chains through the generic
+    persistent FP32 tile kernel (BAE_NO_NARROW=1): the two programs agree to FP32 rounding on every iteration, take the same
+    decisions and the same swaps; cluster sizes 8 (8 chains) and 1 (> 64 chains) give the same traces up to rounding."""
+    from bayesianautoencoders_b200 import DeviceSampler, default_theta_init
+    dims4, ntr, nte = (3, 10, 5, 2), 3750, 1250
+    train, test = synth_data(dims4, ntr, nte)
+    L = bo.Layout(dims4)
+    S = 15
+
+    def run(n_ens, env):
+        if env:
+            monkeypatch.setenv("BAE_NO_NARROW", "1")
+        else:
+            monkeypatch.delenv("BAE_NO_NARROW", raising=False)
+        n = 8 * n_ens
+        s = DeviceSampler(dims4, train, test, n, 8, S, np.tile(bo.temperature_ladder(8, 2), n_ens), swap_interval=5, seed=3)
+        kind = s.step_kernel()
+        rng = np.random.default_rng(7)
+        for j in range(n):
+            s.init_chain(j, default_theta_init(dims4, rng), rng.standard_normal(L.w_size))
+        s.run(S)
+        s.synchronize()
+        tr = [s.traces(j, 0, S) for j in range(8)]
+        out = (kind, tr, s.swap_counts(), [s.get_state(j)["theta"] for j in range(8)])
+        s.close()
+        return out
+
+    k3, tr3, sw3, th3 = run(1, False)        # cluster of 8 CTAs per chain
+    k1, tr1, sw1, th1 = run(1, True)         # generic kernel
+    k3b, tr3b, _, _ = run(9, False)          # 72 chains: one CTA per chain; the first ensemble has the same seeds and ids
+    assert (k3, k1, k3b) == (3, 1, 3)
+    for j in range(8):
+        for a, b in ((tr3[j], tr1[j]), (tr3[j], tr3b[j])):
+            assert np.array_equal(a["accepted"], b["accepted"]) and np.array_equal(a["langevin"], b["langevin"])
+            np.testing.assert_allclose(a["mse_train_proposal"], b["mse_train_proposal"], rtol=2e-5)
+            # the log-likelihood is the difference of two ~1.7e4-sized terms at this size: absolute tolerance
+            np.testing.assert_allclose(a["likelihood_proposal"], b["likelihood_proposal"], rtol=2e-5, atol=0.05)
+            scale = np.abs(a["likelihood_proposal"]) + np.abs(a["likelihood"]) + np.abs(a["prior_proposal"]) + np.abs(a["diff_prop"]) + 1.0
+            assert np.all(np.abs(a["sum_value"] - b["sum_value"]) <= 2e-4 * scale), np.max(np.abs(a["sum_value"] - b["sum_value"]) / scale)
+        assert rel(th3[j], th1[j]) < 1e-4
+    assert sw3 == sw1
