@@ -147,6 +147,29 @@ class NcclComm:
         self._check(self._lib.ncclCommInitRank(C.byref(comm), int(world), uid, int(rank)))
         self.handle = comm
         self.rank, self.world = rank, world
+        self.open_all_pairs()
+
+    def open_all_pairs(self):
+        """NCCL opens point-to-point connections lazily (tens of milliseconds each, on first use). A configuration can travel
+        to any rank in a sweep, so every pair is opened here with a one-float exchange instead of inside a timed round."""
+        import ctypes as C
+        import torch
+        if self.world < 2:
+            return
+        a = torch.zeros(self.world, dtype=torch.float32, device="cuda")
+        b = torch.zeros(self.world, dtype=torch.float32, device="cuda")
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        L = self._lib
+        L.ncclSend.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ncclRecv.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        self._check(L.ncclGroupStart())
+        for peer in range(self.world):
+            if peer == self.rank:
+                continue
+            self._check(L.ncclSend(C.c_void_p(a.data_ptr() + 4 * peer), 1, 7, peer, self.handle, stream))   # 7 = ncclFloat32
+            self._check(L.ncclRecv(C.c_void_p(b.data_ptr() + 4 * peer), 1, 7, peer, self.handle, stream))
+        self._check(L.ncclGroupEnd())
+        torch.cuda.synchronize()
 
     def _check(self, rc):
         if rc != 0:
