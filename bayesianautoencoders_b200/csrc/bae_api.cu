@@ -549,9 +549,12 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     // tcgen05 path only where the layers are real dense contractions (Madelon-like widths); narrow layers
     // (Coil-2000's 50-85, Swiss Roll's 2-10) stay on the FP32 CUDA-core tiles.
     const int dmin = std::min(std::min(s.d0, s.d1), std::min(s.d2, s.d3));
-    const bool eligible = dmin >= 128 && cfg->n_train >= 128 && cfg->n_test >= 128;
-    if (cfg->gemm_path == 2 && !eligible)
-      return fail(BAE_ERR_INVALID, "gemm_path=2 (tcgen05) needs every layer width >= 128 and >= 128 rows");
+    const bool rows_ok = cfg->n_train >= 128 && cfg->n_test >= 128;
+    // automatic choice: wide layers (Madelon and wider) always; mid widths (Coil-2000's 50-85: tiles of 64-96 columns, measured
+    // 2x the FP32 tiles at 64 chains, slower at 8 where a launch per phase costs more than the phase) when many chains are resident
+    const bool eligible = rows_ok && (dmin >= 128 || (dmin >= 48 && cfg->n_chains >= 32));
+    if (cfg->gemm_path == 2 && !(rows_ok && dmin >= 48))
+      return fail(BAE_ERR_INVALID, "gemm_path=2 (tcgen05) needs every layer width >= 48 and >= 128 rows");
     s.tc = (cfg->gemm_path == 2 || (cfg->gemm_path == 0 && eligible)) ? 1 : 0;
     if (s.tc && !get_encode()) return fail(BAE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   }

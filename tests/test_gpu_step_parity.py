@@ -198,6 +198,20 @@ def test_coil_full_size_step_kernel_matches_oracle():
     _check_free("free_coil_fp32", r, 9, temps, tf_traces=tf_traces)
 
 
+def test_coil_on_the_tensor_core_path_matches_oracle():
+    """Coil-2000 widths (50-85) on the tcgen05 engine (chosen automatically from 32 resident chains on; forced here):
+    tiles of 64-96 columns, K = 85 / 70 / 60 / 50 with zero-filled K tails."""
+    dims4, ntr, nte = COIL
+    train, test = synth_data(dims4, ntr, nte)
+    temps = [1.0, 2.0]
+    th0, w0 = _inputs(dims4, 2, 18)
+    rep, tf_traces = run_teacher_forced(dims4, train, test, temps, 9, 3, th0, w0, n_rungs=2, seed=6, gemm_path=2)
+    assert rep["gemm_path"] == 2
+    _check_tf("tf_coil_tc", rep, dict(TOL_TF, grad=2e-5, grad_step0=2e-5))
+    r = run_device_and_oracle(dims4, train, test, temps, 9, 3, th0, w0, n_rungs=2, do_swaps=True, seed=6, gemm_path=2)
+    _check_free("free_coil_tc", r, 9, temps, tf_traces=tf_traces)
+
+
 def test_swiss_full_size_step_kernel_matches_oracle():
     """Swiss Roll shape at full size (3750 / 1250 rows), one 4-rung ensemble x 20 iterations, 4 exchange rounds."""
     dims4, ntr, nte = SWISS
