@@ -1140,6 +1140,20 @@ int bae_eval(bae_handle* h, int chain, int which, const float* w, double* sse, d
   return BAE_OK;
 }
 
+int bae_eval_bn_stats(bae_handle* h, int which, float* mean, float* var) {
+  if (!h || !mean || !var) return fail(BAE_ERR_INVALID, "null argument");
+  if (which != 0 && which != 1) return fail(BAE_ERR_INVALID, "which must be 0 (train) or 1 (test)");
+  const DevState& s = h->hs;
+  CU(cudaSetDevice(h->device));
+  const size_t slot = which == 0 ? 0 : 2, E = s.C;   // the probe's scratch chain
+  std::vector<float> mu(s.ld3), va(s.ld3);
+  CU(cudaMemcpyAsync(mu.data(), s.bn_mu + (slot * s.C_alloc + E) * s.ld3, sizeof(float) * s.ld3, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(va.data(), s.bn_var + (slot * s.C_alloc + E) * s.ld3, sizeof(float) * s.ld3, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  for (int c = 0; c < s.d3; ++c) { mean[c] = mu[c]; var[c] = va[c]; }
+  return BAE_OK;
+}
+
 int bae_forward_all(bae_handle* h, int which, float* features, float* recon, double* sse) {
   if (!h) return fail(BAE_ERR_INVALID, "null handle");
   if (!h->data_loaded) return fail(BAE_ERR_STATE, "upload data first");

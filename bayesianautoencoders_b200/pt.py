@@ -101,8 +101,14 @@ class Model:
         return s
 
     def _bn_side_effects(self, s, n_rows):
-        # train-mode BatchNorm (MAIN:165) mutates the running statistics of the live model on every forward;
-        # they never influence outputs, so they are tracked on the host from the batch statistics.
+        # train-mode BatchNorm (MAIN:165) mutates the buffers of the live model on every forward (they never influence
+        # outputs): running = 0.9 running + 0.1 batch statistic (unbiased variance), num_batches_tracked += 1. The state_dict
+        # `langevin_gradient` returns carries them (MAIN:226).
+        mu, var = s.eval_bn_stats(0)
+        o, n, _ = self._offs["decode.0.running_mean"]
+        self._theta[o:o + n] = 0.9 * self._theta[o:o + n] + 0.1 * mu.astype(np.float64)
+        o, n, _ = self._offs["decode.0.running_var"]
+        self._theta[o:o + n] = 0.9 * self._theta[o:o + n] + 0.1 * var.astype(np.float64) * (n_rows / (n_rows - 1.0))
         o, n, _ = self._offs["decode.0.num_batches_tracked"]
         self._theta[o] += 1
 

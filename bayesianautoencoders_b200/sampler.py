@@ -268,6 +268,12 @@ class DeviceSampler:
                                   g.ctypes.data if grads else None, o.ctypes.data if out else None))
         return dict(sse=sse.value, mse=mse.value, grads=g, out=o)
 
+    def eval_bn_stats(self, which=0):
+        """Batch mean / biased variance of the BatchNorm layer in the most recent `eval` call."""
+        mu, var = np.zeros(self.dims4[3], np.float32), np.zeros(self.dims4[3], np.float32)
+        N.check(self.lib.bae_eval_bn_stats(self._h, int(which), mu.ctypes.data, var.ctypes.data))
+        return mu, var
+
     def debug_draws(self, chain, step):
         noise = np.zeros(self.w_size, np.float32)
         sc = np.zeros(3, np.float64)

@@ -184,6 +184,61 @@ def cpu_chain_steps_per_sec(shape, n_proc, iters_per_proc):
                                                 loop_s=loop, wall_s=wall)
 
 
+def reference_real_chain_steps_per_sec(shape, iters_per_proc):
+    """The UNMODIFIED reference (`/root/reference`, build container only): its own 8-process `ParallelTempering.run_chains()`
+    (MAIN:1013-1090) on the synthetic matrices, `cores // 8` torch threads per replica process (BASELINE.md section 3, timing
+    (ii)). The sampling loop ends at the first `np.savetxt` of a replica (MAIN:632); the classification / plot tail is not timed.
+    Returns None when the reference tree is not mounted (the GPU boxes): the caller falls back to the oracle port."""
+    from oracle import ref_import
+    if not ref_import.available():
+        return None
+    import glob
+    import shutil
+    import torch
+    ref = ref_import.load_reference()
+    dims4, n_train, n_test = SHAPES[shape]
+    ref_import.set_shape(ref, dims4)
+    train, test = synth(dims4, n_train, n_test)
+    train, test = train.astype(np.float64), test.astype(np.float64)
+    ref.data_load = lambda data='train': (train if data == 'train' else test)
+    cores = os.cpu_count() or 1
+    threads = max(1, cores // N_RUNGS)
+    torch.set_num_threads(threads)
+    stamp_dir = tempfile.mkdtemp(prefix="bae_ref_stamp_")
+    orig_savetxt = np.savetxt
+
+    def stamped_savetxt(*a, **k):   # inherited by the forked replica processes
+        fn = os.path.join(stamp_dir, f"{os.getpid()}.t")
+        if not os.path.exists(fn):
+            with open(fn, "w") as f:
+                f.write(repr(time.time()))
+        return orig_savetxt(*a, **k)
+
+    path = os.path.join(ref._scratch, "bench_res")
+    os.makedirs(path, exist_ok=True)
+    old_cwd = os.getcwd()
+    os.chdir(ref._scratch)
+    np.savetxt = stamped_savetxt
+    try:
+        pt = ref.ParallelTempering(True, N_RUNGS, 2, N_RUNGS * iters_per_proc, SWAP_INTERVAL, path, 10, 0.5, 0.005)
+        pt.initialize_chains(0.5)
+        t0 = time.time()
+        try:
+            pt.run_chains()
+        except Exception:
+            pass    # show_results() reads plots / files the stubs do not produce; the loop has been timed by then
+    finally:
+        np.savetxt = orig_savetxt
+        os.chdir(old_cwd)
+    stamps = [float(open(f).read()) for f in glob.glob(os.path.join(stamp_dir, "*.t"))]
+    shutil.rmtree(stamp_dir, ignore_errors=True)
+    if len(stamps) < N_RUNGS:
+        return None
+    loop = max(stamps) - t0
+    return N_RUNGS * iters_per_proc / loop, dict(cores=min(cores, threads * N_RUNGS), procs=N_RUNGS, threads_per_proc=threads,
+                                                  loop_s=loop, wall_s=time.time() - t0)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -193,23 +248,38 @@ def run_reference(args):
     iters = max(1, args.ref_iters)
     vals = []
     info = {}
-    for _ in range(args.warmup if args.warmup < 2 else 1):
-        cpu_chain_steps_per_sec(shape, n_proc, 1)
+    kind = "port"
+    real = None
+    try:
+        real = reference_real_chain_steps_per_sec(shape, iters)
+    except Exception as e:   # the reference cannot run here: fall back to the port and say so
+        print(f"[bench] unmodified reference not runnable here ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
     t_total = 0.0
-    for _ in range(args.steps):
-        v, info = cpu_chain_steps_per_sec(shape, n_proc, iters)
-        vals.append(v)
-        t_total += info["loop_s"]
+    if real is not None:
+        kind = "reference"
+        for k in range(args.steps):
+            v, info = real if k == 0 else reference_real_chain_steps_per_sec(shape, iters)
+            vals.append(v)
+            t_total += info["loop_s"]
+    else:
+        for _ in range(args.warmup if args.warmup < 2 else 1):
+            cpu_chain_steps_per_sec(shape, n_proc, 1)
+        for _ in range(args.steps):
+            v, info = cpu_chain_steps_per_sec(shape, n_proc, iters)
+            vals.append(v)
+            t_total += info["loop_s"]
     value = float(np.mean(vals))
     dims4, n_train, n_test = SHAPES[shape]
-    sample = f"{n_proc} replica processes x {iters} iterations per bench step, float64 numpy (OpenBLAS), {info['threads_per_proc']} threads each"
+    sample = (f"{n_proc} replica processes x {iters} iterations per bench step, " +
+              ("the UNMODIFIED reference's ParallelTempering.run_chains() (torch float64)" if kind == "reference" else
+               "float64 numpy oracle port (OpenBLAS)") + f", {info['threads_per_proc']} threads each")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(shape, args.chains_per_gpu), "shape": shape, "dims": list(dims4),
                    "n_train": n_train, "n_test": n_test},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -130,6 +130,11 @@ int bae_synchronize(bae_handle* h);
  * (which=1) matrix. Does not disturb the chain state. out: n x dims[0] or NULL. */
 int bae_eval(bae_handle* h, int chain, int which, const float* w, double* sse, double* mse, float* grads, float* out);
 
+/* Batch statistics of the BatchNorm layer seen by the most recent bae_eval call on this handle (biased variance, as used
+ * for normalisation): what a train-mode forward folds into running_mean / running_var (momentum 0.1, MAIN:165, 226).
+ * mean, var: dims[3] floats each. */
+int bae_eval_bn_stats(bae_handle* h, int which, float* mean, float* var);
+
 /* Posterior-predictive pass, batched over every resident chain (MAIN:709-818 runs `cae.encode(X)` / `cae.forward(X)` on the
  * final weights of one chain): forward of the training (which = 0) or test (which = 1) matrix through each chain's live
  * model, BatchNorm in training mode on that batch as everywhere in the reference. Any output may be NULL.

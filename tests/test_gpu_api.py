@@ -39,6 +39,9 @@ def test_model_methods_match_oracle():
     d2 = m2.getparameters(m2.langevin_gradient(g.train, m2.dictfromlist(w0)))
     tr = L.trainable_mask
     assert np.abs(d1[tr] - o1[tr]).max() < 2e-5 and np.abs(d2[tr] - o2[tr]).max() < 2e-5
+    # the returned state_dict carries the BatchNorm buffers as updated by the two train-mode forwards (MAIN:226)
+    bufs = ~tr
+    assert np.abs(d2[bufs] - o2[bufs]).max() < 1e-5 * max(1.0, np.abs(o2[bufs]).max())
     assert m2._t == 2    # the optimizer state persists across calls (MAIN:178); with identical gradients the
     #                      bias-corrected steps coincide, so the state is checked directly
     m.close(); m2.close()
