@@ -78,10 +78,13 @@ def tf32_peak():
         return None
 
 
+TRAFFIC_CAPTURE = "r2_v6_traffic.json"   # written by tools/make_profiles.py from the ncu --set full export of the current build
+
+
 def ncu_traffic(shape, cpg, gemm_path):
     """DRAM bytes (read + write) of one launch of the step program from the committed `ncu --set full` capture
-    (profiles/r1_program_kernel_traffic.json), scaled to this run's chains x iterations per launch; None if no capture fits."""
-    p = os.path.join(ROOT, "profiles", "r1_program_kernel_traffic.json")
+    (profiles/<TRAFFIC_CAPTURE>), scaled to this run's chains x iterations per launch; None if no capture fits."""
+    p = os.path.join(ROOT, "profiles", TRAFFIC_CAPTURE)
     try:
         with open(p) as f:
             d = json.load(f)

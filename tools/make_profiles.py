@@ -2,7 +2,7 @@
 """Turns the ncu exports of a profiling session into the committed summaries under profiles/.
 
     ncu -i /tmp/prof_phases_r1.ncu-rep --page raw --csv > gpurun_out/prof_phases_r1_raw.csv      (on the GPU box)
-    python tools/make_profiles.py gpurun_out/launches_r1_final.csv gpurun_out/prof_phases_r1_raw.csv [gpurun_out/phases_final.log]
+    python tools/make_profiles.py <launches.csv> <full_raw.csv> [bench ms per round] [file prefix] [label]   (tools/gpu_round_evidence.sh produces both inputs)
 """
 import csv
 import json
@@ -17,6 +17,8 @@ def kname(full):
 
 launch_csv, raw_csv = sys.argv[1], sys.argv[2]
 bench_ms = sys.argv[3] if len(sys.argv) > 3 else '61-62'
+prefix = sys.argv[4] if len(sys.argv) > 4 else 'r2_v6'      # file-name prefix under profiles/
+label = sys.argv[5] if len(sys.argv) > 5 else 'Round 2, step program v6 (one gradient copy, relaxed hand-backs)'
 rows = [r for r in csv.reader(open(launch_csv)) if len(r) > 5]
 h, data = rows[0], rows[1:]
 iv, ik = h.index('Metric Value'), h.index('Kernel Name')
@@ -26,7 +28,7 @@ names = ['PRO', 'F1', 'F2', 'F3', 'BNF', 'F4', 'F5', 'F6', 'B6 (dW6|dH5)', 'B5',
 PER_IT = 42   # 39 step phases + 3 exchange phases (which return at once unless the step counter says "swap round")
 names_it = names + ['SWAP_DECIDE', 'SWAP_GATHER', 'SWAP_SCATTER']
 assert len(vals) == 5 * PER_IT, f"expected {5 * PER_IT} launches (5 iterations x 42 phases), got {len(vals)}"
-with open('profiles/r1_v5_step_program_launches.csv', 'w') as f:
+with open(f'profiles/{prefix}_step_program_launches.csv', 'w') as f:
     f.write("launch,iteration,phase,kernel,duration_us\n")
     for i, (r, v) in enumerate(zip(data, vals)):
         f.write(f"{i},{i // PER_IT},{names_it[i % PER_IT]},{kname(r[ik])},{v:.3f}\n")
@@ -52,12 +54,12 @@ for n, v, kn in zip(names, it0, kern):
     if base.startswith('ADAM'):
         a += v
     lines.append(f"| {n} | `{kn}` | {v:.1f} | {100 * v / tot:.1f}% | {tf} |")
-md = f"""# Round 1, step program v5 (per-phase kernels in a CUDA graph) - launch list (ncu gpu__time_duration.sum, --clock-control none)
+md = f"""# {label} - launch list (ncu gpu__time_duration.sum, --clock-control none)
 
 Command: `BAE_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv python tools/profile_step.py --chains 64 --rounds 2 --steps-per-round 5 --profile-round 1`
 (Madelon shape, 64 chains, the 2nd PT round = ONE `bae_run(5)` call: 5 iterations x 42 phase launches, the exchange sweep in the last three; these
 are the production kernels - `BAE_NO_GRAPH=1` only makes the library launch them directly instead of replaying the captured graph).
-Raw list: `r1_v5_step_program_launches.csv`. Per-launch times are cold-cache and serialised (and the SM clock is higher than in a back-to-back run, which
+Raw list: `{prefix}_step_program_launches.csv`. Per-launch times are cold-cache and serialised (and the SM clock is higher than in a back-to-back run, which
 sits at the power cap); compare SHARES. Sum per iteration: {', '.join(f'{sum(vals[i * PER_IT:(i + 1) * PER_IT]) / 1000:.2f}' for i in range(5))} ms
 (later iterations have fewer chains on a Langevin step); exchange sweep (decide / gather / scatter): {sw[0]:.0f} / {sw[1]:.0f} / {sw[2]:.0f} us.
 
@@ -70,7 +72,7 @@ sustained-clock ceiling of a 3-way TF32 split is 1381.9 / 6 = 230 TFLOP/s); Batc
 (`bae_aux_kernel<0>`) {100 * a / tot:.1f}%. `bench.py` measures the same program at {bench_ms} ms per round back to back (graph replay, SM clock at the
 power cap): the GEMM kernels' share of the step is the same in both views.
 """
-open('profiles/r1_v5_step_program_launches.md', 'w').write(md)
+open(f'profiles/{prefix}_step_program_launches.md', 'w').write(md)
 
 r = list(csv.reader(open(raw_csv)))
 hdr, units, prow = r[0], r[1], r[2:]
@@ -96,7 +98,7 @@ ptab = "\n".join(f"| {n} | {dur[i]:.1f} | {rdv[i] / 1e6:.1f} | {wrv[i] / 1e6:.1f
                  f"{l2hit[i]:.0f} | {inst[i] / 1e6:.2f} | {lld[i] + lst[i]:.0f} |" for i, n in enumerate(names_it))
 gi = [i for i, n in enumerate(names) if n.split(' ')[0].rstrip('b') in fl]
 gt = sum(dur[i] for i in gi)
-md2 = f"""# Round 1, step program v5 - one `ncu --set full` capture over the 42 kernels of an iteration
+md2 = f"""# {label} - one `ncu --set full` capture over the 42 kernels of an iteration
 
 `BAE_NO_GRAPH=1 ncu --set full --clock-control none --profile-from-start off -k regex:bae_ -c 42 python tools/profile_step.py --chains 8 --rounds 2 --steps-per-round 1 --profile-round 1`
 (Madelon shape, 8 chains, ONE iteration of the production step program: GEMM phases = `bae_phase_kernel_tc<kindA, kindB>`, 148 CTAs = 74 CTA pairs x 512
@@ -108,7 +110,7 @@ Sum of the 42 kernel durations {us / 1e3:.3f} ms under ncu (cold caches, seriali
 a fraction of the 74 CTA pairs per phase; production runs 64 chains per GPU, `bench.py`).
 DRAM traffic per iteration: read {rd / 1e6:.0f} MB + write {wr / 1e6:.0f} MB = {(rd + wr) / 8 / 1e6:.0f} MB per chain-iteration. Algorithmic weight-state traffic is
 22 x 4 B x 1.05 M = 93 MB per chain-iteration (SURVEY 8d); the rest is activations and deltas (41 MB per chain, written once and re-read by the backward
-pass and the weight-gradient GEMMs) plus the four K-split copies of the gradient (4 x 4.2 MB written by the dW GEMMs, read by each Adam phase).
+pass and the weight-gradient GEMMs). The gradient has ONE copy: the K segments of a weight-gradient tile are added in L2 by TMA reduce-add.
 SASS evidence (`cuobjdump -sass libbae_b200.so`): UTCHMMA (tcgen05.mma cta_group::2 kind::tf32), UTMALDG (TMA), LDTM (tcgen05.ld),
 UTCBAR (tcgen05.commit, multicast), USETMAXREG (setmaxnreg), SYNCS (mbarrier), UCGABAR (cluster barrier).
 
@@ -121,8 +123,8 @@ has 3-14 tiles per phase and the traced tile loop runs close to the tensor-pipe 
 {(rdv[15] + wrv[15]) / dur[15] / 1e3:.0f} GB/s = {100 * (rdv[15] + wrv[15]) / dur[15] / 1e3 / 6549:.0f}% of the measured HBM peak (6549 GB/s) at 8 chains. Local-memory instructions of the GEMM kernels are the
 front half's (TMA producer / MMA issuer at 48 registers) per-tile set-up; the epilogue half is spill free since it is specialised per kind.
 """
-open('profiles/r1_v5_step_program_ncu_full.md', 'w').write(md2)
+open(f'profiles/{prefix}_step_program_ncu_full.md', 'w').write(md2)
 json.dump({"shape": "madelon", "gemm_path": 2, "chains": 8, "iterations": 1, "dram_bytes_read": rd, "dram_bytes_write": wr, "kernel_ms_under_ncu": us / 1e3,
-           "source": "ncu --set full over the 42 kernels of one iteration of the step program, 8 chains (profiles/r1_v5_step_program_ncu_full.md)"},
-          open('profiles/r1_program_kernel_traffic.json', 'w'), indent=1)
+           "source": f"ncu --set full over the 42 kernels of one iteration of the step program, 8 chains (profiles/{prefix}_step_program_ncu_full.md)"},
+          open(f'profiles/{prefix}_traffic.json', 'w'), indent=1)
 print("profiles written")
