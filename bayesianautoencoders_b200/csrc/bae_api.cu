@@ -33,6 +33,7 @@ cudaError_t launch_scalars(const DevState* dS, int chain, bae_chain_scalars* sta
 bool narrow_supported(const int dims[4], int n_train, int n_test, int p_used);
 cudaError_t launch_narrow(const DevState* dS, int n_chains, int cluster, int n_iter, int p_used, cudaStream_t st);
 cudaError_t launch_swap_cta(const DevState* dS, int force_swap, cudaStream_t st);
+cudaError_t launch_amax_zero(const DevState* dS, unsigned mask, int c_begin, int c_end, int gated, cudaStream_t st);
 cudaError_t launch_xtable(const DevState* dS, cudaStream_t st);
 cudaError_t launch_xsweep(const DevState* dS, cudaStream_t st);
 cudaError_t launch_xgather(const DevState* dS, int grid, cudaStream_t st);
@@ -60,16 +61,17 @@ static int fail(int code, const std::string& msg) {
 // Phase index map of the step program (see build_program).
 enum PhaseIdx : int {
   P_PRO = 0,
-  P_FWD1 = 1,    // 7 phases
-  P_BWD1 = 8,    // 7 phases
-  P_ADAM1 = 15,
-  P_FWD2 = 16,
-  P_BWD2 = 23,
-  P_ADAM2 = 30,
-  P_FWDT = 31,
-  P_EPI = 38,
-  P_SWAP = 39,   // decide, gather, scatter
-  P_END = 42
+  P_WAMAX0 = 1,  // 3xFP16 split: weight bounds after an exchange round (gated) / forced by the host in front of a program
+  P_FWD1 = 2,    // 7 phases
+  P_BWD1 = 9,    // 7 phases
+  P_ADAM1 = 16,  // (3xFP16 split: also folds the weight bounds of the proposal it writes)
+  P_FWD2 = 17,
+  P_BWD2 = 24,
+  P_ADAM2 = 31,
+  P_FWDT = 32,
+  P_EPI = 39,
+  P_SWAP = 40,   // decide, gather, scatter
+  P_END = 43
 };
 
 struct bae_handle {
@@ -99,6 +101,7 @@ struct bae_handle {
   int narrow_cluster = 1, p_used = 0;
   long long host_step = 0;   // iterations executed since the chains were initialised (all chains advance together)
   int64_t launches = 0;
+  int64_t n_emit = 0;          // kernels issued by launch_one (a phase may come with an amax-zeroing launch, or with none)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   bool phase_launch_env = false;
@@ -316,7 +319,9 @@ static void build_program(bae_handle* h) {
       h->tmaps_host.push_back(tm);
     }
     // instruction descriptor of the pair's MMA (cta_group::2): M = 256, N = tcBN
-    g.idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)g.aMode << 15) | ((unsigned)g.bMode << 16) |
+    // (D format F32 at bit 4; A / B formats at bits 7 / 10: 2 = TF32 for kind::tf32, 0 = F16 for kind::f16)
+    const unsigned fmt = s.f16 ? 0u : ((2u << 7) | (2u << 10));
+    g.idesc = (1u << 4) | fmt | ((unsigned)g.aMode << 15) | ((unsigned)g.bMode << 16) |
               ((unsigned)(g.tcBN >> 3) << 17) | ((unsigned)(256 >> 4) << 24);
   };
   int ng = 0;
@@ -345,6 +350,10 @@ static void build_program(bae_handle* h) {
       g.epi = ls[l].epi;
       g.bias = Wraw(ls[l].bseg); g.sBias = P;
       g.needLang = need;
+      // 3xFP16 split: bounds of the operands (data: host scan; sigmoid outputs: 1; BatchNorm output: tracked; weights: tracked)
+      g.aSc = (l == 0) ? (pass == 2 ? (int)SC_XTEST : (int)SC_XTRAIN) : (l == 3 ? (int)AMAX_Y : (int)SC_UNIT);
+      g.bSc = AMAX_W;
+      g.cSc = (ls[l].epi == EPI_LOSS) ? AMAX_DOUT : -1;
       if (ls[l].epi == EPI_LOSS) {
         g.aux = Xraw; g.sAux = 0; g.ldaux = s.ld0;
         g.scale = 2.0f / ((float)N * (float)s.d0);   // d MSELoss / d out (mean over all N*d0 elements, MAIN:150,223)
@@ -377,6 +386,12 @@ static void build_program(bae_handle* h) {
     g.C = G(bl[l].wseg); g.sC = P; g.ldc = s.seg[bl[l].wseg].ld;
     g.aAct = 1; g.bAct = bl[l].sAin != 0;
     g.epi = EPI_GRADW;
+    // 3xFP16 split: the delta's tracked bound; the layer input's bound (Y: the slot of the most recent forward pass, which is
+    // the one this backward pass differentiates)
+    const int dsl[6] = {AMAX_DOUT, AMAX_D5, AMAX_D4, AMAX_DY, AMAX_D2, AMAX_D1};
+    g.aSc = dsl[l];
+    g.bSc = (l == 5) ? (int)SC_XTRAIN : (l == 2 ? (int)AMAX_Y : (int)SC_UNIT);
+    g.cSc = -1;
     if (bl[l].bseg >= 0) { g.gbias = G(bl[l].bseg); g.sGb = P; }
     {
       const int ks = grad_ksplit(s, h->grid_hint, g, N);
@@ -401,6 +416,8 @@ static void build_program(bae_handle* h) {
       x.C = bl[l].dIn; x.sC = bl[l].sDin; x.ldc = bl[l].lddin;
       x.aAct = 1; x.cAct = 1;
       x.epi = bl[l].epi_x;
+      x.aSc = dsl[l]; x.bSc = AMAX_W;
+      x.cSc = (bl[l].epi_x == EPI_DSIG) ? dsl[l + 1] : -1;   // DY's bound is written by the BatchNorm backward
       if (bl[l].Hin) { x.aux = bl[l].Hin; x.sAux = bl[l].sDin; x.ldaux = bl[l].lddin; x.auxAct = 1; }
       x.needLang = 1;
       add_maps(x);
@@ -442,6 +459,7 @@ static void build_program(bae_handle* h) {
   }
   set(P_ADAM1, PH_ADAM1, -1, -1, 0, 0, 0);
   set(P_ADAM2, PH_ADAM2, -1, -1, 0, 0, 1);
+  set(P_WAMAX0, PH_WAMAX, -1, -1, 1, 0, 0);   // arg 1: gated on "the previous iteration ended with an exchange round"
   set(P_EPI, PH_EPILOGUE, -1, -1, 0, 0, 0);
   set(P_SWAP + 0, PH_SWAP_DECIDE, -1, -1, 0, 0, 0);
   set(P_SWAP + 1, PH_SWAP_GATHER, -1, -1, 0, 0, 0);
@@ -666,7 +684,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   if (s.dbg_flags != 0)
     return fail(BAE_ERR_INVALID, "BAE_TC_DBGFLAGS is set, but this library was built without -DBAE_TC_DEBUG: refusing to sample");
 #endif
-  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW", "BAE_NARROW_CLUSTER"})
+  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW", "BAE_NARROW_CLUSTER", "BAE_TC_TF32"})
     if (getenv(knob)) fprintf(stderr, "[bae_b200] note: tuning variable %s=%s is in effect for this handle\n", knob, getenv(knob));
   s.dbg_phase = getenv("BAE_TC_TRACE_PHASE") ? atoi(getenv("BAE_TC_TRACE_PHASE")) : -1;
   {
@@ -674,6 +692,16 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     CU(cudaMalloc(&q, sizeof(DevState)));
     h->allocs.push_back(q);
     h->dS = reinterpret_cast<DevState*>(q);
+  }
+  if (s.tc && !h->phase_launch_env) h->phase_launch = true;   // (reasons below, where the grids are sized)
+  {
+    // 3xFP16 split (kind::f16, half the tensor-pipe time of 3xTF32 at the same 11-bit operand precision): the default of the
+    // per-phase step program; BAE_TC_TF32=1 keeps the 3xTF32 engine, and the persistent kernel always uses it (the amax
+    // slots are zeroed by launches between phases)
+    const bool tf32_env = getenv("BAE_TC_TF32") && getenv("BAE_TC_TF32")[0] == '1';
+    s.f16 = (s.tc && h->phase_launch && !tf32_env) ? 1 : 0;
+    CU(dalloc(h, &s.amax, (size_t)kAmaxSlots * CA));
+    s.xexp[0] = s.xexp[1] = kF16TopExp;
   }
   build_program(h);
   if (s.tc) {
@@ -691,7 +719,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   if (s.tc) {   // CTA pairs (cluster dimension 2): as many pairs as can be co-resident
     h->grid = max_coop_grid_tc();
     if (h->grid < 2) return fail(BAE_ERR_CUDA, "the tcgen05 step kernel (CTA pairs) cannot be made resident");
-    for (int k = 0; k <= PH_SWAP_SCATTER; ++k) {
+    for (int k = 0; k <= PH_WAMAX; ++k) {
       const int abs = aux_blocks_per_sm(k);
       if (abs < 1) return fail(BAE_ERR_CUDA, "bae_aux_kernel cannot be made resident");
       h->grid_aux[k] = prop.multiProcessorCount * abs;
@@ -752,6 +780,17 @@ int bae_upload_data(bae_handle* h, const float* train, const float* test) {
     CU(cudaMemcpy2DAsync(s.Xtrain + s.d0, (size_t)s.ld0 * 4, h->ones_col.data(), 4, 4, s.n_train, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpy2DAsync(s.Xtest + s.d0, (size_t)s.ld0 * 4, h->ones_col.data(), 4, 4, s.n_test, cudaMemcpyHostToDevice, h->stream));
   }
+  if (s.f16) {
+    // bounds of the two data matrices for the FP16 operand scales (their ones column included)
+    float mx[2] = {1.0f, 1.0f};
+    for (size_t i = 0; i < (size_t)s.n_train * s.d0; ++i) mx[0] = std::max(mx[0], std::fabs(train[i]));
+    for (size_t i = 0; i < (size_t)s.n_test * s.d0; ++i) mx[1] = std::max(mx[1], std::fabs(test[i]));
+    if (!std::isfinite(mx[0]) || !std::isfinite(mx[1])) return fail(BAE_ERR_INVALID, "data contains non-finite values");
+    h->hs.xexp[0] = f16_scale_exp(mx[0]);
+    h->hs.xexp[1] = f16_scale_exp(mx[1]);
+    int rc = upload_state(h);
+    if (rc) return rc;
+  }
   h->data_loaded = true;
   return BAE_OK;
 }
@@ -802,7 +841,25 @@ static int get1(bae_handle* h, const T* dev_arr, int idx, T* v) {
 
 // One phase as its own launch: GEMM phases (and everything on the FP32 path) through the phase kernel of the path, the
 // non-GEMM phases of the tcgen05 path through bae_aux_kernel.
+// 3xFP16 split: the amax slots a phase range produces are zeroed by one small launch in front of its first phase.
+static unsigned amax_zero_mask(int p) {
+  if (p == P_WAMAX0 || p == P_ADAM1) return 1u << AMAX_W;
+  if (p == P_FWD1 || p == P_FWD2 || p == P_FWDT) return (1u << AMAX_Y) | (1u << AMAX_DOUT);
+  if (p == P_BWD1 || p == P_BWD2) return (1u << AMAX_D5) | (1u << AMAX_D4) | (1u << AMAX_DY) | (1u << AMAX_D2) | (1u << AMAX_D1);
+  return 0u;
+}
+
 static cudaError_t launch_one(bae_handle* h, int p, int c_begin, int c_end, int force_swap) {
+  if (h->hs.phase[p].kind == PH_WAMAX && !h->hs.f16) return cudaSuccess;
+  if (h->hs.f16) {
+    const unsigned mask = amax_zero_mask(p);
+    if (mask) {
+      const cudaError_t e = launch_amax_zero(h->dS, mask, c_begin, c_end, (p == P_WAMAX0 && !force_swap) ? 1 : 0, h->stream);
+      if (e != cudaSuccess) return e;
+      h->n_emit++;
+    }
+  }
+  h->n_emit++;
   if (h->hs.tc && h->hs.phase[p].kind != PH_GEMM)
     return launch_aux(h->dS, h->hs.phase[p].kind, h->grid_aux[h->hs.phase[p].kind], p, c_begin, c_end, force_swap, h->stream);
   const PhaseDesc& ph = h->hs.phase[p];
@@ -813,8 +870,9 @@ static cudaError_t launch_one(bae_handle* h, int p, int c_begin, int c_end, int 
 
 static int run_phases_plain(bae_handle* h, int p_begin, int p_end, int c_begin, int c_end) {
   for (int p = p_begin; p < p_end; ++p) {
+    const int64_t n0 = h->n_emit;
     CU(launch_one(h, p, c_begin, c_end, 1));
-    h->launches++;
+    h->launches += h->n_emit - n0;
   }
   return BAE_OK;
 }
@@ -825,6 +883,8 @@ static int forward_one(bae_handle* h, int chain, int pass, double* sse, double* 
   int rc = put1<int>(h, s.ch.is_lang, chain, 1);
   if (rc) return rc;
   const int p0 = (pass == 0) ? P_FWD1 : P_FWDT;
+  rc = run_phases_plain(h, P_WAMAX0, P_WAMAX0 + 1, chain, chain + 1);   // 3xFP16 split: bounds of the weights just written
+  if (rc) return rc;
   rc = run_phases_plain(h, p0, p0 + 7, chain, chain + 1);
   if (rc) return rc;
   std::vector<double> part((size_t)s.loss_stride * 2);
@@ -972,14 +1032,17 @@ static cudaError_t emit_phases(bae_handle* h, int p_begin, int p_end, int n_rep,
   const int C = h->hs.C, G = h->hs.G;
   const int ps_end = std::min(p_end, (int)P_SWAP);
   cudaError_t e = cudaSuccess;
-  int n = 0;
+  const int64_t n0 = h->n_emit;
+  // 3xFP16 split: whatever rewrote theta since the last program (initialisation, set_state, an exchange) - recompute the
+  // weight bounds of every chain once in front of the program
+  if (h->hs.f16 && p_begin == P_PRO) e = launch_one(h, P_WAMAX0, 0, C, 1);
   for (int r = 0; r < n_rep && e == cudaSuccess; ++r) {
     if (p_begin < ps_end)
       for (int cb = 0; cb < C && e == cudaSuccess; cb += G)
-        for (int p = p_begin; p < ps_end && e == cudaSuccess; ++p, ++n) e = launch_one(h, p, cb, std::min(cb + G, C), force_swap);
-    for (int p = std::max(p_begin, (int)P_SWAP); p < p_end && e == cudaSuccess; ++p, ++n) e = launch_one(h, p, 0, C, force_swap);
+        for (int p = p_begin; p < ps_end && e == cudaSuccess; ++p) e = launch_one(h, p, cb, std::min(cb + G, C), force_swap);
+    for (int p = std::max(p_begin, (int)P_SWAP); p < p_end && e == cudaSuccess; ++p) e = launch_one(h, p, 0, C, force_swap);
   }
-  if (n_launch) *n_launch = n;
+  if (n_launch) *n_launch = (int)(h->n_emit - n0);
   return e;
 }
 
@@ -1169,10 +1232,9 @@ int bae_forward_all(bae_handle* h, int which, float* features, float* recon, dou
   const float inv_scale = (float)(((double)rows * s.d0) / 2.0);
   for (int cb = 0; cb < s.C; cb += s.G) {       // chain group after chain group (the activation buffers hold G chains)
     const int ce = std::min(cb + s.G, s.C);
-    for (int p = p0; p < p0 + 7; ++p) {
-      CU(launch_one(h, p, cb, ce, 1));
-      h->launches++;
-    }
+    int rc2 = run_phases_plain(h, P_WAMAX0, P_WAMAX0 + 1, cb, ce);
+    if (rc2) return rc2;
+    if ((rc2 = run_phases_plain(h, p0, p0 + 7, cb, ce))) return rc2;
     for (int c = cb; c < ce; ++c) {
       const size_t slot = (size_t)(c - cb);
       if (features) {

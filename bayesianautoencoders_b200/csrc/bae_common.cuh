@@ -2,6 +2,7 @@
 // Layout, phase program and per-chain state. See DESIGN.md for the data layout in HBM.
 #pragma once
 #include <cstdint>
+#include <cstring>
 #include <cuda_runtime.h>
 
 #include "../../include/bae_b200.h"
@@ -69,17 +70,45 @@ struct GemmDesc {
   int tmIdx[3];         // tensor maps: A, B (loads), C (32 x 32 store boxes of the epilogue)
   unsigned idesc;       // tcgen05 instruction descriptor
   int biasCol;          // EPI_GRADW: output column that holds the bias gradient (ones column trick), or -1
+  // ---- 3xFP16 split (DevState::f16): where the power-of-two scale of each operand comes from (bae_tc.cuh)
+  int aSc, bSc;         // >= 0: amax slot (AmaxSlot, per chain); SC_UNIT: values in [0, 1]; SC_XTRAIN / SC_XTEST: DevState::xexp
+  int cSc;              // amax slot the epilogue folds max |C| into (deltas), or -1
 };
+
+// Magnitude bounds behind the FP16 operand scales: one float per (slot, chain), DevState::amax[slot * C_alloc + chain], folded
+// with atomicMax on the bit pattern (non-negative floats order like unsigned integers) and zeroed by bae_amax_zero_kernel
+// before the phase range that produces them.
+enum AmaxSlot : int {
+  AMAX_W = 0,                          // the six weight matrices of the chain's live model (PH_WAMAX)
+  AMAX_Y,                              // BatchNorm output of the most recent forward pass (run_bn_fwd_wide)
+  AMAX_DOUT, AMAX_D5, AMAX_D4, AMAX_DY, AMAX_D2, AMAX_D1,   // deltas (GEMM epilogues; DY after the BatchNorm backward)
+  kAmaxSlots
+};
+enum ScaleSrc : int { SC_UNIT = -1, SC_XTRAIN = -2, SC_XTEST = -3 };
+constexpr int kF16TopExp = 13;   // operands are scaled so that their bound lands in [2^13, 2^14)
+
+// exponent e with bound * 2^e in [2^13, 2^14), clamped so that sums of two exponents (+ 11) stay inside the FP32 range
+__host__ __device__ inline int f16_scale_exp(float bound) {
+  unsigned u;
+#ifdef __CUDA_ARCH__
+  u = __float_as_uint(bound);
+#else
+  memcpy(&u, &bound, 4);
+#endif
+  const int e = kF16TopExp - ((int)((u >> 23) & 0xFFu) - 127);
+  return e < -50 ? -50 : (e > 50 ? 50 : e);
+}
 
 enum PhaseKind : int {
   PH_PROLOGUE = 0, PH_GEMM, PH_BN_FWD, PH_BN_BWD, PH_ADAM1, PH_ADAM2, PH_EPILOGUE,
-  PH_SWAP_DECIDE, PH_SWAP_GATHER, PH_SWAP_SCATTER
+  PH_SWAP_DECIDE, PH_SWAP_GATHER, PH_SWAP_SCATTER,
+  PH_WAMAX        // 3xFP16 split: max |w| over the weight matrices of every chain (after whatever rewrote theta)
 };
 
 struct PhaseDesc {
   int kind;
   int g0, g1;   // GEMM descriptor indices (g1 = -1 if single)
-  int arg;      // BN: stats slot (0 first train pass, 1 second train pass, 2 test); rows via argRows
+  int arg;      // BN: stats slot (0 first train pass, 1 second train pass, 2 test); rows via argRows; PH_WAMAX: 1 = only after an exchange round
   int argRows;  // BN: number of data rows
   int needLang;
   int sched_off, sched_max;   // tcgen05 path: this phase's item schedule inside DevState::sched ([pair][sched_max], -1 padded), or -1
@@ -151,7 +180,10 @@ struct DevState {
   double* xt_all;     // [world][C][5]  all-gathered
   int* xsrc;          // [E][R]         global rung whose configuration ends at rung p (identical on every rank)
   // ---- tcgen05 path
-  int tc;             // 1: GEMM phases run on the tensor cores (3xTF32); row pitches reserve a ones column
+  int tc;             // 1: GEMM phases run on the tensor cores; row pitches reserve a ones column
+  int f16;            // 1: 3xFP16 split (kind::f16, K = 16 per MMA, scaled operands); 0: 3xTF32 split (kind::tf32)
+  float* amax;        // [kAmaxSlots][C_alloc] magnitude bounds of the scaled operands (AmaxSlot)
+  int xexp[2];        // scale exponents of the training / test matrix (host scan at bae_upload_data)
   void* tmaps;        // CUtensorMap array in global memory (64-byte aligned)
   int* sched;         // longest-first item schedules of the GEMM phases (PhaseDesc::sched_off), built for `sched_chains` chains
   int sched_chains, sched_pairs;   // ... per launch and `sched_pairs` CTA pairs

@@ -320,6 +320,63 @@ __device__ void run_gemm_phase(const DevState* S, const PhaseDesc& ph, int c_beg
 }
 
 // ------------------------------------------------------------------------------------------------
+// Magnitude bounds behind the FP16 operand scales of the 3xFP16 split (bae_common.cuh: AmaxSlot)
+// ------------------------------------------------------------------------------------------------
+// CTA-wide maximum of `v` folded into amax[slot][chain] (one atomic per warp; every thread of the CTA calls this)
+// (v >= 0; the lanes of a warp that are not here - columns beyond d3 in the BatchNorm phases - simply do not take part)
+__device__ __forceinline__ void fold_amax(const DevState* S, int slot, int chain, float v) {
+  const unsigned m = __activemask();
+  const unsigned r = __reduce_max_sync(m, __float_as_uint(v));
+  if ((int)(TID & 31) == __ffs(m) - 1 && r != 0u)
+    atomicMax(reinterpret_cast<unsigned*>(S->amax) + (size_t)slot * S->C_alloc + chain, r);
+}
+
+// PH_WAMAX: max |w| over the six weight matrices of every chain in [c_begin, c_end) (slot AMAX_W, zeroed by the host's
+// bae_amax_zero_kernel launch in front of this phase). Work item = (chain, 4096-float piece of one matrix).
+__device__ void run_wamax(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, int force) {
+  if (!S->f16) return;
+  if (ph.arg == 1 && !force) {
+    // start of an iteration inside a step program: theta changed only if the previous iteration ended with an exchange
+    // round (the swap phases' own gate, seen one iteration later); the first iteration of a call is covered by the forced
+    // launch the host puts in front of the program
+    const int st = S->ch.step[c_begin];
+    if ((st % S->swap_interval) != 0) return;
+  }
+  constexpr int kPiece = 4096;
+  const int wsegs[6] = {SEG_D1_W, SEG_D3_W, SEG_D5_W, SEG_E0_W, SEG_E2_W, SEG_E4_W};
+  int np[6], tot = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { np[i] = (S->seg[wsegs[i]].rows * S->seg[wsegs[i]].ld + kPiece - 1) / kPiece; tot += np[i]; }
+  const int total = tot * (c_end - c_begin);
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int chain = c_begin + item / tot;
+    int p = item % tot, sg = 0;
+    while (p >= np[sg]) { p -= np[sg]; ++sg; }
+    const Seg& sd = S->seg[wsegs[sg]];
+    const int n = sd.rows * sd.ld;
+    const float* w = S->theta + (size_t)chain * S->Pp + sd.pad_off;
+    float amx = 0.f;
+    for (int e = p * kPiece + TID * 4; e < min(n, (p + 1) * kPiece); e += kThreads * 4) {
+      const float4 v = *reinterpret_cast<const float4*>(w + e);   // rows are padded to 4 floats, pads are zero
+      amx = fmaxf(amx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    fold_amax(S, AMAX_W, chain, amx);
+  }
+}
+
+// Zeroes the amax slots in `mask` for chains [c_begin, c_end): launched by the host in front of the phase range that
+// produces them (forward pass: Y of that pass, DOUT; backward pass: the five inner deltas; PH_WAMAX: the weights).
+// `gated`: the same test as the gated PH_WAMAX phase it precedes (run_wamax).
+__global__ void bae_amax_zero_kernel(const DevState* __restrict__ S, unsigned mask, int c_begin, int c_end, int gated) {
+  if (gated && (S->ch.step[c_begin] % S->swap_interval) != 0) return;
+  const int n = c_end - c_begin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kAmaxSlots * n; i += gridDim.x * blockDim.x) {
+    const int slot = i / n, chain = c_begin + i % n;
+    if ((mask >> slot) & 1u) S->amax[(size_t)slot * S->C_alloc + chain] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // BatchNorm1d, training mode (MAIN:165): batch statistics forward, full backward
 // ------------------------------------------------------------------------------------------------
 // ---- BatchNorm phases for wide bottlenecks (d3 >= 16): a work item is (chain, 16 columns). 4 float4 column groups x
@@ -415,6 +472,7 @@ __device__ void run_bn_fwd_wide(const DevState* S, const PhaseDesc& ph, int c_be
       }
     }
     const bool full4 = c0 + 4 <= d3;
+    float amx = 0.f;   // max |y| of this thread's columns: the bound behind the FP16 scale of Y (3xFP16 split)
     for (int base = rl; base < N; base += kBnLanes * kBnUnroll) {
       float4 z[kBnUnroll];
 #pragma unroll
@@ -431,12 +489,17 @@ __device__ void run_bn_fwd_wide(const DevState* S, const PhaseDesc& ph, int c_be
         float* yp = Y + (size_t)r * ld3;
         if (full4) {
           *reinterpret_cast<float4*>(yp) = make_float4(y[0], y[1], y[2], y[3]);
+          amx = fmaxf(amx, fmaxf(fmaxf(fabsf(y[0]), fabsf(y[1])), fmaxf(fabsf(y[2]), fabsf(y[3]))));
         } else {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (c0 + k < d3) yp[k] = y[k];
+            if (c0 + k < d3) { yp[k] = y[k]; amx = fmaxf(amx, fabsf(y[k])); }
         }
       }
+    }
+    if (S->f16) {
+      // the ones column next to Y (bias gradient of decode.1) is part of the operand: the bound is at least 1
+      fold_amax(S, AMAX_Y, chain, fmaxf(amx, 1.0f));
     }
   }
 }
@@ -508,6 +571,7 @@ __device__ void run_bn_bwd_wide(const DevState* S, const PhaseDesc& ph, int c_be
       m2[k] = (float)(s2[k] / N) * gam[k];   // mean(dzhat * zhat)
     }
     const bool full4 = c0 + 4 <= d3;
+    float amx = 0.f;   // max |dz|: the bound behind the FP16 scale of DY in the two GEMMs that read it
     for (int base = rl; base < N; base += kBnLanes * kBnUnroll) {
       float4 dy[kBnUnroll], z[kBnUnroll];
 #pragma unroll
@@ -533,13 +597,15 @@ __device__ void run_bn_bwd_wide(const DevState* S, const PhaseDesc& ph, int c_be
         float* dp = DY + (size_t)r * ld3;
         if (full4) {
           *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
+          amx = fmaxf(amx, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
         } else {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (c0 + k < d3) dp[k] = o[k];
+            if (c0 + k < d3) { dp[k] = o[k]; amx = fmaxf(amx, fabsf(o[k])); }
         }
       }
     }
+    if (S->f16) fold_amax(S, AMAX_DY, chain, amx);
   }
 }
 
@@ -697,6 +763,7 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
     const int sg_first = find_seg(S, it * kAdamChunk), sg_last = find_seg(S, min(Pp, (it + 1) * kAdamChunk) - 4);
     const float inv_sq = 1.0f / sq;   // one IEEE division per item; per element: a multiply and an approximate reciprocal
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    float wmx = 0.f;   // 3xFP16 split: max |proposal| over the entries of weight MATRICES in this item (slot AMAX_W)
 #pragma unroll 2
     for (int u = 0; u < kAdamChunk / (kThreads * 4); ++u) {
       const int p = it * kAdamChunk + (u * kThreads + TID) * 4;
@@ -754,6 +821,7 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
             o[j] = 0.f;
           }
         }
+        if (sd.span > sd.ld) wmx = fmaxf(wmx, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
         *reinterpret_cast<float4*>(&th[p]) = make_float4(o[0], o[1], o[2], o[3]);
       } else if (plain) {
         if (alias) continue;    // w IS the live model: w - w_prop_gd is exactly 0 (MAIN:476 with MAIN:449/555)
@@ -797,6 +865,7 @@ __device__ void run_adam(const DevState* S, int which, int c_begin, int c_end, d
       double s0 = block_sum_d((double)a0, red);
       double s1 = block_sum_d((double)a1, red);
       if (TID == 0) { part[0] = s0; part[1] = s1; }
+      if (S->f16) fold_amax(S, AMAX_W, chain, wmx);   // zeroed by the launch in front of this phase
     } else {
       double s2 = block_sum_d((double)a2, red);
       if (TID == 0) part[2] = s2;
@@ -1481,7 +1550,7 @@ template <bool kSimtGemm>
 __device__ void run_phase(const DevState* S, int pi, int c_begin, int c_end, int force_swap, float* smem,
                           double* red) {
   const PhaseDesc& ph = S->phase[pi];
-  if (ph.kind >= PH_SWAP_DECIDE && !force_swap) {
+  if (ph.kind >= PH_SWAP_DECIDE && ph.kind <= PH_SWAP_SCATTER && !force_swap) {
     // inside bae_run: exchange only after every swap_interval-th iteration (MAIN:594); all chains share the step count
     const int st = S->ch.step[0];
     if (st == 0 || (st % S->swap_interval) != 0) return;
@@ -1505,6 +1574,7 @@ __device__ void run_phase(const DevState* S, int pi, int c_begin, int c_end, int
     case PH_SWAP_DECIDE: run_swap_decide(S); break;
     case PH_SWAP_GATHER: run_swap_gather(S); break;
     case PH_SWAP_SCATTER: run_swap_scatter(S); break;
+    case PH_WAMAX: run_wamax(S, ph, c_begin, c_end, force_swap); break;
     default: break;
   }
 }
@@ -1519,6 +1589,7 @@ bae_program_kernel(const DevState* __restrict__ S, int ph_begin, int ph_end, int
   cg::grid_group grid = cg::this_grid();
   for (int rep = 0; rep < n_rep; ++rep) {
     for (int pi = ph_begin; pi < ph_end; ++pi) {
+      if (S->phase[pi].kind == PH_WAMAX) continue;   // 3xFP16 split only (per-phase launches)
       run_phase<true>(S, pi, c_begin, c_end, force_swap, smem, red);
       grid.sync();
     }
@@ -1611,6 +1682,7 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
     tc::regs_inc<tc::kRegsEpi>();
     for (int rep = 0; rep < n_rep; ++rep) {
       for (int pi = ph_begin; pi < ph_end; ++pi) {
+        if (S->phase[pi].kind == PH_WAMAX) continue;   // 3xFP16 split only (per-phase launches)
         run_phase_tc_back<-1, -1>(S, pi, c_begin, c_end, force_swap, tsm, ring, smem_small, red);
         grid.sync();
         if (S->dbg && blockIdx.x == 0 && threadIdx.x == 128 && rep == 1) {   // debug: phase end times of the 2nd iteration
@@ -1624,6 +1696,7 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
     tc::regs_dec<tc::kRegsLean>();
     for (int rep = 0; rep < n_rep; ++rep) {
       for (int pi = ph_begin; pi < ph_end; ++pi) {
+        if (S->phase[pi].kind == PH_WAMAX) continue;
         run_phase_tc_front(S, pi, c_begin, c_end, tsm, ring);
         grid.sync();
       }
@@ -1639,7 +1712,7 @@ bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_e
   extern __shared__ uint8_t dyn_smem[];
   tc::Smem tsm;
   tc::Ring ring;
-  tc::setup(tsm, dyn_smem);
+  tc::setup(tsm, dyn_smem, S->f16 != 0);
   const int wg = threadIdx.x >> 7;
   if (wg == 1 || wg == 2) {
     tc::regs_inc<tc::kRegsEpi>();
@@ -1868,6 +1941,11 @@ cudaError_t launch_aux(const DevState* dS, int kind, int grid, int pi, int c_beg
     case AUX_BN: bae_aux_kernel<AUX_BN><<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end, force_swap); break;
     default: bae_aux_kernel<AUX_MISC><<<grid, kThreads, 0, st>>>(dS, pi, c_begin, c_end, force_swap); break;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_amax_zero(const DevState* dS, unsigned mask, int c_begin, int c_end, int gated, cudaStream_t st) {
+  bae_amax_zero_kernel<<<1, 256, 0, st>>>(dS, mask, c_begin, c_end, gated);
   return cudaGetLastError();
 }
 

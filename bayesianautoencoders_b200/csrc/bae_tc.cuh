@@ -313,12 +313,156 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 #endif
 }
 
-__device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem) {
+// ---------------------------------------------------------------------------------------------------
+// 3xFP16 split (kind::f16 MMAs, K = 16 per instruction: half the tensor-pipe time of the 3xTF32 split).
+// FP16 has the SAME 11 significant bits as TF32; what it lacks is exponent range (2^-14 .. 2^15 normal). Every operand is
+// therefore multiplied by a power of two s = 2^e chosen from a bound on its magnitude (static for data and sigmoid outputs,
+// tracked per chain for weights, BatchNorm outputs and deltas: DevState::amax) so that |x s| < 2^14, then split
+//     hi = fp16_rn(x s)            11 significant bits (fewer only below 2^-14: 2^-27 of the operand's bound)
+//     lo = fp16_rn(x s - hi)       the exact residual, again 11 bits (fewer only when |x s| < 2^-3, i.e. an absolute error
+//                                  below 2^-38 of the operand's bound: far under the FP32 rounding of the sums it enters)
+// and the three products hi*hi (accumulator 0), lo*hi + hi*lo (accumulator 1) are recombined in the epilogue as
+// (acc0 + acc1) / (sA sB): powers of two throughout, so the result does not depend on the exponents chosen.
+//
+// The converter warps write the FP16 tiles in the NO-SWIZZLE canonical layout, which is the same byte formula for both
+// majors: a "unit" = 8 consecutive elements along the operand's contiguous dimension = 16 bytes, unit index
+//     U = 16 i + 8 j + r     at byte offset 16 U
+//   K-major  (rows of K):   row = 8 i + r, k = 8 j .. 8 j + 7      (core matrix = 8 rows x 16 B; LBO = 128 B between the two
+//   MN-major (rows of MN):  k = 8 j + r,  mn = 8 i .. 8 i + 7       K halves, SBO = 256 B between groups of 8 rows / 8 MN)
+// A quarter warp writes 8 consecutive units = 128 contiguous bytes (conflict free), and its 8 reads of the TMA-written FP32
+// tile fall into 8 different 16-byte bank groups in both source swizzles (for MN-major sources the two halves of a 32-byte
+// swizzle unit are read in opposite order by the lanes with r >= 4).
+constexpr int kF16TileBytes = 128 * kBK * 2;   // 4 KB: 128 rows (or MN) x 16 K of halves; a 16 KB lo stage = [A hi][A lo][B hi][B lo]
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {   // a at the lower address
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+__device__ __forceinline__ void unpack_half2(uint32_t h, float& a, float& b) {
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(a), "=f"(b) : "r"(h));
+}
+
+// source addresses of unit U of an FP32 tile written by TMA; mode 0: K-major rows of 64 B, SWIZZLE_64B; mode 1: MN-major
+// chunks of [16 k][32 mn], SWIZZLE_128B_ATOM_32B. Returns whether the two 16-byte halves come back swapped.
+__device__ __forceinline__ bool f16_unit_src(uint32_t src_s, int U, int mode, uint32_t& a0, uint32_t& a1) {
+  const int r = U & 7, j = (U >> 3) & 1, i = U >> 4;
+  if (mode == 0) {
+    const int row = i * 8 + r;
+    const uint32_t sw = (uint32_t)(row >> 1) & 3u, base = src_s + (uint32_t)row * 64u;
+    a0 = base + ((((uint32_t)(2 * j)) ^ sw) << 4);
+    a1 = base + ((((uint32_t)(2 * j + 1)) ^ sw) << 4);
+    return false;
+  }
+  const int k = j * 8 + r;
+  const uint32_t base = src_s + (uint32_t)(i >> 2) * 2048u + (uint32_t)k * 128u + ((((uint32_t)i & 3u) ^ ((uint32_t)k & 3u)) << 5);
+  const bool swap = (r & 4) != 0;
+  a0 = base + (swap ? 16u : 0u);
+  a1 = base + (swap ? 0u : 16u);
+  return swap;
+}
+
+// 8 scaled values -> 16 B of hi halves and 16 B of lo halves
+__device__ __forceinline__ void f16_split8(const float4& v0, const float4& v1, float s, uint4& hi, uint4& lo) {
+  const float x[8] = {v0.x * s, v0.y * s, v0.z * s, v0.w * s, v1.x * s, v1.y * s, v1.z * s, v1.w * s};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    h[p] = pack_half2(x[2 * p], x[2 * p + 1]);
+    float f0, f1;
+    unpack_half2(h[p], f0, f1);
+    l[p] = pack_half2(x[2 * p] - f0, x[2 * p + 1] - f1);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void sts128u(uint32_t saddr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Converts units [u0, u0 + stride, ...) < n_units of one operand tile (two units in flight per thread)
+__device__ __forceinline__ void f16_convert_tile(uint32_t src_s, uint32_t hi_s, uint32_t lo_s, int mode, float s, int u0, int stride,
+                                                 int n_units) {
+  for (int U = u0; U < n_units; U += 2 * stride) {
+    const int U2 = U + stride;
+    const bool two = U2 < n_units;
+    uint32_t a0, a1, b0 = 0, b1 = 0;
+    const bool swa = f16_unit_src(src_s, U, mode, a0, a1);
+    bool swb = false;
+    if (two) swb = f16_unit_src(src_s, U2, mode, b0, b1);
+    float4 va0 = lds128(a0), va1 = lds128(a1), vb0, vb1;
+    if (two) { vb0 = lds128(b0); vb1 = lds128(b1); }
+    uint4 hi, lo;
+    if (swa) f16_split8(va1, va0, s, hi, lo); else f16_split8(va0, va1, s, hi, lo);
+    sts128u(hi_s + (uint32_t)U * 16u, hi);
+    sts128u(lo_s + (uint32_t)U * 16u, lo);
+    if (two) {
+      if (swb) f16_split8(vb1, vb0, s, hi, lo); else f16_split8(vb0, vb1, s, hi, lo);
+      sts128u(hi_s + (uint32_t)U2 * 16u, hi);
+      sts128u(lo_s + (uint32_t)U2 * 16u, lo);
+    }
+  }
+}
+
+// The same conversion for a 64-thread converter group of the engine (thread gt takes units gt, gt + 64, ...): r = U & 7 and
+// j = (U >> 3) & 1 are then constants of the thread and i = (gt >> 4) + 4 n, which makes BOTH source swizzles collapse to
+//     address(n) = tile + off(thread, mode) + 2048 n,      second half of the unit at address(n) ^ 16
+// (K-major: (row >> 1) & 3 = (r >> 1) & 3 for every n; MN-major: the 32-column chunk index is n). Lanes with r >= 4 of an
+// MN-major source start with the upper half (`swap`): their two loads come back in the opposite order.
+struct ConvLane {
+  uint32_t off[2];   // per source mode
+  bool swap1;        // mode 1 only
+};
+__device__ __forceinline__ ConvLane conv_lane(int gt) {
+  const uint32_t r = gt & 7, j = (gt >> 3) & 1, i0 = gt >> 4;
+  ConvLane c;
+  c.off[0] = (8 * i0 + r) * 64 + (((2 * j) ^ ((r >> 1) & 3)) << 4);
+  const uint32_t k = 8 * j + r;
+  c.swap1 = (r & 4) != 0;
+  c.off[1] = k * 128 + ((i0 ^ (k & 3)) << 5) + (c.swap1 ? 16u : 0u);
+  return c;
+}
+// units gt + 64 n, n = n0 .. n0 + kN - 1, of one operand tile
+template <int kN>
+__device__ __forceinline__ void conv_units(uint32_t src_t, uint32_t hi_t, uint32_t lo_t, bool swap, float s, int n0) {
+  // kN units at once: 2 kN loads in flight
+  float4 p[kN], q[kN];
+#pragma unroll
+  for (int u = 0; u < kN; ++u) {
+    p[u] = lds128(src_t + (uint32_t)(n0 + u) * 2048u);
+    q[u] = lds128((src_t + (uint32_t)(n0 + u) * 2048u) ^ 16u);
+  }
+#pragma unroll
+  for (int u = 0; u < kN; ++u) {
+    if (swap) { const float4 t = p[u]; p[u] = q[u]; q[u] = t; }
+    uint4 hi, lo;
+    f16_split8(p[u], q[u], s, hi, lo);
+    sts128u(hi_t + (uint32_t)(n0 + u) * 1024u, hi);
+    sts128u(lo_t + (uint32_t)(n0 + u) * 1024u, lo);
+  }
+}
+
+// Shared-memory descriptor of an FP16 operand tile in the no-swizzle layout above (either major): LBO = 128 B, SBO = 256 B
+__device__ __forceinline__ uint64_t make_desc_f16(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
+// f16: the raw (FP32) stages are read by this CTA's converter warps only, which release them themselves (one arrival per warp
+// of the converting group); in the 3xTF32 engine the tensor core reads them too and the MMA issuer's commit releases them.
+__device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem, bool f16 = false) {
   uintptr_t base = (reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023;
   sm.tiles = reinterpret_cast<uint8_t*>(base);
   if (threadIdx.x == 0) {
     // `conv` and `tmem_empty` collect arrivals from both CTAs of the pair (only the leader's copies are waited on)
-    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full()[i], 1); mbar_init(&sm.empty()[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full()[i], 1); mbar_init(&sm.empty()[i], f16 ? kConvGroupWarps : 1); }
     for (int i = 0; i < kLoStages; ++i) { mbar_init(&sm.conv()[i], 2 * kConvGroupWarps); mbar_init(&sm.lo_empty()[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full()[i], 1); mbar_init(&sm.tmem_empty()[i], 2 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -366,6 +510,14 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // adds into it (TMA reduce-add in L2 / read-modify-write by the thread that wrote the element), in segment order - one
 // gradient copy in HBM, summed in a fixed order.
 struct Item { const GemmDesc* g; int chain, tile_m, tile_n, split, kb0, nkb, nsplit; };
+
+// 3xFP16 split: scale exponent of an operand of `chain` (GemmDesc::aSc / bSc)
+__device__ __forceinline__ int operand_exp(const DevState* S, int sc, int chain) {
+  if (sc >= 0) return f16_scale_exp(S->amax[(size_t)sc * S->C_alloc + chain]);
+  if (sc == SC_UNIT) return kF16TopExp;
+  return S->xexp[sc == SC_XTRAIN ? 0 : 1];
+}
+__device__ __forceinline__ float exp2i(int e) { return __uint_as_float((uint32_t)(e + 127) << 23); }   // 2^e, -126 <= e <= 127
 
 __device__ __forceinline__ int items_per_chain(const DevState* S, const PhaseDesc& ph, int& ta) {
   const GemmDesc& ga = S->gemm[ph.g0];
@@ -511,10 +663,29 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const int nkb = it.nkb, krem0 = g.K - it.kb0 * kBK;
         // descriptors of stage 0; a stage / K-step offset only moves the 14-bit address field (bytes >> 4)
         const uint64_t dA = make_desc(smem_u32(sm.tiles), amn), dB = make_desc(smem_u32(sm.tiles) + kATileBytes, bmn);
+        const uint64_t d16 = make_desc_f16(smem_u32(sm.tiles));
+        const bool f16 = S->f16 != 0;
         for (int kb = 0; kb < nkb; ++kb) {
           // `conv` is signalled by converter warps that had themselves waited for the TMA bytes (`full`)
           mbar_wait(&sm.conv()[ring.lo], ring.lo_phase);   // both CTAs' raw and lo tiles of the K block are ready
           fence_after_sync();
+          if (f16) {
+            // 3xFP16: the converted stage holds [A hi][A lo][B hi][B lo], 4 KB each; one K = 16 MMA per product
+            if (elect_one()) {
+              trace(dbg, 1, ntr, kb);
+              const uint64_t ah = d16 + (kStages + ring.lo) * (uint32_t)(kStageBytes >> 4);
+              const uint64_t al = ah + (kF16TileBytes >> 4), bh = ah + (2 * kF16TileBytes >> 4), bl = ah + (3 * kF16TileBytes >> 4);
+              const uint32_t acc0 = kb ? 1u : 0u;
+              umma_f16(d_main, ah, bh, idesc, acc0);
+              umma_f16(d_cross, al, bh, idesc, acc0);
+              umma_f16(d_cross, ah, bl, idesc, 1u);
+              umma_commit(&sm.lo_empty()[ring.lo]);
+              if (kb == nkb - 1) {
+                trace(dbg, 1, ntr, 1000);
+                umma_commit(&sm.tmem_full()[0]);
+              }
+            }
+          } else
           if (elect_one()) {
             trace(dbg, 1, ntr, kb);
             const uint32_t so = ring.stage * (uint32_t)(kStageBytes >> 4), lo = (kStages + ring.lo) * (uint32_t)(kStageBytes >> 4);
@@ -554,6 +725,9 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     const int gt = ((warp & 1) << 5) + lane;   // 0..63 inside the group
     const uint32_t tiles_s = smem_u32(sm.tiles) + gt * 16;
     const bool skip = (BAE_DBGF(S) & 1) != 0;
+    const bool f16 = S->f16 != 0;
+    const uint32_t tiles0 = smem_u32(sm.tiles);
+    const ConvLane cl = conv_lane(gt);
     int ntr = (grp == 0) ? 0 : (grp == 1 ? 170 : 340);
     uint32_t kbc = ring.kbc;
     for (int ki = 0;; ++ki) {   // items go to CTA pairs
@@ -562,7 +736,51 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
       Item it;
       if (!decode_item(S, ph, c_begin, item, it)) continue;
       const int nkb = (it.g->K + kBK - 1) / kBK;   // all K segments of the tile, back to back
+      // 3xFP16: operand scales of this item, source majors, units of this CTA's B half (8 columns x 16 k each)
+      float sA = 1.f, sB = 1.f;
+      uint32_t offA = 0, offB = 0;
+      bool swapA = false, swapB = false;
+      int nUB = 0;   // units of this CTA's B half
+      if (f16) {
+        sA = exp2i(operand_exp(S, it.g->aSc, it.chain));
+        sB = exp2i(operand_exp(S, it.g->bSc, it.chain));
+        const int am = it.g->aMode != 0, bm = it.g->bMode != 0;
+        offA = cl.off[am]; offB = cl.off[bm];
+        swapA = am && cl.swap1; swapB = bm && cl.swap1;
+        nUB = it.g->tcBN;
+      }
       for (int kb = 0; kb < nkb; ++kb) {
+        if (f16 && (int)kbc == grp) {
+          mbar_wait(&sm.lo_empty()[ring.lo], ring.lo_phase ^ 1);
+          mbar_wait(&sm.full()[ring.stage], ring.phase);
+          if (gt == 0) trace(dbg, 2, ntr, kb);
+          const uint32_t src = tiles0 + ring.stage * kStageBytes, dst = tiles0 + (kStages + ring.lo) * kStageBytes + gt * 16;
+          // A: 256 units = 4 per thread
+          conv_units<2>(src + offA, dst, dst + kF16TileBytes, swapA, sA, 0);
+          conv_units<2>(src + offA, dst, dst + kF16TileBytes, swapA, sA, 2);
+          // B: tcBN units (a multiple of 16) = this CTA's BN/2 columns
+          const uint32_t srcB = src + kATileBytes + offB, dstB = dst + 2 * kF16TileBytes;
+          if (nUB >= 128) {
+            conv_units<2>(srcB, dstB, dstB + kF16TileBytes, swapB, sB, 0);
+          } else {
+            if (gt < nUB) conv_units<1>(srcB, dstB, dstB + kF16TileBytes, swapB, sB, 0);
+            if (gt + 64 < nUB) conv_units<1>(srcB, dstB, dstB + kF16TileBytes, swapB, sB, 1);
+          }
+          if (nUB >= 256) {
+            conv_units<2>(srcB, dstB, dstB + kF16TileBytes, swapB, sB, 2);
+          } else {
+            if (gt + 128 < nUB) conv_units<1>(srcB, dstB, dstB + kF16TileBytes, swapB, sB, 2);
+            if (gt + 192 < nUB) conv_units<1>(srcB, dstB, dstB + kF16TileBytes, swapB, sB, 3);
+          }
+          if (gt == 0) trace(dbg, 2, ntr, 2000 + kb);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&sm.empty()[ring.stage]);   // the raw stage has been read: the producer may refill it
+            if (rank == 0) mbar_arrive(&sm.conv()[ring.lo]);
+            else mbar_arrive_leader_relaxed(&sm.conv()[ring.lo]);
+          }
+        } else
         if ((int)kbc == grp) {
           // The lo slot first (the MMAs of K block k - 4 are done): it also pins the phase of `full`. Parity waits cannot
           // tell phases two apart, and a raw stage is served by all groups in turn; the MMAs of block k - 4 complete after
@@ -651,6 +869,13 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
     }
   }
 
+  // 3xFP16: undo the operand scales (powers of two). 3xTF32: 1, 1.
+  float unscale0 = 1.f, unscale1 = 1.f;
+  if (S->f16) {
+    const int e = operand_exp(S, g.aSc, it.chain) + operand_exp(S, g.bSc, it.chain);
+    unscale0 = unscale1 = exp2i(-e);
+  }
+
   // ---- drain: both accumulators of this warp's chunks -> registers, then TMEM goes back to the MMA issuer.
   mbar_wait(&sm.tmem_full()[0], ring.acc_phase);
   if (c.et == 0) trace(dbg, 3, ntr, 0);
@@ -664,6 +889,7 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if ((eg + 2 * j) * 32 < ncols) tmem_ld32_issue(tbase + (uint32_t)((eg + 2 * j) * 32), acc[j]);
+    // (the first waiting load below also completes the main-accumulator loads)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int c0 = (eg + 2 * j) * 32;
@@ -674,7 +900,9 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
           tmem_wait_ld16(pa);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            acc[j][hh * 16 + i] = __float_as_uint(__uint_as_float(acc[j][hh * 16 + i]) + __uint_as_float(pa[i]));
+            // (acc[j] is the target of an asynchronous tcgen05.ld: every instruction that reads it must also depend on `pa`,
+            //  whose wait completes all loads issued so far - hence the product with pa first, then ONE fma that reads acc)
+            acc[j][hh * 16 + i] = __float_as_uint(fmaf(__uint_as_float(acc[j][hh * 16 + i]), unscale0, __uint_as_float(pa[i]) * unscale1));
         }
       }
     }
@@ -716,6 +944,8 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
   // accumulators go to the staging tile, and all epilogue math runs in the coalesced (transposed) domain where aux
   // loads, bias and stores share one address pattern.
   float l_sse = 0.f, l_sd = 0.f;
+  float amx = 0.f;   // max |stored value| of this thread (deltas: bound behind the FP16 scale of the next GEMMs' operand)
+  const bool kTrackAmax = (epi == EPI_LOSS || epi == EPI_DSIG);
   const int lim = (epi == EPI_GRADW && biasCol >= 0) ? min(n_end, biasCol) : n_end;   // columns >= lim are not stored
   if (accum) {
     // the previous segment's box stores of this warp are COMPLETE (not just read) before anything is added to them; they
@@ -790,6 +1020,12 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
         }
         o = make_float4(d[0], d[1], d[2], d[3]);
       }
+      if (kTrackAmax) {
+        const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (cc + e < n_end) amx = fmaxf(amx, fabsf(ov[e]));
+      }
       if (box) {
         sts128(sa, o);   // back to where this thread read it from
       } else {
@@ -824,6 +1060,11 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
     __syncwarp();
   }
   if (c.et == 0) trace(dbg, 3, ntr, 2);
+  if (kTrackAmax && g.cSc >= 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amx = fmaxf(amx, __shfl_xor_sync(0xffffffffu, amx, o));
+    if (lane == 0 && amx > 0.f) atomicMax(reinterpret_cast<unsigned*>(S->amax) + (size_t)g.cSc * S->C_alloc + chain, __float_as_uint(amx));
+  }
   if (epi == EPI_LOSS) {
     double s0 = (double)l_sse, s1 = (double)l_sd;
 #pragma unroll

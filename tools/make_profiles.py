@@ -17,17 +17,27 @@ def kname(full):
 
 launch_csv, raw_csv = sys.argv[1], sys.argv[2]
 bench_ms = sys.argv[3] if len(sys.argv) > 3 else '61-62'
-prefix = sys.argv[4] if len(sys.argv) > 4 else 'r2_v6'      # file-name prefix under profiles/
-label = sys.argv[5] if len(sys.argv) > 5 else 'Round 2, step program v6 (one gradient copy, relaxed hand-backs)'
+prefix = sys.argv[4] if len(sys.argv) > 4 else 'r2_v7'      # file-name prefix under profiles/
+label = sys.argv[5] if len(sys.argv) > 5 else 'Round 2, step program v7 (3xFP16 split)'
 rows = [r for r in csv.reader(open(launch_csv)) if len(r) > 5]
 h, data = rows[0], rows[1:]
 iv, ik = h.index('Metric Value'), h.index('Kernel Name')
 vals = [float(r[iv].replace(',', '')) / 1000 for r in data]   # ns -> us
-names = ['PRO', 'F1', 'F2', 'F3', 'BNF', 'F4', 'F5', 'F6', 'B6 (dW6|dH5)', 'B5', 'B4', 'BNB', 'B3', 'B2', 'B1', 'ADAM1', 'F1b', 'F2b', 'F3b',
-         'BNFb', 'F4b', 'F5b', 'F6b', 'B6b', 'B5b', 'B4b', 'BNBb', 'B3b', 'B2b', 'B1b', 'ADAM2', 'T1', 'T2', 'T3', 'BNT', 'T4', 'T5', 'T6', 'EPI']
-PER_IT = 42   # 39 step phases + 3 exchange phases (which return at once unless the step counter says "swap round")
+# one iteration of the step program (3xFP16 split): 'Z' = bae_amax_zero_kernel (zeroes the magnitude-bound slots the next phases fold
+# into), WAMAX = weight bounds after an exchange round (returns at once otherwise); a call starts with a forced (Z, WAMAX) pair
+fwd = lambda sfx: ['Z'] + [f'{n}{sfx}' for n in ('F1', 'F2', 'F3', 'BNF', 'F4', 'F5', 'F6')]
+bwd = lambda sfx: ['Z', f'B6{sfx} (dW6|dH5)'] + [f'{n}{sfx}' for n in ('B5', 'B4', 'BNB', 'B3', 'B2', 'B1')]
+names = ['PRO', 'Z', 'WAMAX'] + fwd('') + bwd('') + ['Z', 'ADAM1'] + fwd('b') + bwd('b') + ['ADAM2', 'Z'] + \
+        ['T1', 'T2', 'T3', 'BNT', 'T4', 'T5', 'T6', 'EPI']
+HEAD = 2      # forced (Z, WAMAX) pair in front of the program
+N_IT = len(names)
+PER_IT = N_IT + 3   # + 3 exchange phases (which return at once unless the step counter says "swap round")
 names_it = names + ['SWAP_DECIDE', 'SWAP_GATHER', 'SWAP_SCATTER']
-assert len(vals) == 5 * PER_IT, f"expected {5 * PER_IT} launches (5 iterations x 42 phases), got {len(vals)}"
+vals_all = vals
+vals = vals[HEAD:]
+data_all = data
+data = data[HEAD:]
+assert len(vals) == 5 * PER_IT, f"expected {HEAD} + {5 * PER_IT} launches (5 iterations x {PER_IT} launches), got {len(vals_all)}"
 with open(f'profiles/{prefix}_step_program_launches.csv', 'w') as f:
     f.write("launch,iteration,phase,kernel,duration_us\n")
     for i, (r, v) in enumerate(zip(data, vals)):
@@ -39,11 +49,11 @@ for k, v in F.items():
     fl[k.replace('F', 'T')] = v * 0.9
 fl.update({'B6': 2 * 2000 * 500 * 450 * 2, 'B5': 2 * 2000 * 450 * 400 * 2, 'B4': 2 * 2000 * 400 * 300 * 2, 'B3': 2 * 2000 * 300 * 400 * 2,
            'B2': 2 * 2000 * 400 * 450 * 2, 'B1': 2 * 2000 * 450 * 500})
-it0 = vals[:39]
-sw = vals[4 * PER_IT + 39:5 * PER_IT]
+it0 = vals[:N_IT]
+sw = vals[4 * PER_IT + N_IT:5 * PER_IT]
 tot = sum(it0)
-lines, g, b, a, gf = [], 0.0, 0.0, 0.0, 0.0
-kern = [kname(r[ik]) for r in data[:39]]
+lines, g, b, a, gf, zz = [], 0.0, 0.0, 0.0, 0.0, 0.0
+kern = [kname(r[ik]) for r in data[:N_IT]]
 for n, v, kn in zip(names, it0, kern):
     base = n.split(' ')[0].rstrip('b')
     tf = f"{fl[base] * 64 / (v * 1e-6) / 1e12:.0f}" if base in fl else ""
@@ -53,11 +63,13 @@ for n, v, kn in zip(names, it0, kern):
         b += v
     if base.startswith('ADAM'):
         a += v
+    if base in ('Z', 'WAMAX'):
+        zz += v
     lines.append(f"| {n} | `{kn}` | {v:.1f} | {100 * v / tot:.1f}% | {tf} |")
 md = f"""# {label} - launch list (ncu gpu__time_duration.sum, --clock-control none)
 
 Command: `BAE_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv python tools/profile_step.py --chains 64 --rounds 2 --steps-per-round 5 --profile-round 1`
-(Madelon shape, 64 chains, the 2nd PT round = ONE `bae_run(5)` call: 5 iterations x 42 phase launches, the exchange sweep in the last three; these
+(Madelon shape, 64 chains, the 2nd PT round = ONE `bae_run(5)` call: 5 iterations x {PER_IT} launches, the exchange sweep in the last three; these
 are the production kernels - `BAE_NO_GRAPH=1` only makes the library launch them directly instead of replaying the captured graph).
 Raw list: `{prefix}_step_program_launches.csv`. Per-launch times are cold-cache and serialised (and the SM clock is higher than in a back-to-back run, which
 sits at the power cap); compare SHARES. Sum per iteration: {', '.join(f'{sum(vals[i * PER_IT:(i + 1) * PER_IT]) / 1000:.2f}' for i in range(5))} ms
@@ -68,15 +80,16 @@ sits at the power cap); compare SHARES. Sum per iteration: {', '.join(f'{sum(val
 """ + "\n".join(lines) + f"""
 
 GEMM phases (`bae_phase_kernel_tc<kindA, kindB>`): {100 * g / tot:.1f}% of the iteration ({gf / (g * 1e-6) / 1e12:.0f} TFLOP/s algorithmic over the GEMM phases; the
-sustained-clock ceiling of a 3-way TF32 split is 1381.9 / 6 = 230 TFLOP/s); BatchNorm (`bae_aux_kernel<1>`) {100 * b / tot:.1f}%; Adam + noise
-(`bae_aux_kernel<0>`) {100 * a / tot:.1f}%. `bench.py` measures the same program at {bench_ms} ms per round back to back (graph replay, SM clock at the
+measured bf16 dense peak is 1381.9 TFLOP/s; three kind::f16 MMAs per product bound the algorithmic rate at 1/3 of the FP16 issue rate); BatchNorm (`bae_aux_kernel<1>`) {100 * b / tot:.1f}%; Adam + noise
+(`bae_aux_kernel<0>`) {100 * a / tot:.1f}%; magnitude-bound bookkeeping of the 3xFP16 split (`bae_amax_zero_kernel`, WAMAX) {100 * zz / tot:.1f}%. `bench.py` measures the same program at {bench_ms} ms per round back to back (graph replay, SM clock at the
 power cap): the GEMM kernels' share of the step is the same in both views.
 """
 open(f'profiles/{prefix}_step_program_launches.md', 'w').write(md)
 
 r = list(csv.reader(open(raw_csv)))
 hdr, units, prow = r[0], r[1], r[2:]
-assert len(prow) == PER_IT, "expected the 42 per-phase launches of one iteration"
+prow = prow[HEAD:]
+assert len(prow) == PER_IT, f"expected {HEAD} + {PER_IT} launches of one iteration, got {len(prow) + HEAD}"
 UNIT = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1, 'ms': 1e3, 's': 1e6}
 
 
@@ -97,30 +110,31 @@ rd, wr, us = sum(rdv), sum(wrv), sum(dur)
 ptab = "\n".join(f"| {n} | {dur[i]:.1f} | {rdv[i] / 1e6:.1f} | {wrv[i] / 1e6:.1f} | {(rdv[i] + wrv[i]) / dur[i] / 1e3:.0f} | {dramp[i]:.1f} | {tens[i]:.1f} | "
                  f"{l2hit[i]:.0f} | {inst[i] / 1e6:.2f} | {lld[i] + lst[i]:.0f} |" for i, n in enumerate(names_it))
 gi = [i for i, n in enumerate(names) if n.split(' ')[0].rstrip('b') in fl]
+iA1 = names.index('ADAM1')
 gt = sum(dur[i] for i in gi)
-md2 = f"""# {label} - one `ncu --set full` capture over the 42 kernels of an iteration
+md2 = f"""# {label} - one `ncu --set full` capture over the launches of an iteration
 
-`BAE_NO_GRAPH=1 ncu --set full --clock-control none --profile-from-start off -k regex:bae_ -c 42 python tools/profile_step.py --chains 8 --rounds 2 --steps-per-round 1 --profile-round 1`
+`BAE_NO_GRAPH=1 ncu --set full --clock-control none --profile-from-start off -k regex:bae_ -c {HEAD + PER_IT} python tools/profile_step.py --chains 8 --rounds 2 --steps-per-round 1 --profile-round 1`
 (Madelon shape, 8 chains, ONE iteration of the production step program: GEMM phases = `bae_phase_kernel_tc<kindA, kindB>`, 148 CTAs = 74 CTA pairs x 512
 threads, 1 CTA/SM, {regs[1]:.0f} registers/thread at launch redistributed by `setmaxnreg`; BatchNorm / Adam / scalar phases = `bae_aux_kernel<family>`,
 256-thread CTAs. The report (>100 MB) stays on the GPU box; this file is built from its raw page export by `tools/make_profiles.py`.)
 
-Sum of the 42 kernel durations {us / 1e3:.3f} ms under ncu (cold caches, serialised). Algorithmic FLOPs of one iteration: 8 chains x 27.18 GFLOP = 217 GFLOP
+Sum of the kernel durations {us / 1e3:.3f} ms under ncu (cold caches, serialised). Algorithmic FLOPs of one iteration: 8 chains x 27.18 GFLOP = 217 GFLOP
 -> {217 / (us / 1e3):.0f} TFLOP/s at 8 chains over the whole iteration, {sum(fl[names[i].split(' ')[0].rstrip('b')] for i in gi) * 8 / (gt * 1e-6) / 1e12:.0f} TFLOP/s over the GEMM phases (8 chains fill only
 a fraction of the 74 CTA pairs per phase; production runs 64 chains per GPU, `bench.py`).
 DRAM traffic per iteration: read {rd / 1e6:.0f} MB + write {wr / 1e6:.0f} MB = {(rd + wr) / 8 / 1e6:.0f} MB per chain-iteration. Algorithmic weight-state traffic is
 22 x 4 B x 1.05 M = 93 MB per chain-iteration (SURVEY 8d); the rest is activations and deltas (41 MB per chain, written once and re-read by the backward
 pass and the weight-gradient GEMMs). The gradient has ONE copy: the K segments of a weight-gradient tile are added in L2 by TMA reduce-add.
-SASS evidence (`cuobjdump -sass libbae_b200.so`): UTCHMMA (tcgen05.mma cta_group::2 kind::tf32), UTMALDG (TMA), LDTM (tcgen05.ld),
+SASS evidence (`cuobjdump -sass libbae_b200.so`): UTCHMMA (tcgen05.mma cta_group::2 kind::f16), UTMALDG (TMA), LDTM (tcgen05.ld),
 UTCBAR (tcgen05.commit, multicast), USETMAXREG (setmaxnreg), SYNCS (mbarrier), UCGABAR (cluster barrier).
 
 | phase | us | DRAM read MB | DRAM write MB | DRAM GB/s | DRAM % of peak | tensor pipe active % | L2 hit % | warp inst (M) | local ld+st inst |
 |---|---:|---:|---:|---:|---:|---:|---:|---:|---:|
 {ptab}
 
-Reading: the GEMM phases keep the tensor pipe {min(tens[i] for i in gi):.0f}-{max(tens[i] for i in gi):.0f}% active at 8 chains (each 3xTF32 K block is 6 MMAs; at 64 chains every CTA pair
-has 3-14 tiles per phase and the traced tile loop runs close to the tensor-pipe pace, see DESIGN.md 4); the Adam phases move {(rdv[15] + wrv[15]) / 1e6:.0f} MB at
-{(rdv[15] + wrv[15]) / dur[15] / 1e3:.0f} GB/s = {100 * (rdv[15] + wrv[15]) / dur[15] / 1e3 / 6549:.0f}% of the measured HBM peak (6549 GB/s) at 8 chains. Local-memory instructions of the GEMM kernels are the
+Reading: the GEMM phases keep the tensor pipe {min(tens[i] for i in gi):.0f}-{max(tens[i] for i in gi):.0f}% active at 8 chains (each 3xFP16 K block is 3 MMAs; at 64 chains every CTA pair
+has 3-14 tiles per phase and the traced tile loop runs close to the tensor-pipe pace, see DESIGN.md 4); the Adam phases move {(rdv[iA1] + wrv[iA1]) / 1e6:.0f} MB at
+{(rdv[iA1] + wrv[iA1]) / dur[iA1] / 1e3:.0f} GB/s = {100 * (rdv[iA1] + wrv[iA1]) / dur[iA1] / 1e3 / 6549:.0f}% of the measured HBM peak (6549 GB/s) at 8 chains. Local-memory instructions of the GEMM kernels are the
 front half's (TMA producer / MMA issuer at 48 registers) per-tile set-up; the epilogue half is spill free since it is specialised per kind.
 """
 open(f'profiles/{prefix}_step_program_ncu_full.md', 'w').write(md2)
