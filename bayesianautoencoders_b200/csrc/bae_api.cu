@@ -417,7 +417,7 @@ static void build_program(bae_handle* h) {
       x.aAct = 1; x.cAct = 1;
       x.epi = bl[l].epi_x;
       x.aSc = dsl[l]; x.bSc = AMAX_W;
-      x.cSc = (bl[l].epi_x == EPI_DSIG) ? dsl[l + 1] : -1;   // DY's bound is written by the BatchNorm backward
+      x.cSc = (bl[l].epi_x == EPI_DSIG) ? dsl[l + 1] : (int)AMAX_DYIN;   // DY's own bound is derived by the BatchNorm backward
       if (bl[l].Hin) { x.aux = bl[l].Hin; x.sAux = bl[l].sDin; x.ldaux = bl[l].lddin; x.auxAct = 1; }
       x.needLang = 1;
       add_maps(x);
@@ -845,7 +845,7 @@ static int get1(bae_handle* h, const T* dev_arr, int idx, T* v) {
 static unsigned amax_zero_mask(int p) {
   if (p == P_WAMAX0 || p == P_ADAM1) return 1u << AMAX_W;
   if (p == P_FWD1 || p == P_FWD2 || p == P_FWDT) return (1u << AMAX_Y) | (1u << AMAX_DOUT);
-  if (p == P_BWD1 || p == P_BWD2) return (1u << AMAX_D5) | (1u << AMAX_D4) | (1u << AMAX_DY) | (1u << AMAX_D2) | (1u << AMAX_D1);
+  if (p == P_BWD1 || p == P_BWD2) return (1u << AMAX_D5) | (1u << AMAX_D4) | (1u << AMAX_DY) | (1u << AMAX_DYIN) | (1u << AMAX_D2) | (1u << AMAX_D1);
   return 0u;
 }
 

@@ -80,8 +80,9 @@ struct GemmDesc {
 // before the phase range that produces them.
 enum AmaxSlot : int {
   AMAX_W = 0,                          // the six weight matrices of the chain's live model (PH_WAMAX)
-  AMAX_Y,                              // BatchNorm output of the most recent forward pass (run_bn_fwd_wide)
-  AMAX_DOUT, AMAX_D5, AMAX_D4, AMAX_DY, AMAX_D2, AMAX_D1,   // deltas (GEMM epilogues; DY after the BatchNorm backward)
+  AMAX_Y,                              // BatchNorm output of the most recent forward pass (bound derived by run_bn_fwd_wide)
+  AMAX_DOUT, AMAX_D5, AMAX_D4, AMAX_DY, AMAX_D2, AMAX_D1,   // deltas (GEMM epilogues; DY: bound derived by the BatchNorm backward)
+  AMAX_DYIN,                           // dy as the GEMM epilogue wrote it, in front of the BatchNorm backward
   kAmaxSlots
 };
 enum ScaleSrc : int { SC_UNIT = -1, SC_XTRAIN = -2, SC_XTEST = -3 };

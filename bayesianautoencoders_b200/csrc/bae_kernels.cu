@@ -472,7 +472,16 @@ __device__ void run_bn_fwd_wide(const DevState* S, const PhaseDesc& ph, int c_be
       }
     }
     const bool full4 = c0 + 4 <= d3;
-    float amx = 0.f;   // max |y| of this thread's columns: the bound behind the FP16 scale of Y (3xFP16 split)
+    if (S->f16 && rl == 0) {
+      // bound behind the FP16 scale of Y (3xFP16 split), without a pass over the data: |zhat| <= sqrt(N) for ANY batch
+      // (var is the biased batch variance, so (z - mean)^2 <= N var), hence |y| <= |gamma| sqrt(N) + |beta|; at least 1,
+      // the ones column next to Y (bias gradient of decode.1) being part of the operand
+      const float rn = sqrtf((float)N);
+      float bnd = 1.0f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bnd = fmaxf(bnd, fmaf(fabsf(gam[k]), rn, fabsf(bet[k])));
+      atomicMax(reinterpret_cast<unsigned*>(S->amax) + (size_t)AMAX_Y * S->C_alloc + chain, __float_as_uint(bnd));
+    }
     for (int base = rl; base < N; base += kBnLanes * kBnUnroll) {
       float4 z[kBnUnroll];
 #pragma unroll
@@ -489,17 +498,12 @@ __device__ void run_bn_fwd_wide(const DevState* S, const PhaseDesc& ph, int c_be
         float* yp = Y + (size_t)r * ld3;
         if (full4) {
           *reinterpret_cast<float4*>(yp) = make_float4(y[0], y[1], y[2], y[3]);
-          amx = fmaxf(amx, fmaxf(fmaxf(fabsf(y[0]), fabsf(y[1])), fmaxf(fabsf(y[2]), fabsf(y[3]))));
         } else {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (c0 + k < d3) { yp[k] = y[k]; amx = fmaxf(amx, fabsf(y[k])); }
+            if (c0 + k < d3) yp[k] = y[k];
         }
       }
-    }
-    if (S->f16) {
-      // the ones column next to Y (bias gradient of decode.1) is part of the operand: the bound is at least 1
-      fold_amax(S, AMAX_Y, chain, fmaxf(amx, 1.0f));
     }
   }
 }
@@ -571,7 +575,15 @@ __device__ void run_bn_bwd_wide(const DevState* S, const PhaseDesc& ph, int c_be
       m2[k] = (float)(s2[k] / N) * gam[k];   // mean(dzhat * zhat)
     }
     const bool full4 = c0 + 4 <= d3;
-    float amx = 0.f;   // max |dz|: the bound behind the FP16 scale of DY in the two GEMMs that read it
+    if (S->f16 && rl == 0) {
+      // bound behind the FP16 scale of the rewritten DY: |dz| <= inv (|gamma| max|dy| + |m1| + sqrt(N) |m2|), with max|dy|
+      // the bound the GEMM epilogue that wrote dy folded into AMAX_DYIN
+      const float din = S->amax[(size_t)AMAX_DYIN * S->C_alloc + chain], rn = sqrtf((float)N);
+      float bnd = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bnd = fmaxf(bnd, inv[k] * (fabsf(gam[k]) * din + fabsf(m1[k]) + rn * fabsf(m2[k])));
+      if (bnd > 0.f) atomicMax(reinterpret_cast<unsigned*>(S->amax) + (size_t)AMAX_DY * S->C_alloc + chain, __float_as_uint(bnd));
+    }
     for (int base = rl; base < N; base += kBnLanes * kBnUnroll) {
       float4 dy[kBnUnroll], z[kBnUnroll];
 #pragma unroll
@@ -597,15 +609,13 @@ __device__ void run_bn_bwd_wide(const DevState* S, const PhaseDesc& ph, int c_be
         float* dp = DY + (size_t)r * ld3;
         if (full4) {
           *reinterpret_cast<float4*>(dp) = make_float4(o[0], o[1], o[2], o[3]);
-          amx = fmaxf(amx, fmaxf(fmaxf(fabsf(o[0]), fabsf(o[1])), fmaxf(fabsf(o[2]), fabsf(o[3]))));
         } else {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (c0 + k < d3) { dp[k] = o[k]; amx = fmaxf(amx, fabsf(o[k])); }
+            if (c0 + k < d3) dp[k] = o[k];
         }
       }
     }
-    if (S->f16) fold_amax(S, AMAX_DY, chain, amx);
   }
 }
 
@@ -1670,16 +1680,17 @@ __global__ void __launch_bounds__(tc::kThreadsTc, 1)
 bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, int n_rep, int c_begin, int c_end,
                       int force_swap) {
   extern __shared__ uint8_t dyn_smem[];
-  __shared__ __align__(16) float smem_small[1024];   // BatchNorm column reductions (512 doubles)
   __shared__ double red[16];
   tc::Smem tsm;
   tc::Ring ring;
   tc::setup(tsm, dyn_smem);
+  // BatchNorm column reductions (512 doubles) of the non-GEMM phases: the epilogue staging tiles, idle outside GEMM phases
+  float* smem_small = tsm.epi_stage();
   load_seg_table(S);
   cg::grid_group grid = cg::this_grid();
   const int wg = threadIdx.x >> 7;
   if (wg == 1 || wg == 2) {
-    tc::regs_inc<tc::kRegsEpi>();
+    tc::regs_inc<tc::kRegsEpiPersist>();
     for (int rep = 0; rep < n_rep; ++rep) {
       for (int pi = ph_begin; pi < ph_end; ++pi) {
         if (S->phase[pi].kind == PH_WAMAX) continue;   // 3xFP16 split only (per-phase launches)
@@ -1693,7 +1704,7 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
       }
     }
   } else {
-    tc::regs_dec<tc::kRegsLean>();
+    tc::regs_dec<tc::kRegsLeanPersist>();
     for (int rep = 0; rep < n_rep; ++rep) {
       for (int pi = ph_begin; pi < ph_end; ++pi) {
         if (S->phase[pi].kind == PH_WAMAX) continue;

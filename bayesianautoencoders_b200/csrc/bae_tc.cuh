@@ -49,7 +49,7 @@ namespace tc {
 
 constexpr int kThreadsTc = 512;
 constexpr int kStages = 7;                     // raw tile pairs (TMA ring): deep, the loads come from HBM (~2000 cycles under load)
-constexpr int kLoStages = 4;                   // lo tile pairs (converter ring): three groups converting + one being read
+constexpr int kLoStages = 5;                   // converted tiles (converter ring): three groups converting + two being read / waiting
 constexpr int kBM = 128;
 constexpr int kBK = 16;                        // floats of K per stage (64-byte rows: SWIZZLE_64B for K-major tiles)
 constexpr int kMaxBN = 256;                    // pair tile width; each CTA holds BN/2 columns of B; 2 accumulators x 256 TMEM columns
@@ -57,18 +57,18 @@ constexpr int kATileBytes = kBM * kBK * 4;     // 8 KB
 constexpr int kBTileBytes = (kMaxBN / 2) * kBK * 4;  // 8 KB: this CTA's half of the B tile
 constexpr int kMnChunkBytes = kBK * 128;       // MN-major chunk: [16 K-rows][32 floats]
 constexpr int kStageBytes = kATileBytes + kBTileBytes;          // one raw stage (A, B half) or one lo stage = 16 KB
-constexpr int kEpiPitch = 36;                  // floats; 144-byte rows keep float4 accesses conflict-free
 constexpr int kEpiWarps = 8;
 constexpr int kConvGroups = 3;                 // converter groups; K block k is converted by group k % 3
 constexpr int kConvGroupWarps = 2;             // 64 threads: every tile pair is a multiple of 64 float4 (no predicates)
 constexpr int kConvGroupThreads = kConvGroupWarps * 32;
-constexpr int kEpiBytes = kEpiWarps * 32 * kEpiPitch * 4;
+constexpr int kEpiBytes = kEpiWarps * 4096;       // one dense, swizzled 32 x 32 staging tile per epilogue warp
 constexpr int kSmemBytes = (kStages + kLoStages) * kStageBytes + 1024 /*align slack*/ + 512 /*barriers*/ + kEpiBytes;
-static_assert(kSmemBytes + 4640 <= 232448, "dynamic + static shared memory of the tcgen05 kernels");
+static_assert(kSmemBytes + 1024 <= 232448, "dynamic + static shared memory of the tcgen05 kernels (static: reduction scratch, segment table)");
 // tile-pair layout: [A 8 KB][B half 8 KB]; kStages raw pairs followed by kLoStages lo pairs
 constexpr int kTmemCols = 512;                 // two accumulators of BN <= 256 columns each, single-buffered
-constexpr int kRegsLean = 48;                  // producer / MMA / converter warpgroups
-constexpr int kRegsEpi = 208;                  // epilogue warpgroups (also run the non-GEMM phases)
+constexpr int kRegsLeanPersist = 48, kRegsEpiPersist = 208;   // persistent kernel (3xTF32 only): its non-GEMM phases need the registers
+constexpr int kRegsLean = 56;                  // producer / MMA / converter warpgroups
+constexpr int kRegsEpi = 200;                  // epilogue warpgroups (also run the non-GEMM phases)
 static_assert(kRegsLean * 256 + kRegsEpi * 256 <= 65536, "register file");
 
 struct Ring {
@@ -89,7 +89,7 @@ struct Smem {
   uint8_t* tiles;        // 1024-byte aligned: tile rings, then the epilogue staging tiles, then barriers and scratch
   static constexpr int kEpiOff = (kStages + kLoStages) * kStageBytes;   // the Adam phases stage through [0, kEpiOff + kEpiBytes)
   static constexpr int kTail = kEpiOff + kEpiBytes;
-  __device__ __forceinline__ float* epi_stage() const { return reinterpret_cast<float*>(tiles + kEpiOff); }           // [8][32][kEpiPitch]
+  __device__ __forceinline__ float* epi_stage() const { return reinterpret_cast<float*>(tiles + kEpiOff); }           // [8 warps][32 rows x 128 B, swizzled]
   __device__ __forceinline__ uint64_t* full() const { return reinterpret_cast<uint64_t*>(tiles + kTail); }            // [kStages] TMA bytes landed
   __device__ __forceinline__ uint64_t* empty() const { return full() + kStages; }       // [kStages] MMAs that read the raw stage completed
   __device__ __forceinline__ uint64_t* conv() const { return empty() + kStages; }       // [kLoStages] lo pair written (leader: both CTAs)
@@ -422,24 +422,32 @@ __device__ __forceinline__ ConvLane conv_lane(int gt) {
   c.off[1] = k * 128 + ((i0 ^ (k & 3)) << 5) + (c.swap1 ? 16u : 0u);
   return c;
 }
-// units gt + 64 n, n = n0 .. n0 + kN - 1, of one operand tile
-template <int kN>
-__device__ __forceinline__ void conv_units(uint32_t src_t, uint32_t hi_t, uint32_t lo_t, bool swap, float s, int n0) {
-  // kN units at once: 2 kN loads in flight
+// units gt + 64 n, n = 0 .. kN - 1, of one operand tile: all loads first (2 kN float4 in flight), then the splits.
+// kSwap: the source is MN-major (only then can `swap` be set; K-major sources compile without the exchange).
+template <int kN, bool kSwap>
+__device__ __forceinline__ void conv_units(uint32_t src_t, uint32_t hi_t, uint32_t lo_t, bool swap, float s) {
   float4 p[kN], q[kN];
 #pragma unroll
   for (int u = 0; u < kN; ++u) {
-    p[u] = lds128(src_t + (uint32_t)(n0 + u) * 2048u);
-    q[u] = lds128((src_t + (uint32_t)(n0 + u) * 2048u) ^ 16u);
+    p[u] = lds128(src_t + (uint32_t)u * 2048u);
+    q[u] = lds128((src_t + (uint32_t)u * 2048u) ^ 16u);
   }
 #pragma unroll
   for (int u = 0; u < kN; ++u) {
-    if (swap) { const float4 t = p[u]; p[u] = q[u]; q[u] = t; }
+    if (kSwap && swap) { const float4 t = p[u]; p[u] = q[u]; q[u] = t; }
     uint4 hi, lo;
     f16_split8(p[u], q[u], s, hi, lo);
-    sts128u(hi_t + (uint32_t)(n0 + u) * 1024u, hi);
-    sts128u(lo_t + (uint32_t)(n0 + u) * 1024u, lo);
+    sts128u(hi_t + (uint32_t)u * 1024u, hi);
+    sts128u(lo_t + (uint32_t)u * 1024u, lo);
   }
+}
+// up to four units (nv of them) of one operand tile
+template <bool kSwap>
+__device__ __forceinline__ void conv_tile(uint32_t src_t, uint32_t hi_t, uint32_t lo_t, bool swap, float s, int nv) {
+  if (nv >= 2) conv_units<2, kSwap>(src_t, hi_t, lo_t, swap, s);
+  else if (nv == 1) conv_units<1, kSwap>(src_t, hi_t, lo_t, swap, s);
+  if (nv >= 4) conv_units<2, kSwap>(src_t + 4096, hi_t + 2048, lo_t + 2048, swap, s);
+  else if (nv == 3) conv_units<1, kSwap>(src_t + 4096, hi_t + 2048, lo_t + 2048, swap, s);
 }
 
 // Shared-memory descriptor of an FP16 operand tile in the no-swizzle layout above (either major): LBO = 128 B, SBO = 256 B
@@ -739,48 +747,50 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
       // 3xFP16: operand scales of this item, source majors, units of this CTA's B half (8 columns x 16 k each)
       float sA = 1.f, sB = 1.f;
       uint32_t offA = 0, offB = 0;
-      bool swapA = false, swapB = false;
-      int nUB = 0;   // units of this CTA's B half
+      bool swapA = false, swapB = false, aM = false, bM = false;
+      int nvB = 0;   // units of this CTA's B half that this thread converts: gt + 64 n < tcBN
       if (f16) {
         sA = exp2i(operand_exp(S, it.g->aSc, it.chain));
         sB = exp2i(operand_exp(S, it.g->bSc, it.chain));
-        const int am = it.g->aMode != 0, bm = it.g->bMode != 0;
-        offA = cl.off[am]; offB = cl.off[bm];
-        swapA = am && cl.swap1; swapB = bm && cl.swap1;
-        nUB = it.g->tcBN;
+        aM = it.g->aMode != 0; bM = it.g->bMode != 0;
+        offA = cl.off[aM ? 1 : 0]; offB = cl.off[bM ? 1 : 0];
+        swapA = aM && cl.swap1; swapB = bM && cl.swap1;
+        nvB = (it.g->tcBN - gt + 63) >> 6;
       }
-      for (int kb = 0; kb < nkb; ++kb) {
-        if (f16 && (int)kbc == grp) {
-          mbar_wait(&sm.lo_empty()[ring.lo], ring.lo_phase ^ 1);
-          mbar_wait(&sm.full()[ring.stage], ring.phase);
+      if (f16) {
+        // This group's K blocks of the item, without touching the others: block kb of the item is block bk + kb of the CTA's
+        // stream, which fixes its group ((bk + kb) % 3), its raw stage and its converted slot. (A per-block loop that merely
+        // skipped the other groups' blocks cost ~250 cycles per skipped block: its loop-carried state lives in local memory.)
+        for (int kb = (grp + kConvGroups - (int)kbc) % kConvGroups; kb < nkb; kb += kConvGroups) {
+          const uint32_t b7 = ring.stage + (uint32_t)kb, b5 = ring.lo + (uint32_t)kb;
+          const uint32_t stage = b7 % kStages, phase = ring.phase ^ ((b7 / kStages) & 1u);
+          const uint32_t lo = b5 % kLoStages, lo_phase = ring.lo_phase ^ ((b5 / kLoStages) & 1u);
+          mbar_wait(&sm.lo_empty()[lo], lo_phase ^ 1);
+          mbar_wait(&sm.full()[stage], phase);
           if (gt == 0) trace(dbg, 2, ntr, kb);
-          const uint32_t src = tiles0 + ring.stage * kStageBytes, dst = tiles0 + (kStages + ring.lo) * kStageBytes + gt * 16;
-          // A: 256 units = 4 per thread
-          conv_units<2>(src + offA, dst, dst + kF16TileBytes, swapA, sA, 0);
-          conv_units<2>(src + offA, dst, dst + kF16TileBytes, swapA, sA, 2);
-          // B: tcBN units (a multiple of 16) = this CTA's BN/2 columns
-          const uint32_t srcB = src + kATileBytes + offB, dstB = dst + 2 * kF16TileBytes;
-          if (nUB >= 128) {
-            conv_units<2>(srcB, dstB, dstB + kF16TileBytes, swapB, sB, 0);
-          } else {
-            if (gt < nUB) conv_units<1>(srcB, dstB, dstB + kF16TileBytes, swapB, sB, 0);
-            if (gt + 64 < nUB) conv_units<1>(srcB, dstB, dstB + kF16TileBytes, swapB, sB, 1);
-          }
-          if (nUB >= 256) {
-            conv_units<2>(srcB, dstB, dstB + kF16TileBytes, swapB, sB, 2);
-          } else {
-            if (gt + 128 < nUB) conv_units<1>(srcB, dstB, dstB + kF16TileBytes, swapB, sB, 2);
-            if (gt + 192 < nUB) conv_units<1>(srcB, dstB, dstB + kF16TileBytes, swapB, sB, 3);
-          }
+          const uint32_t src = tiles0 + stage * kStageBytes, dst = tiles0 + (kStages + lo) * kStageBytes + gt * 16;
+          // A: 256 units = 4 per thread; B: tcBN units (a multiple of 16) = this CTA's BN/2 columns, nvB of them this thread's
+          if (aM) conv_tile<true>(src + offA, dst, dst + kF16TileBytes, swapA, sA, 4);
+          else conv_tile<false>(src + offA, dst, dst + kF16TileBytes, false, sA, 4);
+          if (bM) conv_tile<true>(src + kATileBytes + offB, dst + 2 * kF16TileBytes, dst + 3 * kF16TileBytes, swapB, sB, nvB);
+          else conv_tile<false>(src + kATileBytes + offB, dst + 2 * kF16TileBytes, dst + 3 * kF16TileBytes, false, sB, nvB);
           if (gt == 0) trace(dbg, 2, ntr, 2000 + kb);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
-            mbar_arrive(&sm.empty()[ring.stage]);   // the raw stage has been read: the producer may refill it
-            if (rank == 0) mbar_arrive(&sm.conv()[ring.lo]);
-            else mbar_arrive_leader_relaxed(&sm.conv()[ring.lo]);
+            mbar_arrive(&sm.empty()[stage]);   // the raw stage has been read: the producer may refill it
+            if (rank == 0) mbar_arrive(&sm.conv()[lo]);
+            else mbar_arrive_leader_relaxed(&sm.conv()[lo]);
           }
-        } else
+        }
+        // the item's blocks are done (or left to the other groups): move the ring state past them
+        const uint32_t e7 = ring.stage + (uint32_t)nkb, e5 = ring.lo + (uint32_t)nkb;
+        ring.stage = e7 % kStages; ring.phase ^= (e7 / kStages) & 1u;
+        ring.lo = e5 % kLoStages; ring.lo_phase ^= (e5 / kLoStages) & 1u;
+        kbc = (kbc + (uint32_t)nkb) % kConvGroups;
+        continue;
+      }
+      for (int kb = 0; kb < nkb; ++kb) {
         if ((int)kbc == grp) {
           // The lo slot first (the MMAs of K block k - 4 are done): it also pins the phase of `full`. Parity waits cannot
           // tell phases two apart, and a raw stage is served by all groups in turn; the MMAs of block k - 4 complete after
@@ -945,7 +955,7 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
   // loads, bias and stores share one address pattern.
   float l_sse = 0.f, l_sd = 0.f;
   float amx = 0.f;   // max |stored value| of this thread (deltas: bound behind the FP16 scale of the next GEMMs' operand)
-  const bool kTrackAmax = (epi == EPI_LOSS || epi == EPI_DSIG);
+  const bool kTrackAmax = (epi == EPI_LOSS || epi == EPI_DSIG || epi == EPI_PLAIN);
   const int lim = (epi == EPI_GRADW && biasCol >= 0) ? min(n_end, biasCol) : n_end;   // columns >= lim are not stored
   if (accum) {
     // the previous segment's box stores of this warp are COMPLETE (not just read) before anything is added to them; they
@@ -1020,12 +1030,9 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
         }
         o = make_float4(d[0], d[1], d[2], d[3]);
       }
-      if (kTrackAmax) {
-        const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (cc + e < n_end) amx = fmaxf(amx, fabsf(ov[e]));
-      }
+      // (columns past n_end of a float4 hold at most values of the same magnitude - zero accumulators, or the data's ones
+      //  column under the loss epilogue: a bound, not a maximum, is needed)
+      if (kTrackAmax) amx = fmaxf(amx, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
       if (box) {
         sts128(sa, o);   // back to where this thread read it from
       } else {
