@@ -418,12 +418,28 @@ __device__ __forceinline__ ConvLane conv_lane(int gt) {
   ConvLane c;
   c.off[0] = (8 * i0 + r) * 64 + (((2 * j) ^ ((r >> 1) & 3)) << 4);
   const uint32_t k = 8 * j + r;
-  c.swap1 = (r & 4) != 0;
+  // (the j term keeps the 8-byte stores of conv_units conflict free: units (r, 0) and (r, 1) are 128 B apart)
+  c.swap1 = (((r >> 2) ^ j) & 1) != 0;
   c.off[1] = k * 128 + ((i0 ^ (k & 3)) << 5) + (c.swap1 ? 16u : 0u);
   return c;
 }
+__device__ __forceinline__ void sts64u(uint32_t saddr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(saddr), "r"(a), "r"(b) : "memory");
+}
+// 4 scaled values -> 8 B of hi halves and 8 B of lo halves
+__device__ __forceinline__ void f16_split4(const float4& v, float s, uint32_t (&h)[2], uint32_t (&l)[2]) {
+  const float x[4] = {v.x * s, v.y * s, v.z * s, v.w * s};
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    h[p] = pack_half2(x[2 * p], x[2 * p + 1]);
+    float f0, f1;
+    unpack_half2(h[p], f0, f1);
+    l[p] = pack_half2(x[2 * p] - f0, x[2 * p + 1] - f1);
+  }
+}
 // units gt + 64 n, n = 0 .. kN - 1, of one operand tile: all loads first (2 kN float4 in flight), then the splits.
-// kSwap: the source is MN-major (only then can `swap` be set; K-major sources compile without the exchange).
+// kSwap: the source is MN-major: lanes with `swap` set loaded the upper half of the unit first. Nothing is exchanged in
+// registers; each half is stored as 8 bytes, at exchanged positions for those lanes (half-warp-wide conflict free, see conv_lane).
 template <int kN, bool kSwap>
 __device__ __forceinline__ void conv_units(uint32_t src_t, uint32_t hi_t, uint32_t lo_t, bool swap, float s) {
   float4 p[kN], q[kN];
@@ -432,13 +448,26 @@ __device__ __forceinline__ void conv_units(uint32_t src_t, uint32_t hi_t, uint32
     p[u] = lds128(src_t + (uint32_t)u * 2048u);
     q[u] = lds128((src_t + (uint32_t)u * 2048u) ^ 16u);
   }
+  if (kSwap) {
+    const uint32_t d8 = swap ? 8u : 0u;
 #pragma unroll
-  for (int u = 0; u < kN; ++u) {
-    if (kSwap && swap) { const float4 t = p[u]; p[u] = q[u]; q[u] = t; }
-    uint4 hi, lo;
-    f16_split8(p[u], q[u], s, hi, lo);
-    sts128u(hi_t + (uint32_t)u * 1024u, hi);
-    sts128u(lo_t + (uint32_t)u * 1024u, lo);
+    for (int u = 0; u < kN; ++u) {
+      uint32_t h[2], l[2];
+      f16_split4(p[u], s, h, l);
+      sts64u((hi_t + (uint32_t)u * 1024u) + d8, h[0], h[1]);
+      sts64u((lo_t + (uint32_t)u * 1024u) + d8, l[0], l[1]);
+      f16_split4(q[u], s, h, l);
+      sts64u(((hi_t + (uint32_t)u * 1024u) + d8) ^ 8u, h[0], h[1]);
+      sts64u(((lo_t + (uint32_t)u * 1024u) + d8) ^ 8u, l[0], l[1]);
+    }
+  } else {
+#pragma unroll
+    for (int u = 0; u < kN; ++u) {
+      uint4 hi, lo;
+      f16_split8(p[u], q[u], s, hi, lo);
+      sts128u(hi_t + (uint32_t)u * 1024u, hi);
+      sts128u(lo_t + (uint32_t)u * 1024u, lo);
+    }
   }
 }
 // up to four units (nv of them) of one operand tile
@@ -995,18 +1024,35 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
     // the previous chunk's box store must have read the staging tile before it is rewritten
     if (lane == 0) bulk_wait_read();
     __syncwarp();
+    // Kinds without an aux tile need no pass in the coalesced domain when the chunk leaves as a box: bias (a broadcast load per
+    // four columns) and sigmoid are applied on the way INTO the staging tile, which then already is the box to store - one
+    // shared-memory pass instead of three (shared memory is the unit the main loop is short of).
+    const bool direct = box && (epi == EPI_GRADW || epi == EPI_PLAIN || epi == EPI_SIGMOID || epi == EPI_BIAS);
+    const float* biasc = (kHasBias && direct) ? g.bias + (size_t)chain * g.sBias + n0 + c0 : nullptr;
     // dense 32 x 128 B tile, 16-byte units XOR-swizzled by the row (the layout the store's tensor map expects)
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (j == jj) {
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4)
-          sts128(stg_s + lane * 128 + ((j4 ^ (lane & 7)) << 4),
-                 make_float4(__uint_as_float(acc[j][j4 * 4]), __uint_as_float(acc[j][j4 * 4 + 1]),
-                             __uint_as_float(acc[j][j4 * 4 + 2]), __uint_as_float(acc[j][j4 * 4 + 3])));
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 o = make_float4(__uint_as_float(acc[j][j4 * 4]), __uint_as_float(acc[j][j4 * 4 + 1]),
+                                 __uint_as_float(acc[j][j4 * 4 + 2]), __uint_as_float(acc[j][j4 * 4 + 3]));
+          if (biasc) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(biasc + j4 * 4));
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+            if (epi == EPI_SIGMOID) {
+              o.x = __fdividef(1.0f, 1.0f + __expf(-o.x)); o.y = __fdividef(1.0f, 1.0f + __expf(-o.y));
+              o.z = __fdividef(1.0f, 1.0f + __expf(-o.z)); o.w = __fdividef(1.0f, 1.0f + __expf(-o.w));
+            }
+          }
+          // (rows >= M of the tile hold zero accumulators: they cannot raise the bound)
+          if (direct && epi == EPI_PLAIN) amx = fmaxf(amx, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+          sts128(stg_s + lane * 128 + ((j4 ^ (lane & 7)) << 4), o);
+        }
       }
     __syncwarp();
     if (c.et == 0) trace(dbg, 3, ntr, 20 + jj);
+    if (!direct) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (kHasAux && i == 4) load_aux(1);
@@ -1053,6 +1099,7 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
         }
       }
     }
+    }   // !direct
     // ONE box store per chunk through the copy engine (rows >= M are clipped by it): global
     // stores issued by the epilogue warps themselves slowed the converters' shared-memory stream down (traced: 2.6 k cycles per tile)
     if (box) {
