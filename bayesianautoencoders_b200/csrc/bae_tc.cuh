@@ -67,8 +67,8 @@ static_assert(kSmemBytes + 1024 <= 232448, "dynamic + static shared memory of th
 // tile-pair layout: [A 8 KB][B half 8 KB]; kStages raw pairs followed by kLoStages lo pairs
 constexpr int kTmemCols = 512;                 // two accumulators of BN <= 256 columns each, single-buffered
 constexpr int kRegsLeanPersist = 48, kRegsEpiPersist = 208;   // persistent kernel (3xTF32 only): its non-GEMM phases need the registers
-constexpr int kRegsLean = 56;                  // producer / MMA / converter warpgroups
-constexpr int kRegsEpi = 200;                  // epilogue warpgroups (also run the non-GEMM phases)
+constexpr int kRegsLean = 48;                  // producer / MMA / converter warpgroups
+constexpr int kRegsEpi = 208;                  // epilogue warpgroups (also run the non-GEMM phases)
 static_assert(kRegsLean * 256 + kRegsEpi * 256 <= 65536, "register file");
 
 struct Ring {
