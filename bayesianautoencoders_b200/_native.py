@@ -18,7 +18,7 @@ EXPORTS = [
     "bae_swap_local", "bae_run", "bae_synchronize", "bae_eval", "bae_debug_draws", "bae_debug_swap_uniform",
     "bae_read_traces", "bae_swap_counts", "bae_exchange_pack", "bae_exchange_unpack", "bae_exchange_finish",
     "bae_launch_count", "bae_last_step_ms", "bae_gemm_path", "bae_stream", "bae_debug_buffer", "bae_debug_trace", "bae_debug_profiler", "bae_exchange_table", "bae_exchange_local", "bae_host_sweep", "bae_last_sweep", "bae_forward_all", "bae_shard_config", "bae_swap_exchange", "bae_plan_exchange",
-    "bae_exchange_vectors_sent", "bae_step_kernel", "bae_eval_bn_stats",
+    "bae_exchange_vectors_sent", "bae_step_kernel", "bae_eval_bn_stats", "bae_mma_kind",
 ]
 
 
@@ -110,6 +110,7 @@ def load():
     lib.bae_last_step_ms.argtypes = [C.c_void_p, P(C.c_float)]
     lib.bae_gemm_path.argtypes = [C.c_void_p]
     lib.bae_step_kernel.argtypes = [C.c_void_p]
+    lib.bae_mma_kind.argtypes = [C.c_void_p]
     lib.bae_debug_buffer.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int64, P(C.c_int), C.c_int]
     lib.bae_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.bae_debug_profiler.argtypes = [C.c_int]

@@ -756,6 +756,7 @@ int bae_destroy(bae_handle* h) {
 int bae_w_size(const bae_handle* h) { return h ? h->hs.w_size : BAE_ERR_INVALID; }
 int bae_n_trainable(const bae_handle* h) { return h ? h->hs.w_size - h->hs.nbuf : BAE_ERR_INVALID; }
 int bae_gemm_path(const bae_handle* h) { return h ? (h->hs.tc ? 2 : 1) : BAE_ERR_INVALID; }
+int bae_mma_kind(const bae_handle* h) { return h ? (h->hs.tc ? (h->hs.f16 ? 2 : 1) : 0) : BAE_ERR_INVALID; }
 int bae_step_kernel(const bae_handle* h) { return h ? (h->narrow ? 3 : (h->hs.tc ? 2 : 1)) : BAE_ERR_INVALID; }
 void* bae_stream(bae_handle* h) { return h ? (void*)h->stream : nullptr; }
 int64_t bae_launch_count(const bae_handle* h) { return h ? h->launches : 0; }

@@ -212,6 +212,10 @@ class DeviceSampler:
         """1 = persistent FP32 tile kernel, 2 = tcgen05 phase program, 3 = narrow-width cluster kernel."""
         return int(self.lib.bae_step_kernel(self._h))
 
+    def mma_kind(self):
+        """0 = FFMA tiles, 1 = tcgen05 3xTF32 split, 2 = tcgen05 3xFP16 split (the default on the tensor-core path)."""
+        return int(self.lib.bae_mma_kind(self._h))
+
     def traces(self, chain, first=0, n=None):
         n = self.samples - first if n is None else n
         out = np.zeros(n, dtype=TRACE_DTYPE)

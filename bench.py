@@ -383,8 +383,10 @@ def roofline_block(job, kernel_ms, n_launch_rounds, sharded):
     peaks = measured_peaks()
     gemm_path = job.s.gemm_path()
     if gemm_path == 2:
-        kind = "tcgen05 kind::tf32, 3-way split (3xTF32), FP32 accumulate in TMEM"
-        tf = tf32_peak()
+        f16 = job.s.mma_kind() == 2
+        kind = ("tcgen05 kind::f16, 3-way split of scaled FP32 operands (3xFP16: hi*hi, lo*hi, hi*lo), FP32 accumulate in TMEM" if f16
+                else "tcgen05 kind::tf32, 3-way split (3xTF32), FP32 accumulate in TMEM")
+        tf = None if f16 else tf32_peak()
         out = {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                "frac": achieved_tf / peaks["bf16_sustained"],
                "traffic": ncu_traffic(job.shape, job.chains, gemm_path),
@@ -392,6 +394,10 @@ def roofline_block(job, kernel_ms, n_launch_rounds, sharded):
                           "iterations of all resident chains" + ("" if sharded else " + exchange sweep") +
                           ", one CUDA-graph launch of its per-phase kernels"),
                "peak_source": peaks["source"] + " bf16 dense sustained (MEASURED_PEAKS.json)", "mma_kind": kind}
+        if f16:
+            # kind::f16 issues at the bf16 rate: the measured bf16 peak IS the peak of the MMA kind issued; every algorithmic FLOP
+            # costs three of its FLOPs, so the attainable algorithmic fraction is 1/3
+            out.update({"frac_of_3xf16_ceiling": 3.0 * achieved_tf / peaks["bf16_sustained"], "mma_tflops_issued": 3.0 * achieved_tf})
         if tf:
             # the MMA kind actually issued, measured on this pool (profiles/r2_tf32_peak.json): cuBLAS TF32 sustained; every
             # algorithmic FLOP costs three kind::tf32 MMA FLOPs (hi*hi, hi*lo, lo*hi), so the attainable algorithmic rate is 1/3

@@ -200,7 +200,8 @@ int bae_debug_profiler(int on);                                        /* cudaPr
 /* Introspection for the benchmark: kernels launched so far by this handle, last step-kernel time (ms). */
 int64_t bae_launch_count(const bae_handle* h);
 int bae_last_step_ms(bae_handle* h, float* ms);
-int bae_gemm_path(const bae_handle* h);  /* 1 = FP32 CUDA cores, 2 = tcgen05 3xTF32 */
+int bae_gemm_path(const bae_handle* h);  /* 1 = FP32 CUDA cores, 2 = tcgen05 tensor cores */
+int bae_mma_kind(const bae_handle* h);   /* 0 = FFMA (gemm path 1), 1 = 3xTF32 split (kind::tf32), 2 = 3xFP16 split (kind::f16, scaled operands) */
 int bae_step_kernel(const bae_handle* h); /* which step program runs bae_step / bae_run: 1 = persistent FP32 tile kernel, 2 = tcgen05
                                           * phase program, 3 = narrow-width cluster kernel (Swiss Roll widths, csrc/bae_narrow.cu) */
 void* bae_stream(bae_handle* h);         /* cudaStream_t the handle launches on */

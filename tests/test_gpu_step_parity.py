@@ -59,12 +59,16 @@ TOL_TF = {
 # 0.6e-5 at iteration 0 and settles at 1.0e-5 (measured maximum 1.01e-5): the FP32 floor of this network at these weights
 # (saturated sigmoids, BatchNorm behind a layer with |mean(z)| ~ 2 std(z)); per tensor the encoder layers sit at 2e-5.
 TOL_MADELON_FP32 = dict(TOL_TF, grad=1.2e-5, grad_step0=1.2e-5)
-# Madelon width, tensor cores (3xTF32): every quantity of the MH test is within the FP32-tile bounds, the gradient is
-# not: 1.4e-5 at iteration 0, 2.5e-5 later (2.4 x the FP32 tiles). Cause, measured layer by layer (tools/dev/exp_layers.py):
-# tcgen05.mma adds into its FP32 accumulator with TRUNCATION, a one-sided error of ~0.5 ulp per accumulating MMA (K = 8):
-# a 640-row weight-gradient segment shrinks by ~4e-6 relative where FFMA chains err by 1e-7 at random. Shorter
-# accumulation chains need more TMEM accumulators than 2 x BN <= 512 columns leave.
-TOL_MADELON_TC = dict(TOL_TF, grad=3e-5, grad_step0=3e-5)
+# Madelon width, tensor cores, 3xTF32 split (kind::tf32; BAE_TC_TF32=1 and the persistent kernel): every quantity of the MH
+# test is within the FP32-tile bounds, the gradient is not: 1.4e-5 at iteration 0, 2.5e-5 later (2.4 x the FP32 tiles). Cause,
+# measured layer by layer (tools/dev/exp_layers.py): tcgen05.mma adds into its FP32 accumulator with TRUNCATION, a one-sided
+# error of ~0.5 ulp per accumulating MMA (K = 8): a 640-row weight-gradient segment shrinks by ~4e-6 relative where FFMA
+# chains err by 1e-7 at random.
+TOL_MADELON_TF32 = dict(TOL_TF, grad=3e-5, grad_step0=3e-5)
+# Madelon width, tensor cores, 3xFP16 split (kind::f16, the production engine): the same 11-bit operand pieces, but K = 16 per
+# MMA, i.e. half as many truncating accumulations: gradient 0.8e-5 at iteration 0, 1.4e-5 later (measured maxima; the FP32
+# tiles: 0.6e-5 / 1.0e-5), every other quantity inside the common bounds.
+TOL_MADELON_TC = dict(TOL_TF, grad=2e-5, grad_step0=1.2e-5)
 
 
 def _check_tf(name, rep, tol=TOL_TF, lik_on_value=True):
@@ -151,23 +155,27 @@ def _inputs(dims4, n, seed):
     return [default_theta_init(dims4, rng) for _ in range(n)], [rng.standard_normal(L.w_size) for _ in range(n)]
 
 
-@pytest.mark.parametrize("phase_launch", ["1", "0"])
-def test_madelon_tcgen05_step_program_matches_oracle(phase_launch, monkeypatch):
+@pytest.mark.parametrize("phase_launch,tf32", [("1", "0"), ("1", "1"), ("0", "0")])
+def test_madelon_tcgen05_step_program_matches_oracle(phase_launch, tf32, monkeypatch):
     """2 chains (one 2-rung ensemble) x 10 iterations at the full Madelon shape on the tensor-core path: the tempered ->
     canonical switch at i == 5, two exchange rounds, random-walk iterations at (chain 0, i = 2), (chain 0, i = 7) and
     (chain 1, i = 5: the first iteration after an exchange, fp32 `w`). phase_launch 1 = the CUDA graph of per-phase
-    kernels (production), 0 = the persistent cooperative kernel."""
+    kernels (production; 3xFP16 split, or the 3xTF32 split with BAE_TC_TF32=1), 0 = the persistent cooperative kernel
+    (3xTF32 split)."""
     monkeypatch.setenv("BAE_PHASE_LAUNCH", phase_launch)
+    monkeypatch.setenv("BAE_TC_TF32", tf32)
+    f16 = phase_launch == "1" and tf32 == "0"
     dims4, ntr, nte = MADELON
     train, test = synth_data(dims4, ntr, nte)
     temps = [1.0, 2.0]
     th0, w0 = _inputs(dims4, 2, 17)
     rep, tf_traces = run_teacher_forced(dims4, train, test, temps, 10, 5, th0, w0, n_rungs=2, seed=6, gemm_path=2)
     assert rep["gemm_path"] == 2 and rep["random_walk_steps"] == 3
-    _check_tf(f"tf_madelon_tc_phase_launch{phase_launch}", rep, TOL_MADELON_TC)
+    tag = f"madelon_tc_phase_launch{phase_launch}" + ("" if f16 else "_tf32")
+    _check_tf("tf_" + tag, rep, TOL_MADELON_TC if f16 else TOL_MADELON_TF32)
     r = run_device_and_oracle(dims4, train, test, temps, 10, 5, th0, w0, n_rungs=2, do_swaps=True, seed=6, gemm_path=2)
     assert r["gemm_path"] == 2
-    _check_free(f"free_madelon_tc_phase_launch{phase_launch}", r, 10, temps, tf_traces=tf_traces)
+    _check_free("free_" + tag, r, 10, temps, tf_traces=tf_traces)
 
 
 def test_madelon_fp32_tiles_match_oracle():
