@@ -1040,7 +1040,10 @@ static cudaError_t emit_phases(bae_handle* h, int p_begin, int p_end, int n_rep,
   for (int r = 0; r < n_rep && e == cudaSuccess; ++r) {
     if (p_begin < ps_end)
       for (int cb = 0; cb < C && e == cudaSuccess; cb += G)
-        for (int p = p_begin; p < ps_end && e == cudaSuccess; ++p) e = launch_one(h, p, cb, std::min(cb + G, C), force_swap);
+        for (int p = p_begin; p < ps_end && e == cudaSuccess; ++p) {
+          if (p == P_WAMAX0 && r == 0 && p_begin == P_PRO) continue;   // the forced launch above has just done this
+          e = launch_one(h, p, cb, std::min(cb + G, C), force_swap);
+        }
     for (int p = std::max(p_begin, (int)P_SWAP); p < p_end && e == cudaSuccess; ++p) e = launch_one(h, p, 0, C, force_swap);
   }
   if (n_launch) *n_launch = (int)(h->n_emit - n0);

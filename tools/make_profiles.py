@@ -23,25 +23,51 @@ rows = [r for r in csv.reader(open(launch_csv)) if len(r) > 5]
 h, data = rows[0], rows[1:]
 iv, ik = h.index('Metric Value'), h.index('Kernel Name')
 vals = [float(r[iv].replace(',', '')) / 1000 for r in data]   # ns -> us
-# one iteration of the step program (3xFP16 split): 'Z' = bae_amax_zero_kernel (zeroes the magnitude-bound slots the next phases fold
-# into), WAMAX = weight bounds after an exchange round (returns at once otherwise); a call starts with a forced (Z, WAMAX) pair
-fwd = lambda sfx: ['Z'] + [f'{n}{sfx}' for n in ('F1', 'F2', 'F3', 'BNF', 'F4', 'F5', 'F6')]
-bwd = lambda sfx: ['Z', f'B6{sfx} (dW6|dH5)'] + [f'{n}{sfx}' for n in ('B5', 'B4', 'BNB', 'B3', 'B2', 'B1')]
-names = ['PRO', 'Z', 'WAMAX'] + fwd('') + bwd('') + ['Z', 'ADAM1'] + fwd('b') + bwd('b') + ['ADAM2', 'Z'] + \
-        ['T1', 'T2', 'T3', 'BNT', 'T4', 'T5', 'T6', 'EPI']
-HEAD = 2      # forced (Z, WAMAX) pair in front of the program
-N_IT = len(names)
-PER_IT = N_IT + 3   # + 3 exchange phases (which return at once unless the step counter says "swap round")
-names_it = names + ['SWAP_DECIDE', 'SWAP_GATHER', 'SWAP_SCATTER']
-vals_all = vals
-vals = vals[HEAD:]
-data_all = data
-data = data[HEAD:]
-assert len(vals) == 5 * PER_IT, f"expected {HEAD} + {5 * PER_IT} launches (5 iterations x {PER_IT} launches), got {len(vals_all)}"
+# Launches are named by walking the list: 'Z' = bae_amax_zero_kernel (zeroes the magnitude-bound slots the next phases fold into),
+# WAMAX = the misc kernel right after a Z (weight bounds: forced in front of a program, gated on "after an exchange round" inside
+# it), everything else in program order.
+PHASES = ['PRO', 'F1', 'F2', 'F3', 'BNF', 'F4', 'F5', 'F6', 'B6 (dW6|dH5)', 'B5', 'B4', 'BNB', 'B3', 'B2', 'B1', 'ADAM1', 'F1b', 'F2b', 'F3b',
+        'BNFb', 'F4b', 'F5b', 'F6b', 'B6b', 'B5b', 'B4b', 'BNBb', 'B3b', 'B2b', 'B1b', 'ADAM2', 'T1', 'T2', 'T3', 'BNT', 'T4', 'T5', 'T6', 'EPI',
+        'SWAP_DECIDE', 'SWAP_GATHER', 'SWAP_SCATTER']
+
+
+def label_launches(rows, ik):
+    out, nxt, prev = [], 0, ''
+    for r in rows:
+        k = r[ik]
+        if 'amax_zero' in k:
+            lab = 'Z'
+        elif prev == 'Z' and 'bae_aux_kernel<2>' in k.replace('(int)', '') and PHASES[nxt % len(PHASES)] in ('PRO', 'F1'):
+            lab = 'WAMAX'
+        else:
+            lab = PHASES[nxt % len(PHASES)]
+            nxt += 1
+        out.append(lab)
+        prev = lab
+    return out
+
+
+labels = label_launches(data, ik)
+iters, cur = [], None          # per iteration: list of (label, us, kernel); the forced pair in front of the program joins iteration 0
+pending = []
+for lab, v, r in zip(labels, vals, data):
+    if lab == 'PRO':
+        cur = pending + [(lab, v, kname(r[ik]))]
+        pending = []
+        iters.append(cur)
+    elif cur is None or (lab in ('Z', 'WAMAX') and cur and cur[-1][0] == 'SWAP_SCATTER'):
+        pending.append((lab, v, kname(r[ik])))
+    else:
+        cur.append((lab, v, kname(r[ik])))
+assert len(iters) == 5, f"expected the launches of 5 iterations, got {len(iters)}"
+names = [x[0] for x in iters[0] if not x[0].startswith('SWAP')]
 with open(f'profiles/{prefix}_step_program_launches.csv', 'w') as f:
     f.write("launch,iteration,phase,kernel,duration_us\n")
-    for i, (r, v) in enumerate(zip(data, vals)):
-        f.write(f"{i},{i // PER_IT},{names_it[i % PER_IT]},{kname(r[ik])},{v:.3f}\n")
+    i = 0
+    for it, lst in enumerate(iters):
+        for lab, v, kn in lst:
+            f.write(f"{i},{it},{lab},{kn},{v:.3f}\n")
+            i += 1
 F = {'F1': 2 * 2000 * 450 * 500, 'F2': 2 * 2000 * 400 * 450, 'F3': 2 * 2000 * 300 * 400, 'F4': 2 * 2000 * 400 * 300, 'F5': 2 * 2000 * 450 * 400,
      'F6': 2 * 2000 * 500 * 450}
 fl = dict(F)
@@ -49,11 +75,11 @@ for k, v in F.items():
     fl[k.replace('F', 'T')] = v * 0.9
 fl.update({'B6': 2 * 2000 * 500 * 450 * 2, 'B5': 2 * 2000 * 450 * 400 * 2, 'B4': 2 * 2000 * 400 * 300 * 2, 'B3': 2 * 2000 * 300 * 400 * 2,
            'B2': 2 * 2000 * 400 * 450 * 2, 'B1': 2 * 2000 * 450 * 500})
-it0 = vals[:N_IT]
-sw = vals[4 * PER_IT + N_IT:5 * PER_IT]
+it0 = [x[1] for x in iters[0] if not x[0].startswith('SWAP')]
+sw = [x[1] for x in iters[4] if x[0].startswith('SWAP')]
 tot = sum(it0)
 lines, g, b, a, gf, zz = [], 0.0, 0.0, 0.0, 0.0, 0.0
-kern = [kname(r[ik]) for r in data[:N_IT]]
+kern = [x[2] for x in iters[0] if not x[0].startswith('SWAP')]
 for n, v, kn in zip(names, it0, kern):
     base = n.split(' ')[0].rstrip('b')
     tf = f"{fl[base] * 64 / (v * 1e-6) / 1e12:.0f}" if base in fl else ""
@@ -69,10 +95,10 @@ for n, v, kn in zip(names, it0, kern):
 md = f"""# {label} - launch list (ncu gpu__time_duration.sum, --clock-control none)
 
 Command: `BAE_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv python tools/profile_step.py --chains 64 --rounds 2 --steps-per-round 5 --profile-round 1`
-(Madelon shape, 64 chains, the 2nd PT round = ONE `bae_run(5)` call: 5 iterations x {PER_IT} launches, the exchange sweep in the last three; these
+(Madelon shape, 64 chains, the 2nd PT round = ONE `bae_run(5)` call: 5 iterations of {len(iters[1])} launches (+ the forced weight-bound pair in front), the exchange sweep in the last three; these
 are the production kernels - `BAE_NO_GRAPH=1` only makes the library launch them directly instead of replaying the captured graph).
 Raw list: `{prefix}_step_program_launches.csv`. Per-launch times are cold-cache and serialised (and the SM clock is higher than in a back-to-back run, which
-sits at the power cap); compare SHARES. Sum per iteration: {', '.join(f'{sum(vals[i * PER_IT:(i + 1) * PER_IT]) / 1000:.2f}' for i in range(5))} ms
+sits at the power cap); compare SHARES. Sum per iteration: {', '.join(f'{sum(x[1] for x in lst) / 1000:.2f}' for lst in iters)} ms
 (later iterations have fewer chains on a Langevin step); exchange sweep (decide / gather / scatter): {sw[0]:.0f} / {sw[1]:.0f} / {sw[2]:.0f} us.
 
 | phase | kernel | iteration 0 (us) | share | algorithmic TFLOP/s (64 chains) |
@@ -88,8 +114,8 @@ open(f'profiles/{prefix}_step_program_launches.md', 'w').write(md)
 
 r = list(csv.reader(open(raw_csv)))
 hdr, units, prow = r[0], r[1], r[2:]
-prow = prow[HEAD:]
-assert len(prow) == PER_IT, f"expected {HEAD} + {PER_IT} launches of one iteration, got {len(prow) + HEAD}"
+names_it = label_launches(prow, hdr.index('Kernel Name'))
+assert names_it.count('PRO') == 1, "expected the launches of ONE iteration"
 UNIT = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1, 'ms': 1e3, 's': 1e6}
 
 
@@ -109,18 +135,18 @@ regs = colv('launch__registers_per_thread')
 rd, wr, us = sum(rdv), sum(wrv), sum(dur)
 ptab = "\n".join(f"| {n} | {dur[i]:.1f} | {rdv[i] / 1e6:.1f} | {wrv[i] / 1e6:.1f} | {(rdv[i] + wrv[i]) / dur[i] / 1e3:.0f} | {dramp[i]:.1f} | {tens[i]:.1f} | "
                  f"{l2hit[i]:.0f} | {inst[i] / 1e6:.2f} | {lld[i] + lst[i]:.0f} |" for i, n in enumerate(names_it))
-gi = [i for i, n in enumerate(names) if n.split(' ')[0].rstrip('b') in fl]
-iA1 = names.index('ADAM1')
+gi = [i for i, n in enumerate(names_it) if n.split(' ')[0].rstrip('b') in fl]
+iA1 = names_it.index('ADAM1')
 gt = sum(dur[i] for i in gi)
 md2 = f"""# {label} - one `ncu --set full` capture over the launches of an iteration
 
-`BAE_NO_GRAPH=1 ncu --set full --clock-control none --profile-from-start off -k regex:bae_ -c {HEAD + PER_IT} python tools/profile_step.py --chains 8 --rounds 2 --steps-per-round 1 --profile-round 1`
+`BAE_NO_GRAPH=1 ncu --set full --clock-control none --profile-from-start off -k regex:bae_ -c {len(prow)} python tools/profile_step.py --chains 8 --rounds 2 --steps-per-round 1 --profile-round 1`
 (Madelon shape, 8 chains, ONE iteration of the production step program: GEMM phases = `bae_phase_kernel_tc<kindA, kindB>`, 148 CTAs = 74 CTA pairs x 512
 threads, 1 CTA/SM, {regs[1]:.0f} registers/thread at launch redistributed by `setmaxnreg`; BatchNorm / Adam / scalar phases = `bae_aux_kernel<family>`,
 256-thread CTAs. The report (>100 MB) stays on the GPU box; this file is built from its raw page export by `tools/make_profiles.py`.)
 
 Sum of the kernel durations {us / 1e3:.3f} ms under ncu (cold caches, serialised). Algorithmic FLOPs of one iteration: 8 chains x 27.18 GFLOP = 217 GFLOP
--> {217 / (us / 1e3):.0f} TFLOP/s at 8 chains over the whole iteration, {sum(fl[names[i].split(' ')[0].rstrip('b')] for i in gi) * 8 / (gt * 1e-6) / 1e12:.0f} TFLOP/s over the GEMM phases (8 chains fill only
+-> {217 / (us / 1e3):.0f} TFLOP/s at 8 chains over the whole iteration, {sum(fl[names_it[i].split(' ')[0].rstrip('b')] for i in gi) * 8 / (gt * 1e-6) / 1e12:.0f} TFLOP/s over the GEMM phases (8 chains fill only
 a fraction of the 74 CTA pairs per phase; production runs 64 chains per GPU, `bench.py`).
 DRAM traffic per iteration: read {rd / 1e6:.0f} MB + write {wr / 1e6:.0f} MB = {(rd + wr) / 8 / 1e6:.0f} MB per chain-iteration. Algorithmic weight-state traffic is
 22 x 4 B x 1.05 M = 93 MB per chain-iteration (SURVEY 8d); the rest is activations and deltas (41 MB per chain, written once and re-read by the backward
