@@ -34,6 +34,9 @@ bool narrow_supported(const int dims[4], int n_train, int n_test, int p_used);
 cudaError_t launch_narrow(const DevState* dS, int n_chains, int cluster, int n_iter, int p_used, cudaStream_t st);
 cudaError_t launch_swap_cta(const DevState* dS, int force_swap, cudaStream_t st);
 cudaError_t launch_amax_zero(const DevState* dS, unsigned mask, int c_begin, int c_end, int gated, cudaStream_t st);
+cudaError_t launch_wconv(const DevState* dS, int grid, int c_begin, int c_end, int gated, cudaStream_t st);
+cudaError_t launch_ximg(const float* src, int ld, int R, int ccK, int ccM, int e, unsigned char* imgK, int kbsK, unsigned char* imgM,
+                        int kbsM, cudaStream_t st);
 cudaError_t launch_xtable(const DevState* dS, cudaStream_t st);
 cudaError_t launch_xsweep(const DevState* dS, cudaStream_t st);
 cudaError_t launch_xgather(const DevState* dS, int grid, cudaStream_t st);
@@ -95,6 +98,11 @@ struct bae_handle {
   int32_t* xsrc_host = nullptr;            // pinned [E][R]: the permutation of the last sharded exchange round
   std::vector<int32_t> xops;
   int64_t vectors_sent = 0;
+  // pre-split images of the data matrices (DevState::preconv): K-major of train / test (first forward GEMM), MN-major of train
+  // (weight gradient of encode.0, ones column included)
+  unsigned char* ximgK[2] = {nullptr, nullptr};
+  unsigned char* ximgM = nullptr;
+  int ximgK_kbs[2] = {0, 0}, ximgM_kbs = 0;
   int n_sms = 148;
   // narrow-width step kernel (bae_narrow.cu): one thread-block cluster per chain
   bool narrow = false;
@@ -174,6 +182,11 @@ static int tc_max_bn() {
   }
   return v;
 }
+
+// Pre-split operand image (bae_tc.cuh "operand images") of a matrix used with `extent` tile rows / MN and a contraction of length K:
+// bytes per K block (hi plane + lo plane, the extent padded to whole 256-wide tiles) and in total
+static int img_kbs(int extent) { return 64 * round_up(extent, 256); }
+static size_t img_bytes(int extent, int K) { return (size_t)((K + 15) / 16) * (size_t)img_kbs(extent); }
 
 static GemmDesc make_gemm(const DevState& s, int M, int N, int K, int b_nmajor = 0) {
   GemmDesc g;
@@ -274,6 +287,14 @@ static int tmap_store(CUtensorMap* out, const float* ptr, int cols, int rows, in
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// index of a weight matrix in DevState::wi
+static const int kWimgSegs[6] = {SEG_E0_W, SEG_E2_W, SEG_E4_W, SEG_D1_W, SEG_D3_W, SEG_D5_W};
+static int wimg_index(int seg) {
+  for (int i = 0; i < 6; ++i)
+    if (kWimgSegs[i] == seg) return i;
+  return 0;
+}
+
 static void build_program(bae_handle* h) {
   DevState& s = h->hs;
   const long long P = s.Pp;
@@ -354,6 +375,11 @@ static void build_program(bae_handle* h) {
       g.aSc = (l == 0) ? (pass == 2 ? (int)SC_XTEST : (int)SC_XTRAIN) : (l == 3 ? (int)AMAX_Y : (int)SC_UNIT);
       g.bSc = AMAX_W;
       g.cSc = (ls[l].epi == EPI_LOSS) ? AMAX_DOUT : -1;
+      if (s.preconv) {   // weights and data arrive pre-split
+        const WImg& wi = s.wi[wimg_index(ls[l].wseg)];
+        g.bImg = s.wimg + wi.offK; g.sBImg = s.wimg_stride; g.bKbs = wi.kbsK;
+        if (l == 0) { g.aImg = h->ximgK[pass == 2 ? 1 : 0]; g.sAImg = 0; g.aKbs = h->ximgK_kbs[pass == 2 ? 1 : 0]; }
+      }
       if (ls[l].epi == EPI_LOSS) {
         g.aux = Xraw; g.sAux = 0; g.ldaux = s.ld0;
         g.scale = 2.0f / ((float)N * (float)s.d0);   // d MSELoss / d out (mean over all N*d0 elements, MAIN:150,223)
@@ -403,6 +429,7 @@ static void build_program(bae_handle* h) {
       }
     }
     if (ones) g.biasCol = bl[l].din;
+    if (s.preconv && l == 5) { g.bImg = h->ximgM; g.sBImg = 0; g.bKbs = h->ximgM_kbs; }   // the training matrix, ones column included
     g.needLang = 1;
     add_maps(g);
     bw_idx[l] = ng;
@@ -418,6 +445,10 @@ static void build_program(bae_handle* h) {
       x.epi = bl[l].epi_x;
       x.aSc = dsl[l]; x.bSc = AMAX_W;
       x.cSc = (bl[l].epi_x == EPI_DSIG) ? dsl[l + 1] : (int)AMAX_DYIN;   // DY's own bound is derived by the BatchNorm backward
+      if (s.preconv) {
+        const WImg& wi = s.wi[wimg_index(bl[l].wseg)];
+        x.bImg = s.wimg + wi.offM; x.sBImg = s.wimg_stride; x.bKbs = wi.kbsM;
+      }
       if (bl[l].Hin) { x.aux = bl[l].Hin; x.sAux = bl[l].sDin; x.ldaux = bl[l].lddin; x.auxAct = 1; }
       x.needLang = 1;
       add_maps(x);
@@ -593,6 +624,35 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   const size_t CA = s.C_alloc, P = s.Pp;
   CU(dalloc(h, &s.theta, CA * P)); CU(dalloc(h, &s.m, CA * P)); CU(dalloc(h, &s.v, CA * P));
   CU(dalloc(h, &s.wcur, CA * P));
+  const bool tf32_env = getenv("BAE_TC_TF32") && getenv("BAE_TC_TF32")[0] == '1';
+  // (the 3xFP16 engine belongs to the per-phase step program: see below where s.f16 is set)
+  const bool f16_early = s.tc && (!h->phase_launch_env || h->phase_launch) && !tf32_env;
+  s.preconv = (f16_early && !(getenv("BAE_TC_PRECONV") && getenv("BAE_TC_PRECONV")[0] == '0')) ? 1 : 0;
+  if (s.preconv) {
+    // pre-split images: per chain the six weight matrices (K-major for the forward GEMMs, MN-major for the delta GEMMs of all
+    // layers but the first); once per GPU the data matrices
+    long long off = 0;
+    s.wimg_items = 0;
+    for (int i = 0; i < 6; ++i) {
+      const Seg& sd = s.seg[kWimgSegs[i]];
+      WImg& wi = s.wi[i];
+      wi.seg = kWimgSegs[i];
+      wi.items = ((sd.rows + 7) / 8) * ((((sd.cols + 7) / 8) + 63) / 64);
+      s.wimg_items += wi.items;
+      wi.offK = off; wi.kbsK = img_kbs(sd.rows); off += (long long)img_bytes(sd.rows, sd.cols);
+      if (i > 0) { wi.offM = off; wi.kbsM = img_kbs(sd.cols); off += (long long)img_bytes(sd.cols, sd.rows); }
+      else { wi.offM = -1; wi.kbsM = 0; }
+    }
+    s.wimg_stride = off;
+    CU(dalloc(h, &s.wimg, CA * (size_t)off));
+    const int nx[2] = {cfg->n_train, cfg->n_test};
+    for (int i = 0; i < 2; ++i) {
+      h->ximgK_kbs[i] = img_kbs(nx[i]);
+      CU(dalloc(h, &h->ximgK[i], img_bytes(nx[i], s.d0)));
+    }
+    h->ximgM_kbs = img_kbs(s.d0 + 1);
+    CU(dalloc(h, &h->ximgM, img_bytes(s.d0 + 1, cfg->n_train)));
+  }
   for (int i = 0; i < kNumSegs; ++i) s.seg_ksplit[i] = 1;
   s.max_ksplit = 1;
   {
@@ -684,7 +744,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   if (s.dbg_flags != 0)
     return fail(BAE_ERR_INVALID, "BAE_TC_DBGFLAGS is set, but this library was built without -DBAE_TC_DEBUG: refusing to sample");
 #endif
-  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW", "BAE_NARROW_CLUSTER", "BAE_TC_TF32"})
+  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW", "BAE_NARROW_CLUSTER", "BAE_TC_TF32", "BAE_TC_PRECONV"})
     if (getenv(knob)) fprintf(stderr, "[bae_b200] note: tuning variable %s=%s is in effect for this handle\n", knob, getenv(knob));
   s.dbg_phase = getenv("BAE_TC_TRACE_PHASE") ? atoi(getenv("BAE_TC_TRACE_PHASE")) : -1;
   {
@@ -698,8 +758,8 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     // 3xFP16 split (kind::f16, half the tensor-pipe time of 3xTF32 at the same 11-bit operand precision): the default of the
     // per-phase step program; BAE_TC_TF32=1 keeps the 3xTF32 engine, and the persistent kernel always uses it (the amax
     // slots are zeroed by launches between phases)
-    const bool tf32_env = getenv("BAE_TC_TF32") && getenv("BAE_TC_TF32")[0] == '1';
     s.f16 = (s.tc && h->phase_launch && !tf32_env) ? 1 : 0;
+    if (s.preconv && !s.f16) return fail(BAE_ERR_STATE, "internal: operand images without the 3xFP16 engine");
     CU(dalloc(h, &s.amax, (size_t)kAmaxSlots * CA));
     s.xexp[0] = s.xexp[1] = kF16TopExp;
   }
@@ -791,6 +851,12 @@ int bae_upload_data(bae_handle* h, const float* train, const float* test) {
     h->hs.xexp[1] = f16_scale_exp(mx[1]);
     int rc = upload_state(h);
     if (rc) return rc;
+    if (s.preconv) {
+      // pre-split images of the matrices just uploaded (stream-ordered behind the copies above)
+      CU(launch_ximg(s.Xtrain, s.ld0, s.n_train, s.d0, s.d0 + 1, h->hs.xexp[0], h->ximgK[0], h->ximgK_kbs[0], h->ximgM, h->ximgM_kbs, h->stream));
+      CU(launch_ximg(s.Xtest, s.ld0, s.n_test, s.d0, 0, h->hs.xexp[1], h->ximgK[1], h->ximgK_kbs[1], nullptr, 0, h->stream));
+      h->launches += 2;
+    }
   }
   h->data_loaded = true;
   return BAE_OK;
@@ -861,6 +927,13 @@ static cudaError_t launch_one(bae_handle* h, int p, int c_begin, int c_end, int 
     }
   }
   h->n_emit++;
+  if (h->hs.preconv && (p == P_WAMAX0 || p == P_ADAM1)) {
+    // the phase that folds the weight bounds, then the images of the weights it bounds (same gate)
+    const cudaError_t e = launch_aux(h->dS, h->hs.phase[p].kind, h->grid_aux[h->hs.phase[p].kind], p, c_begin, c_end, force_swap, h->stream);
+    if (e != cudaSuccess) return e;
+    h->n_emit++;
+    return launch_wconv(h->dS, h->n_sms * 8, c_begin, c_end, (p == P_WAMAX0 && !force_swap) ? 1 : 0, h->stream);
+  }
   if (h->hs.tc && h->hs.phase[p].kind != PH_GEMM)
     return launch_aux(h->dS, h->hs.phase[p].kind, h->grid_aux[h->hs.phase[p].kind], p, c_begin, c_end, force_swap, h->stream);
   const PhaseDesc& ph = h->hs.phase[p];

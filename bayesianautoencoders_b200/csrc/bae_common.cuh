@@ -73,6 +73,19 @@ struct GemmDesc {
   // ---- 3xFP16 split (DevState::f16): where the power-of-two scale of each operand comes from (bae_tc.cuh)
   int aSc, bSc;         // >= 0: amax slot (AmaxSlot, per chain); SC_UNIT: values in [0, 1]; SC_XTRAIN / SC_XTEST: DevState::xexp
   int cSc;              // amax slot the epilogue folds max |C| into (deltas), or -1
+  // ---- pre-split operand images (3xFP16 split, DevState::preconv; layout: bae_tc.cuh "operand images"). Null: the converter
+  // warps split this operand's FP32 tile in shared memory. Non-null (weights: once per proposal; data: once per upload): the
+  // producer copies the FP16 hi / lo tiles of a K block straight into the converted stage.
+  const unsigned char* aImg; long long sAImg; int aKbs;   // base, bytes per chain, bytes per K block (hi plane; lo plane at aKbs / 2)
+  const unsigned char* bImg; long long sBImg; int bKbs;
+};
+
+// Pre-split images of one weight matrix inside a chain's image slab (DevState::wimg): K-major (forward GEMMs: contraction over
+// the matrix's columns) and MN-major (delta GEMMs: contraction over its rows; offM < 0: not needed)
+struct WImg {
+  int seg, items;          // tensor; work items of bae_wconv_kernel (8 rows x 64 units of 8 columns)
+  long long offK, offM;    // byte offsets inside the slab
+  int kbsK, kbsM;          // bytes per K block
 };
 
 // Magnitude bounds behind the FP16 operand scales: one float per (slot, chain), DevState::amax[slot * C_alloc + chain], folded
@@ -185,6 +198,11 @@ struct DevState {
   int f16;            // 1: 3xFP16 split (kind::f16, K = 16 per MMA, scaled operands); 0: 3xTF32 split (kind::tf32)
   float* amax;        // [kAmaxSlots][C_alloc] magnitude bounds of the scaled operands (AmaxSlot)
   int xexp[2];        // scale exponents of the training / test matrix (host scan at bae_upload_data)
+  int preconv;        // 1: weights and data are read as pre-split FP16 images (GemmDesc::aImg / bImg), rewritten by bae_wconv_kernel
+  unsigned char* wimg;        // [C_alloc][wimg_stride] bytes
+  long long wimg_stride;
+  int wimg_items;             // work items of bae_wconv_kernel per chain
+  WImg wi[6];
   void* tmaps;        // CUtensorMap array in global memory (64-byte aligned)
   int* sched;         // longest-first item schedules of the GEMM phases (PhaseDesc::sched_off), built for `sched_chains` chains
   int sched_chains, sched_pairs;   // ... per launch and `sched_pairs` CTA pairs

@@ -377,6 +377,77 @@ __global__ void bae_amax_zero_kernel(const DevState* __restrict__ S, unsigned ma
 }
 
 // ------------------------------------------------------------------------------------------------
+// Pre-split operand images of the 3xFP16 split (bae_tc.cuh "operand images"): the FP16 hi / lo units the converter warps
+// would produce, written once per rewrite of the source matrix in the order the tiles are consumed.
+// ------------------------------------------------------------------------------------------------
+// One work item: rows [o0, o0 + 8) x units [g0, g0 + 64) of a row-major FP32 matrix (unit g = columns 8 g .. 8 g + 7). Thread
+// t takes row o0 + (t & 7) and units g0 + (t >> 3), g0 + 32 + (t >> 3): a warp reads 8 rows x 128 contiguous bytes and writes,
+// in each image and plane, runs of 128 contiguous bytes (the 8 rows of a unit column).
+//   imgK (contraction over the columns; columns >= ccK read as 0): unit at (g >> 1) kbsK + (o >> 3) 256 + (g & 1) 128 + (o & 7) 16
+//   imgM (contraction over the rows;    columns >= ccM read as 0): unit at (o >> 4) kbsM + g 256 + ((o >> 3) & 1) 128 + (o & 7) 16
+// lo planes kbs / 2 further. Rows >= R and units beyond the columns are never written: they keep the zeros of the allocation
+// (what the tensor loads' out-of-bounds fill gives the FP32 path).
+__device__ __forceinline__ void split_item_to_images(const float* __restrict__ src, int ld, int R, int ccK, int ccM, float s,
+                                                     unsigned char* imgK, int kbsK, unsigned char* imgM, int kbsM, int o0, int g0) {
+  const int o = o0 + (int)(TID & 7);
+  if (o >= R) return;
+  const int ccmax = max(imgK ? ccK : 0, imgM ? ccM : 0);
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int g = g0 + u * 32 + (int)(TID >> 3);
+    const int c0 = g * 8;
+    if (c0 >= ccmax) continue;
+    const float* p = src + (size_t)o * ld + c0;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 v0 = *reinterpret_cast<const float4*>(p);                         // ld is a multiple of 4 and c0 < cols <= ld
+    const float4 v1 = (c0 + 4 < ld) ? *reinterpret_cast<const float4*>(p + 4) : z4;
+    const float x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    auto emit = [&](unsigned char* img, int cc, size_t off, int kbs) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = (c0 + e < cc) ? x[e] : 0.f;
+      uint4 hi, lo;
+      tc::f16_split8(make_float4(y[0], y[1], y[2], y[3]), make_float4(y[4], y[5], y[6], y[7]), s, hi, lo);
+      *reinterpret_cast<uint4*>(img + off) = hi;
+      *reinterpret_cast<uint4*>(img + off + (size_t)(kbs >> 1)) = lo;
+    };
+    if (imgK && c0 < ccK) emit(imgK, ccK, (size_t)(g >> 1) * kbsK + (size_t)(o >> 3) * 256 + (size_t)(g & 1) * 128 + (size_t)(o & 7) * 16, kbsK);
+    if (imgM && c0 < ccM) emit(imgM, ccM, (size_t)(o >> 4) * kbsM + (size_t)g * 256 + (size_t)((o >> 3) & 1) * 128 + (size_t)(o & 7) * 16, kbsM);
+  }
+}
+
+// Images of the six weight matrices of every chain in [c_begin, c_end), from theta with the scale of the chain's CURRENT weight
+// bound (amax slot AMAX_W: final when this runs - it follows the phase that folded it, PH_WAMAX or PH_ADAM1, on the stream).
+// `gated`: the same test as the gated PH_WAMAX phase it follows.
+__global__ void __launch_bounds__(kThreads) bae_wconv_kernel(const DevState* __restrict__ S, int c_begin, int c_end, int gated) {
+  if (gated && (S->ch.step[c_begin] % S->swap_interval) != 0) return;
+  const int per_chain = S->wimg_items;
+  const int total = per_chain * (c_end - c_begin);
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int chain = c_begin + item / per_chain;
+    int p = item % per_chain, w = 0;
+    while (p >= S->wi[w].items) { p -= S->wi[w].items; ++w; }
+    const WImg wi = S->wi[w];
+    const Seg& sd = S->seg[wi.seg];
+    const int ub = (((sd.cols + 7) >> 3) + 63) >> 6;   // 64-unit blocks per row
+    const float s = tc::exp2i(f16_scale_exp(S->amax[(size_t)AMAX_W * S->C_alloc + chain]));
+    unsigned char* slab = S->wimg + (size_t)chain * S->wimg_stride;
+    split_item_to_images(S->theta + (size_t)chain * S->Pp + sd.pad_off, sd.ld, sd.rows, sd.cols, sd.cols, s, slab + wi.offK, wi.kbsK,
+                         wi.offM >= 0 ? slab + wi.offM : nullptr, wi.kbsM, (p / ub) * 8, (p % ub) * 64);
+  }
+}
+
+// Images of a data matrix (bae_upload_data): static scale 2^e
+__global__ void __launch_bounds__(kThreads) bae_ximg_kernel(const float* __restrict__ src, int ld, int R, int ccK, int ccM, int e,
+                                                           unsigned char* imgK, int kbsK, unsigned char* imgM, int kbsM) {
+  const int ub = (((max(ccK, ccM) + 7) >> 3) + 63) >> 6;
+  const int total = ((R + 7) >> 3) * ub;
+  const float s = tc::exp2i(e);
+  for (int item = blockIdx.x; item < total; item += gridDim.x)
+    split_item_to_images(src, ld, R, ccK, ccM, s, imgK, kbsK, imgM, kbsM, (item / ub) * 8, (item % ub) * 64);
+}
+
+// ------------------------------------------------------------------------------------------------
 // BatchNorm1d, training mode (MAIN:165): batch statistics forward, full backward
 // ------------------------------------------------------------------------------------------------
 // ---- BatchNorm phases for wide bottlenecks (d3 >= 16): a work item is (chain, 16 columns). 4 float4 column groups x
@@ -1957,6 +2028,17 @@ cudaError_t launch_aux(const DevState* dS, int kind, int grid, int pi, int c_beg
 
 cudaError_t launch_amax_zero(const DevState* dS, unsigned mask, int c_begin, int c_end, int gated, cudaStream_t st) {
   bae_amax_zero_kernel<<<1, 256, 0, st>>>(dS, mask, c_begin, c_end, gated);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wconv(const DevState* dS, int grid, int c_begin, int c_end, int gated, cudaStream_t st) {
+  bae_wconv_kernel<<<grid, kThreads, 0, st>>>(dS, c_begin, c_end, gated);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ximg(const float* src, int ld, int R, int ccK, int ccM, int e, unsigned char* imgK, int kbsK, unsigned char* imgM,
+                        int kbsM, cudaStream_t st) {
+  bae_ximg_kernel<<<1184, kThreads, 0, st>>>(src, ld, R, ccK, ccM, e, imgK, kbsK, imgM, kbsM);
   return cudaGetLastError();
 }
 

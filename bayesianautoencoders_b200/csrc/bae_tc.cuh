@@ -48,8 +48,12 @@ namespace bae {
 namespace tc {
 
 constexpr int kThreadsTc = 512;
-constexpr int kStages = 7;                     // raw tile pairs (TMA ring): deep, the loads come from HBM (~2000 cycles under load)
-constexpr int kLoStages = 5;                   // converted tiles (converter ring): three groups converting + two being read / waiting
+#ifndef BAE_TC_STAGES
+#define BAE_TC_STAGES 7
+#define BAE_TC_LOSTAGES 5
+#endif
+constexpr int kStages = BAE_TC_STAGES;         // raw tile pairs (TMA ring): deep, the loads come from HBM (~2000 cycles under load)
+constexpr int kLoStages = BAE_TC_LOSTAGES;     // converted tiles (converter ring): three groups converting + two being read / waiting
 constexpr int kBM = 128;
 constexpr int kBK = 16;                        // floats of K per stage (64-byte rows: SWIZZLE_64B for K-major tiles)
 constexpr int kMaxBN = 256;                    // pair tile width; each CTA holds BN/2 columns of B; 2 accumulators x 256 TMEM columns
@@ -183,6 +187,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, ui
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+// Plain (1-D) bulk copy global -> shared through the copy engine; bytes land on the same transaction barrier as the tensor loads
+__device__ __forceinline__ void bulk_load(uint32_t dst_s, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_s), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
@@ -333,6 +343,17 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 // tile fall into 8 different 16-byte bank groups in both source swizzles (for MN-major sources the two halves of a 32-byte
 // swizzle unit are read in opposite order by the lanes with r >= 4).
 constexpr int kF16TileBytes = 128 * kBK * 2;   // 4 KB: 128 rows (or MN) x 16 K of halves; a 16 KB lo stage = [A hi][A lo][B hi][B lo]
+//
+// OPERAND IMAGES (GemmDesc::aImg / bImg, DevState::preconv): an operand whose values and scale are known before the GEMM runs
+// (the weights: rewritten once per proposal; the data matrices: once per upload) is split ONCE, by bae_wconv_kernel /
+// bae_ximg_kernel, into an image in HBM that holds the units of the canonical layout in tile order:
+//     unit (t8, kb, j, r)  at  kb * kbs + plane * (kbs / 2) + t8 * 256 + j * 128 + r * 16      (plane 0 = hi, 1 = lo)
+//   K-major use  (contraction over the matrix's columns): row = 8 t8 + r,  k = 16 kb + 8 j .. + 7
+//   MN-major use (contraction over the matrix's rows):    k = 16 kb + 8 j + r,  mn = 8 t8 .. + 7
+// so the hi (lo) tile of `n` rows / MN from t0 (a multiple of 8) of K block kb is ONE contiguous run of 32 n bytes: the producer
+// copies it straight into the converted stage (cp.async.bulk, no tensor map) and the converter warps skip that operand -
+// no FP32 tile in shared memory, no LDS / STS / ALU work: 16 KB less shared-memory traffic per operand and K block. The
+// values are those the converters would have produced (same scale exponent, same roundings): results are bit-identical.
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {   // a at the lower address
   uint32_t r;
@@ -499,7 +520,7 @@ __device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem, bool f16 = fa
   sm.tiles = reinterpret_cast<uint8_t*>(base);
   if (threadIdx.x == 0) {
     // `conv` and `tmem_empty` collect arrivals from both CTAs of the pair (only the leader's copies are waited on)
-    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full()[i], 1); mbar_init(&sm.empty()[i], f16 ? kConvGroupWarps : 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full()[i], 1); mbar_init(&sm.empty()[i], f16 ? kConvGroupWarps + 1 : 1); }
     for (int i = 0; i < kLoStages; ++i) { mbar_init(&sm.conv()[i], 2 * kConvGroupWarps); mbar_init(&sm.lo_empty()[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full()[i], 1); mbar_init(&sm.tmem_empty()[i], 2 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -642,7 +663,11 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         // chain coordinate of the tensor maps: activations / deltas are indexed by the slot in the resident chain group
         const int ca = g.sA ? (g.aAct ? it.chain - c_begin : it.chain) : 0, cb = g.sB ? (g.bAct ? it.chain - c_begin : it.chain) : 0;
         const int dbgf = BAE_DBGF(S);
-        const uint32_t bytes = ((dbgf & 64) ? 0u : (uint32_t)kATileBytes) + ((dbgf & 32) ? 0u : (uint32_t)g.tcBBytes);
+        // pre-split operand images: this CTA's hi tile of K block kb0 (the lo tile lies kbs / 2 further)
+        const unsigned char* imgA = g.aImg ? g.aImg + (size_t)ca * g.sAImg + (size_t)it.kb0 * g.aKbs + (size_t)(m0 >> 3) * 256 : nullptr;
+        const unsigned char* imgB = g.bImg ? g.bImg + (size_t)cb * g.sBImg + (size_t)it.kb0 * g.bKbs + (size_t)(n0 >> 3) * 256 : nullptr;
+        const uint32_t aKbs = (uint32_t)g.aKbs, bKbs = (uint32_t)g.bKbs, bPlane = (uint32_t)(g.tcBN >> 1) * 32u;
+        const uint32_t bytes = ((dbgf & 64) ? 0u : (uint32_t)kATileBytes) + ((dbgf & 32) ? 0u : (imgB ? 2u * bPlane : (uint32_t)g.tcBBytes));
         const int aMode = g.aMode, bMode = g.bMode, nchB = g.tcBBytes / kMnChunkBytes, nkb = it.nkb, kb0 = it.kb0;
         const CUtensorMap* mapA = &maps[g.tmIdx[0]];
         const CUtensorMap* mapB = &maps[g.tmIdx[1]];
@@ -651,9 +676,15 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
           if (elect_one()) {
             trace(dbg, 0, ntr, kb);
             uint8_t* st = sm.tiles + ring.stage * kStageBytes;
+            // image tiles take the operand's half of the RAW stage ([hi 4 KB][lo 4 KB]; the tensor core reads them there)
+            const uint32_t cv = smem_u32(st);
             mbar_expect_tx(&sm.full()[ring.stage], bytes);
             const int k0 = (kb0 + kb) * kBK;
             if (dbgf & 64) {
+            } else if (imgA) {
+              const unsigned char* p = imgA + (size_t)kb * aKbs;
+              bulk_load(cv, p, (uint32_t)kF16TileBytes, &sm.full()[ring.stage]);
+              bulk_load(cv + kF16TileBytes, p + (aKbs >> 1), (uint32_t)kF16TileBytes, &sm.full()[ring.stage]);
             } else if (aMode == 0) {
               tma_load_3d(st, mapA, &sm.full()[ring.stage], k0, m0, ca);
             } else {
@@ -664,6 +695,10 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             }
             uint8_t* sb = st + kATileBytes;
             if (dbgf & 32) {
+            } else if (imgB) {
+              const unsigned char* p = imgB + (size_t)kb * bKbs;
+              bulk_load(cv + kATileBytes, p, bPlane, &sm.full()[ring.stage]);
+              bulk_load(cv + kATileBytes + kF16TileBytes, p + (bKbs >> 1), bPlane, &sm.full()[ring.stage]);
             } else if (bMode == 0) {
               tma_load_3d(sb, mapB, &sm.full()[ring.stage], k0, n0, cb);
             } else {
@@ -702,6 +737,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const uint64_t dA = make_desc(smem_u32(sm.tiles), amn), dB = make_desc(smem_u32(sm.tiles) + kATileBytes, bmn);
         const uint64_t d16 = make_desc_f16(smem_u32(sm.tiles));
         const bool f16 = S->f16 != 0;
+        const bool preA = g.aImg != nullptr, preB = g.bImg != nullptr;   // operand images: read in the raw stage, which these MMAs then release
         for (int kb = 0; kb < nkb; ++kb) {
           // `conv` is signalled by converter warps that had themselves waited for the TMA bytes (`full`)
           mbar_wait(&sm.conv()[ring.lo], ring.lo_phase);   // both CTAs' raw and lo tiles of the K block are ready
@@ -710,13 +746,15 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             // 3xFP16: the converted stage holds [A hi][A lo][B hi][B lo], 4 KB each; one K = 16 MMA per product
             if (elect_one()) {
               trace(dbg, 1, ntr, kb);
-              const uint64_t ah = d16 + (kStages + ring.lo) * (uint32_t)(kStageBytes >> 4);
-              const uint64_t al = ah + (kF16TileBytes >> 4), bh = ah + (2 * kF16TileBytes >> 4), bl = ah + (3 * kF16TileBytes >> 4);
+              const uint64_t cvt = d16 + (kStages + ring.lo) * (uint32_t)(kStageBytes >> 4), raw = d16 + ring.stage * (uint32_t)(kStageBytes >> 4);
+              const uint64_t ah = preA ? raw : cvt, al = ah + (kF16TileBytes >> 4);
+              const uint64_t bh = preB ? raw + (kATileBytes >> 4) : cvt + (2 * kF16TileBytes >> 4), bl = bh + (kF16TileBytes >> 4);
               const uint32_t acc0 = kb ? 1u : 0u;
               umma_f16(d_main, ah, bh, idesc, acc0);
               umma_f16(d_cross, al, bh, idesc, acc0);
               umma_f16(d_cross, ah, bl, idesc, 1u);
               umma_commit(&sm.lo_empty()[ring.lo]);
+              if (preA || preB) umma_commit(&sm.empty()[ring.stage]);   // (both CTAs' stages, like every commit here)
               if (kb == nkb - 1) {
                 trace(dbg, 1, ntr, 1000);
                 umma_commit(&sm.tmem_full()[0]);
@@ -778,6 +816,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
       uint32_t offA = 0, offB = 0;
       bool swapA = false, swapB = false, aM = false, bM = false;
       int nvB = 0;   // units of this CTA's B half that this thread converts: gt + 64 n < tcBN
+      const bool preA = it.g->aImg != nullptr, preB = it.g->bImg != nullptr;   // the producer delivers these operands already split
       if (f16) {
         sA = exp2i(operand_exp(S, it.g->aSc, it.chain));
         sB = exp2i(operand_exp(S, it.g->bSc, it.chain));
@@ -799,15 +838,19 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
           if (gt == 0) trace(dbg, 2, ntr, kb);
           const uint32_t src = tiles0 + stage * kStageBytes, dst = tiles0 + (kStages + lo) * kStageBytes + gt * 16;
           // A: 256 units = 4 per thread; B: tcBN units (a multiple of 16) = this CTA's BN/2 columns, nvB of them this thread's
-          if (aM) conv_tile<true>(src + offA, dst, dst + kF16TileBytes, swapA, sA, 4);
+          if ((BAE_DBGF(S) & 3) || preA) {
+          } else if (aM) conv_tile<true>(src + offA, dst, dst + kF16TileBytes, swapA, sA, 4);
           else conv_tile<false>(src + offA, dst, dst + kF16TileBytes, false, sA, 4);
-          if (bM) conv_tile<true>(src + kATileBytes + offB, dst + 2 * kF16TileBytes, dst + 3 * kF16TileBytes, swapB, sB, nvB);
+          if ((BAE_DBGF(S) & 5) || preB) {
+          } else if (bM) conv_tile<true>(src + kATileBytes + offB, dst + 2 * kF16TileBytes, dst + 3 * kF16TileBytes, swapB, sB, nvB);
           else conv_tile<false>(src + kATileBytes + offB, dst + 2 * kF16TileBytes, dst + 3 * kF16TileBytes, false, sB, nvB);
           if (gt == 0) trace(dbg, 2, ntr, 2000 + kb);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(&sm.empty()[stage]);   // the raw stage has been read: the producer may refill it
+            // (third arrival: the MMAs' commit when the stage holds an image tile, else this group's first warp again)
+            if (!(preA || preB) && (warp & 1) == 0) mbar_arrive(&sm.empty()[stage]);
             if (rank == 0) mbar_arrive(&sm.conv()[lo]);
             else mbar_arrive_leader_relaxed(&sm.conv()[lo]);
           }
