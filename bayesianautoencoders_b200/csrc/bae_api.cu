@@ -35,6 +35,7 @@ cudaError_t launch_narrow(const DevState* dS, int n_chains, int cluster, int n_i
 cudaError_t launch_swap_cta(const DevState* dS, int force_swap, cudaStream_t st);
 cudaError_t launch_amax_zero(const DevState* dS, unsigned mask, int c_begin, int c_end, int gated, cudaStream_t st);
 cudaError_t launch_wconv(const DevState* dS, int grid, int c_begin, int c_end, int gated, cudaStream_t st);
+cudaError_t launch_himg_ones(unsigned char* img, long long stride, int kbs, int d, int rows, int nslots, cudaStream_t st);
 cudaError_t launch_ximg(const float* src, int ld, int R, int ccK, int ccM, int e, unsigned char* imgK, int kbsK, unsigned char* imgM,
                         int kbsM, cudaStream_t st);
 cudaError_t launch_xtable(const DevState* dS, cudaStream_t st);
@@ -118,6 +119,9 @@ struct bae_handle {
   int grid_aux[16] = {};       // CTAs of bae_aux_kernel per phase kind (non-GEMM phases of the tcgen05 path)
   std::map<std::array<int, 4>, cudaGraphExec_t> graphs;   // (p_begin, p_end, n_rep, force_swap) -> instantiated graph
   std::map<std::array<int, 4>, int> graph_launches;       // kernel nodes of each graph
+  // BAE_PHASE_TIMES=1 (debug): direct launches with an event after every phase; bae_debug_phase_times sums the intervals
+  bool phase_times = false;
+  std::vector<std::pair<int, cudaEvent_t>> pt_events;   // (phase index or -1 = start marker, event)
 };
 
 template <typename T>
@@ -295,6 +299,21 @@ static int wimg_index(int seg) {
   return 0;
 }
 
+// Plane (hi or lo) of an MN-major activation image as the target of the converters' box stores: a converted K-major A tile
+// [row group 2 kbrow + jrow][k half jc][r][16 B] is the box (jc and r: 256 contiguous bytes at column unit 2 kb; jrow; 8 kbrow)
+static int tmap_image_store(CUtensorMap* out, unsigned char* plane, int kbs, int rows, int nslot, long long slot_stride) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return -1;
+  const cuuint64_t t8 = (cuuint64_t)kbs / 512;
+  cuuint64_t dims[4] = {t8 * 64, 2, (cuuint64_t)((rows + 15) / 16), (cuuint64_t)std::max(1, nslot)};
+  cuuint64_t strides[3] = {t8 * 128, (cuuint64_t)kbs, (cuuint64_t)slot_stride};
+  cuuint32_t box[4] = {128, 2, 8, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT16, 4, (void*)plane, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 static void build_program(bae_handle* h) {
   DevState& s = h->hs;
   const long long P = s.Pp;
@@ -316,7 +335,7 @@ static void build_program(bae_handle* h) {
       memset(&tm, 0, sizeof(tm));
       int rc;
       if (i < 1) {
-        rc = g.aMode == 0 ? tmap_kmajor(&tm, ptrs[i], g.K, g.M, g.lda, nchA, g.sA, 128)
+        rc = g.aMode == 0 ? tmap_kmajor(&tm, ptrs[i], g.K + (g.aOut ? 1 : 0), g.M, g.lda, nchA, g.sA, 128)
                           : tmap_mnmajor(&tm, ptrs[i], g.M, g.K, g.lda, nchA, g.sA, 4);
       } else {
         rc = g.bMode == 0 ? tmap_kmajor(&tm, ptrs[i], g.K, g.N, g.ldb, nchB, g.sB, g.tcBN / 2)
@@ -379,6 +398,19 @@ static void build_program(bae_handle* h) {
         const WImg& wi = s.wi[wimg_index(ls[l].wseg)];
         g.bImg = s.wimg + wi.offK; g.sBImg = s.wimg_stride; g.bKbs = wi.kbsK;
         if (l == 0) { g.aImg = h->ximgK[pass == 2 ? 1 : 0]; g.sAImg = 0; g.aKbs = h->ximgK_kbs[pass == 2 ? 1 : 0]; }
+        // the activation a pass over the training matrix reads as its A operand is persisted as an image by the converter warps
+        if (pass != 2 && l >= 1 && s.himg[l - 1]) {
+          g.aOut = s.himg[l - 1];
+          g.tmOut = (int)h->tmaps_host.size();
+          for (int pl = 0; pl < 2; ++pl) {
+            CUtensorMap tm;
+            memset(&tm, 0, sizeof(tm));
+            const int rc = tmap_image_store(&tm, s.himg[l - 1] + (size_t)pl * (s.himg_kbs[l - 1] / 2), s.himg_kbs[l - 1], s.n_train, s.G, s.himg_stride[l - 1]);
+            if (rc != 0 && h->tmap_error.empty())
+              h->tmap_error = "cuTensorMapEncodeTiled failed (CUresult " + std::to_string(rc) + ") for an activation image";
+            h->tmaps_host.push_back(tm);
+          }
+        }
       }
       if (ls[l].epi == EPI_LOSS) {
         g.aux = Xraw; g.sAux = 0; g.ldaux = s.ld0;
@@ -430,6 +462,10 @@ static void build_program(bae_handle* h) {
     }
     if (ones) g.biasCol = bl[l].din;
     if (s.preconv && l == 5) { g.bImg = h->ximgM; g.sBImg = 0; g.bKbs = h->ximgM_kbs; }   // the training matrix, ones column included
+    if (s.preconv && l != 5 && s.himg[4 - l]) {   // the layer input: H5, H4, Y, H2, H1
+      const int k = 4 - l;
+      g.bImg = s.himg[k]; g.sBImg = s.himg_stride[k]; g.bKbs = s.himg_kbs[k];
+    }
     g.needLang = 1;
     add_maps(g);
     bw_idx[l] = ng;
@@ -588,6 +624,8 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   h->phase_launch = getenv("BAE_PHASE_LAUNCH") != nullptr && getenv("BAE_PHASE_LAUNCH")[0] == '1';
   h->phase_launch_env = getenv("BAE_PHASE_LAUNCH") != nullptr;
   h->use_graph = !(getenv("BAE_NO_GRAPH") != nullptr && getenv("BAE_NO_GRAPH")[0] == '1');
+  h->phase_times = getenv("BAE_PHASE_TIMES") != nullptr && getenv("BAE_PHASE_TIMES")[0] == '1';
+  if (h->phase_times) h->use_graph = false;
   CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CU(cudaEventCreate(&h->ev0));
   CU(cudaEventCreate(&h->ev1));
@@ -667,7 +705,9 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   const size_t nm = s.n_max;
   {
     // chain groups: activation / delta buffers exist for G chains at a time (G = C unless they do not fit)
-    const size_t per_chain = nm * (size_t)(s.ld0 + 4 * s.ld1 + 4 * s.ld2 + 3 * s.ld3) * sizeof(float);   // H1 H2 Z Y H4 H5 + DOUT D5 D4 DY D2 D1
+    size_t per_chain = nm * (size_t)(s.ld0 + 4 * s.ld1 + 4 * s.ld2 + 3 * s.ld3) * sizeof(float);   // H1 H2 Z Y H4 H5 + DOUT D5 D4 DY D2 D1
+    if (s.preconv && !(getenv("BAE_TC_HIMG") && getenv("BAE_TC_HIMG")[0] == '0'))
+      per_chain += 2 * (img_bytes(s.d1 + 1, s.n_train) + img_bytes(s.d2 + 1, s.n_train)) + img_bytes(s.d3 + 1, s.n_train);   // images of H1 H5, H2 H4, Y
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     int G = s.C;
@@ -684,6 +724,21 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   CU(dalloc(h, &s.Y, CA_act * nm * s.ld3)); CU(dalloc(h, &s.H4, CA_act * nm * s.ld2)); CU(dalloc(h, &s.H5, CA_act * nm * s.ld1));
   CU(dalloc(h, &s.DOUT, CA_act * nm * s.ld0)); CU(dalloc(h, &s.D5, CA_act * nm * s.ld1)); CU(dalloc(h, &s.D4, CA_act * nm * s.ld2));
   CU(dalloc(h, &s.DY, CA_act * nm * s.ld3)); CU(dalloc(h, &s.D2, CA_act * nm * s.ld2)); CU(dalloc(h, &s.D1, CA_act * nm * s.ld1));
+  if (s.preconv && !(getenv("BAE_TC_HIMG") && getenv("BAE_TC_HIMG")[0] == '0')) {
+    // MN-major images of the activations (B operands of the weight-gradient GEMMs), written by the converter warps of the forward
+    // GEMM that reads the activation as its A operand
+    const int hd[5] = {s.d1, s.d2, s.d3, s.d2, s.d1};   // H1, H2, Y, H4, H5
+    for (int i = 0; i < 5; ++i) {
+      // Y (BatchNorm output, scale tracked per chain): when no forward K block reaches its ones column (d3 a multiple of 16) the
+      // column would have to be static, which a per-chain scale does not allow - that one operand then stays with the converters
+      if (i == 2 && hd[i] % 16 == 0) continue;
+      s.himg_kbs[i] = img_kbs(hd[i] + 1);
+      s.himg_stride[i] = (long long)img_bytes(hd[i] + 1, s.n_train);
+      CU(dalloc(h, &s.himg[i], CA_act * (size_t)s.himg_stride[i]));
+      // (static content of the ones column of a sigmoid output - static scale 2^13 - where no forward K block reaches it)
+      if (hd[i] % 16 == 0) CU(launch_himg_ones(s.himg[i], s.himg_stride[i], s.himg_kbs[i], hd[i], s.n_train, (int)CA_act, h->stream));
+    }
+  }
   {
     const int per_tile = s.tc ? 2 : 1;   // tcgen05 path: each CTA of a pair writes the partial of its 128 rows
     GemmDesc t = make_gemm(s, s.n_max, s.d0, s.d1);
@@ -744,7 +799,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   if (s.dbg_flags != 0)
     return fail(BAE_ERR_INVALID, "BAE_TC_DBGFLAGS is set, but this library was built without -DBAE_TC_DEBUG: refusing to sample");
 #endif
-  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW", "BAE_NARROW_CLUSTER", "BAE_TC_TF32", "BAE_TC_PRECONV"})
+  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW", "BAE_NARROW_CLUSTER", "BAE_TC_TF32", "BAE_TC_PRECONV", "BAE_TC_HIMG"})
     if (getenv(knob)) fprintf(stderr, "[bae_b200] note: tuning variable %s=%s is in effect for this handle\n", knob, getenv(knob));
   s.dbg_phase = getenv("BAE_TC_TRACE_PHASE") ? atoi(getenv("BAE_TC_TRACE_PHASE")) : -1;
   {
@@ -808,6 +863,7 @@ int bae_destroy(bae_handle* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& pe : h->pt_events) cudaEventDestroy(pe.second);
   cudaStreamDestroy(h->stream);
   delete h;
   return BAE_OK;
@@ -1109,15 +1165,24 @@ static cudaError_t emit_phases(bae_handle* h, int p_begin, int p_end, int n_rep,
   const int64_t n0 = h->n_emit;
   // 3xFP16 split: whatever rewrote theta since the last program (initialisation, set_state, an exchange) - recompute the
   // weight bounds of every chain once in front of the program
-  if (h->hs.f16 && p_begin == P_PRO) e = launch_one(h, P_WAMAX0, 0, C, 1);
+  auto mark = [&](int p) {
+    if (!h->phase_times) return;
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, h->stream);
+    h->pt_events.emplace_back(p, ev);
+  };
+  mark(-1);
+  if (h->hs.f16 && p_begin == P_PRO) { e = launch_one(h, P_WAMAX0, 0, C, 1); mark(P_WAMAX0); }
   for (int r = 0; r < n_rep && e == cudaSuccess; ++r) {
     if (p_begin < ps_end)
       for (int cb = 0; cb < C && e == cudaSuccess; cb += G)
         for (int p = p_begin; p < ps_end && e == cudaSuccess; ++p) {
           if (p == P_WAMAX0 && r == 0 && p_begin == P_PRO) continue;   // the forced launch above has just done this
           e = launch_one(h, p, cb, std::min(cb + G, C), force_swap);
+          mark(p);
         }
-    for (int p = std::max(p_begin, (int)P_SWAP); p < p_end && e == cudaSuccess; ++p) e = launch_one(h, p, 0, C, force_swap);
+    for (int p = std::max(p_begin, (int)P_SWAP); p < p_end && e == cudaSuccess; ++p) { e = launch_one(h, p, 0, C, force_swap); mark(p); }
   }
   if (n_launch) *n_launch = (int)(h->n_emit - n0);
   return e;
@@ -1718,6 +1783,23 @@ int bae_debug_trace(bae_handle* h, long long* out, int clear) {
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaMemcpy(out, h->hs.dbg, 4096 * sizeof(long long), cudaMemcpyDeviceToHost));
   if (clear) CU(cudaMemset(h->hs.dbg, 0, 4096 * sizeof(long long)));
+  return BAE_OK;
+}
+
+// Debug (BAE_PHASE_TIMES=1): milliseconds spent per phase index (the amax-zeroing / image launches that belong to a phase
+// included) since the last call, measured with an event after every phase of back-to-back direct launches; ms64 / n64: [64].
+int bae_debug_phase_times(bae_handle* h, double* ms64, int* n64) {
+  if (!h || !ms64 || !n64) return fail(BAE_ERR_INVALID, "null argument");
+  CU(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 64; ++i) { ms64[i] = 0.0; n64[i] = 0; }
+  for (size_t i = 1; i < h->pt_events.size(); ++i) {
+    const int p = h->pt_events[i].first;
+    if (p < 0 || p >= 64) continue;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->pt_events[i - 1].second, h->pt_events[i].second) == cudaSuccess) { ms64[p] += ms; n64[p]++; }
+  }
+  for (auto& pe : h->pt_events) cudaEventDestroy(pe.second);
+  h->pt_events.clear();
   return BAE_OK;
 }
 

@@ -78,6 +78,11 @@ struct GemmDesc {
   // producer copies the FP16 hi / lo tiles of a K block straight into the converted stage.
   const unsigned char* aImg; long long sAImg; int aKbs;   // base, bytes per chain, bytes per K block (hi plane; lo plane at aKbs / 2)
   const unsigned char* bImg; long long sBImg; int bKbs;
+  // Forward GEMMs over the training matrix whose A operand is an activation (H1, H2, Y, H4, H5): the converter group that split
+  // a K block of the A tile also sends the converted tiles to the MN-major image of that activation (tensor maps tmOut: hi plane,
+  // tmOut + 1: lo plane), which the weight-gradient GEMM of the same layer reads as its B operand (indexed by the chain's group
+  // slot). Only tile_n == 0 items store. The A tensor map of such a GEMM reaches one column further: the ones column.
+  unsigned char* aOut; int tmOut;
 };
 
 // Pre-split images of one weight matrix inside a chain's image slab (DevState::wimg): K-major (forward GEMMs: contraction over
@@ -202,6 +207,9 @@ struct DevState {
   unsigned char* wimg;        // [C_alloc][wimg_stride] bytes
   long long wimg_stride;
   int wimg_items;             // work items of bae_wconv_kernel per chain
+  unsigned char* himg[5];     // MN-major images of the activations H1, H2, Y, H4, H5 of the resident chain group: [G][himg_stride[i]]
+  long long himg_stride[5];
+  int himg_kbs[5];
   WImg wi[6];
   void* tmaps;        // CUtensorMap array in global memory (64-byte aligned)
   int* sched;         // longest-first item schedules of the GEMM phases (PhaseDesc::sched_off), built for `sched_chains` chains

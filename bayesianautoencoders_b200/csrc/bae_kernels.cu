@@ -382,9 +382,9 @@ __global__ void bae_amax_zero_kernel(const DevState* __restrict__ S, unsigned ma
 // ------------------------------------------------------------------------------------------------
 // One work item: rows [o0, o0 + 8) x units [g0, g0 + 64) of a row-major FP32 matrix (unit g = columns 8 g .. 8 g + 7). Thread
 // t takes row o0 + (t & 7) and units g0 + (t >> 3), g0 + 32 + (t >> 3): a warp reads 8 rows x 128 contiguous bytes and writes,
-// in each image and plane, runs of 128 contiguous bytes (the 8 rows of a unit column).
+// in each image and plane, runs of 128 contiguous bytes or more (the 8 rows of a unit column).
 //   imgK (contraction over the columns; columns >= ccK read as 0): unit at (g >> 1) kbsK + (o >> 3) 256 + (g & 1) 128 + (o & 7) 16
-//   imgM (contraction over the rows;    columns >= ccM read as 0): unit at (o >> 4) kbsM + g 256 + ((o >> 3) & 1) 128 + (o & 7) 16
+//   imgM (contraction over the rows;    columns >= ccM read as 0): unit at (o >> 4) kbsM + ((o >> 3) & 1) kbsM / 4 + g 128 + (o & 7) 16
 // lo planes kbs / 2 further. Rows >= R and units beyond the columns are never written: they keep the zeros of the allocation
 // (what the tensor loads' out-of-bounds fill gives the FP32 path).
 __device__ __forceinline__ void split_item_to_images(const float* __restrict__ src, int ld, int R, int ccK, int ccM, float s,
@@ -412,7 +412,7 @@ __device__ __forceinline__ void split_item_to_images(const float* __restrict__ s
       *reinterpret_cast<uint4*>(img + off + (size_t)(kbs >> 1)) = lo;
     };
     if (imgK && c0 < ccK) emit(imgK, ccK, (size_t)(g >> 1) * kbsK + (size_t)(o >> 3) * 256 + (size_t)(g & 1) * 128 + (size_t)(o & 7) * 16, kbsK);
-    if (imgM && c0 < ccM) emit(imgM, ccM, (size_t)(o >> 4) * kbsM + (size_t)g * 256 + (size_t)((o >> 3) & 1) * 128 + (size_t)(o & 7) * 16, kbsM);
+    if (imgM && c0 < ccM) emit(imgM, ccM, (size_t)(o >> 4) * kbsM + (size_t)((o >> 3) & 1) * (size_t)(kbsM >> 2) + (size_t)g * 128 + (size_t)(o & 7) * 16, kbsM);
   }
 }
 
@@ -445,6 +445,19 @@ __global__ void __launch_bounds__(kThreads) bae_ximg_kernel(const float* __restr
   const float s = tc::exp2i(e);
   for (int item = blockIdx.x; item < total; item += gridDim.x)
     split_item_to_images(src, ld, R, ccK, ccM, s, imgK, kbsK, imgM, kbsM, (item / ub) * 8, (item % ub) * 64);
+}
+
+// Ones column (index d) of the MN-major image of a sigmoid layer's output, rows < `rows` of every group slot: 1.0 at the static
+// scale 2^13 = FP16 0x7000 in the hi plane, 0 in the lo plane (the allocation's zeros). The epilogue that writes the image
+// rewrites the unit that holds the column only when the layer's last 8 columns share it.
+__global__ void bae_himg_ones_kernel(unsigned char* img, long long stride, int kbs, int d, int rows, int nslots) {
+  const long long total = (long long)rows * nslots;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int slot = (int)(i / rows), row = (int)(i % rows);
+    unsigned char* p = img + (size_t)slot * stride + (size_t)(row >> 4) * kbs + (size_t)((row >> 3) & 1) * (size_t)(kbs >> 2) + (size_t)(d >> 3) * 128 +
+                       (size_t)(row & 7) * 16 + (size_t)(d & 7) * 2;
+    *reinterpret_cast<unsigned short*>(p) = 0x7000;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -2039,6 +2052,11 @@ cudaError_t launch_wconv(const DevState* dS, int grid, int c_begin, int c_end, i
 cudaError_t launch_ximg(const float* src, int ld, int R, int ccK, int ccM, int e, unsigned char* imgK, int kbsK, unsigned char* imgM,
                         int kbsM, cudaStream_t st) {
   bae_ximg_kernel<<<1184, kThreads, 0, st>>>(src, ld, R, ccK, ccM, e, imgK, kbsK, imgM, kbsM);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_himg_ones(unsigned char* img, long long stride, int kbs, int d, int rows, int nslots, cudaStream_t st) {
+  bae_himg_ones_kernel<<<592, 256, 0, st>>>(img, stride, kbs, d, rows, nslots);
   return cudaGetLastError();
 }
 

@@ -347,13 +347,19 @@ constexpr int kF16TileBytes = 128 * kBK * 2;   // 4 KB: 128 rows (or MN) x 16 K 
 // OPERAND IMAGES (GemmDesc::aImg / bImg, DevState::preconv): an operand whose values and scale are known before the GEMM runs
 // (the weights: rewritten once per proposal; the data matrices: once per upload) is split ONCE, by bae_wconv_kernel /
 // bae_ximg_kernel, into an image in HBM that holds the units of the canonical layout in tile order:
-//     unit (t8, kb, j, r)  at  kb * kbs + plane * (kbs / 2) + t8 * 256 + j * 128 + r * 16      (plane 0 = hi, 1 = lo)
-//   K-major use  (contraction over the matrix's columns): row = 8 t8 + r,  k = 16 kb + 8 j .. + 7
-//   MN-major use (contraction over the matrix's rows):    k = 16 kb + 8 j + r,  mn = 8 t8 .. + 7
-// so the hi (lo) tile of `n` rows / MN from t0 (a multiple of 8) of K block kb is ONE contiguous run of 32 n bytes: the producer
-// copies it straight into the converted stage (cp.async.bulk, no tensor map) and the converter warps skip that operand -
-// no FP32 tile in shared memory, no LDS / STS / ALU work: 16 KB less shared-memory traffic per operand and K block. The
-// values are those the converters would have produced (same scale exponent, same roundings): results are bit-identical.
+//   K-major use  (contraction over the matrix's columns; row = 8 t8 + r, k = 16 kb + 8 j .. + 7):
+//     unit (t8, kb, j, r)  at  kb * kbs + plane * (kbs / 2) + t8 * 256 + j * 128 + r * 16            (plane 0 = hi, 1 = lo)
+//   MN-major use (contraction over the matrix's rows; k = 16 kb + 8 j + r, mn = 8 t8 .. + 7), T8 = kbs / 512 MN groups:
+//     unit (t8, kb, j, r)  at  kb * kbs + plane * (kbs / 2) + j * (128 T8) + t8 * 128 + r * 16
+// so the hi (lo) tile of `n` rows / MN from t0 (a multiple of 8) of K block kb is ONE contiguous run of 32 n bytes (K-major) or
+// one run of 16 n bytes per K half (MN-major: tile layout [j][t8][r], i.e. descriptor strides LBO = 16 n, SBO = 128): the producer
+// copies the runs into the operand's half of the raw stage (cp.async.bulk, no tensor map), the tensor core reads them there
+// and the converter warps skip that operand - no LDS / STS / ALU work, 16 KB less shared-memory traffic per operand and K
+// block. The values are those the converters would have produced (same scale exponent, same roundings): bit-identical results.
+// ACTIVATION images (GemmDesc::aOut; MN-major use by the weight-gradient GEMMs): the forward GEMM that reads the activation as
+// its K-major A operand converts every unit anyway; the converter group that finished a K block of a tile_n == 0 (1) item sends
+// the converted [A hi] ([A lo]) tile to the image with one 4-D box store (the image's [j][t8][r] order is the tile's
+// [row group][k half][r] order under a permutation of the dimensions, which the tensor map expresses).
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {   // a at the lower address
   uint32_t r;
@@ -499,10 +505,14 @@ __device__ __forceinline__ void conv_tile(uint32_t src_t, uint32_t hi_t, uint32_
   if (nv >= 4) conv_units<2, kSwap>(src_t + 4096, hi_t + 2048, lo_t + 2048, swap, s);
   else if (nv == 3) conv_units<1, kSwap>(src_t + 4096, hi_t + 2048, lo_t + 2048, swap, s);
 }
-
 // Shared-memory descriptor of an FP16 operand tile in the no-swizzle layout above (either major): LBO = 128 B, SBO = 256 B
-__device__ __forceinline__ uint64_t make_desc_f16(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(256u >> 4) << 32) | (1ull << 46);
+__device__ __forceinline__ uint64_t make_desc_f16(uint32_t saddr, uint32_t lbo = 128u, uint32_t sbo = 256u) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// 4-D box store shared -> global (a converted A tile into an activation image, see "operand images")
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src_s, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(tm), "r"(src_s), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
@@ -521,7 +531,7 @@ __device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem, bool f16 = fa
   if (threadIdx.x == 0) {
     // `conv` and `tmem_empty` collect arrivals from both CTAs of the pair (only the leader's copies are waited on)
     for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full()[i], 1); mbar_init(&sm.empty()[i], f16 ? kConvGroupWarps + 1 : 1); }
-    for (int i = 0; i < kLoStages; ++i) { mbar_init(&sm.conv()[i], 2 * kConvGroupWarps); mbar_init(&sm.lo_empty()[i], 1); }
+    for (int i = 0; i < kLoStages; ++i) { mbar_init(&sm.conv()[i], 2 * kConvGroupWarps); mbar_init(&sm.lo_empty()[i], f16 ? 2 : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full()[i], 1); mbar_init(&sm.tmem_empty()[i], 2 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -665,7 +675,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const int dbgf = BAE_DBGF(S);
         // pre-split operand images: this CTA's hi tile of K block kb0 (the lo tile lies kbs / 2 further)
         const unsigned char* imgA = g.aImg ? g.aImg + (size_t)ca * g.sAImg + (size_t)it.kb0 * g.aKbs + (size_t)(m0 >> 3) * 256 : nullptr;
-        const unsigned char* imgB = g.bImg ? g.bImg + (size_t)cb * g.sBImg + (size_t)it.kb0 * g.bKbs + (size_t)(n0 >> 3) * 256 : nullptr;
+        const unsigned char* imgB = g.bImg ? g.bImg + (size_t)cb * g.sBImg + (size_t)it.kb0 * g.bKbs + (size_t)(n0 >> 3) * (g.bMode ? 128 : 256) : nullptr;
         const uint32_t aKbs = (uint32_t)g.aKbs, bKbs = (uint32_t)g.bKbs, bPlane = (uint32_t)(g.tcBN >> 1) * 32u;
         const uint32_t bytes = ((dbgf & 64) ? 0u : (uint32_t)kATileBytes) + ((dbgf & 32) ? 0u : (imgB ? 2u * bPlane : (uint32_t)g.tcBBytes));
         const int aMode = g.aMode, bMode = g.bMode, nchB = g.tcBBytes / kMnChunkBytes, nkb = it.nkb, kb0 = it.kb0;
@@ -697,8 +707,16 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             if (dbgf & 32) {
             } else if (imgB) {
               const unsigned char* p = imgB + (size_t)kb * bKbs;
-              bulk_load(cv + kATileBytes, p, bPlane, &sm.full()[ring.stage]);
-              bulk_load(cv + kATileBytes + kF16TileBytes, p + (bKbs >> 1), bPlane, &sm.full()[ring.stage]);
+              if (bMode == 0) {
+                bulk_load(cv + kATileBytes, p, bPlane, &sm.full()[ring.stage]);
+                bulk_load(cv + kATileBytes + kF16TileBytes, p + (bKbs >> 1), bPlane, &sm.full()[ring.stage]);
+              } else {   // MN-major image: one run per K half; the halves lie 128 T8 = kbs / 4 bytes apart
+                const uint32_t run = bPlane >> 1, jstep = bKbs >> 2;
+                bulk_load(cv + kATileBytes, p, run, &sm.full()[ring.stage]);
+                bulk_load(cv + kATileBytes + run, p + jstep, run, &sm.full()[ring.stage]);
+                bulk_load(cv + kATileBytes + kF16TileBytes, p + (bKbs >> 1), run, &sm.full()[ring.stage]);
+                bulk_load(cv + kATileBytes + kF16TileBytes + run, p + (bKbs >> 1) + jstep, run, &sm.full()[ring.stage]);
+              }
             } else if (bMode == 0) {
               tma_load_3d(sb, mapB, &sm.full()[ring.stage], k0, n0, cb);
             } else {
@@ -738,6 +756,9 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const uint64_t d16 = make_desc_f16(smem_u32(sm.tiles));
         const bool f16 = S->f16 != 0;
         const bool preA = g.aImg != nullptr, preB = g.bImg != nullptr;   // operand images: read in the raw stage, which these MMAs then release
+        // B image in the raw stage: K-major [t8][j][r] like a converted tile; MN-major [j][t8][r] (strides: K half 16 n, MN group 128)
+        const uint64_t rawB = bmn ? make_desc_f16(smem_u32(sm.tiles) + kATileBytes, (uint32_t)(g.tcBN >> 1) * 16u, 128u)
+                                  : make_desc_f16(smem_u32(sm.tiles) + kATileBytes);
         for (int kb = 0; kb < nkb; ++kb) {
           // `conv` is signalled by converter warps that had themselves waited for the TMA bytes (`full`)
           mbar_wait(&sm.conv()[ring.lo], ring.lo_phase);   // both CTAs' raw and lo tiles of the K block are ready
@@ -748,7 +769,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
               trace(dbg, 1, ntr, kb);
               const uint64_t cvt = d16 + (kStages + ring.lo) * (uint32_t)(kStageBytes >> 4), raw = d16 + ring.stage * (uint32_t)(kStageBytes >> 4);
               const uint64_t ah = preA ? raw : cvt, al = ah + (kF16TileBytes >> 4);
-              const uint64_t bh = preB ? raw + (kATileBytes >> 4) : cvt + (2 * kF16TileBytes >> 4), bl = bh + (kF16TileBytes >> 4);
+              const uint64_t bh = preB ? rawB + ring.stage * (uint32_t)(kStageBytes >> 4) : cvt + (2 * kF16TileBytes >> 4), bl = bh + (kF16TileBytes >> 4);
               const uint32_t acc0 = kb ? 1u : 0u;
               umma_f16(d_main, ah, bh, idesc, acc0);
               umma_f16(d_cross, al, bh, idesc, acc0);
@@ -804,6 +825,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     const uint32_t tiles0 = smem_u32(sm.tiles);
     const ConvLane cl = conv_lane(gt);
     int ntr = (grp == 0) ? 0 : (grp == 1 ? 170 : 340);
+    int pending = -1;   // converted slot whose box stores (activation image) may still be reading it (meaningful in thread gt == 0)
     uint32_t kbc = ring.kbc;
     for (int ki = 0;; ++ki) {   // items go to CTA pairs
       const int item = sched_next(sched, ki);
@@ -817,6 +839,14 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
       bool swapA = false, swapB = false, aM = false, bM = false;
       int nvB = 0;   // units of this CTA's B half that this thread converts: gt + 64 n < tcBN
       const bool preA = it.g->aImg != nullptr, preB = it.g->bImg != nullptr;   // the producer delivers these operands already split
+      // A operand persisted as an activation image (GemmDesc::aOut): after every K block this group sends the converted tiles
+      // [A hi], [A lo] to the image (one box store each); the slot may be rewritten once the stores have READ it - the second
+      // arrival on `lo_empty` (next to the MMAs' commit), made when this group comes back for its next block
+      // (the hi plane by the tile_n == 0 item of a row block, the lo plane by its tile_n == 1 item when there is one: the items
+      //  of a phase then cost the same, which its schedule assumes)
+      const bool outHi = f16 && it.g->aOut && it.tile_n == 0, outLo = f16 && it.g->aOut && it.tile_n == (it.g->tn > 1 ? 1 : 0);
+      const CUtensorMap* mapOut = (outHi || outLo) ? &maps[it.g->tmOut] : nullptr;
+      const int outRow = (it.tile_m * (2 * kBM) + (int)rank * kBM) >> 4, outSlot = it.chain - c_begin;
       if (f16) {
         sA = exp2i(operand_exp(S, it.g->aSc, it.chain));
         sB = exp2i(operand_exp(S, it.g->bSc, it.chain));
@@ -833,6 +863,10 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
           const uint32_t b7 = ring.stage + (uint32_t)kb, b5 = ring.lo + (uint32_t)kb;
           const uint32_t stage = b7 % kStages, phase = ring.phase ^ ((b7 / kStages) & 1u);
           const uint32_t lo = b5 % kLoStages, lo_phase = ring.lo_phase ^ ((b5 / kLoStages) & 1u);
+          if (pending >= 0) {   // the box stores of this group's previous block have read their slot
+            if (gt == 0) { bulk_wait_read(); mbar_arrive(&sm.lo_empty()[pending]); }
+            pending = -1;
+          }
           mbar_wait(&sm.lo_empty()[lo], lo_phase ^ 1);
           mbar_wait(&sm.full()[stage], phase);
           if (gt == 0) trace(dbg, 2, ntr, kb);
@@ -846,6 +880,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
           else conv_tile<false>(src + kATileBytes + offB, dst + 2 * kF16TileBytes, dst + 3 * kF16TileBytes, false, sB, nvB);
           if (gt == 0) trace(dbg, 2, ntr, 2000 + kb);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          if (mapOut) asm volatile("bar.sync %0, 64;" ::"r"(3 + grp) : "memory");   // both warps of the group have written (and fenced) the tile
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(&sm.empty()[stage]);   // the raw stage has been read: the producer may refill it
@@ -853,7 +888,22 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             if (!(preA || preB) && (warp & 1) == 0) mbar_arrive(&sm.empty()[stage]);
             if (rank == 0) mbar_arrive(&sm.conv()[lo]);
             else mbar_arrive_leader_relaxed(&sm.conv()[lo]);
+            if ((warp & 1) == 0) {   // gt == 0
+              if (mapOut) {
+                const uint32_t cvs = tiles0 + (kStages + lo) * kStageBytes;
+                if (outHi) tma_store_4d(mapOut, cvs, (it.kb0 + kb) * 128, 0, outRow, outSlot);
+                if (outLo) tma_store_4d(mapOut + 1, cvs + kF16TileBytes, (it.kb0 + kb) * 128, 0, outRow, outSlot);
+                bulk_commit();
+                pending = (int)lo;
+              } else {
+                mbar_arrive(&sm.lo_empty()[lo]);   // nothing but the MMAs reads the slot
+              }
+            }
           }
+        }
+        if (pending >= 0) {
+          if (gt == 0) { bulk_wait_read(); mbar_arrive(&sm.lo_empty()[pending]); }
+          pending = -1;
         }
         // the item's blocks are done (or left to the other groups): move the ring state past them
         const uint32_t e7 = ring.stage + (uint32_t)nkb, e5 = ring.lo + (uint32_t)nkb;

@@ -195,6 +195,7 @@ int bae_exchange_finish(bae_handle* h);
 int bae_debug_buffer(bae_handle* h, const char* name, int chain, float* out, int64_t n_floats, int* ld, int lo_part);
 
 int bae_debug_trace(bae_handle* h, long long* out4096, int clear);   /* CTA-0 role timeline, BAE_TC_TRACE=1 */
+int bae_debug_phase_times(bae_handle* h, double* ms64, int* n64);      /* per-phase milliseconds, BAE_PHASE_TIMES=1 */
 int bae_debug_profiler(int on);                                        /* cudaProfilerStart (1) / Stop (0) */
 
 /* Introspection for the benchmark: kernels launched so far by this handle, last step-kernel time (ms). */
