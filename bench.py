@@ -78,7 +78,7 @@ def tf32_peak():
         return None
 
 
-TRAFFIC_CAPTURE = "r2_v7_traffic.json"   # written by tools/make_profiles.py from the ncu --set full export of the current build
+TRAFFIC_CAPTURE = "r2_v8_traffic.json"   # written by tools/make_profiles.py from the ncu --set full export of the current build
 
 
 def ncu_traffic(shape, cpg, gemm_path):

@@ -86,3 +86,52 @@ def test_operand_layout_probe_runs():
                        cwd=os.path.dirname(src), timeout=300)
     p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert p.returncode == 0 and "PROBE_F16 OK" in p.stdout, p.stdout + p.stderr
+
+
+def _run_images(monkeypatch, preconv, dims, n_train, n_test, chains, rungs, steps, si, act_group=0, himg="1"):
+    """One free-running PT run; returns the raw trace bytes and the final (theta, m, v) of every chain."""
+    from bayesianautoencoders_b200 import DeviceSampler, default_theta_init
+    monkeypatch.setenv("BAE_TC_PRECONV", preconv)
+    monkeypatch.setenv("BAE_TC_HIMG", himg)
+    train, test = synth_data(dims, n_train, n_test)
+    T = np.tile(2.0 ** (np.arange(rungs) / max(1, rungs - 1)), chains // rungs)
+    kw = dict(act_group=act_group) if act_group else {}
+    s = DeviceSampler(dims, train, test, chains, rungs, steps, T, swap_interval=si, seed=5, gemm_path=2, **kw)
+    assert s.mma_kind() == 2
+    rng = np.random.default_rng(3)
+    for j in range(chains):
+        s.init_chain(j, default_theta_init(dims, rng), rng.standard_normal(s.w_size))
+    s.run(steps - 2)
+    s.run(2)          # a second call shape: the forced weight-bound / image pass in front of a program
+    s.synchronize()
+    out = []
+    for j in range(chains):
+        st = s.get_state(j)
+        out.append((s.traces(j, 0, steps).tobytes(), st["theta"].copy(), st["m"].copy(), st["v"].copy()))
+    ev = s.eval(0, 0, grads=True)          # the parity probe runs the image path on the scratch chain
+    s.close()
+    return out, ev
+
+
+@pytest.mark.parametrize("case", ["madelon", "groups", "d3_mult16"])
+def test_operand_images_bit_identical(monkeypatch, case):
+    """Pre-split operand images (weights once per proposal, data once per upload, activations persisted by the converter warps:
+    bae_tc.cuh "operand images") hold exactly the FP16 hi / lo units the converter warps produce in shared memory, so every
+    trace record, the final weights and the Adam state must be BIT-identical to the converter-only engine (BAE_TC_PRECONV=0).
+    Cases: Madelon widths over an exchange round; chain groups smaller than the ensemble (activation images are per group
+    slot); a bottleneck width that is a multiple of 16 (the BatchNorm output then keeps the converter path, the sigmoid
+    outputs' ones column is static)."""
+    if case == "madelon":
+        cfg = dict(dims=WIDE, n_train=2000, n_test=1800, chains=4, rungs=4, steps=8, si=3)
+    elif case == "groups":
+        cfg = dict(dims=WIDE, n_train=520, n_test=300, chains=6, rungs=3, steps=7, si=2, act_group=4)
+    else:
+        cfg = dict(dims=(272, 256, 240, 128), n_train=700, n_test=400, chains=2, rungs=2, steps=6, si=2)
+    ref, ev_ref = _run_images(monkeypatch, "0", **cfg)
+    for himg in ("0", "1"):          # weights / data images only, then with the activation images as well
+        got, ev = _run_images(monkeypatch, "1", himg=himg, **cfg)
+        for j, (a, b) in enumerate(zip(ref, got)):
+            assert a[0] == b[0], f"trace records of chain {j} differ (BAE_TC_HIMG={himg})"
+            for k in (1, 2, 3):
+                assert a[k].tobytes() == b[k].tobytes(), f"state vector {k} of chain {j} differs (BAE_TC_HIMG={himg})"
+        assert ev["sse"] == ev_ref["sse"] and ev["grads"].tobytes() == ev_ref["grads"].tobytes()

@@ -17,15 +17,15 @@ def kname(full):
 
 launch_csv, raw_csv = sys.argv[1], sys.argv[2]
 bench_ms = sys.argv[3] if len(sys.argv) > 3 else '61-62'
-prefix = sys.argv[4] if len(sys.argv) > 4 else 'r2_v7'      # file-name prefix under profiles/
-label = sys.argv[5] if len(sys.argv) > 5 else 'Round 2, step program v7 (3xFP16 split)'
+prefix = sys.argv[4] if len(sys.argv) > 4 else 'r2_v8'      # file-name prefix under profiles/
+label = sys.argv[5] if len(sys.argv) > 5 else 'Round 2, step program v8 (3xFP16 split, pre-split operand images)'
 rows = [r for r in csv.reader(open(launch_csv)) if len(r) > 5]
 h, data = rows[0], rows[1:]
 iv, ik = h.index('Metric Value'), h.index('Kernel Name')
 vals = [float(r[iv].replace(',', '')) / 1000 for r in data]   # ns -> us
 # Launches are named by walking the list: 'Z' = bae_amax_zero_kernel (zeroes the magnitude-bound slots the next phases fold into),
 # WAMAX = the misc kernel right after a Z (weight bounds: forced in front of a program, gated on "after an exchange round" inside
-# it), everything else in program order.
+# it), WCONV = bae_wconv_kernel (images of the weights just bounded), everything else in program order.
 PHASES = ['PRO', 'F1', 'F2', 'F3', 'BNF', 'F4', 'F5', 'F6', 'B6 (dW6|dH5)', 'B5', 'B4', 'BNB', 'B3', 'B2', 'B1', 'ADAM1', 'F1b', 'F2b', 'F3b',
         'BNFb', 'F4b', 'F5b', 'F6b', 'B6b', 'B5b', 'B4b', 'BNBb', 'B3b', 'B2b', 'B1b', 'ADAM2', 'T1', 'T2', 'T3', 'BNT', 'T4', 'T5', 'T6', 'EPI',
         'SWAP_DECIDE', 'SWAP_GATHER', 'SWAP_SCATTER']
@@ -37,6 +37,8 @@ def label_launches(rows, ik):
         k = r[ik]
         if 'amax_zero' in k:
             lab = 'Z'
+        elif 'bae_wconv_kernel' in k:
+            lab = 'WCONV'      # pre-split images of the weights, behind the phase that bounded them (WAMAX / ADAM1)
         elif prev == 'Z' and 'bae_aux_kernel<2>' in k.replace('(int)', '') and PHASES[nxt % len(PHASES)] in ('PRO', 'F1'):
             lab = 'WAMAX'
         else:
@@ -55,7 +57,7 @@ for lab, v, r in zip(labels, vals, data):
         cur = pending + [(lab, v, kname(r[ik]))]
         pending = []
         iters.append(cur)
-    elif cur is None or (lab in ('Z', 'WAMAX') and cur and cur[-1][0] == 'SWAP_SCATTER'):
+    elif cur is None:
         pending.append((lab, v, kname(r[ik])))
     else:
         cur.append((lab, v, kname(r[ik])))
@@ -78,7 +80,7 @@ fl.update({'B6': 2 * 2000 * 500 * 450 * 2, 'B5': 2 * 2000 * 450 * 400 * 2, 'B4':
 it0 = [x[1] for x in iters[0] if not x[0].startswith('SWAP')]
 sw = [x[1] for x in iters[4] if x[0].startswith('SWAP')]
 tot = sum(it0)
-lines, g, b, a, gf, zz = [], 0.0, 0.0, 0.0, 0.0, 0.0
+lines, g, b, a, gf, zz, wc = [], 0.0, 0.0, 0.0, 0.0, 0.0, 0.0
 kern = [x[2] for x in iters[0] if not x[0].startswith('SWAP')]
 for n, v, kn in zip(names, it0, kern):
     base = n.split(' ')[0].rstrip('b')
@@ -91,11 +93,13 @@ for n, v, kn in zip(names, it0, kern):
         a += v
     if base in ('Z', 'WAMAX'):
         zz += v
+    if base == 'WCONV':
+        wc += v
     lines.append(f"| {n} | `{kn}` | {v:.1f} | {100 * v / tot:.1f}% | {tf} |")
 md = f"""# {label} - launch list (ncu gpu__time_duration.sum, --clock-control none)
 
 Command: `BAE_NO_GRAPH=1 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv python tools/profile_step.py --chains 64 --rounds 2 --steps-per-round 5 --profile-round 1`
-(Madelon shape, 64 chains, the 2nd PT round = ONE `bae_run(5)` call: 5 iterations of {len(iters[1])} launches (+ the forced weight-bound pair in front), the exchange sweep in the last three; these
+(Madelon shape, 64 chains, the 2nd PT round = ONE `bae_run(5)` call: 5 iterations of {len(iters[1])} launches (+ the forced weight-bound / image launches in front), the exchange sweep in the last three; these
 are the production kernels - `BAE_NO_GRAPH=1` only makes the library launch them directly instead of replaying the captured graph).
 Raw list: `{prefix}_step_program_launches.csv`. Per-launch times are cold-cache and serialised (and the SM clock is higher than in a back-to-back run, which
 sits at the power cap); compare SHARES. Sum per iteration: {', '.join(f'{sum(x[1] for x in lst) / 1000:.2f}' for lst in iters)} ms
@@ -107,7 +111,8 @@ sits at the power cap); compare SHARES. Sum per iteration: {', '.join(f'{sum(x[1
 
 GEMM phases (`bae_phase_kernel_tc<kindA, kindB>`): {100 * g / tot:.1f}% of the iteration ({gf / (g * 1e-6) / 1e12:.0f} TFLOP/s algorithmic over the GEMM phases; the
 measured bf16 dense peak is 1381.9 TFLOP/s; three kind::f16 MMAs per product bound the algorithmic rate at 1/3 of the FP16 issue rate); BatchNorm (`bae_aux_kernel<1>`) {100 * b / tot:.1f}%; Adam + noise
-(`bae_aux_kernel<0>`) {100 * a / tot:.1f}%; magnitude-bound bookkeeping of the 3xFP16 split (`bae_amax_zero_kernel`, WAMAX) {100 * zz / tot:.1f}%. `bench.py` measures the same program at {bench_ms} ms per round back to back (graph replay, SM clock at the
+(`bae_aux_kernel<0>`) {100 * a / tot:.1f}%; magnitude-bound bookkeeping of the 3xFP16 split (`bae_amax_zero_kernel`, WAMAX) {100 * zz / tot:.1f}%; pre-split images of the weights
+(`bae_wconv_kernel`) {100 * wc / tot:.1f}%. `bench.py` measures the same program at {bench_ms} ms per round back to back (graph replay, SM clock at the
 power cap): the GEMM kernels' share of the step is the same in both views.
 """
 open(f'profiles/{prefix}_step_program_launches.md', 'w').write(md)
@@ -150,7 +155,7 @@ Sum of the kernel durations {us / 1e3:.3f} ms under ncu (cold caches, serialised
 a fraction of the 74 CTA pairs per phase; production runs 64 chains per GPU, `bench.py`).
 DRAM traffic per iteration: read {rd / 1e6:.0f} MB + write {wr / 1e6:.0f} MB = {(rd + wr) / 8 / 1e6:.0f} MB per chain-iteration. Algorithmic weight-state traffic is
 22 x 4 B x 1.05 M = 93 MB per chain-iteration (SURVEY 8d); the rest is activations and deltas (41 MB per chain, written once and re-read by the backward
-pass and the weight-gradient GEMMs). The gradient has ONE copy: the K segments of a weight-gradient tile are added in L2 by TMA reduce-add.
+pass and the weight-gradient GEMMs) and the pre-split images (weights: 10 MB written per proposal; activations: 27 MB written per drift call). The gradient has ONE copy: the K segments of a weight-gradient tile are added in L2 by TMA reduce-add.
 SASS evidence (`cuobjdump -sass libbae_b200.so`): UTCHMMA (tcgen05.mma cta_group::2 kind::f16), UTMALDG (TMA), LDTM (tcgen05.ld),
 UTCBAR (tcgen05.commit, multicast), USETMAXREG (setmaxnreg), SYNCS (mbarrier), UCGABAR (cluster barrier).
 
