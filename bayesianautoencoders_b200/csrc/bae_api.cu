@@ -335,7 +335,7 @@ static void build_program(bae_handle* h) {
       memset(&tm, 0, sizeof(tm));
       int rc;
       if (i < 1) {
-        rc = g.aMode == 0 ? tmap_kmajor(&tm, ptrs[i], g.K + (g.aOut ? 1 : 0), g.M, g.lda, nchA, g.sA, 128)
+        rc = g.aMode == 0 ? tmap_kmajor(&tm, ptrs[i], g.K + (g.aOnes ? 1 : 0), g.M, g.lda, nchA, g.sA, 128)
                           : tmap_mnmajor(&tm, ptrs[i], g.M, g.K, g.lda, nchA, g.sA, 4);
       } else {
         rc = g.bMode == 0 ? tmap_kmajor(&tm, ptrs[i], g.K, g.N, g.ldb, nchB, g.sB, g.tcBN / 2)
@@ -363,6 +363,19 @@ static void build_program(bae_handle* h) {
     const unsigned fmt = s.f16 ? 0u : ((2u << 7) | (2u << 10));
     g.idesc = (1u << 4) | fmt | ((unsigned)g.aMode << 15) | ((unsigned)g.bMode << 16) |
               ((unsigned)(g.tcBN >> 3) << 17) | ((unsigned)(256 >> 4) << 24);
+  };
+  // registers the two box-store maps (hi plane, lo plane) of an image the converters of `g` persist their A tiles into
+  auto add_out_maps = [&](GemmDesc& g, unsigned char* img, int kbs, long long stride) {
+    g.aOut = img;
+    g.tmOut = (int)h->tmaps_host.size();
+    for (int pl = 0; pl < 2; ++pl) {
+      CUtensorMap tm;
+      memset(&tm, 0, sizeof(tm));
+      const int rc = tmap_image_store(&tm, img + (size_t)pl * (kbs / 2), kbs, s.n_train, s.G, stride);
+      if (rc != 0 && h->tmap_error.empty())
+        h->tmap_error = "cuTensorMapEncodeTiled failed (CUresult " + std::to_string(rc) + ") for an operand image";
+      h->tmaps_host.push_back(tm);
+    }
   };
   int ng = 0;
   // ---- forward descriptors for (train, first pass), (train, second pass), (test)
@@ -400,16 +413,8 @@ static void build_program(bae_handle* h) {
         if (l == 0) { g.aImg = h->ximgK[pass == 2 ? 1 : 0]; g.sAImg = 0; g.aKbs = h->ximgK_kbs[pass == 2 ? 1 : 0]; }
         // the activation a pass over the training matrix reads as its A operand is persisted as an image by the converter warps
         if (pass != 2 && l >= 1 && s.himg[l - 1]) {
-          g.aOut = s.himg[l - 1];
-          g.tmOut = (int)h->tmaps_host.size();
-          for (int pl = 0; pl < 2; ++pl) {
-            CUtensorMap tm;
-            memset(&tm, 0, sizeof(tm));
-            const int rc = tmap_image_store(&tm, s.himg[l - 1] + (size_t)pl * (s.himg_kbs[l - 1] / 2), s.himg_kbs[l - 1], s.n_train, s.G, s.himg_stride[l - 1]);
-            if (rc != 0 && h->tmap_error.empty())
-              h->tmap_error = "cuTensorMapEncodeTiled failed (CUresult " + std::to_string(rc) + ") for an activation image";
-            h->tmaps_host.push_back(tm);
-          }
+          add_out_maps(g, s.himg[l - 1], s.himg_kbs[l - 1], s.himg_stride[l - 1]);
+          g.aOnes = 1;
         }
       }
       if (ls[l].epi == EPI_LOSS) {
@@ -462,6 +467,7 @@ static void build_program(bae_handle* h) {
     }
     if (ones) g.biasCol = bl[l].din;
     if (s.preconv && l == 5) { g.bImg = h->ximgM; g.sBImg = 0; g.bKbs = h->ximgM_kbs; }   // the training matrix, ones column included
+    if (s.preconv && l != 5 && s.dimg[l]) { g.aImg = s.dimg[l]; g.sAImg = s.dimg_stride[l]; g.aKbs = s.dimg_kbs[l]; }   // the delta, persisted one phase earlier
     if (s.preconv && l != 5 && s.himg[4 - l]) {   // the layer input: H5, H4, Y, H2, H1
       const int k = 4 - l;
       g.bImg = s.himg[k]; g.sBImg = s.himg_stride[k]; g.bKbs = s.himg_kbs[k];
@@ -484,6 +490,7 @@ static void build_program(bae_handle* h) {
       if (s.preconv) {
         const WImg& wi = s.wi[wimg_index(bl[l].wseg)];
         x.bImg = s.wimg + wi.offM; x.sBImg = s.wimg_stride; x.bKbs = wi.kbsM;
+        if (s.dimg[l]) add_out_maps(x, s.dimg[l], s.dimg_kbs[l], s.dimg_stride[l]);
       }
       if (bl[l].Hin) { x.aux = bl[l].Hin; x.sAux = bl[l].sDin; x.ldaux = bl[l].lddin; x.auxAct = 1; }
       x.needLang = 1;
@@ -514,15 +521,34 @@ static void build_program(bae_handle* h) {
     set(p0 + 6, PH_GEMM, b + 5, -1, 0, 0, need);
   }
   const int bstart[2] = {P_BWD1, P_BWD2};
+  // tcgen05 path: the lagged order below unless BAE_TC_LAG=0 (A/B measurements); the FP32 path keeps the side-by-side order
+  const bool lag = s.dimg[0] != nullptr || (tcm && !(getenv("BAE_TC_LAG") && getenv("BAE_TC_LAG")[0] == '0'));
   for (int pass = 0; pass < 2; ++pass) {
     const int p0 = bstart[pass];
-    set(p0 + 0, PH_GEMM, bw_idx[0], bx_idx[0], 0, 0, 1);
-    set(p0 + 1, PH_GEMM, bw_idx[1], bx_idx[1], 0, 0, 1);
-    set(p0 + 2, PH_GEMM, bw_idx[2], bx_idx[2], 0, 0, 1);
+    if (!lag) {
+      // weight-gradient GEMM and delta GEMM of a layer side by side: both read the layer's output delta in the same phase
+      set(p0 + 0, PH_GEMM, bw_idx[0], bx_idx[0], 0, 0, 1);
+      set(p0 + 1, PH_GEMM, bw_idx[1], bx_idx[1], 0, 0, 1);
+      set(p0 + 2, PH_GEMM, bw_idx[2], bx_idx[2], 0, 0, 1);
+      set(p0 + 3, PH_BN_BWD, -1, -1, pass, s.n_train, 1);
+      set(p0 + 4, PH_GEMM, bw_idx[3], bx_idx[3], 0, 0, 1);
+      set(p0 + 5, PH_GEMM, bw_idx[4], bx_idx[4], 0, 0, 1);
+      set(p0 + 6, PH_GEMM, bw_idx[5], -1, 0, 0, 1);
+      continue;
+    }
+    // The weight-gradient GEMM of a layer runs ONE PHASE AFTER the delta GEMM of the same layer (neither depends on the other).
+    // Measured at Madelon, 64 chains: backward phases -4.7% (2539 -> 2420 us per pass): the last phase no longer consists of
+    // 4 long weight-gradient tiles per chain (256 items on 74 CTA pairs: a quarter of the last round idle) and the first one
+    // is 1024 short delta tiles. The price is a second HBM read of every delta (+27 MB per chain and pass); HBM is far from
+    // being the binding unit of these phases. (With the opt-in delta images, BAE_TC_DIMG=1, the order is what lets the
+    // delta GEMM's converter warps persist the split delta for the weight-gradient GEMM.)
+    set(p0 + 0, PH_GEMM, bx_idx[0], -1, 0, 0, 1);                  // dH5
+    set(p0 + 1, PH_GEMM, bw_idx[0], bx_idx[1], 0, 0, 1);           // dW6 | dH4
+    set(p0 + 2, PH_GEMM, bw_idx[1], bx_idx[2], 0, 0, 1);           // dW5 | dY
     set(p0 + 3, PH_BN_BWD, -1, -1, pass, s.n_train, 1);
-    set(p0 + 4, PH_GEMM, bw_idx[3], bx_idx[3], 0, 0, 1);
-    set(p0 + 5, PH_GEMM, bw_idx[4], bx_idx[4], 0, 0, 1);
-    set(p0 + 6, PH_GEMM, bw_idx[5], -1, 0, 0, 1);
+    set(p0 + 4, PH_GEMM, bw_idx[2], bx_idx[3], 0, 0, 1);           // dW4 | dH2 (reads dY behind the BatchNorm backward)
+    set(p0 + 5, PH_GEMM, bw_idx[3], bx_idx[4], 0, 0, 1);           // dW3 | dH1
+    set(p0 + 6, PH_GEMM, bw_idx[4], bw_idx[5], 0, 0, 1);           // dW2 | dW1
   }
   set(P_ADAM1, PH_ADAM1, -1, -1, 0, 0, 0);
   set(P_ADAM2, PH_ADAM2, -1, -1, 0, 0, 1);
@@ -707,7 +733,9 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     // chain groups: activation / delta buffers exist for G chains at a time (G = C unless they do not fit)
     size_t per_chain = nm * (size_t)(s.ld0 + 4 * s.ld1 + 4 * s.ld2 + 3 * s.ld3) * sizeof(float);   // H1 H2 Z Y H4 H5 + DOUT D5 D4 DY D2 D1
     if (s.preconv && !(getenv("BAE_TC_HIMG") && getenv("BAE_TC_HIMG")[0] == '0'))
-      per_chain += 2 * (img_bytes(s.d1 + 1, s.n_train) + img_bytes(s.d2 + 1, s.n_train)) + img_bytes(s.d3 + 1, s.n_train);   // images of H1 H5, H2 H4, Y
+      per_chain += 2 * (img_bytes(s.d1 + 1, s.n_train) + img_bytes(s.d2 + 1, s.n_train)) + img_bytes(s.d3 + 1, s.n_train);
+    if (s.preconv && (getenv("BAE_TC_DIMG") && getenv("BAE_TC_DIMG")[0] == '1'))
+      per_chain += img_bytes(s.d0, s.n_train) + img_bytes(s.d1, s.n_train) + 2 * img_bytes(s.d2, s.n_train) + img_bytes(s.d3, s.n_train);   // images of H1 H5, H2 H4, Y
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     int G = s.C;
@@ -724,6 +752,17 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   CU(dalloc(h, &s.Y, CA_act * nm * s.ld3)); CU(dalloc(h, &s.H4, CA_act * nm * s.ld2)); CU(dalloc(h, &s.H5, CA_act * nm * s.ld1));
   CU(dalloc(h, &s.DOUT, CA_act * nm * s.ld0)); CU(dalloc(h, &s.D5, CA_act * nm * s.ld1)); CU(dalloc(h, &s.D4, CA_act * nm * s.ld2));
   CU(dalloc(h, &s.DY, CA_act * nm * s.ld3)); CU(dalloc(h, &s.D2, CA_act * nm * s.ld2)); CU(dalloc(h, &s.D1, CA_act * nm * s.ld1));
+  if (s.preconv && (getenv("BAE_TC_DIMG") && getenv("BAE_TC_DIMG")[0] == '1')) {
+    // Opt-in (BAE_TC_DIMG=1), measured and NOT adopted as the default: with the deltas pre-split too the weight-gradient tiles run
+    // without any conversion (-12% per K block), but the image writes (33 MB per chain-iteration at Madelon) cost the delta GEMMs
+    // as much DRAM time as the weight-gradient GEMMs gain (-0.7% per step).
+    const int dd[5] = {s.d0, s.d1, s.d2, s.d3, s.d2};   // DOUT, D5, D4, DY, D2
+    for (int i = 0; i < 5; ++i) {
+      s.dimg_kbs[i] = img_kbs(dd[i]);
+      s.dimg_stride[i] = (long long)img_bytes(dd[i], s.n_train);
+      CU(dalloc(h, &s.dimg[i], CA_act * (size_t)s.dimg_stride[i]));
+    }
+  }
   if (s.preconv && !(getenv("BAE_TC_HIMG") && getenv("BAE_TC_HIMG")[0] == '0')) {
     // MN-major images of the activations (B operands of the weight-gradient GEMMs), written by the converter warps of the forward
     // GEMM that reads the activation as its A operand
@@ -799,7 +838,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   if (s.dbg_flags != 0)
     return fail(BAE_ERR_INVALID, "BAE_TC_DBGFLAGS is set, but this library was built without -DBAE_TC_DEBUG: refusing to sample");
 #endif
-  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW", "BAE_NARROW_CLUSTER", "BAE_TC_TF32", "BAE_TC_PRECONV", "BAE_TC_HIMG"})
+  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW", "BAE_NARROW_CLUSTER", "BAE_TC_TF32", "BAE_TC_PRECONV", "BAE_TC_HIMG", "BAE_TC_DIMG", "BAE_TC_LAG"})
     if (getenv(knob)) fprintf(stderr, "[bae_b200] note: tuning variable %s=%s is in effect for this handle\n", knob, getenv(knob));
   s.dbg_phase = getenv("BAE_TC_TRACE_PHASE") ? atoi(getenv("BAE_TC_TRACE_PHASE")) : -1;
   {

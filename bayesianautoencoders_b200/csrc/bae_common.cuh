@@ -83,6 +83,7 @@ struct GemmDesc {
   // tmOut + 1: lo plane), which the weight-gradient GEMM of the same layer reads as its B operand (indexed by the chain's group
   // slot). Only tile_n == 0 items store. The A tensor map of such a GEMM reaches one column further: the ones column.
   unsigned char* aOut; int tmOut;
+  int aOnes;            // 1: the A tensor map reaches one column further than K (the activation's ones column goes into the image)
 };
 
 // Pre-split images of one weight matrix inside a chain's image slab (DevState::wimg): K-major (forward GEMMs: contraction over
@@ -210,6 +211,9 @@ struct DevState {
   unsigned char* himg[5];     // MN-major images of the activations H1, H2, Y, H4, H5 of the resident chain group: [G][himg_stride[i]]
   long long himg_stride[5];
   int himg_kbs[5];
+  unsigned char* dimg[5];     // MN-major images of the deltas DOUT, D5, D4, DY, D2 (persisted by the converters of the delta GEMM that
+  long long dimg_stride[5];   // reads them as its K-major A operand; A operands of the weight-gradient GEMMs, which run one phase later)
+  int dimg_kbs[5];
   WImg wi[6];
   void* tmaps;        // CUtensorMap array in global memory (64-byte aligned)
   int* sched;         // longest-first item schedules of the GEMM phases (PhaseDesc::sched_off), built for `sched_chains` chains

@@ -1954,6 +1954,7 @@ int max_coop_blocks_per_sm(int use_tc) {
     cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_BIAS, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_LOSS, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_GRADW, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_DSIG, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_DSIG, EPI_GRADW>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_PLAIN, EPI_GRADW>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel_tc, tc::kThreadsTc, tc::kSmemBytes);
@@ -1999,6 +2000,7 @@ cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c
         case EPI_BIAS: fn = (const void*)bae_phase_kernel_tc<EPI_BIAS, -1>; break;
         case EPI_LOSS: fn = (const void*)bae_phase_kernel_tc<EPI_LOSS, -1>; break;
         case EPI_GRADW: fn = (const void*)bae_phase_kernel_tc<EPI_GRADW, -1>; break;
+        case EPI_DSIG: fn = (const void*)bae_phase_kernel_tc<EPI_DSIG, -1>; break;
         default: break;
       }
     } else if (epi_a == EPI_DSIG && epi_b == EPI_GRADW) {

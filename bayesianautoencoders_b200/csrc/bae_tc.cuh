@@ -674,7 +674,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const int ca = g.sA ? (g.aAct ? it.chain - c_begin : it.chain) : 0, cb = g.sB ? (g.bAct ? it.chain - c_begin : it.chain) : 0;
         const int dbgf = BAE_DBGF(S);
         // pre-split operand images: this CTA's hi tile of K block kb0 (the lo tile lies kbs / 2 further)
-        const unsigned char* imgA = g.aImg ? g.aImg + (size_t)ca * g.sAImg + (size_t)it.kb0 * g.aKbs + (size_t)(m0 >> 3) * 256 : nullptr;
+        const unsigned char* imgA = g.aImg ? g.aImg + (size_t)ca * g.sAImg + (size_t)it.kb0 * g.aKbs + (size_t)(m0 >> 3) * (g.aMode ? 128 : 256) : nullptr;
         const unsigned char* imgB = g.bImg ? g.bImg + (size_t)cb * g.sBImg + (size_t)it.kb0 * g.bKbs + (size_t)(n0 >> 3) * (g.bMode ? 128 : 256) : nullptr;
         const uint32_t aKbs = (uint32_t)g.aKbs, bKbs = (uint32_t)g.bKbs, bPlane = (uint32_t)(g.tcBN >> 1) * 32u;
         const uint32_t bytes = ((dbgf & 64) ? 0u : (uint32_t)kATileBytes) + ((dbgf & 32) ? 0u : (imgB ? 2u * bPlane : (uint32_t)g.tcBBytes));
@@ -693,8 +693,16 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             if (dbgf & 64) {
             } else if (imgA) {
               const unsigned char* p = imgA + (size_t)kb * aKbs;
-              bulk_load(cv, p, (uint32_t)kF16TileBytes, &sm.full()[ring.stage]);
-              bulk_load(cv + kF16TileBytes, p + (aKbs >> 1), (uint32_t)kF16TileBytes, &sm.full()[ring.stage]);
+              if (aMode == 0) {
+                bulk_load(cv, p, (uint32_t)kF16TileBytes, &sm.full()[ring.stage]);
+                bulk_load(cv + kF16TileBytes, p + (aKbs >> 1), (uint32_t)kF16TileBytes, &sm.full()[ring.stage]);
+              } else {   // MN-major image: one run of 128 MN x 16 B per K half, the halves kbs / 4 bytes apart
+                const uint32_t run = kF16TileBytes >> 1, jstep = aKbs >> 2;
+                bulk_load(cv, p, run, &sm.full()[ring.stage]);
+                bulk_load(cv + run, p + jstep, run, &sm.full()[ring.stage]);
+                bulk_load(cv + kF16TileBytes, p + (aKbs >> 1), run, &sm.full()[ring.stage]);
+                bulk_load(cv + kF16TileBytes + run, p + (aKbs >> 1) + jstep, run, &sm.full()[ring.stage]);
+              }
             } else if (aMode == 0) {
               tma_load_3d(st, mapA, &sm.full()[ring.stage], k0, m0, ca);
             } else {
@@ -757,6 +765,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const bool f16 = S->f16 != 0;
         const bool preA = g.aImg != nullptr, preB = g.bImg != nullptr;   // operand images: read in the raw stage, which these MMAs then release
         // B image in the raw stage: K-major [t8][j][r] like a converted tile; MN-major [j][t8][r] (strides: K half 16 n, MN group 128)
+        const uint64_t rawA = amn ? make_desc_f16(smem_u32(sm.tiles), 16u * kBM, 128u) : d16;
         const uint64_t rawB = bmn ? make_desc_f16(smem_u32(sm.tiles) + kATileBytes, (uint32_t)(g.tcBN >> 1) * 16u, 128u)
                                   : make_desc_f16(smem_u32(sm.tiles) + kATileBytes);
         for (int kb = 0; kb < nkb; ++kb) {
@@ -767,8 +776,8 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             // 3xFP16: the converted stage holds [A hi][A lo][B hi][B lo], 4 KB each; one K = 16 MMA per product
             if (elect_one()) {
               trace(dbg, 1, ntr, kb);
-              const uint64_t cvt = d16 + (kStages + ring.lo) * (uint32_t)(kStageBytes >> 4), raw = d16 + ring.stage * (uint32_t)(kStageBytes >> 4);
-              const uint64_t ah = preA ? raw : cvt, al = ah + (kF16TileBytes >> 4);
+              const uint64_t cvt = d16 + (kStages + ring.lo) * (uint32_t)(kStageBytes >> 4);
+              const uint64_t ah = preA ? rawA + ring.stage * (uint32_t)(kStageBytes >> 4) : cvt, al = ah + (kF16TileBytes >> 4);
               const uint64_t bh = preB ? rawB + ring.stage * (uint32_t)(kStageBytes >> 4) : cvt + (2 * kF16TileBytes >> 4), bl = bh + (kF16TileBytes >> 4);
               const uint32_t acc0 = kb ? 1u : 0u;
               umma_f16(d_main, ah, bh, idesc, acc0);
@@ -880,7 +889,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
           else conv_tile<false>(src + kATileBytes + offB, dst + 2 * kF16TileBytes, dst + 3 * kF16TileBytes, false, sB, nvB);
           if (gt == 0) trace(dbg, 2, ntr, 2000 + kb);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          if (mapOut) asm volatile("bar.sync %0, 64;" ::"r"(3 + grp) : "memory");   // both warps of the group have written (and fenced) the tile
+          if (mapOut && !(BAE_DBGF(S) & 256)) asm volatile("bar.sync %0, 64;" ::"r"(3 + grp) : "memory");   // both warps of the group have written (and fenced) the tile
           __syncwarp();
           if (lane == 0) {
             mbar_arrive(&sm.empty()[stage]);   // the raw stage has been read: the producer may refill it
@@ -889,12 +898,19 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             if (rank == 0) mbar_arrive(&sm.conv()[lo]);
             else mbar_arrive_leader_relaxed(&sm.conv()[lo]);
             if ((warp & 1) == 0) {   // gt == 0
-              if (mapOut) {
+              if (mapOut && !(BAE_DBGF(S) & 128)) {
                 const uint32_t cvs = tiles0 + (kStages + lo) * kStageBytes;
                 if (outHi) tma_store_4d(mapOut, cvs, (it.kb0 + kb) * 128, 0, outRow, outSlot);
                 if (outLo) tma_store_4d(mapOut + 1, cvs + kF16TileBytes, (it.kb0 + kb) * 128, 0, outRow, outSlot);
                 bulk_commit();
+#ifdef BAE_TC_DEFER_OUT
                 pending = (int)lo;
+#else
+                // (waiting here costs this thread the few hundred cycles the copy engine needs to read 4 KB; leaving the arrival to
+                //  the group's next block - three blocks later - kept three of the five converted slots occupied)
+                bulk_wait_read();
+                mbar_arrive(&sm.lo_empty()[lo]);
+#endif
               } else {
                 mbar_arrive(&sm.lo_empty()[lo]);   // nothing but the MMAs reads the slot
               }

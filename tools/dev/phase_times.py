@@ -29,8 +29,9 @@ libs = sys.argv[1:] or [None]   # a library under build/, or VAR=value (an envir
 cols = []
 for l in libs:
     env = dict(os.environ, BAE_PHASE_TIMES="1")
-    if l and "=" in l: env[l.split("=")[0]] = l.split("=")[1]
-    elif l: env["BAE_B200_LIB"] = os.path.join(os.getcwd(), "build", l)
+    for part in (l.split(":") if l else []):   # lib.so, VAR=value, or lib.so:VAR=value
+        if "=" in part: env[part.split("=")[0]] = part.split("=")[1]
+        else: env["BAE_B200_LIB"] = os.path.join(os.getcwd(), "build", part)
     subprocess.run([sys.executable, __file__, "child", "/tmp/pt.npy"], env=env, check=True, stderr=subprocess.DEVNULL)
     cols.append(np.load("/tmp/pt.npy"))
 print("%-6s" % "phase" + "".join("%14s" % (l or "in-tree")[:13] for l in libs))

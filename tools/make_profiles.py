@@ -26,9 +26,10 @@ vals = [float(r[iv].replace(',', '')) / 1000 for r in data]   # ns -> us
 # Launches are named by walking the list: 'Z' = bae_amax_zero_kernel (zeroes the magnitude-bound slots the next phases fold into),
 # WAMAX = the misc kernel right after a Z (weight bounds: forced in front of a program, gated on "after an exchange round" inside
 # it), WCONV = bae_wconv_kernel (images of the weights just bounded), everything else in program order.
-PHASES = ['PRO', 'F1', 'F2', 'F3', 'BNF', 'F4', 'F5', 'F6', 'B6 (dW6|dH5)', 'B5', 'B4', 'BNB', 'B3', 'B2', 'B1', 'ADAM1', 'F1b', 'F2b', 'F3b',
-        'BNFb', 'F4b', 'F5b', 'F6b', 'B6b', 'B5b', 'B4b', 'BNBb', 'B3b', 'B2b', 'B1b', 'ADAM2', 'T1', 'T2', 'T3', 'BNT', 'T4', 'T5', 'T6', 'EPI',
-        'SWAP_DECIDE', 'SWAP_GATHER', 'SWAP_SCATTER']
+# (backward phases: the weight-gradient GEMM of a layer runs one phase behind the delta GEMM of the same layer)
+PHASES = ['PRO', 'F1', 'F2', 'F3', 'BNF', 'F4', 'F5', 'F6', 'B6 (dH5)', 'B5 (dW6|dH4)', 'B4 (dW5|dY)', 'BNB', 'B3 (dW4|dH2)', 'B2 (dW3|dH1)', 'B1 (dW2|dW1)',
+          'ADAM1', 'F1b', 'F2b', 'F3b', 'BNFb', 'F4b', 'F5b', 'F6b', 'B6b', 'B5b', 'B4b', 'BNBb', 'B3b', 'B2b', 'B1b', 'ADAM2', 'T1', 'T2', 'T3', 'BNT',
+          'T4', 'T5', 'T6', 'EPI', 'SWAP_DECIDE', 'SWAP_GATHER', 'SWAP_SCATTER']
 
 
 def label_launches(rows, ik):
@@ -75,8 +76,8 @@ F = {'F1': 2 * 2000 * 450 * 500, 'F2': 2 * 2000 * 400 * 450, 'F3': 2 * 2000 * 30
 fl = dict(F)
 for k, v in F.items():
     fl[k.replace('F', 'T')] = v * 0.9
-fl.update({'B6': 2 * 2000 * 500 * 450 * 2, 'B5': 2 * 2000 * 450 * 400 * 2, 'B4': 2 * 2000 * 400 * 300 * 2, 'B3': 2 * 2000 * 300 * 400 * 2,
-           'B2': 2 * 2000 * 400 * 450 * 2, 'B1': 2 * 2000 * 450 * 500})
+w6, w5, w4 = 2 * 2000 * 500 * 450, 2 * 2000 * 450 * 400, 2 * 2000 * 400 * 300      # one GEMM over the 6th / 5th / 4th (= 1st / 2nd / 3rd) weight matrix
+fl.update({'B6': w6, 'B5': w6 + w5, 'B4': w5 + w4, 'B3': w4 + w4, 'B2': w4 + w5, 'B1': w5 + w6})
 it0 = [x[1] for x in iters[0] if not x[0].startswith('SWAP')]
 sw = [x[1] for x in iters[4] if x[0].startswith('SWAP')]
 tot = sum(it0)
