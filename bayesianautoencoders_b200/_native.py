@@ -114,7 +114,8 @@ def load():
     lib.bae_debug_buffer.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_int64, P(C.c_int), C.c_int]
     lib.bae_debug_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.bae_debug_profiler.argtypes = [C.c_int]
-    lib.bae_debug_phase_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    if hasattr(lib, "bae_debug_phase_times"):   # (an older build selected through BAE_B200_LIB for an A/B run may lack it)
+        lib.bae_debug_phase_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bae_stream.argtypes = [C.c_void_p]
     lib.bae_stream.restype = C.c_void_p
     _lib = lib

@@ -21,7 +21,7 @@ int max_coop_grid_tc();
 cudaError_t launch_program(const DevState* dS, int use_tc, int grid, int ph_begin, int ph_end, int n_rep, int c_begin,
                            int c_end, int force_swap, cudaStream_t st);
 cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, int force_swap,
-                         int epi_a, int epi_b, cudaStream_t st);
+                         int epi_a, int epi_b, int front_mode, cudaStream_t st);
 int aux_blocks_per_sm(int kind);
 cudaError_t launch_aux(const DevState* dS, int kind, int grid, int pi, int c_begin, int c_end, int force_swap,
                        cudaStream_t st);
@@ -467,7 +467,6 @@ static void build_program(bae_handle* h) {
     }
     if (ones) g.biasCol = bl[l].din;
     if (s.preconv && l == 5) { g.bImg = h->ximgM; g.sBImg = 0; g.bKbs = h->ximgM_kbs; }   // the training matrix, ones column included
-    if (s.preconv && l != 5 && s.dimg[l]) { g.aImg = s.dimg[l]; g.sAImg = s.dimg_stride[l]; g.aKbs = s.dimg_kbs[l]; }   // the delta, persisted one phase earlier
     if (s.preconv && l != 5 && s.himg[4 - l]) {   // the layer input: H5, H4, Y, H2, H1
       const int k = 4 - l;
       g.bImg = s.himg[k]; g.sBImg = s.himg_stride[k]; g.bKbs = s.himg_kbs[k];
@@ -490,7 +489,6 @@ static void build_program(bae_handle* h) {
       if (s.preconv) {
         const WImg& wi = s.wi[wimg_index(bl[l].wseg)];
         x.bImg = s.wimg + wi.offM; x.sBImg = s.wimg_stride; x.bKbs = wi.kbsM;
-        if (s.dimg[l]) add_out_maps(x, s.dimg[l], s.dimg_kbs[l], s.dimg_stride[l]);
       }
       if (bl[l].Hin) { x.aux = bl[l].Hin; x.sAux = bl[l].sDin; x.ldaux = bl[l].lddin; x.auxAct = 1; }
       x.needLang = 1;
@@ -522,7 +520,7 @@ static void build_program(bae_handle* h) {
   }
   const int bstart[2] = {P_BWD1, P_BWD2};
   // tcgen05 path: the lagged order below unless BAE_TC_LAG=0 (A/B measurements); the FP32 path keeps the side-by-side order
-  const bool lag = s.dimg[0] != nullptr || (tcm && !(getenv("BAE_TC_LAG") && getenv("BAE_TC_LAG")[0] == '0'));
+  const bool lag = tcm && !(getenv("BAE_TC_LAG") && getenv("BAE_TC_LAG")[0] == '0');
   for (int pass = 0; pass < 2; ++pass) {
     const int p0 = bstart[pass];
     if (!lag) {
@@ -540,8 +538,9 @@ static void build_program(bae_handle* h) {
     // Measured at Madelon, 64 chains: backward phases -4.7% (2539 -> 2420 us per pass): the last phase no longer consists of
     // 4 long weight-gradient tiles per chain (256 items on 74 CTA pairs: a quarter of the last round idle) and the first one
     // is 1024 short delta tiles. The price is a second HBM read of every delta (+27 MB per chain and pass); HBM is far from
-    // being the binding unit of these phases. (With the opt-in delta images, BAE_TC_DIMG=1, the order is what lets the
-    // delta GEMM's converter warps persist the split delta for the weight-gradient GEMM.)
+    // being the binding unit of these phases. (Persisting the split deltas as images for the weight-gradient GEMMs, which this
+    // order allows, was measured too: their K blocks ran 12% faster without any conversion, the image writes - 33 MB per
+    // chain-iteration - cost the delta GEMMs as much: not kept.)
     set(p0 + 0, PH_GEMM, bx_idx[0], -1, 0, 0, 1);                  // dH5
     set(p0 + 1, PH_GEMM, bw_idx[0], bx_idx[1], 0, 0, 1);           // dW6 | dH4
     set(p0 + 2, PH_GEMM, bw_idx[1], bx_idx[2], 0, 0, 1);           // dW5 | dY
@@ -734,8 +733,6 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
     size_t per_chain = nm * (size_t)(s.ld0 + 4 * s.ld1 + 4 * s.ld2 + 3 * s.ld3) * sizeof(float);   // H1 H2 Z Y H4 H5 + DOUT D5 D4 DY D2 D1
     if (s.preconv && !(getenv("BAE_TC_HIMG") && getenv("BAE_TC_HIMG")[0] == '0'))
       per_chain += 2 * (img_bytes(s.d1 + 1, s.n_train) + img_bytes(s.d2 + 1, s.n_train)) + img_bytes(s.d3 + 1, s.n_train);
-    if (s.preconv && (getenv("BAE_TC_DIMG") && getenv("BAE_TC_DIMG")[0] == '1'))
-      per_chain += img_bytes(s.d0, s.n_train) + img_bytes(s.d1, s.n_train) + 2 * img_bytes(s.d2, s.n_train) + img_bytes(s.d3, s.n_train);   // images of H1 H5, H2 H4, Y
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     int G = s.C;
@@ -752,17 +749,6 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   CU(dalloc(h, &s.Y, CA_act * nm * s.ld3)); CU(dalloc(h, &s.H4, CA_act * nm * s.ld2)); CU(dalloc(h, &s.H5, CA_act * nm * s.ld1));
   CU(dalloc(h, &s.DOUT, CA_act * nm * s.ld0)); CU(dalloc(h, &s.D5, CA_act * nm * s.ld1)); CU(dalloc(h, &s.D4, CA_act * nm * s.ld2));
   CU(dalloc(h, &s.DY, CA_act * nm * s.ld3)); CU(dalloc(h, &s.D2, CA_act * nm * s.ld2)); CU(dalloc(h, &s.D1, CA_act * nm * s.ld1));
-  if (s.preconv && (getenv("BAE_TC_DIMG") && getenv("BAE_TC_DIMG")[0] == '1')) {
-    // Opt-in (BAE_TC_DIMG=1), measured and NOT adopted as the default: with the deltas pre-split too the weight-gradient tiles run
-    // without any conversion (-12% per K block), but the image writes (33 MB per chain-iteration at Madelon) cost the delta GEMMs
-    // as much DRAM time as the weight-gradient GEMMs gain (-0.7% per step).
-    const int dd[5] = {s.d0, s.d1, s.d2, s.d3, s.d2};   // DOUT, D5, D4, DY, D2
-    for (int i = 0; i < 5; ++i) {
-      s.dimg_kbs[i] = img_kbs(dd[i]);
-      s.dimg_stride[i] = (long long)img_bytes(dd[i], s.n_train);
-      CU(dalloc(h, &s.dimg[i], CA_act * (size_t)s.dimg_stride[i]));
-    }
-  }
   if (s.preconv && !(getenv("BAE_TC_HIMG") && getenv("BAE_TC_HIMG")[0] == '0')) {
     // MN-major images of the activations (B operands of the weight-gradient GEMMs), written by the converter warps of the forward
     // GEMM that reads the activation as its A operand
@@ -838,7 +824,7 @@ int bae_create(const bae_config* cfg, int device, bae_handle** out) {
   if (s.dbg_flags != 0)
     return fail(BAE_ERR_INVALID, "BAE_TC_DBGFLAGS is set, but this library was built without -DBAE_TC_DEBUG: refusing to sample");
 #endif
-  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW", "BAE_NARROW_CLUSTER", "BAE_TC_TF32", "BAE_TC_PRECONV", "BAE_TC_HIMG", "BAE_TC_DIMG", "BAE_TC_LAG"})
+  for (const char* knob : {"BAE_TC_KSPLIT_ROWS", "BAE_TC_MAXBN", "BAE_PHASE_LAUNCH", "BAE_NO_GRAPH", "BAE_TC_TRACE", "BAE_TC_NO_SCHED", "BAE_NO_NARROW", "BAE_NARROW_CLUSTER", "BAE_TC_TF32", "BAE_TC_PRECONV", "BAE_TC_HIMG", "BAE_TC_LAG"})
     if (getenv(knob)) fprintf(stderr, "[bae_b200] note: tuning variable %s=%s is in effect for this handle\n", knob, getenv(knob));
   s.dbg_phase = getenv("BAE_TC_TRACE_PHASE") ? atoi(getenv("BAE_TC_TRACE_PHASE")) : -1;
   {
@@ -1034,7 +1020,17 @@ static cudaError_t launch_one(bae_handle* h, int p, int c_begin, int c_end, int 
   const PhaseDesc& ph = h->hs.phase[p];
   const int ea = ph.kind == PH_GEMM ? h->hs.gemm[ph.g0].epi : -1;
   const int eb = (ph.kind == PH_GEMM && ph.g1 >= 0) ? h->hs.gemm[ph.g1].epi : -1;
-  return launch_phase(h->dS, h->hs.tc, h->grid, p, c_begin, c_end, force_swap, ea, eb, h->stream);
+  // what every GEMM of the phase does with operand images (bae_tc.cuh: FrontMode; 0 = decided per GEMM at run time)
+  int mode = 0;
+  if (ph.kind == PH_GEMM && h->hs.f16) {
+    const GemmDesc& ga = h->hs.gemm[ph.g0];
+    const GemmDesc* gb = ph.g1 >= 0 ? &h->hs.gemm[ph.g1] : nullptr;
+    const bool allB = ga.bImg && (!gb || gb->bImg), anyA = ga.aImg || (gb && gb->aImg), anyOut = ga.aOut || (gb && gb->aOut);
+    if (allB && !anyA && !anyOut) mode = 1;                       // FM_B
+    else if (allB && !gb && ga.aImg && !ga.aOut) mode = 2;        // FM_AB
+    else if (allB && !gb && !ga.aImg && ga.aOut) mode = 3;        // FM_B_OUT
+  }
+  return launch_phase(h->dS, h->hs.tc, h->grid, p, c_begin, c_end, force_swap, ea, eb, mode, h->stream);
 }
 
 static int run_phases_plain(bae_handle* h, int p_begin, int p_end, int c_begin, int c_end) {

@@ -211,9 +211,6 @@ struct DevState {
   unsigned char* himg[5];     // MN-major images of the activations H1, H2, Y, H4, H5 of the resident chain group: [G][himg_stride[i]]
   long long himg_stride[5];
   int himg_kbs[5];
-  unsigned char* dimg[5];     // MN-major images of the deltas DOUT, D5, D4, DY, D2 (persisted by the converters of the delta GEMM that
-  long long dimg_stride[5];   // reads them as its K-major A operand; A operands of the weight-gradient GEMMs, which run one phase later)
-  int dimg_kbs[5];
   WImg wi[6];
   void* tmaps;        // CUtensorMap array in global memory (64-byte aligned)
   int* sched;         // longest-first item schedules of the GEMM phases (PhaseDesc::sched_off), built for `sched_chains` chains

@@ -1754,10 +1754,11 @@ __device__ __forceinline__ void run_phase_tc_back(const DevState* S, int pi, int
   tc::fence_proxy_async();
 }
 
+template <int kMode>
 __device__ __forceinline__ void run_phase_tc_front(const DevState* S, int pi, int c_begin, int c_end, tc::Smem& tsm,
                                                    tc::Ring& ring) {
   const PhaseDesc& ph = S->phase[pi];
-  if (ph.kind == PH_GEMM) tc::gemm_phase_front(S, ph, c_begin, c_end, tsm, ring);
+  if (ph.kind == PH_GEMM) tc::gemm_phase_front<kMode>(S, ph, c_begin, c_end, tsm, ring);
 }
 
 __global__ void __launch_bounds__(tc::kThreadsTc, 1)
@@ -1792,7 +1793,7 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
     for (int rep = 0; rep < n_rep; ++rep) {
       for (int pi = ph_begin; pi < ph_end; ++pi) {
         if (S->phase[pi].kind == PH_WAMAX) continue;
-        run_phase_tc_front(S, pi, c_begin, c_end, tsm, ring);
+        run_phase_tc_front<tc::FM_GENERIC>(S, pi, c_begin, c_end, tsm, ring);
         grid.sync();
       }
     }
@@ -1800,21 +1801,23 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
   tc::teardown(tsm);
 }
 
-// One GEMM phase as its own launch (the production path on tcgen05), specialised by the epilogue kinds of its GEMMs.
-template <int kEpiA, int kEpiB>
+// One GEMM phase as its own launch (the production path on tcgen05), specialised by the epilogue kinds of its GEMMs and by
+// what they do with operand images (tc::FrontMode).
+template <int kEpiA, int kEpiB, int kMode>
 __global__ void __launch_bounds__(tc::kThreadsTc, 1)
 bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_end, int force_swap) {
   extern __shared__ uint8_t dyn_smem[];
   tc::Smem tsm;
   tc::Ring ring;
-  tc::setup(tsm, dyn_smem, S->f16 != 0);
+  const bool out = kMode == tc::FM_B_OUT || (kMode == tc::FM_GENERIC && tc::phase_has_out(S, S->phase[pi]));
+  tc::setup(tsm, dyn_smem, S->f16 != 0, tc::kConvGroupWarps + ((kMode != tc::FM_GENERIC || S->preconv) ? 1 : 0), out ? 2 : 1);
   const int wg = threadIdx.x >> 7;
   if (wg == 1 || wg == 2) {
     tc::regs_inc<tc::kRegsEpi>();
     tc::gemm_phase_epilogue<kEpiA, kEpiB>(S, S->phase[pi], c_begin, c_end, tsm, ring);
   } else {
     tc::regs_dec<tc::kRegsLean>();
-    run_phase_tc_front(S, pi, c_begin, c_end, tsm, ring);
+    run_phase_tc_front<kMode>(S, pi, c_begin, c_end, tsm, ring);
   }
   tc::teardown(tsm);
 }
@@ -1946,17 +1949,30 @@ static cudaError_t launch_tc(const void* fn, int grid, void** args, bool coopera
   return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
+// The instantiated phase kernels: epilogue kinds (sorted, epi_b < 0: one kind) x front mode; null: not instantiated
+static const void* phase_kernel_fn(int epi_a, int epi_b, int mode) {
+#define BAE_PK(A, B, M) if (epi_a == (A) && epi_b == (B) && mode == (M)) return (const void*)bae_phase_kernel_tc<A, B, M>;
+  // forward layers: generic; B image (test matrix pass); both images (first layer); B image + activation image out
+  BAE_PK(EPI_SIGMOID, -1, tc::FM_GENERIC) BAE_PK(EPI_SIGMOID, -1, tc::FM_B) BAE_PK(EPI_SIGMOID, -1, tc::FM_AB) BAE_PK(EPI_SIGMOID, -1, tc::FM_B_OUT)
+  BAE_PK(EPI_BIAS, -1, tc::FM_GENERIC) BAE_PK(EPI_BIAS, -1, tc::FM_B) BAE_PK(EPI_BIAS, -1, tc::FM_B_OUT)
+  BAE_PK(EPI_LOSS, -1, tc::FM_GENERIC) BAE_PK(EPI_LOSS, -1, tc::FM_B) BAE_PK(EPI_LOSS, -1, tc::FM_B_OUT)
+  // backward phases: generic; every B operand an image
+  BAE_PK(EPI_GRADW, -1, tc::FM_GENERIC) BAE_PK(EPI_GRADW, -1, tc::FM_B)
+  BAE_PK(EPI_DSIG, -1, tc::FM_GENERIC) BAE_PK(EPI_DSIG, -1, tc::FM_B)
+  BAE_PK(EPI_DSIG, EPI_GRADW, tc::FM_GENERIC) BAE_PK(EPI_DSIG, EPI_GRADW, tc::FM_B)
+  BAE_PK(EPI_PLAIN, EPI_GRADW, tc::FM_GENERIC) BAE_PK(EPI_PLAIN, EPI_GRADW, tc::FM_B)
+#undef BAE_PK
+  return nullptr;
+}
+
 int max_coop_blocks_per_sm(int use_tc) {
   int nb = 0;
   if (use_tc) {
     cudaFuncSetAttribute(bae_program_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_SIGMOID, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_BIAS, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_LOSS, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_GRADW, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_DSIG, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_DSIG, EPI_GRADW>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    cudaFuncSetAttribute(bae_phase_kernel_tc<EPI_PLAIN, EPI_GRADW>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    for (int ea = 0; ea <= EPI_GRADW; ++ea)
+      for (int eb = -1; eb <= EPI_GRADW; ++eb)
+        for (int m = 0; m < 4; ++m)
+          if (const void* fn = phase_kernel_fn(ea, eb, m)) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel_tc, tc::kThreadsTc, tc::kSmemBytes);
   } else {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel, kThreads, 0);
@@ -1989,25 +2005,13 @@ cudaError_t launch_program(const DevState* dS, int use_tc, int grid, int ph_begi
 
 // epi_a / epi_b: epilogue kinds of the phase's GEMMs (host copy of the program; epi_b < 0: one GEMM)
 cudaError_t launch_phase(const DevState* dS, int use_tc, int grid, int pi, int c_begin, int c_end, int force_swap,
-                         int epi_a, int epi_b, cudaStream_t st) {
+                         int epi_a, int epi_b, int front_mode, cudaStream_t st) {
   if (use_tc) {
     void* args[] = {(void*)&dS, (void*)&pi, (void*)&c_begin, (void*)&c_end, (void*)&force_swap};
-    const void* fn = nullptr;
     if (epi_b >= 0 && epi_b < epi_a) { const int t = epi_a; epi_a = epi_b; epi_b = t; }
-    if (epi_b < 0 || epi_b == epi_a) {
-      switch (epi_a) {
-        case EPI_SIGMOID: fn = (const void*)bae_phase_kernel_tc<EPI_SIGMOID, -1>; break;
-        case EPI_BIAS: fn = (const void*)bae_phase_kernel_tc<EPI_BIAS, -1>; break;
-        case EPI_LOSS: fn = (const void*)bae_phase_kernel_tc<EPI_LOSS, -1>; break;
-        case EPI_GRADW: fn = (const void*)bae_phase_kernel_tc<EPI_GRADW, -1>; break;
-        case EPI_DSIG: fn = (const void*)bae_phase_kernel_tc<EPI_DSIG, -1>; break;
-        default: break;
-      }
-    } else if (epi_a == EPI_DSIG && epi_b == EPI_GRADW) {
-      fn = (const void*)bae_phase_kernel_tc<EPI_DSIG, EPI_GRADW>;
-    } else if (epi_a == EPI_PLAIN && epi_b == EPI_GRADW) {
-      fn = (const void*)bae_phase_kernel_tc<EPI_PLAIN, EPI_GRADW>;
-    }
+    if (epi_b == epi_a) epi_b = -1;
+    const void* fn = phase_kernel_fn(epi_a, epi_b, front_mode);
+    if (!fn) fn = phase_kernel_fn(epi_a, epi_b, tc::FM_GENERIC);
     if (!fn) return cudaErrorInvalidDeviceFunction;   // a GEMM-kind combination the step program does not contain
     return launch_tc(fn, grid, args, false, st);
   }

@@ -71,8 +71,12 @@ static_assert(kSmemBytes + 1024 <= 232448, "dynamic + static shared memory of th
 // tile-pair layout: [A 8 KB][B half 8 KB]; kStages raw pairs followed by kLoStages lo pairs
 constexpr int kTmemCols = 512;                 // two accumulators of BN <= 256 columns each, single-buffered
 constexpr int kRegsLeanPersist = 48, kRegsEpiPersist = 208;   // persistent kernel (3xTF32 only): its non-GEMM phases need the registers
-constexpr int kRegsLean = 48;                  // producer / MMA / converter warpgroups
-constexpr int kRegsEpi = 208;                  // epilogue warpgroups (also run the non-GEMM phases)
+#ifndef BAE_TC_REGS_LEAN
+#define BAE_TC_REGS_LEAN 48
+#define BAE_TC_REGS_EPI 208
+#endif
+constexpr int kRegsLean = BAE_TC_REGS_LEAN;    // producer / MMA / converter warpgroups
+constexpr int kRegsEpi = BAE_TC_REGS_EPI;      // epilogue warpgroups (also run the non-GEMM phases)
 static_assert(kRegsLean * 256 + kRegsEpi * 256 <= 65536, "register file");
 
 struct Ring {
@@ -525,13 +529,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 
 // f16: the raw (FP32) stages are read by this CTA's converter warps only, which release them themselves (one arrival per warp
 // of the converting group); in the 3xTF32 engine the tensor core reads them too and the MMA issuer's commit releases them.
-__device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem, bool f16 = false) {
+// f16: arrivals that free a raw stage / a converted slot (see gemm_phase_front):
+//   n_empty    converter warps of the group (2), + 1 where stages may hold operand images (the MMAs' commit, or the group again)
+//   n_lo_empty the MMAs' commit, + 1 in phases whose converted tiles are also read by image stores (the storing group)
+__device__ __forceinline__ void setup(Smem& sm, uint8_t* dyn_smem, bool f16 = false, int n_empty = 1, int n_lo_empty = 1) {
   uintptr_t base = (reinterpret_cast<uintptr_t>(dyn_smem) + 1023) & ~(uintptr_t)1023;
   sm.tiles = reinterpret_cast<uint8_t*>(base);
   if (threadIdx.x == 0) {
     // `conv` and `tmem_empty` collect arrivals from both CTAs of the pair (only the leader's copies are waited on)
-    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full()[i], 1); mbar_init(&sm.empty()[i], f16 ? kConvGroupWarps + 1 : 1); }
-    for (int i = 0; i < kLoStages; ++i) { mbar_init(&sm.conv()[i], 2 * kConvGroupWarps); mbar_init(&sm.lo_empty()[i], f16 ? 2 : 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&sm.full()[i], 1); mbar_init(&sm.empty()[i], f16 ? n_empty : 1); }
+    for (int i = 0; i < kLoStages; ++i) { mbar_init(&sm.conv()[i], 2 * kConvGroupWarps); mbar_init(&sm.lo_empty()[i], f16 ? n_lo_empty : 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm.tmem_full()[i], 1); mbar_init(&sm.tmem_empty()[i], 2 * kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -646,6 +653,21 @@ __device__ __forceinline__ int sched_next(const Sched& sc, int k) {
 // One GEMM phase on the tensor cores, front half: TMA producer, MMA issuer and the hi/lo converters
 // (warpgroups 0 and 3). Returns when this CTA's last MMA has been issued / last lo tile written.
 // ---------------------------------------------------------------------------------------------------
+// a phase whose converter warps send converted tiles to an activation image (GemmDesc::aOut)
+__device__ __forceinline__ bool phase_has_out(const DevState* S, const PhaseDesc& ph) {
+  return S->gemm[ph.g0].aOut != nullptr || (ph.g1 >= 0 && S->gemm[ph.g1].aOut != nullptr);
+}
+
+// kMode: what the GEMMs of the phase do with operand images, fixed at compile time where the host knows it for every GEMM of
+// the phase (bae_kernels.cu: launch_phase) - the converter loop at 48 registers is sensitive to every live value and every
+// inlined copy of the conversion code (measured: the mere presence of the image bookkeeping cost the converter-only engine 10%
+// per step, the presence of the store bookkeeping alone 5%):
+//   FM_GENERIC  everything decided per GEMM at run time (3xTF32, the persistent kernel, images switched off, mixed phases)
+//   FM_B        B operands are images, A operands are converted (backward phases; forward phases over the test matrix)
+//   FM_AB       both operands are images: the converter warps only relay the barrier (first layer: data x weights)
+//   FM_B_OUT    B operands are images, the converted A tiles are persisted as an activation image (forward, training matrix)
+enum FrontMode : int { FM_GENERIC = 0, FM_B = 1, FM_AB = 2, FM_B_OUT = 3 };
+template <int kMode>
 __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, Smem& sm, Ring& ring) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Sched sched = make_sched(S, ph, c_begin, c_end);
@@ -674,7 +696,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const int ca = g.sA ? (g.aAct ? it.chain - c_begin : it.chain) : 0, cb = g.sB ? (g.bAct ? it.chain - c_begin : it.chain) : 0;
         const int dbgf = BAE_DBGF(S);
         // pre-split operand images: this CTA's hi tile of K block kb0 (the lo tile lies kbs / 2 further)
-        const unsigned char* imgA = g.aImg ? g.aImg + (size_t)ca * g.sAImg + (size_t)it.kb0 * g.aKbs + (size_t)(m0 >> 3) * (g.aMode ? 128 : 256) : nullptr;
+        const unsigned char* imgA = (kMode == FM_B || kMode == FM_B_OUT) ? nullptr : g.aImg ? g.aImg + (size_t)ca * g.sAImg + (size_t)it.kb0 * g.aKbs + (size_t)(m0 >> 3) * 256 : nullptr;   // (A images are K-major: the data matrix)
         const unsigned char* imgB = g.bImg ? g.bImg + (size_t)cb * g.sBImg + (size_t)it.kb0 * g.bKbs + (size_t)(n0 >> 3) * (g.bMode ? 128 : 256) : nullptr;
         const uint32_t aKbs = (uint32_t)g.aKbs, bKbs = (uint32_t)g.bKbs, bPlane = (uint32_t)(g.tcBN >> 1) * 32u;
         const uint32_t bytes = ((dbgf & 64) ? 0u : (uint32_t)kATileBytes) + ((dbgf & 32) ? 0u : (imgB ? 2u * bPlane : (uint32_t)g.tcBBytes));
@@ -693,16 +715,8 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             if (dbgf & 64) {
             } else if (imgA) {
               const unsigned char* p = imgA + (size_t)kb * aKbs;
-              if (aMode == 0) {
-                bulk_load(cv, p, (uint32_t)kF16TileBytes, &sm.full()[ring.stage]);
-                bulk_load(cv + kF16TileBytes, p + (aKbs >> 1), (uint32_t)kF16TileBytes, &sm.full()[ring.stage]);
-              } else {   // MN-major image: one run of 128 MN x 16 B per K half, the halves kbs / 4 bytes apart
-                const uint32_t run = kF16TileBytes >> 1, jstep = aKbs >> 2;
-                bulk_load(cv, p, run, &sm.full()[ring.stage]);
-                bulk_load(cv + run, p + jstep, run, &sm.full()[ring.stage]);
-                bulk_load(cv + kF16TileBytes, p + (aKbs >> 1), run, &sm.full()[ring.stage]);
-                bulk_load(cv + kF16TileBytes + run, p + (aKbs >> 1) + jstep, run, &sm.full()[ring.stage]);
-              }
+              bulk_load(cv, p, (uint32_t)kF16TileBytes, &sm.full()[ring.stage]);
+              bulk_load(cv + kF16TileBytes, p + (aKbs >> 1), (uint32_t)kF16TileBytes, &sm.full()[ring.stage]);
             } else if (aMode == 0) {
               tma_load_3d(st, mapA, &sm.full()[ring.stage], k0, m0, ca);
             } else {
@@ -763,9 +777,8 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const uint64_t dA = make_desc(smem_u32(sm.tiles), amn), dB = make_desc(smem_u32(sm.tiles) + kATileBytes, bmn);
         const uint64_t d16 = make_desc_f16(smem_u32(sm.tiles));
         const bool f16 = S->f16 != 0;
-        const bool preA = g.aImg != nullptr, preB = g.bImg != nullptr;   // operand images: read in the raw stage, which these MMAs then release
+        const bool preA = kMode == FM_GENERIC ? g.aImg != nullptr : kMode == FM_AB, preB = kMode == FM_GENERIC ? g.bImg != nullptr : true;   // operand images: read in the raw stage, which these MMAs then release
         // B image in the raw stage: K-major [t8][j][r] like a converted tile; MN-major [j][t8][r] (strides: K half 16 n, MN group 128)
-        const uint64_t rawA = amn ? make_desc_f16(smem_u32(sm.tiles), 16u * kBM, 128u) : d16;
         const uint64_t rawB = bmn ? make_desc_f16(smem_u32(sm.tiles) + kATileBytes, (uint32_t)(g.tcBN >> 1) * 16u, 128u)
                                   : make_desc_f16(smem_u32(sm.tiles) + kATileBytes);
         for (int kb = 0; kb < nkb; ++kb) {
@@ -777,7 +790,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             if (elect_one()) {
               trace(dbg, 1, ntr, kb);
               const uint64_t cvt = d16 + (kStages + ring.lo) * (uint32_t)(kStageBytes >> 4);
-              const uint64_t ah = preA ? rawA + ring.stage * (uint32_t)(kStageBytes >> 4) : cvt, al = ah + (kF16TileBytes >> 4);
+              const uint64_t ah = preA ? d16 + ring.stage * (uint32_t)(kStageBytes >> 4) : cvt, al = ah + (kF16TileBytes >> 4);
               const uint64_t bh = preB ? rawB + ring.stage * (uint32_t)(kStageBytes >> 4) : cvt + (2 * kF16TileBytes >> 4), bl = bh + (kF16TileBytes >> 4);
               const uint32_t acc0 = kb ? 1u : 0u;
               umma_f16(d_main, ah, bh, idesc, acc0);
@@ -834,7 +847,8 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     const uint32_t tiles0 = smem_u32(sm.tiles);
     const ConvLane cl = conv_lane(gt);
     int ntr = (grp == 0) ? 0 : (grp == 1 ? 170 : 340);
-    int pending = -1;   // converted slot whose box stores (activation image) may still be reading it (meaningful in thread gt == 0)
+    const bool preMode = kMode != FM_GENERIC || S->preconv != 0;   // barrier counts of this launch (setup)
+    const bool outMode = kMode == FM_B_OUT || (kMode == FM_GENERIC && phase_has_out(S, ph));
     uint32_t kbc = ring.kbc;
     for (int ki = 0;; ++ki) {   // items go to CTA pairs
       const int item = sched_next(sched, ki);
@@ -847,13 +861,14 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
       uint32_t offA = 0, offB = 0;
       bool swapA = false, swapB = false, aM = false, bM = false;
       int nvB = 0;   // units of this CTA's B half that this thread converts: gt + 64 n < tcBN
-      const bool preA = it.g->aImg != nullptr, preB = it.g->bImg != nullptr;   // the producer delivers these operands already split
+      const bool preA = kMode == FM_GENERIC ? it.g->aImg != nullptr : kMode == FM_AB, preB = kMode == FM_GENERIC ? it.g->bImg != nullptr : true;   // the producer delivers these operands already split
       // A operand persisted as an activation image (GemmDesc::aOut): after every K block this group sends the converted tiles
       // [A hi], [A lo] to the image (one box store each); the slot may be rewritten once the stores have READ it - the second
       // arrival on `lo_empty` (next to the MMAs' commit), made when this group comes back for its next block
       // (the hi plane by the tile_n == 0 item of a row block, the lo plane by its tile_n == 1 item when there is one: the items
       //  of a phase then cost the same, which its schedule assumes)
-      const bool outHi = f16 && it.g->aOut && it.tile_n == 0, outLo = f16 && it.g->aOut && it.tile_n == (it.g->tn > 1 ? 1 : 0);
+      const bool outK = kMode == FM_B_OUT || (kMode == FM_GENERIC && f16 && it.g->aOut);
+      const bool outHi = outK && it.tile_n == 0, outLo = outK && it.tile_n == (it.g->tn > 1 ? 1 : 0);
       const CUtensorMap* mapOut = (outHi || outLo) ? &maps[it.g->tmOut] : nullptr;
       const int outRow = (it.tile_m * (2 * kBM) + (int)rank * kBM) >> 4, outSlot = it.chain - c_begin;
       if (f16) {
@@ -872,10 +887,6 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
           const uint32_t b7 = ring.stage + (uint32_t)kb, b5 = ring.lo + (uint32_t)kb;
           const uint32_t stage = b7 % kStages, phase = ring.phase ^ ((b7 / kStages) & 1u);
           const uint32_t lo = b5 % kLoStages, lo_phase = ring.lo_phase ^ ((b5 / kLoStages) & 1u);
-          if (pending >= 0) {   // the box stores of this group's previous block have read their slot
-            if (gt == 0) { bulk_wait_read(); mbar_arrive(&sm.lo_empty()[pending]); }
-            pending = -1;
-          }
           mbar_wait(&sm.lo_empty()[lo], lo_phase ^ 1);
           mbar_wait(&sm.full()[stage], phase);
           if (gt == 0) trace(dbg, 2, ntr, kb);
@@ -894,32 +905,24 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
           if (lane == 0) {
             mbar_arrive(&sm.empty()[stage]);   // the raw stage has been read: the producer may refill it
             // (third arrival: the MMAs' commit when the stage holds an image tile, else this group's first warp again)
-            if (!(preA || preB) && (warp & 1) == 0) mbar_arrive(&sm.empty()[stage]);
+            if (preMode && !(preA || preB) && (warp & 1) == 0) mbar_arrive(&sm.empty()[stage]);
             if (rank == 0) mbar_arrive(&sm.conv()[lo]);
             else mbar_arrive_leader_relaxed(&sm.conv()[lo]);
-            if ((warp & 1) == 0) {   // gt == 0
+            if (outMode && (warp & 1) == 0) {   // gt == 0
               if (mapOut && !(BAE_DBGF(S) & 128)) {
                 const uint32_t cvs = tiles0 + (kStages + lo) * kStageBytes;
                 if (outHi) tma_store_4d(mapOut, cvs, (it.kb0 + kb) * 128, 0, outRow, outSlot);
                 if (outLo) tma_store_4d(mapOut + 1, cvs + kF16TileBytes, (it.kb0 + kb) * 128, 0, outRow, outSlot);
                 bulk_commit();
-#ifdef BAE_TC_DEFER_OUT
-                pending = (int)lo;
-#else
                 // (waiting here costs this thread the few hundred cycles the copy engine needs to read 4 KB; leaving the arrival to
                 //  the group's next block - three blocks later - kept three of the five converted slots occupied)
                 bulk_wait_read();
                 mbar_arrive(&sm.lo_empty()[lo]);
-#endif
               } else {
                 mbar_arrive(&sm.lo_empty()[lo]);   // nothing but the MMAs reads the slot
               }
             }
           }
-        }
-        if (pending >= 0) {
-          if (gt == 0) { bulk_wait_read(); mbar_arrive(&sm.lo_empty()[pending]); }
-          pending = -1;
         }
         // the item's blocks are done (or left to the other groups): move the ring state past them
         const uint32_t e7 = ring.stage + (uint32_t)nkb, e5 = ring.lo + (uint32_t)nkb;

@@ -88,12 +88,11 @@ def test_operand_layout_probe_runs():
     assert p.returncode == 0 and "PROBE_F16 OK" in p.stdout, p.stdout + p.stderr
 
 
-def _run_images(monkeypatch, preconv, dims, n_train, n_test, chains, rungs, steps, si, act_group=0, himg="1", dimg="0"):
+def _run_images(monkeypatch, preconv, dims, n_train, n_test, chains, rungs, steps, si, act_group=0, himg="1"):
     """One free-running PT run; returns the raw trace bytes and the final (theta, m, v) of every chain."""
     from bayesianautoencoders_b200 import DeviceSampler, default_theta_init
     monkeypatch.setenv("BAE_TC_PRECONV", preconv)
     monkeypatch.setenv("BAE_TC_HIMG", himg)
-    monkeypatch.setenv("BAE_TC_DIMG", dimg)
     train, test = synth_data(dims, n_train, n_test)
     T = np.tile(2.0 ** (np.arange(rungs) / max(1, rungs - 1)), chains // rungs)
     kw = dict(act_group=act_group) if act_group else {}
@@ -129,11 +128,10 @@ def test_operand_images_bit_identical(monkeypatch, case):
     else:
         cfg = dict(dims=(272, 256, 240, 128), n_train=700, n_test=400, chains=2, rungs=2, steps=6, si=2)
     ref, ev_ref = _run_images(monkeypatch, "0", **cfg)
-    # weights / data images only; with the activation images as well (the default); with the opt-in delta images on top
-    for himg, dimg in (("0", "0"), ("1", "0"), ("1", "1")):
-        got, ev = _run_images(monkeypatch, "1", himg=himg, dimg=dimg, **cfg)
+    for himg in ("0", "1"):          # weights / data images only, then with the activation images as well (the default)
+        got, ev = _run_images(monkeypatch, "1", himg=himg, **cfg)
         for j, (a, b) in enumerate(zip(ref, got)):
-            assert a[0] == b[0], f"trace records of chain {j} differ (BAE_TC_HIMG={himg}, BAE_TC_DIMG={dimg})"
+            assert a[0] == b[0], f"trace records of chain {j} differ (BAE_TC_HIMG={himg})"
             for k in (1, 2, 3):
-                assert a[k].tobytes() == b[k].tobytes(), f"state vector {k} of chain {j} differs (BAE_TC_HIMG={himg}, BAE_TC_DIMG={dimg})"
+                assert a[k].tobytes() == b[k].tobytes(), f"state vector {k} of chain {j} differs (BAE_TC_HIMG={himg})"
         assert ev["sse"] == ev_ref["sse"] and ev["grads"].tobytes() == ev_ref["grads"].tobytes()

@@ -9,7 +9,7 @@ if len(sys.argv) > 2 and sys.argv[2] == "child":
     dims4, ntr, nte = SHAPES[shape]
     train, test = synth(dims4, ntr, nte)
     C = int(os.environ.get("EXP_CHAINS", "8"))
-    s = DeviceSampler(dims4, train, test, C, 8, 100, np.tile(2.0 ** (np.arange(8) / 7), C // 8), swap_interval=3, gemm_path=2)
+    s = DeviceSampler(dims4, train, test, C, 8, 100, np.tile(2.0 ** (np.arange(8) / 7), C // 8), swap_interval=int(os.environ.get("EXP_SI", "3")), gemm_path=2)
     rng = np.random.default_rng(0)
     for j in range(C): s.init_chain(j, default_theta_init(dims4, rng), rng.standard_normal(s.w_size))
     s.run(7); s.synchronize()
