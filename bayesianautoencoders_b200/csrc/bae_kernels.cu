@@ -1754,11 +1754,11 @@ __device__ __forceinline__ void run_phase_tc_back(const DevState* S, int pi, int
   tc::fence_proxy_async();
 }
 
-template <int kMode>
+template <int kMode, bool kAK>
 __device__ __forceinline__ void run_phase_tc_front(const DevState* S, int pi, int c_begin, int c_end, tc::Smem& tsm,
                                                    tc::Ring& ring) {
   const PhaseDesc& ph = S->phase[pi];
-  if (ph.kind == PH_GEMM) tc::gemm_phase_front<kMode>(S, ph, c_begin, c_end, tsm, ring);
+  if (ph.kind == PH_GEMM) tc::gemm_phase_front<kMode, kAK>(S, ph, c_begin, c_end, tsm, ring);
 }
 
 __global__ void __launch_bounds__(tc::kThreadsTc, 1)
@@ -1793,7 +1793,7 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
     for (int rep = 0; rep < n_rep; ++rep) {
       for (int pi = ph_begin; pi < ph_end; ++pi) {
         if (S->phase[pi].kind == PH_WAMAX) continue;
-        run_phase_tc_front<tc::FM_GENERIC>(S, pi, c_begin, c_end, tsm, ring);
+        run_phase_tc_front<tc::FM_GENERIC, false>(S, pi, c_begin, c_end, tsm, ring);
         grid.sync();
       }
     }
@@ -1817,7 +1817,8 @@ bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_e
     tc::gemm_phase_epilogue<kEpiA, kEpiB>(S, S->phase[pi], c_begin, c_end, tsm, ring);
   } else {
     tc::regs_dec<tc::kRegsLean>();
-    run_phase_tc_front<kMode>(S, pi, c_begin, c_end, tsm, ring);
+    constexpr bool kAK = kMode != tc::FM_GENERIC && kEpiB < 0 && (kEpiA == EPI_SIGMOID || kEpiA == EPI_BIAS || kEpiA == EPI_LOSS);   // a forward layer
+    run_phase_tc_front<kMode, kAK>(S, pi, c_begin, c_end, tsm, ring);
   }
   tc::teardown(tsm);
 }

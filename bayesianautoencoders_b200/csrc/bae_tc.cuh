@@ -666,13 +666,16 @@ __device__ __forceinline__ bool phase_has_out(const DevState* S, const PhaseDesc
 //   FM_B        B operands are images, A operands are converted (backward phases; forward phases over the test matrix)
 //   FM_AB       both operands are images: the converter warps only relay the barrier (first layer: data x weights)
 //   FM_B_OUT    B operands are images, the converted A tiles are persisted as an activation image (forward, training matrix)
+// kAK: every A operand of the phase is K-major (forward layers): no MN-major copy of the conversion code.
 enum FrontMode : int { FM_GENERIC = 0, FM_B = 1, FM_AB = 2, FM_B_OUT = 3 };
-template <int kMode>
+#pragma nv_diag_suppress 128   // (a mode fixed at compile time leaves the other engine's loops unreachable)
+template <int kMode, bool kAK>
 __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, Smem& sm, Ring& ring) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Sched sched = make_sched(S, ph, c_begin, c_end);
   const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(S->tmaps);
-  long long* dbg = (blockIdx.x == 0 && (S->dbg_phase < 0 || S->dbg_phase == (int)(&ph - S->phase))) ? S->dbg : nullptr;
+  // (the timeline trace is compiled into the generic kernels only; with BAE_TC_TRACE=1 the host launches those)
+  long long* dbg = (kMode == FM_GENERIC && blockIdx.x == 0 && (S->dbg_phase < 0 || S->dbg_phase == (int)(&ph - S->phase))) ? S->dbg : nullptr;
   const uint32_t rank = cluster_rank();
   // NOTE: every descriptor field used inside a K loop is copied into a local first. The loops are full of
   // asm volatile statements with memory clobbers, after which the compiler would re-load fields of *it.g from
@@ -776,7 +779,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         // descriptors of stage 0; a stage / K-step offset only moves the 14-bit address field (bytes >> 4)
         const uint64_t dA = make_desc(smem_u32(sm.tiles), amn), dB = make_desc(smem_u32(sm.tiles) + kATileBytes, bmn);
         const uint64_t d16 = make_desc_f16(smem_u32(sm.tiles));
-        const bool f16 = S->f16 != 0;
+        const bool f16 = kMode != FM_GENERIC || S->f16 != 0;   // (operand images exist on the 3xFP16 engine only)
         const bool preA = kMode == FM_GENERIC ? g.aImg != nullptr : kMode == FM_AB, preB = kMode == FM_GENERIC ? g.bImg != nullptr : true;   // operand images: read in the raw stage, which these MMAs then release
         // B image in the raw stage: K-major [t8][j][r] like a converted tile; MN-major [j][t8][r] (strides: K half 16 n, MN group 128)
         const uint64_t rawB = bmn ? make_desc_f16(smem_u32(sm.tiles) + kATileBytes, (uint32_t)(g.tcBN >> 1) * 16u, 128u)
@@ -843,7 +846,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     const int gt = ((warp & 1) << 5) + lane;   // 0..63 inside the group
     const uint32_t tiles_s = smem_u32(sm.tiles) + gt * 16;
     const bool skip = (BAE_DBGF(S) & 1) != 0;
-    const bool f16 = S->f16 != 0;
+    const bool f16 = kMode != FM_GENERIC || S->f16 != 0;
     const uint32_t tiles0 = smem_u32(sm.tiles);
     const ConvLane cl = conv_lane(gt);
     int ntr = (grp == 0) ? 0 : (grp == 1 ? 170 : 340);
@@ -874,7 +877,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
       if (f16) {
         sA = exp2i(operand_exp(S, it.g->aSc, it.chain));
         sB = exp2i(operand_exp(S, it.g->bSc, it.chain));
-        aM = it.g->aMode != 0; bM = it.g->bMode != 0;
+        aM = !kAK && it.g->aMode != 0; bM = it.g->bMode != 0;
         offA = cl.off[aM ? 1 : 0]; offB = cl.off[bM ? 1 : 0];
         swapA = aM && cl.swap1; swapB = bM && cl.swap1;
         nvB = (it.g->tcBN - gt + 63) >> 6;
