@@ -702,7 +702,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const unsigned char* imgA = (kMode == FM_B || kMode == FM_B_OUT) ? nullptr : g.aImg ? g.aImg + (size_t)ca * g.sAImg + (size_t)it.kb0 * g.aKbs + (size_t)(m0 >> 3) * 256 : nullptr;   // (A images are K-major: the data matrix)
         const unsigned char* imgB = g.bImg ? g.bImg + (size_t)cb * g.sBImg + (size_t)it.kb0 * g.bKbs + (size_t)(n0 >> 3) * (g.bMode ? 128 : 256) : nullptr;
         const uint32_t aKbs = (uint32_t)g.aKbs, bKbs = (uint32_t)g.bKbs, bPlane = (uint32_t)(g.tcBN >> 1) * 32u;
-        const uint32_t bytes = ((dbgf & 64) ? 0u : (uint32_t)kATileBytes) + ((dbgf & 32) ? 0u : (imgB ? 2u * bPlane : (uint32_t)g.tcBBytes));
+        const uint32_t bytes = ((dbgf & 64) ? 0u : (uint32_t)kATileBytes) + ((dbgf & 32) ? 0u : ((kMode != FM_GENERIC || imgB) ? 2u * bPlane : (uint32_t)g.tcBBytes));
         const int aMode = g.aMode, bMode = g.bMode, nchB = g.tcBBytes / kMnChunkBytes, nkb = it.nkb, kb0 = it.kb0;
         const CUtensorMap* mapA = &maps[g.tmIdx[0]];
         const CUtensorMap* mapB = &maps[g.tmIdx[1]];
@@ -716,7 +716,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             mbar_expect_tx(&sm.full()[ring.stage], bytes);
             const int k0 = (kb0 + kb) * kBK;
             if (dbgf & 64) {
-            } else if (imgA) {
+            } else if (kMode == FM_AB || imgA) {   // (fast modes: the host has checked every GEMM of the phase)
               const unsigned char* p = imgA + (size_t)kb * aKbs;
               bulk_load(cv, p, (uint32_t)kF16TileBytes, &sm.full()[ring.stage]);
               bulk_load(cv + kF16TileBytes, p + (aKbs >> 1), (uint32_t)kF16TileBytes, &sm.full()[ring.stage]);
@@ -730,7 +730,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             }
             uint8_t* sb = st + kATileBytes;
             if (dbgf & 32) {
-            } else if (imgB) {
+            } else if (kMode != FM_GENERIC || imgB) {
               const unsigned char* p = imgB + (size_t)kb * bKbs;
               if (bMode == 0) {
                 bulk_load(cv + kATileBytes, p, bPlane, &sm.full()[ring.stage]);
