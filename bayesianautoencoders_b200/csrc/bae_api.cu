@@ -1022,7 +1022,8 @@ static cudaError_t launch_one(bae_handle* h, int p, int c_begin, int c_end, int 
   const int eb = (ph.kind == PH_GEMM && ph.g1 >= 0) ? h->hs.gemm[ph.g1].epi : -1;
   // what every GEMM of the phase does with operand images (bae_tc.cuh: FrontMode; 0 = decided per GEMM at run time)
   int mode = 0;
-  if (ph.kind == PH_GEMM && h->hs.f16 && !h->hs.dbg) {   // (BAE_TC_TRACE=1: the timeline trace lives in the generic kernels)
+  if (ph.kind == PH_GEMM && !h->hs.preconv && !h->hs.dbg) mode = 4;   // FM_NONE: no operand images anywhere
+  if (ph.kind == PH_GEMM && h->hs.preconv && !h->hs.dbg) {   // (BAE_TC_TRACE=1: the timeline trace lives in the generic kernels)
     const GemmDesc& ga = h->hs.gemm[ph.g0];
     const GemmDesc* gb = ph.g1 >= 0 ? &h->hs.gemm[ph.g1] : nullptr;
     const bool allB = ga.bImg && (!gb || gb->bImg), anyA = ga.aImg || (gb && gb->aImg), anyOut = ga.aOut || (gb && gb->aOut);

@@ -1793,7 +1793,7 @@ bae_program_kernel_tc(const DevState* __restrict__ S, int ph_begin, int ph_end, 
     for (int rep = 0; rep < n_rep; ++rep) {
       for (int pi = ph_begin; pi < ph_end; ++pi) {
         if (S->phase[pi].kind == PH_WAMAX) continue;
-        run_phase_tc_front<tc::FM_GENERIC, false>(S, pi, c_begin, c_end, tsm, ring);
+        run_phase_tc_front<tc::FM_NONE, false>(S, pi, c_begin, c_end, tsm, ring);   // (3xTF32 only: no operand images)
         grid.sync();
       }
     }
@@ -1810,14 +1810,15 @@ bae_phase_kernel_tc(const DevState* __restrict__ S, int pi, int c_begin, int c_e
   tc::Smem tsm;
   tc::Ring ring;
   const bool out = kMode == tc::FM_B_OUT || (kMode == tc::FM_GENERIC && tc::phase_has_out(S, S->phase[pi]));
-  tc::setup(tsm, dyn_smem, S->f16 != 0, tc::kConvGroupWarps + ((kMode != tc::FM_GENERIC || S->preconv) ? 1 : 0), out ? 2 : 1);
+  const bool pre = kMode == tc::FM_GENERIC ? S->preconv != 0 : kMode != tc::FM_NONE;
+  tc::setup(tsm, dyn_smem, S->f16 != 0, tc::kConvGroupWarps + (pre ? 1 : 0), out ? 2 : 1);
   const int wg = threadIdx.x >> 7;
   if (wg == 1 || wg == 2) {
     tc::regs_inc<tc::kRegsEpi>();
     tc::gemm_phase_epilogue<kEpiA, kEpiB>(S, S->phase[pi], c_begin, c_end, tsm, ring);
   } else {
     tc::regs_dec<tc::kRegsLean>();
-    constexpr bool kAK = kMode != tc::FM_GENERIC && kEpiB < 0 && (kEpiA == EPI_SIGMOID || kEpiA == EPI_BIAS || kEpiA == EPI_LOSS);   // a forward layer
+    constexpr bool kAK = kMode != tc::FM_GENERIC && kMode != tc::FM_NONE && kEpiB < 0 && (kEpiA == EPI_SIGMOID || kEpiA == EPI_BIAS || kEpiA == EPI_LOSS);   // a forward layer
     run_phase_tc_front<kMode, kAK>(S, pi, c_begin, c_end, tsm, ring);
   }
   tc::teardown(tsm);
@@ -1954,6 +1955,8 @@ static cudaError_t launch_tc(const void* fn, int grid, void** args, bool coopera
 static const void* phase_kernel_fn(int epi_a, int epi_b, int mode) {
 #define BAE_PK(A, B, M) if (epi_a == (A) && epi_b == (B) && mode == (M)) return (const void*)bae_phase_kernel_tc<A, B, M>;
   // forward layers: generic; B image (test matrix pass); both images (first layer); B image + activation image out
+  BAE_PK(EPI_SIGMOID, -1, tc::FM_NONE) BAE_PK(EPI_BIAS, -1, tc::FM_NONE) BAE_PK(EPI_LOSS, -1, tc::FM_NONE) BAE_PK(EPI_GRADW, -1, tc::FM_NONE)
+  BAE_PK(EPI_DSIG, -1, tc::FM_NONE) BAE_PK(EPI_DSIG, EPI_GRADW, tc::FM_NONE) BAE_PK(EPI_PLAIN, EPI_GRADW, tc::FM_NONE)
   BAE_PK(EPI_SIGMOID, -1, tc::FM_GENERIC) BAE_PK(EPI_SIGMOID, -1, tc::FM_B) BAE_PK(EPI_SIGMOID, -1, tc::FM_AB) BAE_PK(EPI_SIGMOID, -1, tc::FM_B_OUT)
   BAE_PK(EPI_BIAS, -1, tc::FM_GENERIC) BAE_PK(EPI_BIAS, -1, tc::FM_B) BAE_PK(EPI_BIAS, -1, tc::FM_B_OUT)
   BAE_PK(EPI_LOSS, -1, tc::FM_GENERIC) BAE_PK(EPI_LOSS, -1, tc::FM_B) BAE_PK(EPI_LOSS, -1, tc::FM_B_OUT)
@@ -1972,7 +1975,7 @@ int max_coop_blocks_per_sm(int use_tc) {
     cudaFuncSetAttribute(bae_program_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     for (int ea = 0; ea <= EPI_GRADW; ++ea)
       for (int eb = -1; eb <= EPI_GRADW; ++eb)
-        for (int m = 0; m < 4; ++m)
+        for (int m = 0; m < 5; ++m)
           if (const void* fn = phase_kernel_fn(ea, eb, m)) cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, bae_program_kernel_tc, tc::kThreadsTc, tc::kSmemBytes);
   } else {

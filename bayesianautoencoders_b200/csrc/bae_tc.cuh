@@ -667,7 +667,8 @@ __device__ __forceinline__ bool phase_has_out(const DevState* S, const PhaseDesc
 //   FM_AB       both operands are images: the converter warps only relay the barrier (first layer: data x weights)
 //   FM_B_OUT    B operands are images, the converted A tiles are persisted as an activation image (forward, training matrix)
 // kAK: every A operand of the phase is K-major (forward layers): no MN-major copy of the conversion code.
-enum FrontMode : int { FM_GENERIC = 0, FM_B = 1, FM_AB = 2, FM_B_OUT = 3 };
+//   FM_NONE     no GEMM of the phase touches an image (3xTF32 engines, BAE_TC_PRECONV=0): the converter-only engine as it was
+enum FrontMode : int { FM_GENERIC = 0, FM_B = 1, FM_AB = 2, FM_B_OUT = 3, FM_NONE = 4 };
 #pragma nv_diag_suppress 128   // (a mode fixed at compile time leaves the other engine's loops unreachable)
 template <int kMode, bool kAK>
 __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_begin, int c_end, Smem& sm, Ring& ring) {
@@ -699,10 +700,10 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         const int ca = g.sA ? (g.aAct ? it.chain - c_begin : it.chain) : 0, cb = g.sB ? (g.bAct ? it.chain - c_begin : it.chain) : 0;
         const int dbgf = BAE_DBGF(S);
         // pre-split operand images: this CTA's hi tile of K block kb0 (the lo tile lies kbs / 2 further)
-        const unsigned char* imgA = (kMode == FM_B || kMode == FM_B_OUT) ? nullptr : g.aImg ? g.aImg + (size_t)ca * g.sAImg + (size_t)it.kb0 * g.aKbs + (size_t)(m0 >> 3) * 256 : nullptr;   // (A images are K-major: the data matrix)
-        const unsigned char* imgB = g.bImg ? g.bImg + (size_t)cb * g.sBImg + (size_t)it.kb0 * g.bKbs + (size_t)(n0 >> 3) * (g.bMode ? 128 : 256) : nullptr;
+        const unsigned char* imgA = (kMode == FM_B || kMode == FM_B_OUT || kMode == FM_NONE) ? nullptr : g.aImg ? g.aImg + (size_t)ca * g.sAImg + (size_t)it.kb0 * g.aKbs + (size_t)(m0 >> 3) * 256 : nullptr;   // (A images are K-major: the data matrix)
+        const unsigned char* imgB = kMode == FM_NONE ? nullptr : g.bImg ? g.bImg + (size_t)cb * g.sBImg + (size_t)it.kb0 * g.bKbs + (size_t)(n0 >> 3) * (g.bMode ? 128 : 256) : nullptr;
         const uint32_t aKbs = (uint32_t)g.aKbs, bKbs = (uint32_t)g.bKbs, bPlane = (uint32_t)(g.tcBN >> 1) * 32u;
-        const uint32_t bytes = ((dbgf & 64) ? 0u : (uint32_t)kATileBytes) + ((dbgf & 32) ? 0u : ((kMode != FM_GENERIC || imgB) ? 2u * bPlane : (uint32_t)g.tcBBytes));
+        const uint32_t bytes = ((dbgf & 64) ? 0u : (uint32_t)kATileBytes) + ((dbgf & 32) ? 0u : (((kMode != FM_GENERIC && kMode != FM_NONE) || imgB) ? 2u * bPlane : (uint32_t)g.tcBBytes));
         const int aMode = g.aMode, bMode = g.bMode, nchB = g.tcBBytes / kMnChunkBytes, nkb = it.nkb, kb0 = it.kb0;
         const CUtensorMap* mapA = &maps[g.tmIdx[0]];
         const CUtensorMap* mapB = &maps[g.tmIdx[1]];
@@ -730,7 +731,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
             }
             uint8_t* sb = st + kATileBytes;
             if (dbgf & 32) {
-            } else if (kMode != FM_GENERIC || imgB) {
+            } else if ((kMode != FM_GENERIC && kMode != FM_NONE) || imgB) {
               const unsigned char* p = imgB + (size_t)kb * bKbs;
               if (bMode == 0) {
                 bulk_load(cv + kATileBytes, p, bPlane, &sm.full()[ring.stage]);
@@ -779,8 +780,8 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
         // descriptors of stage 0; a stage / K-step offset only moves the 14-bit address field (bytes >> 4)
         const uint64_t dA = make_desc(smem_u32(sm.tiles), amn), dB = make_desc(smem_u32(sm.tiles) + kATileBytes, bmn);
         const uint64_t d16 = make_desc_f16(smem_u32(sm.tiles));
-        const bool f16 = kMode != FM_GENERIC || S->f16 != 0;   // (operand images exist on the 3xFP16 engine only)
-        const bool preA = kMode == FM_GENERIC ? g.aImg != nullptr : kMode == FM_AB, preB = kMode == FM_GENERIC ? g.bImg != nullptr : true;   // operand images: read in the raw stage, which these MMAs then release
+        const bool f16 = (kMode != FM_GENERIC && kMode != FM_NONE) || S->f16 != 0;   // (operand images exist on the 3xFP16 engine only)
+        const bool preA = kMode == FM_GENERIC ? g.aImg != nullptr : kMode == FM_AB, preB = kMode == FM_GENERIC ? g.bImg != nullptr : kMode != FM_NONE;   // operand images: read in the raw stage, which these MMAs then release
         // B image in the raw stage: K-major [t8][j][r] like a converted tile; MN-major [j][t8][r] (strides: K half 16 n, MN group 128)
         const uint64_t rawB = bmn ? make_desc_f16(smem_u32(sm.tiles) + kATileBytes, (uint32_t)(g.tcBN >> 1) * 16u, 128u)
                                   : make_desc_f16(smem_u32(sm.tiles) + kATileBytes);
@@ -846,11 +847,11 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
     const int gt = ((warp & 1) << 5) + lane;   // 0..63 inside the group
     const uint32_t tiles_s = smem_u32(sm.tiles) + gt * 16;
     const bool skip = (BAE_DBGF(S) & 1) != 0;
-    const bool f16 = kMode != FM_GENERIC || S->f16 != 0;
+    const bool f16 = (kMode != FM_GENERIC && kMode != FM_NONE) || S->f16 != 0;
     const uint32_t tiles0 = smem_u32(sm.tiles);
     const ConvLane cl = conv_lane(gt);
     int ntr = (grp == 0) ? 0 : (grp == 1 ? 170 : 340);
-    const bool preMode = kMode != FM_GENERIC || S->preconv != 0;   // barrier counts of this launch (setup)
+    const bool preMode = kMode == FM_GENERIC ? S->preconv != 0 : kMode != FM_NONE;   // barrier counts of this launch (setup)
     const bool outMode = kMode == FM_B_OUT || (kMode == FM_GENERIC && phase_has_out(S, ph));
     uint32_t kbc = ring.kbc;
     for (int ki = 0;; ++ki) {   // items go to CTA pairs
@@ -864,7 +865,7 @@ __device__ void gemm_phase_front(const DevState* S, const PhaseDesc& ph, int c_b
       uint32_t offA = 0, offB = 0;
       bool swapA = false, swapB = false, aM = false, bM = false;
       int nvB = 0;   // units of this CTA's B half that this thread converts: gt + 64 n < tcBN
-      const bool preA = kMode == FM_GENERIC ? it.g->aImg != nullptr : kMode == FM_AB, preB = kMode == FM_GENERIC ? it.g->bImg != nullptr : true;   // the producer delivers these operands already split
+      const bool preA = kMode == FM_GENERIC ? it.g->aImg != nullptr : kMode == FM_AB, preB = kMode == FM_GENERIC ? it.g->bImg != nullptr : kMode != FM_NONE;   // the producer delivers these operands already split
       // A operand persisted as an activation image (GemmDesc::aOut): after every K block this group sends the converted tiles
       // [A hi], [A lo] to the image (one box store each); the slot may be rewritten once the stores have READ it - the second
       // arrival on `lo_empty` (next to the MMAs' commit), made when this group comes back for its next block

@@ -187,3 +187,38 @@ def test_exchange_local_matches_pack_unpack():
     for p in range(n):
         np.testing.assert_array_equal(a.get_state(p)["theta"], b.get_state(p)["theta"])
     a.close(); b.close()
+
+
+def test_phase_times_debug_api(monkeypatch):
+    """BAE_PHASE_TIMES=1: direct launches with an event behind every phase; the per-phase milliseconds of bae_debug_phase_times
+    add up to the launch time bae_last_step_ms reports, and the traces equal those of the graph-replayed run."""
+    import numpy as np
+    from bayesianautoencoders_b200 import DeviceSampler, default_theta_init
+    from bayesianautoencoders_b200 import _native as N
+    from tests.parity_util import synth_data
+    dims = (500, 450, 400, 300)
+    train, test = synth_data(dims, 600, 300)
+
+    def run(timed):
+        if timed:
+            monkeypatch.setenv("BAE_PHASE_TIMES", "1")
+        else:
+            monkeypatch.delenv("BAE_PHASE_TIMES", raising=False)
+        s = DeviceSampler(dims, train, test, 4, 4, 6, 2.0 ** (np.arange(4) / 3), swap_interval=3, seed=9, gemm_path=2)
+        rng = np.random.default_rng(1)
+        for j in range(4):
+            s.init_chain(j, default_theta_init(dims, rng), rng.standard_normal(s.w_size))
+        s.run(6)
+        s.synchronize()
+        ms, n = np.zeros(64), np.zeros(64, np.int32)
+        if timed:
+            N.check(s.lib.bae_debug_phase_times(s._h, ms.ctypes.data, n.ctypes.data))
+        out = (s.last_ms(), ms, n, [s.traces(j, 0, 6).tobytes() for j in range(4)])
+        s.close()
+        return out
+
+    total, ms, n, tr_timed = run(True)
+    assert n[:40].min() >= 6 and n[40:43].min() >= 6          # every step phase 6 times (the weight-bound phase once more), the exchange phases too
+    assert ms.sum() > 0 and abs(ms.sum() - total) <= 0.25 * total
+    _, _, _, tr_graph = run(False)
+    assert tr_timed == tr_graph

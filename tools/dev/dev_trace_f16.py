@@ -31,13 +31,14 @@ for name, ev in (("producer", p), ("mma", m)):
 for g, (lo, hi) in enumerate(((0, 170), (170, 340), (340, 510))):
     ev = events(2, lo, hi)
     w_lo, w_full, conv, idle, t7, tend = [], [], [], [], None, None
+    t8 = t0k = tf = 0   # (the 3xFP16 converter loop stamps only block start / end)
     fence, arr = [], []
     for a, b in ev:     # per K block: 7000 + kb (arrived), 8000 + kb (lo slot free), kb (TMA bytes landed), 2000 + kb (converted)
         if 7000 <= a < 8000:
             t7 = b
             if tend is not None: idle.append(b - tend)
         elif 8000 <= a < 9000: t8 = b; w_lo.append(b - t7)
-        elif a < 1000: t0k = b; w_full.append(b - t8)
+        elif a < 1000: t0k = b; w_full.append(b - t8 if t8 else 0)
         elif 2000 <= a < 3000: conv.append(b - t0k); tend = b
         elif 3000 <= a < 4000: fence.append(b - tend); tf = b
         elif 4000 <= a < 5000: arr.append(b - tf); tend = b
