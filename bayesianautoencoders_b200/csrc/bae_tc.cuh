@@ -1039,7 +1039,9 @@ __device__ __forceinline__ void epilogue_tile(const DevState* S, const Item& it,
   {
     // all main-accumulator chunks are requested at once, then the cross-term chunks 16 columns at a time.
     // (Handing the main accumulator back first, so that the next tile's hi*hi products start during the cross-term drain,
-    // was measured: the gap between tiles shrank by 1.7 k cycles, the step did not get faster - not kept.)
+    // was measured twice - on the converter-bound engine: the gap between tiles shrank by 1.7 k cycles, the step did not get
+    // faster; on the operand-image engine, with the hi*hi products of the first four K blocks issued ahead of the cross
+    // terms: again no change of the step time - not kept.)
     uint32_t pa[16];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
