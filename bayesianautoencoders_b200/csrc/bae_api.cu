@@ -222,10 +222,13 @@ static GemmDesc make_gemm(const DevState& s, int M, int N, int K, int b_nmajor =
 // work items so the phase fills the grid; the copies are summed in fixed order (deterministic) by the Adam phase.
 static int grad_ksplit(const DevState& s, int grid_hint, const GemmDesc& g, int rows) {
   if (s.tc) {
-    // tcgen05 path: the tensor core truncates when it adds into its accumulator, so keep every accumulation chain
-    // at the length of a forward layer's (<= ~640 rows, 40 K blocks); extra splits also balance the phase
+    // tcgen05 path: the tensor core truncates when it adds into its accumulator, so the accumulation chains stay short:
+    // 3xTF32 (K = 8 per MMA): the length of a forward layer's (<= ~640 rows, 80 accumulations); 3xFP16 (K = 16 per MMA):
+    // 1000 rows = 63 accumulations. Every segment costs a drain and an epilogue pass (a reduce-add of the whole tile): at
+    // Madelon 2 segments of 1000 rows instead of 4 of 500 are worth 4.4% of the step, for a gradient error of 0.78e-5
+    // instead of 0.73e-5 at iteration 0 (tolerance 1.2e-5; profiles/r2_parity_measured.md)
     const char* e = getenv("BAE_TC_KSPLIT_ROWS");
-    const int per = e ? std::max(64, atoi(e)) : 640;
+    const int per = e ? std::max(64, atoi(e)) : (s.f16 ? 1000 : 640);
     return std::max(1, (rows + per - 1) / per);   // segments run back to back on one CTA pair and accumulate into one copy
   }
   const int tiles = g.tm * g.tn * s.C;

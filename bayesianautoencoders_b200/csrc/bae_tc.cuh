@@ -581,7 +581,7 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 
 // Work items of a GEMM phase (same arithmetic in every role): one item = one output tile of one chain. The K SEGMENTS of
 // a weight-gradient tile (GemmDesc::ksplit: the contraction over the data rows, cut so that no TMEM accumulation chain is
-// longer than ~640 rows) are processed back to back by the SAME CTA pair: segment 0 stores the tile, every later segment
+// longer than ~1000 rows; ~640 on the 3xTF32 engines) are processed back to back by the SAME CTA pair: segment 0 stores the tile, every later segment
 // adds into it (TMA reduce-add in L2 / read-modify-write by the thread that wrote the element), in segment order - one
 // gradient copy in HBM, summed in a fixed order.
 struct Item { const GemmDesc* g; int chain, tile_m, tile_n, split, kb0, nkb, nsplit; };
