@@ -1,7 +1,11 @@
-// tcgen05 / TMEM / TMA tile engine (sm_100a): chain-batched GEMM tiles with 3xTF32 split operands.
+// tcgen05 / TMEM / TMA tile engine (sm_100a): chain-batched GEMM tiles with three-way split FP32 operands.
 //
 //   D[128 x BN] (FP32, TMEM) = sum_k  A_hi*B_hi   (accumulator 0)   +   A_lo*B_hi + A_hi*B_lo   (accumulator 1)
 //
+// Two engines share this file. The production one is the 3xFP16 split (kind::f16, scaled operands: further down, "3xFP16
+// split"), with operands that are known before the GEMM runs arriving as pre-split images ("operand images") and the front
+// half compiled per mode (FrontMode). The round-1 engine, kept as a fallback (BAE_TC_TF32=1, the persistent kernel), is
+// the 3xTF32 split described first:
 // Operands live in HBM as plain FP32. The tensor core reads a 32-bit container and ignores the low 13
 // mantissa bits (measured: tests/cuda/tc_selftest.cu), so the raw tile IS the `hi` operand; converter warps
 // compute lo = x - trunc_tf32(x) (exact in FP32) into a second shared-memory tile. Three kind::tf32 MMAs per
@@ -15,7 +19,7 @@
 // (shared-memory latency bound, tests/cuda/tc_microbench.cu) is what paces the tile loop.
 //
 // 512-thread CTA, one per SM, four warpgroups with their own register budgets (setmaxnreg):
-//   warp 0      TMA producer: raw tiles (16 floats of K per stage) into a 5-stage ring
+//   warp 0      TMA producer: raw tiles (16 floats of K per stage; operand-image tiles by plain bulk copies) into a 7-stage ring
 //   warp 1      MMA issuer (leader CTA only; warp-uniform loop, one elected lane issues)
 //   warps 2-3, 12-15   hi/lo converters, three groups of two warps that take K blocks round-robin, so the
 //                      wait -> LDS -> STS -> proxy fence -> arrive latency of one block overlaps the next ones
@@ -28,8 +32,8 @@
 // `empty` (stage free) and `tmem_full` (accumulators complete) are signalled in both CTAs by multicast tcgen05.commit.
 // The tensor core adds into its FP32 accumulator with truncation, a bias that grows with the number of
 // accumulating MMAs: the two small cross terms therefore go to their own accumulator, and long contractions
-// (weight gradients, K = rows) are split over work items whose partial gradients are summed in FP32 by the
-// Adam phase (GemmDesc::ksplit).
+// (weight gradients, K = rows) are cut into segments that one CTA pair processes back to back, adding each into the
+// gradient with a TMA reduce-add (GemmDesc::ksplit).
 #pragma once
 #include <cuda.h>
 
