@@ -16,7 +16,7 @@ EXPORTS = [
     "bae_last_error", "bae_version", "bae_create", "bae_destroy", "bae_w_size", "bae_n_trainable",
     "bae_upload_data", "bae_set_ladder", "bae_init_chain", "bae_get_state", "bae_set_state", "bae_step",
     "bae_swap_local", "bae_run", "bae_synchronize", "bae_eval", "bae_debug_draws", "bae_debug_swap_uniform",
-    "bae_read_traces", "bae_swap_counts", "bae_exchange_pack", "bae_exchange_unpack", "bae_exchange_finish",
+    "bae_read_traces", "bae_read_traces_all", "bae_swap_counts", "bae_exchange_pack", "bae_exchange_unpack", "bae_exchange_finish",
     "bae_launch_count", "bae_last_step_ms", "bae_gemm_path", "bae_stream", "bae_debug_buffer", "bae_debug_trace", "bae_debug_profiler", "bae_debug_phase_times", "bae_exchange_table", "bae_exchange_local", "bae_host_sweep", "bae_last_sweep", "bae_forward_all", "bae_shard_config", "bae_swap_exchange", "bae_plan_exchange",
     "bae_exchange_vectors_sent", "bae_step_kernel", "bae_eval_bn_stats", "bae_mma_kind",
 ]
@@ -90,6 +90,7 @@ def load():
     lib.bae_debug_draws.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.bae_debug_swap_uniform.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, P(C.c_double)]
     lib.bae_read_traces.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.bae_read_traces_all.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.bae_swap_counts.argtypes = [C.c_void_p, P(C.c_int64), P(C.c_int64)]
     lib.bae_last_sweep.argtypes = [C.c_void_p, C.c_void_p]
     lib.bae_shard_config.argtypes = [C.c_void_p, C.c_int, C.c_int]

@@ -927,10 +927,28 @@ int bae_upload_data(bae_handle* h, const float* train, const float* test) {
   }
   if (s.f16) {
     // bounds of the two data matrices for the FP16 operand scales (their ones column included)
-    float mx[2] = {1.0f, 1.0f};
-    for (size_t i = 0; i < (size_t)s.n_train * s.d0; ++i) mx[0] = std::max(mx[0], std::fabs(train[i]));
-    for (size_t i = 0; i < (size_t)s.n_test * s.d0; ++i) mx[1] = std::max(mx[1], std::fabs(test[i]));
-    if (!std::isfinite(mx[0]) || !std::isfinite(mx[1])) return fail(BAE_ERR_INVALID, "data contains non-finite values");
+    // (sixteen independent running maxima: the scan is on the caller's critical path of every upload; `x - x` is 0 for finite
+    //  values and NaN otherwise, so one sum finds non-finite data without a test per element)
+    auto absmax = [](const float* p, size_t n, float& bad) {
+      float m[16], z[16];
+      for (int k = 0; k < 16; ++k) { m[k] = 1.0f; z[k] = 0.f; }
+      size_t i = 0;
+      for (; i + 16 <= n; i += 16)
+        for (int k = 0; k < 16; ++k) {
+          const float v = p[i + k], a = std::fabs(v);
+          m[k] = a > m[k] ? a : m[k];
+          z[k] += v - v;
+        }
+      for (; i < n; ++i) { const float v = p[i], a = std::fabs(v); m[0] = a > m[0] ? a : m[0]; z[0] += v - v; }
+      float r = m[0];
+      for (int k = 1; k < 16; ++k) { r = m[k] > r ? m[k] : r; z[0] += z[k]; }
+      bad = z[0];
+      return r;
+    };
+    float bad[2];
+    float mx[2] = {absmax(train, (size_t)s.n_train * s.d0, bad[0]), absmax(test, (size_t)s.n_test * s.d0, bad[1])};
+    if (!(bad[0] == 0.f) || !(bad[1] == 0.f) || !std::isfinite(mx[0]) || !std::isfinite(mx[1]))
+      return fail(BAE_ERR_INVALID, "data contains non-finite values");
     h->hs.xexp[0] = f16_scale_exp(mx[0]);
     h->hs.xexp[1] = f16_scale_exp(mx[1]);
     int rc = upload_state(h);
@@ -1475,6 +1493,19 @@ int bae_read_traces(bae_handle* h, int chain, int first_step, int n, bae_trace* 
     return fail(BAE_ERR_INVALID, "trace range out of bounds");
   CU(cudaSetDevice(h->device));
   CU(cudaMemcpyAsync(outp, s.traces + (size_t)chain * s.samples + first_step, sizeof(bae_trace) * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  return BAE_OK;
+}
+
+// The same records of EVERY resident chain in one strided copy and one synchronisation: out[chain][n]
+int bae_read_traces_all(bae_handle* h, int first_step, int n, bae_trace* outp) {
+  if (!h || !outp) return fail(BAE_ERR_INVALID, "null argument");
+  const DevState& s = h->hs;
+  if (first_step < 0 || n < 0 || first_step + n > s.samples) return fail(BAE_ERR_INVALID, "trace range out of bounds");
+  if (n == 0) return BAE_OK;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpy2DAsync(outp, sizeof(bae_trace) * n, s.traces + first_step, sizeof(bae_trace) * s.samples, sizeof(bae_trace) * n, s.C,
+                       cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   return BAE_OK;
 }

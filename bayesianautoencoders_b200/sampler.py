@@ -222,6 +222,13 @@ class DeviceSampler:
         N.check(self.lib.bae_read_traces(self._h, int(chain), int(first), int(n), out.ctypes.data))
         return out
 
+    def traces_all(self, first=0, n=None):
+        """Trace records [n_chains][n] of every resident chain in one device -> host copy."""
+        n = self.samples - first if n is None else n
+        out = np.zeros((self.n_chains, n), dtype=TRACE_DTYPE)
+        N.check(self.lib.bae_read_traces_all(self._h, int(first), int(n), out.ctypes.data))
+        return out
+
     def swap_counts(self):
         a, b = C.c_int64(), C.c_int64()
         N.check(self.lib.bae_swap_counts(self._h, C.byref(a), C.byref(b)))

@@ -504,10 +504,8 @@ def run_gpu(args):
     for _ in range(e2e_steps):
         s.upload_data(pin_train.numpy(), pin_test.numpy())
         job.pt_round()
-        d2h = 0
-        for j in range(job.chains):
-            tr = s.traces(j, job.iters_done - SWAP_INTERVAL, SWAP_INTERVAL)   # device -> host read of the step's results
-            d2h += tr.nbytes
+        tr = s.traces_all(job.iters_done - SWAP_INTERVAL, SWAP_INTERVAL)   # device -> host read of the step's results, every chain
+        d2h = tr.nbytes
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:

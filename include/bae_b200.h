@@ -152,6 +152,8 @@ int bae_debug_swap_uniform(bae_handle* h, int ensemble, int round, int pair, dou
 
 /* Trace ring: records of iterations [first_step, first_step+n) of one chain. */
 int bae_read_traces(bae_handle* h, int chain, int first_step, int n, bae_trace* out);
+/* the same records of every resident chain, out[n_chains][n]: one copy, one synchronisation */
+int bae_read_traces_all(bae_handle* h, int first_step, int n, bae_trace* out);
 int bae_swap_counts(bae_handle* h, int64_t* num_swap, int64_t* total_swap_proposals);
 /* Result of the most recent exchange sweep on this handle (MAIN:1059-1065): src[p] = local chain whose configuration
  * ended at ladder position p (length n_chains). Pair (p, p+1) of an ensemble swapped iff src[p] == p + 1 (`swapped`,

@@ -214,6 +214,8 @@ def test_phase_times_debug_api(monkeypatch):
         if timed:
             N.check(s.lib.bae_debug_phase_times(s._h, ms.ctypes.data, n.ctypes.data))
         out = (s.last_ms(), ms, n, [s.traces(j, 0, 6).tobytes() for j in range(4)])
+        allt = s.traces_all(1, 4)          # the batched read returns the same records
+        assert allt.shape == (4, 4) and all(allt[j].tobytes() == s.traces(j, 1, 4).tobytes() for j in range(4))
         s.close()
         return out
 
@@ -222,3 +224,22 @@ def test_phase_times_debug_api(monkeypatch):
     assert ms.sum() > 0 and abs(ms.sum() - total) <= 0.25 * total
     _, _, _, tr_graph = run(False)
     assert tr_timed == tr_graph
+
+
+@pytest.mark.parametrize("bad", [np.nan, np.inf, -np.inf])
+def test_upload_rejects_non_finite_data(bad):
+    """The 3xFP16 engine scales the data by a bound taken at upload: NaN / inf anywhere in either matrix is refused."""
+    import numpy as np
+    from bayesianautoencoders_b200 import DeviceSampler
+    from bayesianautoencoders_b200._native import BaeError
+    from tests.parity_util import synth_data
+    dims = (500, 450, 400, 300)
+    train, test = synth_data(dims, 300, 200)
+    s = DeviceSampler(dims, train, test, 1, 1, 4, np.ones(1), seed=3, gemm_path=2)      # finite data: accepted
+    for which, pos in ((0, 17), (0, train.size - 1), (1, 5)):
+        tr, te = train.copy(), test.copy()
+        (tr if which == 0 else te).reshape(-1)[pos] = bad
+        with pytest.raises(BaeError):
+            s.upload_data(tr, te)
+    s.upload_data(train, test)
+    s.close()
