@@ -171,6 +171,6 @@ front half's (TMA producer / MMA issuer at 48 registers) per-tile set-up; the ep
 """
 open(f'profiles/{prefix}_step_program_ncu_full.md', 'w').write(md2)
 json.dump({"shape": "madelon", "gemm_path": 2, "chains": 8, "iterations": 1, "dram_bytes_read": rd, "dram_bytes_write": wr, "kernel_ms_under_ncu": us / 1e3,
-           "source": f"ncu --set full over the 42 kernels of one iteration of the step program, 8 chains (profiles/{prefix}_step_program_ncu_full.md)"},
+           "source": f"ncu --set full over the {len(prow)} kernels of one iteration of the step program, 8 chains (profiles/{prefix}_step_program_ncu_full.md)"},
           open(f'profiles/{prefix}_traffic.json', 'w'), indent=1)
 print("profiles written")
